@@ -136,7 +136,7 @@ DEFAULT_OPTS: Dict[str, float] = {
     "cost_reduction_ths": 1e-6,
     "mu0": 0.0,
     # extensions (not reference option names)
-    "multiple_shooting": 0,
+    "multiple_shooting": 1,                # pyddp is a multiple-shooting DDP (README.md:5-6, ddp.py:116-117)
     "defect_contraction_rate": 0.0,        # README.md:6; <=0 means rho = alpha
     "mu_min": 1e-6,
     "mu_max": 1e10,
