@@ -1,0 +1,154 @@
+/*
+ * sddp.h -- C ABI of the B200-native batched DDP solver for srbd_horizon.
+ *
+ * This is the drop-in boundary for the one hot path of hucebot/srbd_horizon:
+ * the DDP solve behind python/ddp.py's `DDPSolver`.  In the reference that
+ * boundary is the pybind module `pyddp` (not in the tree), reached from
+ *
+ *   ddp.py:14-35    pyddp.DdpSolverOptions()         -> fields of SddpConfig
+ *   ddp.py:93-94    pyddp.DdpSolver(nx,nu,f,L,L_N,o) -> sddp_create
+ *   ddp.py:101      ddp_solver.solve(params)         -> sddp_solve_batch (B = 1 for the reference's use)
+ *   ddp.py:106      ddp_solver.is_converged()        -> status[b] == SDDP_CONVERGED
+ *   ddp.py:114,117  set_u_warmstart / set_x_warmstart-> the X / U buffers on entry
+ *   ddp.py:123      set_initial_state(x0)            -> the x0 buffer
+ *
+ * pyddp receives CasADi Function objects for f_k, L_k, L_N (ddp.py:179-230); here
+ * the two problems of prb.py are hand-written sm_100a CUDA, selected by
+ * SddpConfig.model, and the numeric constants prb.py reads from ROS/URDF are
+ * plain fields of SddpConfig.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all array arguments are DEVICE pointers to
+ *     fp64 (int32 for iters/status) unless the function name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *     work is enqueued on it, nothing synchronises except the *_host calls;
+ *   - every function returns 0 on success, a negative SDDP_E* code otherwise,
+ *     never throws; sddp_last_error() gives the message for the calling handle;
+ *   - a handle is bound to the device current at sddp_create, owns only its
+ *     workspace, is not thread-safe; distinct handles are independent;
+ *   - per-problem numerical outcome is reported in status[b], not in the return code.
+ *
+ * Layouts (row-major, problem-major):
+ *   x0[B][nx]  params[B][N+1][np]  X[B][N+1][nx]  U[B][N][nu]
+ *   K[B][N][nu][nx]  kff[B][N][nu]  hist[B][max_iters][SDDP_HIST]
+ *   iters[B] status[B] (int32)  cost[B]
+ * State / input / parameter layouts: see srbd_horizon_b200/config.py (prb.py:32-68, 264-295).
+ */
+#ifndef SDDP_H
+#define SDDP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDDP_ABI_VERSION 1
+
+enum { SDDP_MODEL_SRBD = 0, SDDP_MODEL_LIP = 1 };
+enum { SDDP_INERTIA_LITERAL = 0, SDDP_INERTIA_ROTATED = 1 };   /* prb.py:99 as written / README.md:2 intent */
+enum { SDDP_HESSIAN_EXACT = 0, SDDP_HESSIAN_GN = 1 };
+enum { SDDP_NODE_FIRST = 0, SDDP_NODE_MID = 1, SDDP_NODE_TERM = 2 };
+enum { SDDP_CONVERGED = 0, SDDP_MAX_ITERS = 1, SDDP_LS_FAILED = 2, SDDP_REG_FAILED = 3, SDDP_NAN = 4 };
+enum { SDDP_HIST = 4 };   /* per iteration: cost, alpha (0 = no step), mu, max|defect| */
+enum { SDDP_EINVAL = -1, SDDP_ECUDA = -2, SDDP_ENOMEM = -3, SDDP_ECAPACITY = -4 };
+
+typedef struct SddpConfig {
+    int32_t model;             /* SDDP_MODEL_*  (prb.py:16-246 / 248-441) */
+    int32_t N;                 /* shooting intervals `ns`; nodes 0..N (prb.py:21) */
+    int32_t inertia_mode;      /* SDDP_INERTIA_* */
+    int32_t hessian_mode;      /* SDDP_HESSIAN_* */
+    int32_t multiple_shooting; /* 1: keep the x warm start, carry defects (README.md:5-6) */
+    int32_t max_iters;         /* ddp.py:17-19 */
+    int32_t reserved0;
+    int32_t reserved1;
+    double dt;                 /* prb.py:110 */
+    double mass;               /* prb.py:92 */
+    double inertia[9];         /* prb.py:94-95, row-major */
+    double com[3];             /* prb.py:138-139 */
+    double foot[12];           /* prb.py:127-135 */
+    double force_scaling;      /* prb.py:98 */
+    double gravity;
+    double eta2;               /* prb.py:317 */
+    double r_tracking_gain;    /* prb.py:142 */
+    double rdot_tracking_gain; /* prb.py:145 */
+    double w_tracking_gain;    /* prb.py:146 */
+    double rel_position_gain;  /* prb.py:147 */
+    double force_switch_weight;/* prb.py:148 */
+    double min_qddot_gain;     /* prb.py:149 */
+    double min_f_gain;         /* prb.py:150 */
+    double zmp_tracking_gain;  /* prb.py:361 */
+    double constraint_weight;  /* ddp.py:181 */
+    double alpha_0;                      /* ddp.py:20-22 */
+    double alpha_converge_threshold;     /* ddp.py:23-25 */
+    double line_search_decrease_factor;  /* ddp.py:26-28 */
+    double beta;                         /* ddp.py:29-31 */
+    double cost_reduction_ths;           /* ddp.py:32-33 */
+    double mu0;                          /* ddp.py:34-35 */
+    double defect_contraction_rate;      /* README.md:6; <= 0: rho = alpha */
+    double mu_min, mu_max, mu_factor;
+    double defect_ths;
+} SddpConfig;
+
+typedef struct SddpHandle SddpHandle;
+
+int sddp_abi_version(void);
+size_t sddp_config_size(void);
+/* nx, nu, np of a model */
+int sddp_dims(int model, int *nx, int *nu, int *np);
+
+/* Bytes of device workspace a handle allocates (independent of the batch size:
+ * scratch is per resident CTA, not per problem). */
+size_t sddp_workspace_bytes(const SddpConfig *cfg);
+
+int sddp_create(const SddpConfig *cfg, SddpHandle **out);
+int sddp_destroy(SddpHandle *h);
+const char *sddp_last_error(const SddpHandle *h);   /* h may be NULL: last create error */
+/* replace the solver options / mode switches of a live handle (model and N must not change) */
+int sddp_set_config(SddpHandle *h, const SddpConfig *cfg);
+
+/* Stage 1 alone (north_star stage one; the CasADi evaluation of f_k, L_k, L_N built at
+ * ddp.py:179-230): for M independent (x,u,p) points of node kind `kind[m]`, writes
+ * f[M][nx], fx[M][nx][nx], fu[M][nx][nu], l[M], lx[M][nx], lu[M][nu], lxx[M][nx][nx],
+ * lux[M][nu][nx], luu[M][nu][nu].  Any output pointer may be NULL.  For SDDP_NODE_TERM
+ * the dynamics and input outputs are written as zeros. */
+int sddp_eval_derivatives(SddpHandle *h, int M, const int32_t *kind, const double *x, const double *u,
+                          const double *p, double *f, double *fx, double *fu, double *l, double *lx,
+                          double *lu, double *lxx, double *lux, double *luu, void *stream);
+
+/* The solve (ddp.py:101).  X and U carry the warm start in and the solution out.
+ * K, kff, hist may be NULL (gains then stay in the workspace). */
+int sddp_solve_batch(SddpHandle *h, int B, const double *x0, const double *params, double *X, double *U,
+                     double *K, double *kff, double *hist, int32_t *iters, int32_t *status, double *cost,
+                     void *stream);
+
+/* Stage entry points used by the stage parity tests (north_star stages two to four).
+ * defect[B][N][nx]; dV[B][3] = {D1, D2, C0}; rc[B] = 0 or failing node + 1. */
+int sddp_backward_pass(SddpHandle *h, int B, const double *X, const double *U, const double *params,
+                       const double *defect, double mu, double *K, double *kff, double *dV, int32_t *rc,
+                       void *stream);
+/* n_alpha candidate step sizes per problem, evaluated in parallel: Jn[B][n_alpha],
+ * Xn[B][n_alpha][N+1][nx], Un[B][n_alpha][N][nu] (Xn/Un may be NULL). rho[n_alpha] as alpha. */
+int sddp_forward_pass(SddpHandle *h, int B, int n_alpha, const double *alpha, const double *rho,
+                      const double *x0, const double *X, const double *U, const double *params,
+                      const double *defect, const double *K, const double *kff, double *Jn, double *Xn,
+                      double *Un, void *stream);
+/* defect[B][N][nx] = f(X_k,U_k) - X_{k+1},  cost[B] = total cost (either may be NULL) */
+int sddp_defects(SddpHandle *h, int B, const double *X, const double *U, const double *params,
+                 double *defect, double *cost, void *stream);
+
+/* Same solve with HOST buffers: copies in, solves, copies out, synchronises.
+ * This is what a non-CUDA caller (the reference's Python loop) binds. */
+int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *params, double *X, double *U,
+                          double *K, double *kff, double *hist, int32_t *iters, int32_t *status, double *cost);
+
+/* Measured FP64 FMA rate of the device (microbenchmark, TFLOP/s); used as the roofline peak. */
+int sddp_fp64_peak_tflops(double *out, void *stream);
+
+/* counters since create: kernels launched by this handle */
+int sddp_launch_count(const SddpHandle *h, long long *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,76 @@
+"""ctypes binding of csrc/libsddp.so (include/sddp.h).  There is no CPU fallback: if the
+library is missing or no CUDA device is present the product path raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+from .config import SddpConfig
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libsddp.so")
+
+_vp = ctypes.c_void_p
+_ip = ctypes.POINTER(ctypes.c_int)
+
+#: every symbol include/sddp.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "sddp_abi_version": (ctypes.c_int, []),
+    "sddp_config_size": (ctypes.c_size_t, []),
+    "sddp_dims": (ctypes.c_int, [ctypes.c_int, _ip, _ip, _ip]),
+    "sddp_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(SddpConfig)]),
+    "sddp_create": (ctypes.c_int, [ctypes.POINTER(SddpConfig), ctypes.POINTER(_vp)]),
+    "sddp_destroy": (ctypes.c_int, [_vp]),
+    "sddp_last_error": (ctypes.c_char_p, [_vp]),
+    "sddp_set_config": (ctypes.c_int, [_vp, ctypes.POINTER(SddpConfig)]),
+    "sddp_eval_derivatives": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 13 + [_vp]),
+    "sddp_solve_batch": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 10 + [_vp]),
+    "sddp_backward_pass": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "sddp_forward_pass": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int] + [_vp] * 12 + [_vp]),
+    "sddp_defects": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sddp_solve_batch_host": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 10),
+    "sddp_fp64_peak_tflops": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), _vp]),
+    "sddp_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
+}
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("sddp.cu", "sddp_solver.cuh", "sddp_model.cuh")]
+    srcs.append(os.path.join(_HERE, "..", "include", "sddp.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", CSRC, "-B", "libsddp.so"])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.sddp_abi_version() != 1:
+            raise RuntimeError("libsddp.so ABI version mismatch")
+        if L.sddp_config_size() != ctypes.sizeof(SddpConfig):
+            raise RuntimeError("SddpConfig layout mismatch between config.py and include/sddp.h")
+        _lib = L
+    return _lib
+
+
+class SddpError(RuntimeError):
+    pass
+
+
+def check(rc: int, handle=None) -> None:
+    if rc != 0:
+        msg = lib().sddp_last_error(handle)
+        raise SddpError(f"sddp error {rc}: {msg.decode() if msg else '?'}")

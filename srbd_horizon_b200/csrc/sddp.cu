@@ -1,0 +1,489 @@
+// sddp.cu -- kernels and the C ABI (include/sddp.h) of the B200-native batched DDP solver.
+// Built for sm_100a only:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/sddp.h"
+#include "sddp_solver.cuh"
+
+// ===================================================================================== kernels
+template <class M>
+__global__ void __launch_bounds__(NT) solve_kernel(DevCfg c, SolveArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    __shared__ int s_prob;
+    const int tid = threadIdx.x;
+    for (;;) {   // persistent CTA: pull problems from a queue (iteration counts differ per problem)
+        if (tid == 0) s_prob = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int b = s_prob;
+        if (b >= a.B) break;
+        solve_one<M>(c, a, S, b, blockIdx.x, tid);
+        __syncthreads();
+    }
+}
+
+// Stage 1 alone: one CTA per (x,u,p) point, dense outputs.
+template <class M>
+__global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int* kind, const double* x, const double* u, const double* p,
+                                                  double* f, double* fx, double* fu, double* l, double* lx, double* lu, double* lxx,
+                                                  double* lux, double* luu) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    const int tid = threadIdx.x;
+    SyncBlock sync;
+    for (int m = blockIdx.x; m < npts; m += gridDim.x) {
+        const int kd = kind[m];
+        for (int i = tid; i < NX; i += NT) S.xk[i] = x[(size_t)m * NX + i];
+        for (int i = tid; i < NU; i += NT) S.uk[i] = u[(size_t)m * NU + i];
+        for (int i = tid; i < NP; i += NT) S.pk[i] = p[(size_t)m * NP + i];
+        __syncthreads();
+        if (tid == 0 && kd != NODE_TERM) M::pack(c, kd, S.xk, S.uk, S.pack);
+        __syncthreads();
+        M::expand(c, kd, S.xk, S.uk, S.pk, S.pack, S.Qx, S.Qu, S.Qxx, S.Qux, S.Quu, tid, NT, sync);
+        if (kd != NODE_TERM) M::expand_f(c, S.xk, S.uk, S.pack, S.fx, S.fu, tid, NT, sync);
+        else {
+            for (int e = tid; e < NX * NX; e += NT) S.fx[e] = 0.0;
+            for (int e = tid; e < NX * NU; e += NT) S.fu[e] = 0.0;
+            for (int e = tid; e < NX; e += NT) S.vp[e] = 0.0;
+            __syncthreads();
+        }
+        if (tid < 32) {
+            double J = warp_node<M>(c, kd, S.xk, S.uk, S.pk, S.vp, nullptr, 0.0, tid);
+            if (tid == 0 && l) l[m] = J;
+        }
+        __syncthreads();
+        if (f)   for (int e = tid; e < NX; e += NT) f[(size_t)m * NX + e] = S.vp[e];
+        if (fx)  for (int e = tid; e < NX * NX; e += NT) fx[(size_t)m * NX * NX + e] = S.fx[e];
+        if (fu)  for (int e = tid; e < NX * NU; e += NT) fu[(size_t)m * NX * NU + e] = S.fu[e];
+        if (lx)  for (int e = tid; e < NX; e += NT) lx[(size_t)m * NX + e] = S.Qx[e];
+        if (lu)  for (int e = tid; e < NU; e += NT) lu[(size_t)m * NU + e] = S.Qu[e];
+        if (lxx) for (int e = tid; e < NX * NX; e += NT) lxx[(size_t)m * NX * NX + e] = S.Qxx[e];
+        if (lux) for (int e = tid; e < NU * NX; e += NT) lux[(size_t)m * NU * NX + e] = S.Qux[e];
+        if (luu) for (int e = tid; e < NU * NU; e += NT) luu[(size_t)m * NU * NU + e] = S.Quu[e];
+        __syncthreads();
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(NT) backward_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, const double* D,
+                                                      double mu, double* K, double* kff, double* dV, int* rc, double* ws_pack) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    const int tid = threadIdx.x, N = c.N;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const double* Xb = X + (size_t)b * (N + 1) * NX;
+        const double* Ub = U + (size_t)b * N * NU;
+        double* packs = ws_pack + (size_t)blockIdx.x * N * M::PACK;
+        compute_packs<M>(c, Xb, Ub, packs, tid);
+        int r = backward_pass<M>(c, S, Xb, Ub, P + (size_t)b * (N + 1) * NP, D + (size_t)b * N * NX, packs, mu,
+                                 K + (size_t)b * N * NU * NX, kff + (size_t)b * N * NU, &S.red[12], tid);
+        if (tid == 0) { rc[b] = r; dV[3 * b] = S.red[12]; dV[3 * b + 1] = S.red[13]; dV[3 * b + 2] = S.red[14]; }
+        __syncthreads();
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(NT) forward_kernel(DevCfg c, int B, int n_alpha, const double* alpha, const double* rho, const double* x0,
+                                                     const double* X, const double* U, const double* P, const double* D, const double* K,
+                                                     const double* kff, double* Jn, double* Xn, double* Un, double* ws_xn, double* ws_un) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    const int tid = threadIdx.x, N = c.N;
+    const size_t xsz = (size_t)(N + 1) * NX, usz = (size_t)N * NU;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int base = 0; base < n_alpha; base += NCAND) {
+            const int ncand = min(NCAND, n_alpha - base);
+            __syncthreads();
+            if (tid < ncand) { S.alpha[tid] = alpha[base + tid]; S.rho[tid] = rho[base + tid]; }
+            __syncthreads();
+            double* xo = Xn ? Xn + ((size_t)b * n_alpha + base) * xsz : ws_xn + (size_t)blockIdx.x * NCAND * xsz;
+            double* uo = Un ? Un + ((size_t)b * n_alpha + base) * usz : ws_un + (size_t)blockIdx.x * NCAND * usz;
+            forward_wave<M>(c, S, x0 + (size_t)b * NX, X + (size_t)b * xsz, U + (size_t)b * usz, P + (size_t)b * (N + 1) * NP,
+                            D + (size_t)b * N * NX, K + (size_t)b * N * NU * NX, kff + (size_t)b * usz, ncand, xo, xsz, uo, usz, tid);
+            if (tid < ncand) Jn[(size_t)b * n_alpha + base + tid] = S.Jc[tid];
+        }
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(NT) defects_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, double* D, double* cost) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    const int tid = threadIdx.x, N = c.N;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        double J = defects_and_cost<M>(c, S, X + (size_t)b * (N + 1) * NX, U + (size_t)b * N * NU, P + (size_t)b * (N + 1) * NP,
+                                       D ? D + (size_t)b * N * NX : nullptr, tid);
+        if (tid == 0 && cost) cost[b] = J;
+    }
+}
+
+// FP64 FMA-rate microbenchmark: 8 independent chains per thread
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = fma(v[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// ===================================================================================== host side
+struct SddpHandle {
+    SddpConfig cfg;
+    DevCfg dc;
+    int device, sms, slots;
+    size_t smem_bytes, ws_bytes;
+    double *ws_d, *ws_pack, *ws_xn, *ws_un, *ws_K, *ws_k;
+    int* counter;
+    // staging for the *_host entry point
+    void* stage; size_t stage_bytes;
+    long long launches;
+    char err[512];
+};
+static char g_create_err[512] = "";
+
+static int fail(SddpHandle* h, int code, const char* fmt, const char* a, const char* b) {
+    char* dst = h ? h->err : g_create_err;
+    snprintf(dst, 512, fmt, a, b);
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail(h, SDDP_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static int check_config(const SddpConfig* c, SddpHandle* h) {
+    if (!c) return fail(h, SDDP_EINVAL, "%s%s", "config is NULL", "");
+    if (c->model != SDDP_MODEL_SRBD && c->model != SDDP_MODEL_LIP) return fail(h, SDDP_EINVAL, "%s%s", "unknown model", "");
+    if (c->N < 1 || c->N > 4096) return fail(h, SDDP_EINVAL, "%s%s", "N must be in 1..4096", "");
+    if (c->max_iters < 1) return fail(h, SDDP_EINVAL, "%s%s", "max_iters must be >= 1", "");
+    if (!(c->dt > 0.0)) return fail(h, SDDP_EINVAL, "%s%s", "dt must be > 0", "");
+    if (!(c->line_search_decrease_factor > 0.0 && c->line_search_decrease_factor < 1.0))
+        return fail(h, SDDP_EINVAL, "%s%s", "line_search_decrease_factor must be in (0,1)", "");
+    if (!(c->alpha_converge_threshold > 0.0)) return fail(h, SDDP_EINVAL, "%s%s", "alpha_converge_threshold must be > 0", "");
+    if (!(c->mu_factor > 1.0)) return fail(h, SDDP_EINVAL, "%s%s", "mu_factor must be > 1", "");
+    if (c->defect_contraction_rate > 1.0) return fail(h, SDDP_EINVAL, "%s%s", "defect_contraction_rate must be <= 1", "");
+    return 0;
+}
+
+static void make_devcfg(const SddpConfig& s, DevCfg& d) {
+    d.model = s.model; d.N = s.N; d.inertia_mode = s.inertia_mode; d.hessian_mode = s.hessian_mode;
+    d.ms = s.multiple_shooting; d.max_iters = s.max_iters;
+    d.dt = s.dt; d.fs = s.force_scaling; d.g = s.gravity; d.eta2 = s.eta2;
+    d.mscaled = s.mass / s.force_scaling; d.inv_ms = 1.0 / d.mscaled;
+    for (int i = 0; i < 9; i++) d.Ib[i] = s.inertia[i] / s.force_scaling;
+    for (int i = 0; i < 3; i++) d.com[i] = s.com[i];
+    for (int i = 0; i < 12; i++) d.foot[i] = s.foot[i];
+    d.w_r = s.r_tracking_gain; d.w_rdot = s.rdot_tracking_gain; d.w_w = s.w_tracking_gain; d.w_rel = s.rel_position_gain;
+    d.w_fsw = s.force_scaling * s.force_scaling * s.force_switch_weight;
+    d.w_minf = s.force_scaling * s.force_scaling * s.min_f_gain;
+    d.gq = s.min_qddot_gain; d.w_zmp = s.zmp_tracking_gain; d.cw = s.constraint_weight;
+    for (int pr = 0; pr < 2; pr++)
+        for (int ax = 0; ax < 2; ax++) d.drel[pr][ax] = -(s.foot[3 * pr + ax] - s.foot[3 * (pr + 2) + ax]);
+    d.alpha0 = s.alpha_0; d.alpha_min = s.alpha_converge_threshold; d.ls_factor = s.line_search_decrease_factor;
+    d.beta = s.beta; d.cost_ths = s.cost_reduction_ths; d.mu0 = s.mu0; d.rho_fixed = s.defect_contraction_rate;
+    d.mu_min = s.mu_min; d.mu_max = s.mu_max; d.mu_factor = s.mu_factor; d.defect_ths = s.defect_ths;
+}
+
+template <class M> static size_t smem_of() { return sizeof(Smem<M>); }
+
+template <class M>
+static cudaError_t set_smem_attr() {
+    cudaError_t e;
+    int bytes = (int)sizeof(Smem<M>);
+    if ((e = cudaFuncSetAttribute(solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(eval_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(backward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(forward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(defects_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    return cudaSuccess;
+}
+
+static void model_dims(int model, int& nx, int& nu, int& np, int& pack) {
+    if (model == SDDP_MODEL_SRBD) { nx = Srbd::NX; nu = Srbd::NU; np = Srbd::NP; pack = Srbd::PACK; }
+    else { nx = Lip::NX; nu = Lip::NU; np = Lip::NP; pack = Lip::PACK; }
+}
+
+struct WsLayout { size_t d, pack, xn, un, K, k, total; };
+static WsLayout ws_layout(const SddpConfig& c, int slots) {
+    int nx, nu, np, pack;
+    model_dims(c.model, nx, nu, np, pack);
+    WsLayout w;
+    size_t N = (size_t)c.N;
+    w.d = (size_t)slots * N * nx;
+    w.pack = (size_t)slots * N * pack;
+    w.xn = (size_t)slots * NCAND * (N + 1) * nx;
+    w.un = (size_t)slots * NCAND * N * nu;
+    w.K = (size_t)slots * N * nu * nx;
+    w.k = (size_t)slots * N * nu;
+    w.total = (w.d + w.pack + w.xn + w.un + w.K + w.k) * sizeof(double) + 256;
+    return w;
+}
+static const int kMaxSlotsPerSM = 4;
+
+extern "C" {
+
+int sddp_abi_version(void) { return SDDP_ABI_VERSION; }
+size_t sddp_config_size(void) { return sizeof(SddpConfig); }
+
+int sddp_dims(int model, int* nx, int* nu, int* np) {
+    if (model != SDDP_MODEL_SRBD && model != SDDP_MODEL_LIP) return SDDP_EINVAL;
+    int a, b, c, d;
+    model_dims(model, a, b, c, d);
+    if (nx) *nx = a;
+    if (nu) *nu = b;
+    if (np) *np = c;
+    return 0;
+}
+
+size_t sddp_workspace_bytes(const SddpConfig* cfg) {
+    if (!cfg || check_config(cfg, nullptr)) return 0;
+    return ws_layout(*cfg, 148 * kMaxSlotsPerSM).total;   // upper bound for a B200 (148 SMs)
+}
+
+const char* sddp_last_error(const SddpHandle* h) { return h ? h->err : g_create_err; }
+
+int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
+    SddpHandle* h = nullptr;
+    if (!out) return fail(h, SDDP_EINVAL, "%s%s", "out is NULL", "");
+    *out = nullptr;
+    int rc = check_config(cfg, nullptr);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SDDP_ECUDA, "no CUDA device (%s); this library has no CPU path%s", cudaGetErrorString(e), "");
+    SddpHandle* hh = new (std::nothrow) SddpHandle();
+    if (!hh) return fail(nullptr, SDDP_ENOMEM, "%s%s", "host allocation failed", "");
+    memset(hh, 0, sizeof(*hh));
+    h = hh;
+    h->cfg = *cfg;
+    make_devcfg(h->cfg, h->dc);
+    cudaError_t ce;
+#define CUC(call) do { ce = (call); if (ce != cudaSuccess) { fail(nullptr, SDDP_ECUDA, "%s: %s", #call, cudaGetErrorString(ce)); sddp_destroy(h); return SDDP_ECUDA; } } while (0)
+    CUC(cudaGetDevice(&h->device));
+    CUC(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
+    int occ = 0;
+    if (cfg->model == SDDP_MODEL_SRBD) {
+        h->smem_bytes = smem_of<Srbd>();
+        CUC(set_smem_attr<Srbd>());
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<Srbd>, NT, h->smem_bytes));
+    } else {
+        h->smem_bytes = smem_of<Lip>();
+        CUC(set_smem_attr<Lip>());
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<Lip>, NT, h->smem_bytes));
+    }
+    if (occ < 1) { fail(nullptr, SDDP_ECUDA, "%s%s", "solve kernel does not fit on this device", ""); sddp_destroy(h); return SDDP_ECUDA; }
+    if (occ > kMaxSlotsPerSM) occ = kMaxSlotsPerSM;
+    h->slots = h->sms * occ;
+    WsLayout w = ws_layout(h->cfg, h->slots);
+    h->ws_bytes = w.total;
+    double* base = nullptr;
+    ce = cudaMalloc((void**)&base, w.total);
+    if (ce != cudaSuccess) { fail(nullptr, SDDP_ENOMEM, "cudaMalloc(workspace): %s%s", cudaGetErrorString(ce), ""); sddp_destroy(h); return SDDP_ENOMEM; }
+    h->ws_d = base;
+    h->ws_pack = h->ws_d + w.d;
+    h->ws_xn = h->ws_pack + w.pack;
+    h->ws_un = h->ws_xn + w.xn;
+    h->ws_K = h->ws_un + w.un;
+    h->ws_k = h->ws_K + w.K;
+    h->counter = (int*)(h->ws_k + w.k);
+    CUC(cudaMemset(base, 0, w.total));
+#undef CUC
+    *out = h;
+    return 0;
+}
+
+int sddp_destroy(SddpHandle* h) {
+    if (!h) return 0;
+    if (h->ws_d) cudaFree(h->ws_d);
+    if (h->stage) cudaFree(h->stage);
+    delete h;
+    return 0;
+}
+
+int sddp_set_config(SddpHandle* h, const SddpConfig* cfg) {
+    if (!h) return SDDP_EINVAL;
+    int rc = check_config(cfg, h);
+    if (rc) return rc;
+    if (cfg->model != h->cfg.model || cfg->N != h->cfg.N) return fail(h, SDDP_EINVAL, "%s%s", "model and N are fixed at create", "");
+    h->cfg = *cfg;
+    make_devcfg(h->cfg, h->dc);
+    return 0;
+}
+
+int sddp_launch_count(const SddpHandle* h, long long* out) {
+    if (!h || !out) return SDDP_EINVAL;
+    *out = h->launches;
+    return 0;
+}
+
+#define DISPATCH(h, KERNEL, grid, stream, ...)                                                      \
+    do {                                                                                            \
+        if ((h)->cfg.model == SDDP_MODEL_SRBD) KERNEL<Srbd><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__); \
+        else KERNEL<Lip><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);                       \
+        (h)->launches++;                                                                            \
+        CU(cudaGetLastError());                                                                     \
+    } while (0)
+
+int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const double* x, const double* u, const double* p,
+                          double* f, double* fx, double* fu, double* l, double* lx, double* lu, double* lxx, double* lux,
+                          double* luu, void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (M < 0 || (M > 0 && (!kind || !x || !u || !p))) return fail(h, SDDP_EINVAL, "%s%s", "eval_derivatives: bad arguments", "");
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = M < h->sms * 8 ? M : h->sms * 8;
+    DISPATCH(h, eval_kernel, grid, st, h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
+    return 0;
+}
+
+int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* params, double* X, double* U, double* K,
+                     double* kff, double* hist, int32_t* iters, int32_t* status, double* cost, void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (B < 0 || (B > 0 && (!x0 || !params || !X || !U || !iters || !status || !cost)))
+        return fail(h, SDDP_EINVAL, "%s%s", "solve_batch: x0, params, X, U, iters, status, cost are required", "");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(h->counter, 0, sizeof(int), st));
+    SolveArgs a;
+    a.B = B; a.x0 = x0; a.params = params; a.X = X; a.U = U; a.K = K; a.kff = kff; a.hist = hist;
+    a.iters = iters; a.status = status; a.cost = cost;
+    a.ws_d = h->ws_d; a.ws_pack = h->ws_pack; a.ws_xn = h->ws_xn; a.ws_un = h->ws_un; a.ws_K = h->ws_K; a.ws_k = h->ws_k;
+    a.counter = h->counter;
+    int grid = B < h->slots ? B : h->slots;
+    DISPATCH(h, solve_kernel, grid, st, h->dc, a);
+    return 0;
+}
+
+int sddp_backward_pass(SddpHandle* h, int B, const double* X, const double* U, const double* params, const double* defect,
+                       double mu, double* K, double* kff, double* dV, int32_t* rc, void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (B < 0 || (B > 0 && (!X || !U || !params || !defect || !K || !kff || !dV || !rc)))
+        return fail(h, SDDP_EINVAL, "%s%s", "backward_pass: all arrays are required", "");
+    if (B == 0) return 0;
+    int grid = B < h->slots ? B : h->slots;
+    DISPATCH(h, backward_kernel, grid, (cudaStream_t)stream, h->dc, B, X, U, params, defect, mu, K, kff, dV, rc, h->ws_pack);
+    return 0;
+}
+
+int sddp_forward_pass(SddpHandle* h, int B, int n_alpha, const double* alpha, const double* rho, const double* x0,
+                      const double* X, const double* U, const double* params, const double* defect, const double* K,
+                      const double* kff, double* Jn, double* Xn, double* Un, void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (B < 0 || n_alpha < 1 || (B > 0 && (!alpha || !rho || !x0 || !X || !U || !params || !defect || !K || !kff || !Jn)))
+        return fail(h, SDDP_EINVAL, "%s%s", "forward_pass: bad arguments", "");
+    if (B == 0) return 0;
+    int grid = B < h->slots ? B : h->slots;
+    DISPATCH(h, forward_kernel, grid, (cudaStream_t)stream, h->dc, B, n_alpha, alpha, rho, x0, X, U, params, defect, K, kff, Jn, Xn, Un,
+             h->ws_xn, h->ws_un);
+    return 0;
+}
+
+int sddp_defects(SddpHandle* h, int B, const double* X, const double* U, const double* params, double* defect, double* cost,
+                 void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (B < 0 || (B > 0 && (!X || !U || !params))) return fail(h, SDDP_EINVAL, "%s%s", "defects: bad arguments", "");
+    if (B == 0) return 0;
+    int grid = B < h->slots ? B : h->slots;
+    DISPATCH(h, defects_kernel, grid, (cudaStream_t)stream, h->dc, B, X, U, params, defect, cost);
+    return 0;
+}
+
+int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* params, double* X, double* U, double* K,
+                          double* kff, double* hist, int32_t* iters, int32_t* status, double* cost) {
+    if (!h) return SDDP_EINVAL;
+    if (B < 0 || (B > 0 && (!x0 || !params || !X || !U || !iters || !status || !cost)))
+        return fail(h, SDDP_EINVAL, "%s%s", "solve_batch_host: x0, params, X, U, iters, status, cost are required", "");
+    if (B == 0) return 0;
+    int nx, nu, np, pack;
+    model_dims(h->cfg.model, nx, nu, np, pack);
+    const size_t N = (size_t)h->cfg.N, Bz = (size_t)B;
+    const size_t n_x0 = Bz * nx, n_p = Bz * (N + 1) * np, n_X = Bz * (N + 1) * nx, n_U = Bz * N * nu;
+    const size_t n_K = K ? Bz * N * nu * nx : 0, n_k = kff ? n_U : 0, n_h = hist ? Bz * h->cfg.max_iters * SDDP_HIST : 0;
+    const size_t n_d = n_x0 + n_p + n_X + n_U + n_K + n_k + n_h + Bz;
+    const size_t bytes = n_d * sizeof(double) + 2 * Bz * sizeof(int32_t);
+    if (bytes > h->stage_bytes) {
+        if (h->stage) cudaFree(h->stage);
+        h->stage = nullptr; h->stage_bytes = 0;
+        cudaError_t e = cudaMalloc(&h->stage, bytes);
+        if (e != cudaSuccess) return fail(h, SDDP_ENOMEM, "cudaMalloc(staging): %s%s", cudaGetErrorString(e), "");
+        h->stage_bytes = bytes;
+    }
+    double* d_x0 = (double*)h->stage;
+    double* d_p = d_x0 + n_x0;
+    double* d_X = d_p + n_p;
+    double* d_U = d_X + n_X;
+    double* d_K = d_U + n_U;
+    double* d_k = d_K + n_K;
+    double* d_h = d_k + n_k;
+    double* d_c = d_h + n_h;
+    int32_t* d_it = (int32_t*)(d_c + Bz);
+    int32_t* d_st = d_it + Bz;
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(d_x0, x0, n_x0 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_p, params, n_p * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_X, X, n_X * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_U, U, n_U * 8, cudaMemcpyHostToDevice, st));
+    int rc = sddp_solve_batch(h, B, d_x0, d_p, d_X, d_U, K ? d_K : nullptr, kff ? d_k : nullptr, hist ? d_h : nullptr, d_it, d_st, d_c, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(X, d_X, n_X * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(U, d_U, n_U * 8, cudaMemcpyDeviceToHost, st));
+    if (K) CU(cudaMemcpyAsync(K, d_K, n_K * 8, cudaMemcpyDeviceToHost, st));
+    if (kff) CU(cudaMemcpyAsync(kff, d_k, n_k * 8, cudaMemcpyDeviceToHost, st));
+    if (hist) CU(cudaMemcpyAsync(hist, d_h, n_h * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cost, d_c, Bz * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(iters, d_it, Bz * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status, d_st, Bz * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int sddp_fp64_peak_tflops(double* out, void* stream) {
+    SddpHandle* h = nullptr;
+    if (!out) return SDDP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* d = nullptr;
+    CU(cudaMalloc((void**)&d, 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 4096, grid = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, st));
+        fp64_peak_kernel<<<grid, 256, 0, st>>>(d, iters, 1.0000001, 1e-9);
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)grid;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *out = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,637 @@
+// sddp_model.cuh -- analytic dynamics / cost / derivatives of the two srbd_horizon problems
+// as sm_100a device code (north_star stage one).
+//
+// What is implemented (file:line under /root/reference/python):
+//   SRBD ode    prb.py:97-109    rdot, quaternion kinematics (world-aligned w), cdot_i,
+//                                rddot = sum f_i/(m/fs) - g e_z,
+//                                wdot  = J(o)^-1 (sum (c_i - r) x f_i - w x J(o) w),
+//                                J = R o (I/fs) o R^T element-wise as written at prb.py:99 ("literal")
+//                                or R (I/fs) R^T ("rotated", README.md:2), cddot_i
+//   LIP ode     prb.py:315-329
+//   L_k, L_N    ddp.py:179-226 over the residuals prb.py:184-204 / 390-402 and the equality
+//               constraints prb.py:166-181 / 379-387 (weight 1e6, ddp.py:181)
+//   f_k         ddp.py:228-230 explicit Euler
+//
+// Organisation (one model = one struct of static device functions):
+//   accel      the non-elementwise part of the ode (SRBD: wdot, rddot), uniform per node
+//   xdot_i     i-th component of the ode given accel        -> lanes own state components
+//   cost_lane  this lane's share of L (lanes own residuals) -> warp-shuffle sum
+//   pack       single-thread "rigid-body pack": wdot, its Jacobian wrt the 34 variables it
+//              depends on, and the sparse curvature blocks of lambda^T wdot -- evaluated for all
+//              nodes of a problem in parallel, one thread per node
+//   expand     block-parallel: writes lx,lu,lxx,lux,luu of a node into the Q buffers from the pack
+//   expand_f   block-parallel: dense fx, fu (generic path / stage-one kernel)
+#pragma once
+#include <math.h>
+
+struct DevCfg {
+    int model, N, inertia_mode, hessian_mode, ms, max_iters;
+    double dt, mscaled, inv_ms, Ib[9], com[3], foot[12], fs, g, eta2;
+    double w_r, w_rdot, w_w, w_rel, w_fsw, gq, w_minf, w_zmp, cw;
+    double drel[2][2];   // drel[pair][axis] = -(foot[pair][axis] - foot[pair+2][axis])   prb.py:153-154
+    double alpha0, alpha_min, ls_factor, beta, cost_ths, mu0, rho_fixed, mu_min, mu_max, mu_factor, defect_ths;
+};
+
+enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2 };
+
+#define SDDP_DEV __device__ __forceinline__
+
+namespace m3 {
+SDDP_DEV void cross(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+SDDP_DEV double dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+SDDP_DEV void mv(const double* A, const double* v, double* o) {
+    o[0] = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+    o[1] = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+    o[2] = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+}
+SDDP_DEV void mm(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+SDDP_DEV void mmT(const double* A, const double* B, double* C) {   // A * B^T
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+}
+SDDP_DEV void inv(const double* A, double* M) {
+    double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+    double id = 1.0 / (A[0] * c00 + A[1] * c01 + A[2] * c02);
+    M[0] = c00 * id; M[1] = (A[2] * A[7] - A[1] * A[8]) * id; M[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    M[3] = c01 * id; M[4] = (A[0] * A[8] - A[2] * A[6]) * id; M[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    M[6] = c02 * id; M[7] = (A[1] * A[6] - A[0] * A[7]) * id; M[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+// skew(v)[a][b]
+SDDP_DEV double skew_ab(const double* v, int a, int b) {
+    if (a == b) return 0.0;
+    int k = 3 - a - b;                       // the remaining axis
+    double s = ((b - a + 3) % 3 == 1) ? -1.0 : 1.0;   // (0,1)->-v2, (1,2)->-v0, (2,0)->-v1
+    return s * v[k];
+}
+}  // namespace m3
+
+// rotation of a (non-normalised) quaternion (x,y,z,w): horizon utils.toRot as used at prb.py:97
+SDDP_DEV void quat_R(const double* q, double* R) {
+    double x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1.0 - 2.0 * (y * y + z * z); R[1] = 2.0 * (x * y - z * w); R[2] = 2.0 * (x * z + y * w);
+    R[3] = 2.0 * (x * y + z * w); R[4] = 1.0 - 2.0 * (x * x + z * z); R[5] = 2.0 * (y * z - x * w);
+    R[6] = 2.0 * (x * z - y * w); R[7] = 2.0 * (y * z + x * w); R[8] = 1.0 - 2.0 * (x * x + y * y);
+}
+// dR/dq_a (linear in q, so d2R/dq_a dq_b = quat_dR(e_b, a))
+SDDP_DEV void quat_dR(const double* q, int a, double* D) {
+    double x = 2.0 * q[0], y = 2.0 * q[1], z = 2.0 * q[2], w = 2.0 * q[3];
+    switch (a) {
+    case 0: D[0] = 0; D[1] = y; D[2] = z; D[3] = y; D[4] = -2 * x; D[5] = -w; D[6] = z; D[7] = w; D[8] = -2 * x; break;
+    case 1: D[0] = -2 * y; D[1] = x; D[2] = w; D[3] = x; D[4] = 0; D[5] = z; D[6] = -w; D[7] = z; D[8] = -2 * y; break;
+    case 2: D[0] = -2 * z; D[1] = -w; D[2] = x; D[3] = w; D[4] = -2 * z; D[5] = y; D[6] = x; D[7] = y; D[8] = 0; break;
+    default: D[0] = 0; D[1] = -z; D[2] = y; D[3] = z; D[4] = 0; D[5] = -x; D[6] = -y; D[7] = x; D[8] = 0; break;
+    }
+}
+
+// =====================================================================================  SRBD
+struct Srbd {
+    static constexpr int NX = 37, NU = 24, NP = 19, NACC = 6, PACK = 256, NZ = 34;
+    // x: r[0:3] o[3:7] c_i[7+3i] rdot[19:22] w[22:25] cdot_i[25+3i];  u: cddot_i[6i] f_i[6i+3]
+    // p: rdot_ref[0:3] w_ref[3:6] otg[6] (c_ref_i, sw_i)[7+2i, 8+2i] oref[15:19]
+    enum { XR = 0, XO = 3, XC = 7, XRD = 19, XW = 22, XCD = 25 };
+    enum { ZR = 0, ZO = 3, ZC = 7, ZW = 19, ZF = 22 };
+    enum { PK_WD = 0, PK_RDD = 3, PK_NU = 6, PK_HWW = 9, PK_JAC = 18, PK_HO = 120 };
+
+    SDDP_DEV static void inertia(const DevCfg& c, const double* R, double* J) {
+        if (c.inertia_mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) J[3 * i + j] = R[3 * i + j] * R[3 * j + i] * c.Ib[3 * i + j];
+        } else {
+            double T[9];
+            m3::mm(R, c.Ib, T);
+            m3::mmT(T, R, J);
+        }
+    }
+    // d/dq_a of the inertia given R, Ra
+    SDDP_DEV static void inertia_d(const DevCfg& c, const double* R, const double* Ra, double* Ja) {
+        if (c.inertia_mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    Ja[3 * i + j] = (Ra[3 * i + j] * R[3 * j + i] + R[3 * i + j] * Ra[3 * j + i]) * c.Ib[3 * i + j];
+        } else {
+            double T[9], A[9], B[9];
+            m3::mm(Ra, c.Ib, T); m3::mmT(T, R, A);
+            m3::mm(R, c.Ib, T);  m3::mmT(T, Ra, B);
+#pragma unroll
+            for (int i = 0; i < 9; i++) Ja[i] = A[i] + B[i];
+        }
+    }
+    // d2/dq_a dq_b
+    SDDP_DEV static void inertia_dd(const DevCfg& c, const double* R, const double* Ra, const double* Rb, const double* Rab, double* Jab) {
+        if (c.inertia_mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    int ij = 3 * i + j, ji = 3 * j + i;
+                    Jab[ij] = (Rab[ij] * R[ji] + Ra[ij] * Rb[ji] + Rb[ij] * Ra[ji] + R[ij] * Rab[ji]) * c.Ib[ij];
+                }
+        } else {
+            double T[9], A[9];
+            m3::mm(Rab, c.Ib, T); m3::mmT(T, R, Jab);
+            m3::mm(Ra, c.Ib, T);  m3::mmT(T, Rb, A);
+#pragma unroll
+            for (int i = 0; i < 9; i++) Jab[i] += A[i];
+            m3::mm(Rb, c.Ib, T);  m3::mmT(T, Ra, A);
+#pragma unroll
+            for (int i = 0; i < 9; i++) Jab[i] += A[i];
+            m3::mm(R, c.Ib, T);   m3::mmT(T, Rab, A);
+#pragma unroll
+            for (int i = 0; i < 9; i++) Jab[i] += A[i];
+        }
+    }
+
+    // acc[0:3] = wdot, acc[3:6] = rddot      (kin_dyn.fSRBD as called at prb.py:99)
+    SDDP_DEV static void accel(const DevCfg& c, const double* x, const double* u, double* acc) {
+        double R[9], J[9], M[9];
+        quat_R(x + XO, R);
+        inertia(c, R, J);
+        m3::inv(J, M);
+        double tau[3] = {0, 0, 0}, fsum[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double* ci = x + XC + 3 * i;
+            const double* fi = u + 6 * i + 3;
+            double d[3] = {ci[0] - x[0], ci[1] - x[1], ci[2] - x[2]}, t[3];
+            m3::cross(d, fi, t);
+            tau[0] += t[0]; tau[1] += t[1]; tau[2] += t[2];
+            fsum[0] += fi[0]; fsum[1] += fi[1]; fsum[2] += fi[2];
+        }
+        double Jw[3], wJw[3];
+        m3::mv(J, x + XW, Jw);
+        m3::cross(x + XW, Jw, wJw);
+        double h[3] = {tau[0] - wJw[0], tau[1] - wJw[1], tau[2] - wJw[2]};
+        m3::mv(M, h, acc);
+        acc[3] = fsum[0] * c.inv_ms; acc[4] = fsum[1] * c.inv_ms; acc[5] = fsum[2] * c.inv_ms - c.g;
+    }
+
+    SDDP_DEV static double xdot_i(const DevCfg& c, int i, const double* x, const double* u, const double* acc) {
+        if (i < 3) return x[XRD + i];
+        if (i < 7) {   // odot = quat_prod([w/2, 0], o)
+            const double* o = x + XO;
+            const double* w = x + XW;
+            if (i == 6) return -0.5 * (w[0] * o[0] + w[1] * o[1] + w[2] * o[2]);
+            int a = i - 3, b = (a + 1) % 3, d = (a + 2) % 3;
+            return 0.5 * (o[3] * w[a] + (w[b] * o[d] - w[d] * o[b]));
+        }
+        if (i < 19) return x[i + 18];
+        if (i < 22) return acc[3 + (i - 19)];
+        if (i < 25) return acc[i - 22];
+        int j = (i - 25) / 3, k = (i - 25) % 3;
+        return u[6 * j + k];
+    }
+
+    // quaternion error rows: quat_prod(o, oref) = E(oref) o        (prb.py:187)
+    SDDP_DEV static double E_row(const double* q, int i, int a) {
+        // row i, column a of E
+        const double E[4][4] = {{q[3], q[2], -q[1], q[0]}, {-q[2], q[3], q[0], q[1]}, {q[1], -q[0], q[3], q[2]}, {-q[0], -q[1], -q[2], q[3]}};
+        return E[i][a];
+    }
+
+    SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double* acc) {
+        double s = 0.0;
+        for (int i = lane; i < NX; i += 32) {
+            if (kind != NODE_FIRST) {   // nodes 1..N: prb.py:184-199
+                if (i == 2) { double r = x[2] - c.com[2]; s += c.w_r * r * r; }
+                else if (i >= 3 && i < 7) {
+                    const double* q = p + 15;
+                    const double* o = x + XO;
+                    int a = i - 3;
+                    double r = E_row(q, a, 0) * o[0] + E_row(q, a, 1) * o[1] + E_row(q, a, 2) * o[2] + E_row(q, a, 3) * o[3] - (a == 3 ? 1.0 : 0.0);
+                    s += p[6] * p[6] * r * r;
+                } else if (i >= 7 && i < 13 && (i - 7) % 3 < 2) {
+                    int j = (i - 7) / 3, ax = (i - 7) % 3;
+                    double r = -x[i] + x[i + 6] - c.drel[j][ax];
+                    s += c.w_rel * r * r;
+                } else if (i >= 19 && i < 22) { double r = x[i] - p[i - 19]; s += c.w_rdot * r * r; }
+                else if (i >= 22 && i < 25) { double r = x[i] - p[3 + i - 22]; s += c.w_w * r * r; }
+            }
+            if (kind != NODE_TERM) {    // equality constraints on nodes 0..N-1: prb.py:166-181, ddp.py:191-196
+                if (i >= 7 && i < 19 && (i - 7) % 3 == 2) { double r = x[i] - p[7 + 2 * ((i - 7) / 3)]; s += c.cw * r * r; }
+                else if (i >= 25 && (i - 25) % 3 < 2) {
+                    int j = (i - 25) / 3;
+                    double r = p[8 + 2 * j] * x[i];
+                    s += c.cw * r * r;
+                    if (j == 0 || j == 2) { double r2 = x[i] - x[i + 3]; s += c.cw * r2 * r2; }
+                }
+            }
+        }
+        if (kind != NODE_TERM) {        // nodes 0..N-1: prb.py:200-204
+            if (lane < NU) {
+                int i = lane / 6, r = lane % 6;
+                double v = u[lane];
+                if (r < 3) s += c.gq * v * v;
+                else { double a = 1.0 - p[8 + 2 * i]; s += (c.w_minf + c.w_fsw * a * a) * v * v; }
+            }
+            if (lane < 3) s += c.gq * (acc[lane] * acc[lane] + acc[3 + lane] * acc[3 + lane]);
+        }
+        return s;
+    }
+
+    // ---- single-thread rigid-body pack (see file header) ------------------------------------
+    // pk[PK_WD..] wd(3) rdd(3) nu(3) Hww(9) Jac[3][34] Ho[4][34]
+    __device__ static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk) {
+        if (kind == NODE_TERM) return;
+        const double* r = x;
+        const double* o = x + XO;
+        const double* w = x + XW;
+        double R[9], Ra[4][9], J[9], Ja[4][9], M[9];
+        quat_R(o, R);
+        inertia(c, R, J);
+        m3::inv(J, M);
+        for (int a = 0; a < 4; a++) { quat_dR(o, a, Ra[a]); inertia_d(c, R, Ra[a], Ja[a]); }
+        double tau[3] = {0, 0, 0}, fsum[3] = {0, 0, 0};
+        for (int i = 0; i < 4; i++) {
+            const double* ci = x + XC + 3 * i;
+            const double* fi = u + 6 * i + 3;
+            double d[3] = {ci[0] - r[0], ci[1] - r[1], ci[2] - r[2]}, t[3];
+            m3::cross(d, fi, t);
+            for (int k = 0; k < 3; k++) { tau[k] += t[k]; fsum[k] += fi[k]; }
+        }
+        double Jw[3], wJw[3], h[3], wd[3];
+        m3::mv(J, w, Jw);
+        m3::cross(w, Jw, wJw);
+        for (int k = 0; k < 3; k++) h[k] = tau[k] - wJw[k];
+        m3::mv(M, h, wd);
+        for (int k = 0; k < 3; k++) pk[PK_WD + k] = wd[k];
+        pk[PK_RDD + 0] = fsum[0] * c.inv_ms; pk[PK_RDD + 1] = fsum[1] * c.inv_ms; pk[PK_RDD + 2] = fsum[2] * c.inv_ms - c.g;
+
+        // Jacobian columns: Jac[:,p] = M (dh/dp - J_p wd)
+        double* Jac = pk + PK_JAC;   // [3][34]
+        auto put_col = [&](int pcol, const double* col) {
+            double out[3];
+            m3::mv(M, col, out);
+            Jac[pcol] = out[0]; Jac[NZ + pcol] = out[1]; Jac[2 * NZ + pcol] = out[2];
+        };
+        for (int b = 0; b < 3; b++) {
+            // d tau / d r_b = sum_i skew(f_i)[:,b];  d tau / d c_ib = -skew(f_i)[:,b];  d tau / d f_ib = skew(c_i - r)[:,b]
+            double colr[3] = {0, 0, 0};
+            for (int i = 0; i < 4; i++) {
+                const double* ci = x + XC + 3 * i;
+                const double* fi = u + 6 * i + 3;
+                double d[3] = {ci[0] - r[0], ci[1] - r[1], ci[2] - r[2]};
+                double cf[3] = {m3::skew_ab(fi, 0, b), m3::skew_ab(fi, 1, b), m3::skew_ab(fi, 2, b)};
+                double cc[3] = {-cf[0], -cf[1], -cf[2]};
+                double cd[3] = {m3::skew_ab(d, 0, b), m3::skew_ab(d, 1, b), m3::skew_ab(d, 2, b)};
+                for (int k = 0; k < 3; k++) colr[k] += cf[k];
+                put_col(ZC + 3 * i + b, cc);
+                put_col(ZF + 3 * i + b, cd);
+            }
+            put_col(ZR + b, colr);
+            // d(-w x Jw)/dw_b = skew(Jw)[:,b] - (skew(w) J)[:,b]
+            double Jcol[3] = {J[b], J[3 + b], J[6 + b]}, t[3];
+            m3::cross(w, Jcol, t);
+            double cw_[3] = {m3::skew_ab(Jw, 0, b) - t[0], m3::skew_ab(Jw, 1, b) - t[1], m3::skew_ab(Jw, 2, b) - t[2]};
+            put_col(ZW + b, cw_);
+        }
+        for (int a = 0; a < 4; a++) {
+            double Jaw[3], t[3], Jawd[3];
+            m3::mv(Ja[a], w, Jaw); m3::cross(w, Jaw, t); m3::mv(Ja[a], wd, Jawd);
+            double co[3] = {-t[0] - Jawd[0], -t[1] - Jawd[1], -t[2] - Jawd[2]};
+            put_col(ZO + a, co);
+        }
+        if (c.hessian_mode != 0) return;
+
+        // curvature of lambda^T wdot at lambda = wd:  nu = M wd
+        //   phi_pq = nu^T ( h_pq - J_p wd_q - J_q wd_p - J_pq wd )
+        double nu[3];
+        m3::mv(M, wd, nu);
+        for (int k = 0; k < 3; k++) pk[PK_NU + k] = nu[k];
+        double wxn[3];
+        m3::cross(w, nu, wxn);       // w^T skew(nu) A w = (w x nu) . (A w)
+        {   // (w,w): skew(nu) J - J skew(nu)
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) {
+                    double s1 = 0, s2 = 0;
+                    for (int k = 0; k < 3; k++) { s1 += m3::skew_ab(nu, a, k) * J[3 * k + b]; s2 += J[3 * a + k] * m3::skew_ab(nu, k, b); }
+                    pk[PK_HWW + 3 * a + b] = s1 - s2;
+                }
+        }
+        double* Ho = pk + PK_HO;   // [4][34]
+        for (int a = 0; a < 4; a++) {
+            double Jan[3];
+            m3::mv(Ja[a], nu, Jan);
+            for (int q = 0; q < NZ; q++) Ho[a * NZ + q] = -(Jan[0] * Jac[q] + Jan[1] * Jac[NZ + q] + Jan[2] * Jac[2 * NZ + q]);
+        }
+        for (int a = 0; a < 4; a++) {
+            // (o_a, w): (skew(nu) J_a - J_a skew(nu)) w = nu x (J_a w) - J_a (nu x w)
+            double Jaw[3], t1[3], nxw[3], t2[3];
+            m3::mv(Ja[a], w, Jaw); m3::cross(nu, Jaw, t1);
+            m3::cross(nu, w, nxw); m3::mv(Ja[a], nxw, t2);
+            for (int k = 0; k < 3; k++) Ho[a * NZ + ZW + k] += t1[k] - t2[k];
+            // symmetric counterpart of the -(J_b nu).Jac[:,o_a] term inside the (o,o) block
+            for (int b = 0; b < 4; b++) {
+                double Jbn[3];
+                m3::mv(Ja[b], nu, Jbn);
+                Ho[a * NZ + ZO + b] -= Jbn[0] * Jac[ZO + a] + Jbn[1] * Jac[NZ + ZO + a] + Jbn[2] * Jac[2 * NZ + ZO + a];
+            }
+            for (int b = a; b < 4; b++) {
+                double eb[4] = {0, 0, 0, 0};
+                eb[b] = 1.0;
+                double Rab[9], Jab[9], t3[3], t4[3];
+                quat_dR(eb, a, Rab);
+                inertia_dd(c, R, Ra[a], Ra[b], Rab, Jab);
+                m3::mv(Jab, w, t3); m3::mv(Jab, wd, t4);
+                double v = m3::dot(wxn, t3) - m3::dot(nu, t4);
+                Ho[a * NZ + ZO + b] += v;
+                if (b != a) Ho[b * NZ + ZO + a] += v;
+            }
+        }
+    }
+
+    SDDP_DEV static int zmap_x(int pi) { return pi < 19 ? pi : (pi < 22 ? XW + (pi - 19) : -1); }
+    SDDP_DEV static int zmap_u(int pi) { return 6 * ((pi - 22) / 3) + 3 + (pi - 22) % 3; }
+
+    // curvature entry Hc[pi][qi] from the pack
+    SDDP_DEV static double hc(const double* pk, int pi, int qi) {
+        if (pi >= ZO && pi < ZC) return pk[PK_HO + (pi - ZO) * NZ + qi];
+        if (qi >= ZO && qi < ZC) return pk[PK_HO + (qi - ZO) * NZ + pi];
+        if (pi >= ZW && pi < ZF && qi >= ZW && qi < ZF) return pk[PK_HWW + 3 * (pi - ZW) + (qi - ZW)];
+        const double* nu = pk + PK_NU;
+        if (pi >= ZF && qi < ZF) { int t = pi; pi = qi; qi = t; }     // make pi the x-side, qi the f-side
+        if (qi >= ZF) {
+            int fi = (qi - ZF) / 3, b = (qi - ZF) % 3;
+            if (pi < ZO) return m3::skew_ab(nu, pi, b);                                         // (r_a, f_ib): +skew(nu)[a][b]
+            if (pi >= ZC && pi < ZW && (pi - ZC) / 3 == fi) return -m3::skew_ab(nu, (pi - ZC) % 3, b);   // (c_ia, f_ib)
+        }
+        return 0.0;
+    }
+
+    // Q buffers <- lx, lu, lxx, lux, luu of this node.  Every thread of the block must call.
+    template <class Sync>
+    __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double* pk,
+                                  double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync) {
+        for (int e = tid; e < NX * NX; e += nthr) Qxx[e] = 0.0;
+        for (int e = tid; e < NU * NX; e += nthr) Qux[e] = 0.0;
+        for (int e = tid; e < NU * NU; e += nthr) Quu[e] = 0.0;
+        for (int e = tid; e < NX; e += nthr) Qx[e] = 0.0;
+        for (int e = tid; e < NU; e += nthr) Qu[e] = 0.0;
+        sync();
+        const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
+        if (input) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc)
+            const double* Jac = pk + PK_JAC;
+            const double g2 = 2.0 * c.gq;
+            const bool exact = c.hessian_mode == 0;
+            for (int e = tid; e < NZ * NZ; e += nthr) {
+                int pi = e / NZ, qi = e % NZ;
+                int xi = zmap_x(pi), xj = zmap_x(qi);
+                if (xi >= 0 && xj < 0) continue;       // (x,u) pairs are stored once, as lux[u][x]
+                double hh = Jac[pi] * Jac[qi] + Jac[NZ + pi] * Jac[NZ + qi] + Jac[2 * NZ + pi] * Jac[2 * NZ + qi];
+                if (exact) hh += hc(pk, pi, qi);
+                hh *= g2;
+                if (xi >= 0) Qxx[xi * NX + xj] = hh;
+                else if (xj >= 0) Qux[zmap_u(pi) * NX + xj] = hh;
+                else Quu[zmap_u(pi) * NU + zmap_u(qi)] = hh;
+            }
+            for (int pi = tid; pi < NZ; pi += nthr) {
+                double g = g2 * (Jac[pi] * pk[PK_WD] + Jac[NZ + pi] * pk[PK_WD + 1] + Jac[2 * NZ + pi] * pk[PK_WD + 2]);
+                int xi = zmap_x(pi);
+                if (xi >= 0) Qx[xi] = g; else Qu[zmap_u(pi)] = g;
+            }
+        }
+        sync();
+        // affine residuals: each task owns a disjoint set of entries
+        const int t = tid;
+        if (t == 0 && track) {                                      // rz_tracking, prb.py:184
+            Qxx[2 * NX + 2] += 2.0 * c.w_r; Qx[2] += 2.0 * c.w_r * (x[2] - c.com[2]);
+        } else if (t == 1 && track) {                               // o_tracking_xyz / _w, prb.py:185-189
+            const double* q = p + 15;
+            const double* o = x + XO;
+            double w2 = 2.0 * p[6] * p[6], res[4];
+            for (int i = 0; i < 4; i++)
+                res[i] = E_row(q, i, 0) * o[0] + E_row(q, i, 1) * o[1] + E_row(q, i, 2) * o[2] + E_row(q, i, 3) * o[3] - (i == 3 ? 1.0 : 0.0);
+            for (int a = 0; a < 4; a++) {
+                double g = 0;
+                for (int i = 0; i < 4; i++) g += E_row(q, i, a) * res[i];
+                Qx[XO + a] += w2 * g;
+                for (int b = 0; b < 4; b++) {
+                    double hh = 0;
+                    for (int i = 0; i < 4; i++) hh += E_row(q, i, a) * E_row(q, i, b);
+                    Qxx[(XO + a) * NX + XO + b] += w2 * hh;
+                }
+            }
+        } else if (t >= 2 && t < 5 && track) {                      // rdot_tracking, prb.py:190
+            int i = XRD + t - 2;
+            Qxx[i * NX + i] += 2.0 * c.w_rdot; Qx[i] += 2.0 * c.w_rdot * (x[i] - p[t - 2]);
+        } else if (t >= 5 && t < 8 && track) {                      // w_tracking, prb.py:191
+            int i = XW + t - 5;
+            Qxx[i * NX + i] += 2.0 * c.w_w; Qx[i] += 2.0 * c.w_w * (x[i] - p[3 + t - 5]);
+        } else if (t >= 8 && t < 12 && track) {                     // rel_pos_*, prb.py:192-199
+            int j = (t - 8) / 2, ax = (t - 8) % 2;
+            int ia = XC + 3 * j + ax, ib = ia + 6;
+            double w2 = 2.0 * c.w_rel, res = -x[ia] + x[ib] - c.drel[j][ax];
+            Qxx[ia * NX + ia] += w2; Qxx[ib * NX + ib] += w2; Qxx[ia * NX + ib] -= w2; Qxx[ib * NX + ia] -= w2;
+            Qx[ia] -= w2 * res; Qx[ib] += w2 * res;
+        } else if (t >= 12 && t < 16 && input) {                    // cz_tracking_i, prb.py:180
+            int i = t - 12, id = XC + 3 * i + 2;
+            Qxx[id * NX + id] += 2.0 * c.cw; Qx[id] += 2.0 * c.cw * (x[id] - p[7 + 2 * i]);
+        } else if (t >= 16 && t < 19 && input) {                    // rddot rows of min_qddot + min_f + f_active
+            int k = t - 16;
+            double h2 = 2.0 * c.gq * c.inv_ms * c.inv_ms, g = 2.0 * c.gq * c.inv_ms * pk[PK_RDD + k];
+            for (int i = 0; i < 4; i++) {
+                int ui = 6 * i + 3 + k;
+                double a = 1.0 - p[8 + 2 * i], wf = 2.0 * (c.w_minf + c.w_fsw * a * a);
+                Qu[ui] += g + wf * u[ui];
+                Quu[ui * NU + ui] += wf;
+                for (int j = 0; j < 4; j++) Quu[ui * NU + 6 * j + 3 + k] += h2;
+            }
+        } else if (t >= 19 && t < 31 && input) {                    // cddot rows of min_qddot
+            int i = (t - 19) / 3, k = (t - 19) % 3, ui = 6 * i + k;
+            Quu[ui * NU + ui] += 2.0 * c.gq; Qu[ui] += 2.0 * c.gq * u[ui];
+        } else if (t >= 31 && t < 35 && input) {                    // relative_vel_* and cdotxy_tracking_*, prb.py:166-181
+            int leg = (t - 31) / 2, ax = (t - 31) % 2;
+            int ia = XCD + 3 * (2 * leg) + ax, ib = ia + 3;
+            double w2 = 2.0 * c.cw, res = x[ia] - x[ib];
+            double sa = p[8 + 2 * (2 * leg)], sb = p[8 + 2 * (2 * leg + 1)];
+            Qxx[ia * NX + ia] += w2 * (1.0 + sa * sa); Qxx[ib * NX + ib] += w2 * (1.0 + sb * sb);
+            Qxx[ia * NX + ib] -= w2; Qxx[ib * NX + ia] -= w2;
+            Qx[ia] += w2 * (res + sa * sa * x[ia]); Qx[ib] += w2 * (-res + sb * sb * x[ib]);
+        }
+        sync();
+    }
+
+    // dense fx = I + dt A, fu = dt B.  Every thread of the block must call.
+    template <class Sync>
+    __device__ static void expand_f(const DevCfg& c, const double* x, const double* u, const double* pk, double* fx, double* fu,
+                                    int tid, int nthr, Sync sync) {
+        for (int e = tid; e < NX * NX; e += nthr) fx[e] = (e / NX == e % NX) ? 1.0 : 0.0;
+        for (int e = tid; e < NX * NU; e += nthr) fu[e] = 0.0;
+        sync();
+        const double dt = c.dt;
+        const double* o = x + XO;
+        const double* w = x + XW;
+        const double* Jac = pk + PK_JAC;
+        for (int e = tid; e < 105 + 60; e += nthr) {
+            if (e < 3) fx[(XR + e) * NX + XRD + e] += dt;
+            else if (e < 15) fx[(XC + e - 3) * NX + XCD + e - 3] += dt;
+            else if (e < 24) {            // d odot_v / d o_v = skew(w)/2
+                int a = (e - 15) / 3, b = (e - 15) % 3;
+                if (a != b) fx[(XO + a) * NX + XO + b] += 0.5 * dt * m3::skew_ab(w, a, b);
+            } else if (e < 27) {          // d odot_v / d o_w = w/2 ; d odot_w / d o_v = -w/2
+                int a = e - 24;
+                fx[(XO + a) * NX + XO + 3] += 0.5 * dt * w[a];
+                fx[(XO + 3) * NX + XO + a] += -0.5 * dt * w[a];
+            } else if (e < 36) {          // d odot_v / d w = (o_w I - skew(o_v))/2
+                int a = (e - 27) / 3, b = (e - 27) % 3;
+                fx[(XO + a) * NX + XW + b] += 0.5 * dt * ((a == b ? o[3] : 0.0) - m3::skew_ab(o, a, b));
+            } else if (e < 39) {          // d odot_w / d w = -o_v/2
+                int a = e - 36;
+                fx[(XO + 3) * NX + XW + a] += -0.5 * dt * o[a];
+            } else if (e < 105) {         // wdot rows: r(3) o(4) c(12) w(3) = first 22 z-columns
+                int a = (e - 39) / 22, pz = (e - 39) % 22;
+                fx[(XW + a) * NX + zmap_x(pz)] += dt * Jac[a * NZ + pz];
+            } else if (e < 117) {         // rddot / f
+                int i = (e - 105) / 3, k = (e - 105) % 3;
+                fu[(XRD + k) * NU + 6 * i + 3 + k] += dt * c.inv_ms;
+            } else if (e < 129) {         // cddot
+                int i = (e - 117) / 3, k = (e - 117) % 3;
+                fu[(XCD + 3 * i + k) * NU + 6 * i + k] += dt;
+            } else {                      // wdot / f
+                int a = (e - 129) / 12, pf = (e - 129) % 12;
+                fu[(XW + a) * NU + zmap_u(ZF + pf)] += dt * Jac[a * NZ + ZF + pf];
+            }
+        }
+        sync();
+    }
+};
+
+// =====================================================================================  LIP
+struct Lip {
+    static constexpr int NX = 30, NU = 15, NP = 11, NACC = 1, PACK = 1;
+    // x: r[0:3] c_i[3+3i] rdot[15:18] cdot_i[18+3i];  u: z[0:3] cddot_i[3+3i];  p: rdot_ref[0:3] (c_ref_i, sw_i)[3+2i, 4+2i]
+    enum { XR = 0, XC = 3, XRD = 15, XCD = 18 };
+
+    SDDP_DEV static void accel(const DevCfg&, const double*, const double*, double*) {}
+    SDDP_DEV static double xdot_i(const DevCfg& c, int i, const double* x, const double* u, const double*) {
+        if (i < 15) return x[i + 15];
+        if (i < 18) { int k = i - 15; return c.eta2 * (x[k] - u[k]) - (k == 2 ? c.g : 0.0); }   // prb.py:317-318
+        return u[3 + i - 18];
+    }
+    SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double*) {
+        double s = 0.0;
+        if (lane < NX) {
+            int i = lane;
+            if (kind != NODE_FIRST) {   // prb.py:390-392, 394-401
+                if (i == 2) { double r = x[2] - c.com[2]; s += c.w_r * r * r; }
+                else if (i < 2) { double r = x[i] - 0.25 * (x[3 + i] + x[6 + i] + x[9 + i] + x[12 + i]); s += c.w_r * r * r; }
+                else if (i >= 3 && i < 9 && (i - 3) % 3 < 2) {
+                    int j = (i - 3) / 3, ax = (i - 3) % 3;
+                    double r = -x[i] + x[i + 6] - c.drel[j][ax];
+                    s += c.w_rel * r * r;
+                } else if (i >= 15 && i < 18) { double r = x[i] - p[i - 15]; s += c.w_rdot * r * r; }
+            }
+            if (kind != NODE_TERM) {    // prb.py:379-387
+                if (i >= 3 && i < 15 && (i - 3) % 3 == 2) { double r = x[i] - p[3 + 2 * ((i - 3) / 3)]; s += c.cw * r * r; }
+                else if (i >= 18 && (i - 18) % 3 < 2) {
+                    int j = (i - 18) / 3;
+                    double r = p[4 + 2 * j] * x[i];
+                    s += c.cw * r * r;
+                    if (j == 0 || j == 2) { double r2 = x[i] - x[i + 3]; s += c.cw * r2 * r2; }
+                }
+            }
+        }
+        if (kind != NODE_TERM && lane < NU) {   // prb.py:393, 402
+            if (lane < 3) {
+                int k = lane;
+                double r = u[k] - 0.25 * (x[3 + k] + x[6 + k] + x[9 + k] + x[12 + k]);
+                double a = c.eta2 * (x[k] - u[k]) - (k == 2 ? c.g : 0.0);
+                s += c.w_zmp * r * r + c.gq * a * a;
+            } else s += c.gq * u[lane] * u[lane];
+        }
+        return s;
+    }
+    __device__ static void pack(const DevCfg&, int, const double*, const double*, double*) {}
+
+    template <class Sync>
+    __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double*,
+                                  double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync) {
+        for (int e = tid; e < NX * NX; e += nthr) Qxx[e] = 0.0;
+        for (int e = tid; e < NU * NX; e += nthr) Qux[e] = 0.0;
+        for (int e = tid; e < NU * NU; e += nthr) Quu[e] = 0.0;
+        for (int e = tid; e < NX; e += nthr) Qx[e] = 0.0;
+        for (int e = tid; e < NU; e += nthr) Qu[e] = 0.0;
+        sync();
+        const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
+        const int t = tid;
+        if (t < 3) {   // axis group {r_k, c_0k..c_3k, z_k}
+            int k = t;
+            int ci[4] = {XC + k, XC + 3 + k, XC + 6 + k, XC + 9 + k};
+            double csum = 0.25 * (x[ci[0]] + x[ci[1]] + x[ci[2]] + x[ci[3]]);
+            if (track) {
+                if (k == 2) { Qxx[2 * NX + 2] += 2.0 * c.w_r; Qx[2] += 2.0 * c.w_r * (x[2] - c.com[2]); }
+                else {     // rxy_tracking, prb.py:391
+                    double w2 = 2.0 * c.w_r, res = x[k] - csum;
+                    Qxx[k * NX + k] += w2; Qx[k] += w2 * res;
+                    for (int a = 0; a < 4; a++) {
+                        Qxx[k * NX + ci[a]] -= 0.25 * w2; Qxx[ci[a] * NX + k] -= 0.25 * w2; Qx[ci[a]] -= 0.25 * w2 * res;
+                        for (int b = 0; b < 4; b++) Qxx[ci[a] * NX + ci[b]] += w2 / 16.0;
+                    }
+                    for (int j = 0; j < 2; j++) {   // rel_pos, prb.py:394-401
+                        int ia = ci[j], ib = ci[j + 2];
+                        double wr = 2.0 * c.w_rel, rr = -x[ia] + x[ib] - c.drel[j][k];
+                        Qxx[ia * NX + ia] += wr; Qxx[ib * NX + ib] += wr; Qxx[ia * NX + ib] -= wr; Qxx[ib * NX + ia] -= wr;
+                        Qx[ia] -= wr * rr; Qx[ib] += wr * rr;
+                    }
+                }
+            }
+            if (input) {
+                double w2 = 2.0 * c.w_zmp, res = u[k] - csum;   // zmp_tracking, prb.py:393
+                Quu[k * NU + k] += w2; Qu[k] += w2 * res;
+                for (int a = 0; a < 4; a++) {
+                    Qux[k * NX + ci[a]] -= 0.25 * w2; Qx[ci[a]] -= 0.25 * w2 * res;
+                    for (int b = 0; b < 4; b++) Qxx[ci[a] * NX + ci[b]] += w2 / 16.0;
+                }
+                double e2 = c.eta2, wq = 2.0 * c.gq * e2 * e2;   // min_qddot rddot rows, prb.py:402
+                double acc = e2 * (x[k] - u[k]) - (k == 2 ? c.g : 0.0);
+                Qxx[k * NX + k] += wq; Quu[k * NU + k] += wq; Qux[k * NX + k] -= wq;
+                Qx[k] += 2.0 * c.gq * e2 * acc; Qu[k] -= 2.0 * c.gq * e2 * acc;
+                if (k == 2)
+                    for (int i = 0; i < 4; i++) { Qxx[ci[i] * NX + ci[i]] += 2.0 * c.cw; Qx[ci[i]] += 2.0 * c.cw * (x[ci[i]] - p[3 + 2 * i]); }
+            }
+        } else if (t < 6 && track) {
+            int i = XRD + t - 3;
+            Qxx[i * NX + i] += 2.0 * c.w_rdot; Qx[i] += 2.0 * c.w_rdot * (x[i] - p[t - 3]);
+        } else if (t >= 6 && t < 10 && input) {
+            int leg = (t - 6) / 2, ax = (t - 6) % 2;
+            int ia = XCD + 3 * (2 * leg) + ax, ib = ia + 3;
+            double w2 = 2.0 * c.cw, res = x[ia] - x[ib];
+            double sa = p[4 + 2 * (2 * leg)], sb = p[4 + 2 * (2 * leg + 1)];
+            Qxx[ia * NX + ia] += w2 * (1.0 + sa * sa); Qxx[ib * NX + ib] += w2 * (1.0 + sb * sb);
+            Qxx[ia * NX + ib] -= w2; Qxx[ib * NX + ia] -= w2;
+            Qx[ia] += w2 * (res + sa * sa * x[ia]); Qx[ib] += w2 * (-res + sb * sb * x[ib]);
+        } else if (t >= 10 && t < 22 && input) {
+            int ui = 3 + t - 10;
+            Quu[ui * NU + ui] += 2.0 * c.gq; Qu[ui] += 2.0 * c.gq * u[ui];
+        }
+        sync();
+    }
+
+    template <class Sync>
+    __device__ static void expand_f(const DevCfg& c, const double*, const double*, const double*, double* fx, double* fu,
+                                    int tid, int nthr, Sync sync) {
+        for (int e = tid; e < NX * NX; e += nthr) fx[e] = (e / NX == e % NX) ? 1.0 : 0.0;
+        for (int e = tid; e < NX * NU; e += nthr) fu[e] = 0.0;
+        sync();
+        const double dt = c.dt;
+        for (int e = tid; e < 33; e += nthr) {
+            if (e < 15) { fx[e * NX + e + 15] += dt; if (e >= 3) fu[(XCD + e - 3) * NU + 3 + e - 3] += dt; }
+            else if (e < 18) { int k = e - 15; fx[(XRD + k) * NX + k] += dt * c.eta2; fu[(XRD + k) * NU + k] += -dt * c.eta2; }
+        }
+        sync();
+    }
+};

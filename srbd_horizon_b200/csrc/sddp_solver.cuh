@@ -1,0 +1,490 @@
+// sddp_solver.cuh -- the DDP iteration as sm_100a device code: one CTA per problem.
+//
+// Stages (BASELINE.json north_star):
+//   1. derivatives   node packs, one thread per horizon node (Model::pack), expanded block-parallel
+//   2. backward      sequential Riccati recursion over nodes; matrices in shared memory; Quu
+//                    regularisation, in-warp Cholesky (one lane per row, warp shuffles for the pivot),
+//                    one thread per right-hand side for the gain solves
+//   3. forward       one warp per candidate step size (parallel line search), lanes own the rows of
+//                    K dx and the state components; warp-shuffle cost reduction
+//   4. defects       multiple-shooting gaps d_k = f(x_k,u_k) - x_{k+1}, contracted by (1 - rho)
+//
+// The algorithm is the one documented in oracle/sddp_oracle.c (it restates pyddp's role; the reference's
+// ddp.py:96-106 only calls it).  Algebraic form used here (W-form, Quu_r = L L^T):
+//   W = L^-1 Qux, w0 = L^-1 Qu, K = -L^-T W, k = -L^-T w0
+//   Vx = Qx - W^T w0 - mu K^T k,  Vxx = sym(Qxx) - W^T W - mu K^T K
+//   Qu.k = -|w0|^2,  k^T Quu k = |w0|^2 - mu |k|^2
+#pragma once
+#include "sddp_model.cuh"
+
+constexpr int NT = 128;      // threads per CTA
+constexpr int NWARP = NT / 32;
+constexpr int NCAND = NWARP; // line-search candidates evaluated per wave
+constexpr unsigned FULL = 0xffffffffu;
+
+template <class M>
+struct Smem {
+    static constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    double Vxx[NX * NX], Qxx[NX * NX], Qux[NU * NX], Quu[NU * NU];
+    double T[NX * (NX + NU)];            // Vxx [fx fu]; afterwards K of the node (NU*NX); forward: K_k
+    double fx[NX * NX], fu[NX * NU];     // dense; forward: per-candidate x^, u^, x^+
+    double Vx[NX], y[NX], Qx[NX], Qu[NU], vp[NX], cg[NX], sv[NX], ys[NX], quy[NU], qxy[NX], kk[NU], w0[NU];
+    double xk[NX], uk[NU], pk[NP], pack[M::PACK];
+    double red[16];
+    double alpha[NCAND], rho[NCAND], Jc[NCAND];
+    int iflag[4];
+};
+enum { R_TOT = 0, R_ACC1 = 1, R_ACC2 = 2, R_G1 = 3, R_G2 = 4, R_YG = 5, R_W0 = 8 };
+
+struct SyncBlock { __device__ void operator()() const { __syncthreads(); } };
+
+SDDP_DEV int node_kind(int k, int N) { return k == 0 ? NODE_FIRST : (k == N ? NODE_TERM : NODE_MID); }
+
+SDDP_DEV double warp_sum(double s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    return s;
+}
+SDDP_DEV double warp_max(double s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(FULL, s, o));
+    return s;
+}
+
+// cost of one node (all lanes get the sum) and, if xnext != null, the Euler step
+//   xnext = xs + dt*ode(xs,us) - omr*dk
+template <class M>
+__device__ double warp_node(const DevCfg& c, int kind, const double* xs, const double* us, const double* ps,
+                            double* xnext, const double* dk, double omr, int lane) {
+    double acc[M::NACC];
+    if (kind != NODE_TERM) M::accel(c, xs, us, acc);
+    double s = warp_sum(M::cost_lane(c, kind, lane, xs, us, ps, acc));
+    if (xnext != nullptr && kind != NODE_TERM) {
+        for (int i = lane; i < M::NX; i += 32) {
+            double v = xs[i] + c.dt * M::xdot_i(c, i, xs, us, acc);
+            if (dk != nullptr) v -= omr * dk[i];
+            xnext[i] = v;
+        }
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// defects d_k = f(X_k,U_k) - X_{k+1} (if dout) and the total cost; warps stride over nodes.
+// Returns J to every thread.  Uses S.fx as per-warp scratch.
+template <class M>
+__device__ double defects_and_cost(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P,
+                                   double* dout, int tid) {
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    const int N = c.N, lane = tid & 31, w = tid >> 5;
+    double* xs = S.fx + w * (2 * NX + NU + NP);
+    double* us = xs + NX;
+    double* ps = us + NU;
+    double* xn = ps + NP;
+    double part = 0.0;
+    for (int k = w; k <= N; k += NWARP) {
+        const int kind = node_kind(k, N);
+        for (int i = lane; i < NX; i += 32) xs[i] = X[(size_t)k * NX + i];
+        if (k < N) for (int i = lane; i < NU; i += 32) us[i] = U[(size_t)k * NU + i];
+        for (int i = lane; i < NP; i += 32) ps[i] = P[(size_t)k * NP + i];
+        __syncwarp();
+        part += warp_node<M>(c, kind, xs, us, ps, (dout && k < N) ? xn : nullptr, nullptr, 0.0, lane);
+        __syncwarp();
+        if (dout && k < N)
+            for (int i = lane; i < NX; i += 32) dout[(size_t)k * NX + i] = xn[i] - X[(size_t)(k + 1) * NX + i];
+        __syncwarp();
+    }
+    if (lane == 0) S.red[R_W0 + w] = part;
+    __syncthreads();
+    double J = 0.0;
+#pragma unroll
+    for (int i = 0; i < NWARP; i++) J += S.red[R_W0 + i];
+    __syncthreads();
+    return J;
+}
+
+// open-loop rollout X_{k+1} = f(X_k, U_k) by warp 0 (single-shooting initialisation)
+template <class M>
+__device__ void open_loop_rollout(const DevCfg& c, Smem<M>& S, double* X, const double* U, int tid) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int lane = tid & 31;
+    if (tid < 32) {
+        double* xs = S.fx;
+        double* us = xs + NX;
+        double* xn = us + NU;
+        for (int i = lane; i < NX; i += 32) xs[i] = X[i];
+        for (int k = 0; k < c.N; k++) {
+            for (int i = lane; i < NU; i += 32) us[i] = U[(size_t)k * NU + i];
+            __syncwarp();
+            double acc[M::NACC];
+            M::accel(c, xs, us, acc);
+            for (int i = lane; i < NX; i += 32) xn[i] = xs[i] + c.dt * M::xdot_i(c, i, xs, us, acc);
+            __syncwarp();
+            for (int i = lane; i < NX; i += 32) { xs[i] = xn[i]; X[(size_t)(k + 1) * NX + i] = xn[i]; }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2.  Returns 0 or (failing node + 1) to every thread.  dV3[0..2] (shared) = {D1, D2, C0}.
+template <class M>
+__device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P,
+                             const double* D, const double* packs, double mu, double* Kg, double* kg, double* dV3, int tid) {
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP, LD = NX + NU;
+    const int N = c.N, lane = tid & 31, warp = tid >> 5;
+    const bool fixed = c.rho_fixed > 0.0;
+    const double rho_b = fixed ? c.rho_fixed : 1.0;
+    SyncBlock sync;
+
+    // terminal node: Vx = l_Nx, Vxx = l_Nxx (ddp.py:216-226: costs only)
+    for (int i = tid; i < NX; i += NT) S.xk[i] = X[(size_t)N * NX + i];
+    for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)N * NP + i];
+    if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; }
+    __syncthreads();
+    M::expand(c, NODE_TERM, S.xk, nullptr, S.pk, nullptr, S.Vx, S.Qu, S.Vxx, S.Qux, S.Quu, tid, NT, sync);
+    for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
+    __syncthreads();
+
+    for (int k = N - 1; k >= 0; k--) {
+        const int kind = node_kind(k, N);
+        for (int i = tid; i < NX; i += NT) {
+            S.xk[i] = X[(size_t)k * NX + i];
+            S.cg[i] = (D != nullptr) ? rho_b * D[(size_t)k * NX + i] : 0.0;
+        }
+        for (int i = tid; i < NU; i += NT) S.uk[i] = U[(size_t)k * NU + i];
+        for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)k * NP + i];
+        for (int i = tid; i < M::PACK; i += NT) S.pack[i] = packs[(size_t)k * M::PACK + i];
+        __syncthreads();
+        M::expand(c, kind, S.xk, S.uk, S.pk, S.pack, S.Qx, S.Qu, S.Qxx, S.Qux, S.Quu, tid, NT, sync);
+        M::expand_f(c, S.xk, S.uk, S.pack, S.fx, S.fu, tid, NT, sync);
+
+        // sv = Vxx' c, v+ = Vx' + sv, ys = y' (+ sv)
+        if (tid < NX) {
+            double s = 0.0;
+            for (int j = 0; j < NX; j++) s += S.Vxx[tid * NX + j] * S.cg[j];
+            S.sv[tid] = s;
+            S.vp[tid] = S.Vx[tid] + s;
+            S.ys[tid] = fixed ? S.y[tid] + s : S.y[tid];
+        }
+        // T = Vxx' [fx fu]
+        for (int e = tid; e < NX * LD; e += NT) {
+            int i = e / LD, j = e % LD;
+            double s = 0.0;
+            if (j < NX) for (int l = 0; l < NX; l++) s += S.Vxx[i * NX + l] * S.fx[l * NX + j];
+            else        for (int l = 0; l < NX; l++) s += S.Vxx[i * NX + l] * S.fu[l * NU + (j - NX)];
+            S.T[e] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {   // gap terms of the model
+            double g1 = 0, g2 = 0, yg = 0;
+            for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * S.cg[i]; g2 += S.cg[i] * S.sv[i]; yg += S.y[i] * S.cg[i]; }
+            g1 = warp_sum(g1); g2 = warp_sum(g2); yg = warp_sum(yg);
+            if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
+        }
+        // first-order quantities (Qx, Qu still hold lx, lu)
+        if (tid < NX) {
+            double a = 0.0, b = 0.0;
+            for (int l = 0; l < NX; l++) { a += S.fx[l * NX + tid] * S.ys[l]; b += S.fx[l * NX + tid] * S.vp[l]; }
+            S.qxy[tid] = S.Qx[tid] + a;
+            S.Qx[tid] += b;
+        } else if (tid >= 64 && tid < 64 + NU) {
+            int j = tid - 64;
+            double a = 0.0, b = 0.0;
+            for (int l = 0; l < NX; l++) { a += S.fu[l * NU + j] * S.ys[l]; b += S.fu[l * NU + j] * S.vp[l]; }
+            S.quy[j] = S.Qu[j] + a;
+            S.Qu[j] += b;
+        }
+        // Qxx += fx^T Tx, Qux += fu^T Tx, Quu += fu^T Tu
+        for (int e = tid; e < NX * NX; e += NT) {
+            int i = e / NX, j = e % NX;
+            double s = 0.0;
+            for (int l = 0; l < NX; l++) s += S.fx[l * NX + i] * S.T[l * LD + j];
+            S.Qxx[e] += s;
+        }
+        for (int e = tid; e < NU * NX; e += NT) {
+            int i = e / NX, j = e % NX;
+            double s = 0.0;
+            for (int l = 0; l < NX; l++) s += S.fu[l * NU + i] * S.T[l * LD + j];
+            S.Qux[e] += s;
+        }
+        for (int e = tid; e < NU * NU; e += NT) {
+            int i = e / NU, j = e % NU;
+            double s = 0.0;
+            for (int l = 0; l < NX; l++) s += S.fu[l * NU + i] * S.T[l * LD + NX + j];
+            S.Quu[e] += s;
+        }
+        __syncthreads();
+
+        // Cholesky of sym(Quu) + mu I, left-looking, lane i owns row i; L overwrites the lower triangle
+        if (warp == 0) {
+            int ok = 1;
+            for (int j = 0; j < NU; j++) {
+                double s = 0.0;
+                if (lane < NU && lane >= j) {
+                    s = 0.5 * (S.Quu[lane * NU + j] + S.Quu[j * NU + lane]) + (lane == j ? mu : 0.0);
+                    for (int l = 0; l < j; l++) s -= S.Quu[lane * NU + l] * S.Quu[j * NU + l];
+                }
+                double piv = __shfl_sync(FULL, s, j);
+                if (!(piv > 0.0) || !isfinite(piv)) { ok = 0; break; }
+                double d = sqrt(piv);
+                if (lane < NU && lane >= j) S.Quu[lane * NU + j] = (lane == j) ? d : s / d;
+                __syncwarp();
+            }
+            if (lane == 0) S.iflag[0] = ok;
+        }
+        __syncthreads();
+        if (!S.iflag[0]) { __syncthreads(); return k + 1; }
+
+        // gains: one thread per right-hand side (NX columns of Qux, then Qu)
+        if (tid <= NX) {
+            const int t = tid;
+            double b[NU], kc[NU];
+#pragma unroll
+            for (int i = 0; i < NU; i++) b[i] = (t < NX) ? S.Qux[i * NX + t] : S.Qu[i];
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+                double s = b[i];
+#pragma unroll
+                for (int l = 0; l < i; l++) s -= S.Quu[i * NU + l] * b[l];
+                b[i] = s / S.Quu[i * NU + i];
+            }
+#pragma unroll
+            for (int i = NU - 1; i >= 0; i--) {
+                double s = -b[i];
+#pragma unroll
+                for (int l = i + 1; l < NU; l++) s -= S.Quu[l * NU + i] * kc[l];
+                kc[i] = s / S.Quu[i * NU + i];
+            }
+            if (t < NX) {
+                double yv = S.qxy[t];
+#pragma unroll
+                for (int i = 0; i < NU; i++) {
+                    S.Qux[i * NX + t] = b[i];                       // W
+                    S.T[i * NX + t] = kc[i];                        // K (shared copy)
+                    Kg[((size_t)k * NU + i) * NX + t] = kc[i];
+                    yv += kc[i] * S.quy[i];
+                }
+                S.y[t] = yv;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NU; i++) { S.w0[i] = b[i]; S.kk[i] = kc[i]; kg[(size_t)k * NU + i] = kc[i]; }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {   // model accumulators
+            double sw = 0, sk = 0, sq = 0;
+            for (int i = lane; i < NU; i += 32) { sw += S.w0[i] * S.w0[i]; sk += S.kk[i] * S.kk[i]; sq += S.quy[i] * S.kk[i]; }
+            sw = warp_sum(sw); sk = warp_sum(sk); sq = warp_sum(sq);
+            if (lane == 0) {
+                double kQk = sw - mu * sk;
+                S.red[R_TOT] += S.red[R_G1] + 0.5 * S.red[R_G2] + (-sw) + 0.5 * kQk;
+                S.red[R_ACC2] += 0.5 * kQk;
+                S.red[R_ACC1] += fixed ? (S.red[R_YG] + 0.5 * S.red[R_G2]) : (S.red[R_YG] + sq);
+            }
+        }
+        // Vx = Qx - W^T w0 - mu K^T k
+        if (tid >= 64 && tid < 64 + NX) {
+            int t = tid - 64;
+            double s = S.Qx[t];
+            for (int l = 0; l < NU; l++) s -= S.Qux[l * NX + t] * S.w0[l] + mu * S.T[l * NX + t] * S.kk[l];
+            S.Vx[t] = s;
+        }
+        // Vxx = sym(Qxx) - W^T W - mu K^T K   (upper triangle, mirrored)
+        for (int e = tid; e < NX * NX; e += NT) {
+            int i = e / NX, j = e % NX;
+            if (j < i) continue;
+            double s = 0.5 * (S.Qxx[i * NX + j] + S.Qxx[j * NX + i]);
+            for (int l = 0; l < NU; l++) s -= S.Qux[l * NX + i] * S.Qux[l * NX + j];
+            if (mu != 0.0) {
+                double t = 0.0;
+                for (int l = 0; l < NU; l++) t += S.T[l * NX + i] * S.T[l * NX + j];
+                s -= mu * t;
+            }
+            S.Vxx[i * NX + j] = s;
+            S.Vxx[j * NX + i] = s;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double tot = S.red[R_TOT], a1 = S.red[R_ACC1], a2 = S.red[R_ACC2];
+        if (fixed) { dV3[2] = a1; dV3[1] = a2; dV3[0] = tot - a1 - a2; }
+        else       { dV3[2] = 0.0; dV3[0] = a1; dV3[1] = tot - a1; }
+    }
+    __syncthreads();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 3.  ncand (<= NCAND) candidate step sizes S.alpha[], S.rho[] rolled out in parallel, one warp each.
+// Trial trajectories go to Xn + cand*xn_stride / Un + cand*un_stride (global); costs to S.Jc[].
+template <class M>
+__device__ void forward_wave(const DevCfg& c, Smem<M>& S, const double* x0, const double* X, const double* U, const double* P,
+                             const double* D, const double* Kg, const double* kg, int ncand, double* Xn, size_t xn_stride,
+                             double* Un, size_t un_stride, int tid) {
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    const int N = c.N, lane = tid & 31, w = tid >> 5;
+    double* xh = S.fx + w * (2 * NX + NU);
+    double* uh = xh + NX;
+    double* xn = uh + NU;
+    double* Xo = Xn + (size_t)w * xn_stride;
+    double* Uo = Un + (size_t)w * un_stride;
+    const bool active = w < ncand;
+    const double alpha = active ? S.alpha[w] : 0.0, omr = active ? 1.0 - S.rho[w] : 0.0;
+    double J = 0.0;
+    for (int i = lane; i < NX; i += 32) xh[i] = x0[i];
+    for (int k = 0; k < N; k++) {
+        __syncthreads();
+        for (int e = tid; e < NU * NX; e += NT) S.T[e] = Kg[(size_t)k * NU * NX + e];
+        for (int i = tid; i < NU; i += NT) { S.kk[i] = kg[(size_t)k * NU + i]; S.uk[i] = U[(size_t)k * NU + i]; }
+        for (int i = tid; i < NX; i += NT) { S.xk[i] = X[(size_t)k * NX + i]; S.cg[i] = (D != nullptr) ? D[(size_t)k * NX + i] : 0.0; }
+        for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)k * NP + i];
+        __syncthreads();
+        if (active) {
+            for (int j = lane; j < NU; j += 32) {
+                double t = 0.0;
+                for (int i = 0; i < NX; i++) t += S.T[j * NX + i] * (xh[i] - S.xk[i]);
+                double v = S.uk[j] + alpha * S.kk[j] + t;
+                uh[j] = v;
+                Uo[(size_t)k * NU + j] = v;
+            }
+            for (int i = lane; i < NX; i += 32) Xo[(size_t)k * NX + i] = xh[i];
+            __syncwarp();
+            J += warp_node<M>(c, node_kind(k, N), xh, uh, S.pk, xn, S.cg, omr, lane);
+            __syncwarp();
+            for (int i = lane; i < NX; i += 32) xh[i] = xn[i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)N * NP + i];
+    __syncthreads();
+    if (active) {
+        for (int i = lane; i < NX; i += 32) Xo[(size_t)N * NX + i] = xh[i];
+        J += warp_node<M>(c, NODE_TERM, xh, nullptr, S.pk, nullptr, nullptr, 0.0, lane);
+        if (lane == 0) S.Jc[w] = J;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SolveArgs {
+    int B;
+    const double* x0; const double* params;
+    double* X; double* U; double* K; double* kff; double* hist;
+    int* iters; int* status; double* cost;
+    // workspace, per resident CTA
+    double* ws_d; double* ws_pack; double* ws_xn; double* ws_un; double* ws_K; double* ws_k;
+    int* counter;
+};
+
+template <class M>
+__device__ void compute_packs(const DevCfg& c, const double* X, const double* U, double* packs, int tid) {
+    if (M::PACK > 1)
+        for (int k = tid; k < c.N; k += NT) M::pack(c, node_kind(k, c.N), X + (size_t)k * M::NX, U + (size_t)k * M::NU, packs + (size_t)k * M::PACK);
+    __syncthreads();
+}
+
+template <class M>
+__device__ void solve_one(const DevCfg& c, const SolveArgs& a, Smem<M>& S, int b, int slot, int tid) {
+    constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    const int N = c.N;
+    const size_t xsz = (size_t)(N + 1) * NX, usz = (size_t)N * NU;
+    const double* x0 = a.x0 + (size_t)b * NX;
+    const double* P = a.params + (size_t)b * (N + 1) * NP;
+    double* X = a.X + (size_t)b * xsz;
+    double* U = a.U + (size_t)b * usz;
+    double* Kg = a.K ? a.K + (size_t)b * N * NU * NX : a.ws_K + (size_t)slot * N * NU * NX;
+    double* kg = a.kff ? a.kff + (size_t)b * usz : a.ws_k + (size_t)slot * usz;
+    double* hist = a.hist ? a.hist + (size_t)b * c.max_iters * 4 : nullptr;
+    double* d = a.ws_d + (size_t)slot * N * NX;
+    double* packs = a.ws_pack + (size_t)slot * N * M::PACK;
+    double* Xn = a.ws_xn + (size_t)slot * NCAND * xsz;
+    double* Un = a.ws_un + (size_t)slot * NCAND * usz;
+    const bool fixed = c.rho_fixed > 0.0;
+
+    for (int i = tid; i < NX; i += NT) X[i] = x0[i];
+    if (hist) for (int i = tid; i < c.max_iters * 4; i += NT) hist[i] = 0.0;
+    __syncthreads();
+    double J, dmax = 0.0;
+    if (!c.ms) {
+        open_loop_rollout<M>(c, S, X, U, tid);
+        for (int i = tid; i < N * NX; i += NT) d[i] = 0.0;
+        __syncthreads();
+        J = defects_and_cost<M>(c, S, X, U, P, nullptr, tid);
+    } else {
+        J = defects_and_cost<M>(c, S, X, U, P, d, tid);
+        double m = 0.0;
+        for (int i = tid; i < N * NX; i += NT) { double v = fabs(d[i]); if (v > m || v != v) m = v; }
+        m = warp_max(m);
+        if ((tid & 31) == 0) S.red[R_W0 + (tid >> 5)] = m;
+        __syncthreads();
+        for (int i = 0; i < NWARP; i++) dmax = fmax(dmax, S.red[R_W0 + i]);
+        __syncthreads();
+    }
+    double mu = c.mu0;
+    int status = 1 /*MAX_ITERS*/, it = 0;
+    for (it = 0; it < c.max_iters; it++) {
+        compute_packs<M>(c, X, U, packs, tid);
+        bool reg_fail = false;
+        while (backward_pass<M>(c, S, X, U, P, d, packs, mu, Kg, kg, &S.red[12], tid)) {
+            mu = fmax(mu * c.mu_factor, c.mu_min);
+            if (mu > c.mu_max) { reg_fail = true; break; }
+        }
+        const double D1 = S.red[12], D2 = S.red[13], C0 = S.red[14];
+        double* h = hist ? hist + it * 4 : nullptr;
+        if (h && tid == 0) { h[0] = J; h[1] = 0.0; h[2] = mu; h[3] = dmax; }
+        if (reg_fail) { status = 3; it++; break; }
+        if (!isfinite(D1) || !isfinite(D2) || !isfinite(J)) { status = 4; it++; break; }
+        const double a0 = c.alpha0;
+        const double dJ0 = C0 + a0 * D1 + a0 * a0 * D2;
+        if (fabs(dJ0) <= 1e-3 * c.cost_ths * (1.0 + fabs(J)) && dmax <= c.defect_ths) { status = 0; it++; break; }
+        // parallel line search: waves of NCAND candidates, first (largest) passing alpha wins
+        bool accepted = false;
+        double alpha = a0, Jn = J, alpha_acc = 0.0, rho_acc = 0.0;
+        int sel = 0;
+        while (!accepted && alpha >= c.alpha_min) {
+            int ncand = 0;
+            double al[NCAND];
+            for (int j = 0; j < NCAND; j++) {
+                al[j] = alpha;
+                if (alpha >= c.alpha_min) ncand++;
+                alpha *= c.ls_factor;
+            }
+            __syncthreads();
+            if (tid < NCAND) { S.alpha[tid] = al[tid]; S.rho[tid] = fixed ? c.rho_fixed : al[tid]; }
+            __syncthreads();
+            forward_wave<M>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid);
+            for (int j = 0; j < ncand; j++) {
+                double am = al[j], dJm = C0 + am * D1 + am * am * D2, Jj = S.Jc[j];
+                if (isfinite(Jj) && Jj - J <= dJm + (1.0 - c.beta) * fabs(dJm)) {
+                    accepted = true; sel = j; Jn = Jj; alpha_acc = am; rho_acc = fixed ? c.rho_fixed : am;
+                    break;
+                }
+            }
+        }
+        if (accepted) {
+            const double* Xs = Xn + (size_t)sel * xsz;
+            const double* Us = Un + (size_t)sel * usz;
+            for (size_t i = tid; i < xsz; i += NT) X[i] = Xs[i];
+            for (size_t i = tid; i < usz; i += NT) U[i] = Us[i];
+            const double omr = 1.0 - rho_acc;
+            for (int i = tid; i < N * NX; i += NT) d[i] *= omr;
+            dmax *= omr;
+            const double dJ = J - Jn;
+            J = Jn;
+            if (h && tid == 0) { h[0] = J; h[1] = alpha_acc; h[3] = dmax; }
+            mu = mu / c.mu_factor;
+            if (mu < c.mu_min) mu = 0.0;
+            if (mu < c.mu0) mu = c.mu0;
+            __syncthreads();
+            if (dJ <= c.cost_ths * (1.0 + fabs(J)) && dmax <= c.defect_ths) { status = 0; it++; break; }
+        } else {
+            mu = fmax(mu * c.mu_factor, c.mu_min);
+            if (mu > c.mu_max) { status = 2; it++; break; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
+}

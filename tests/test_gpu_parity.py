@@ -1,0 +1,210 @@
+"""GPU parity: every stage of the CUDA path, called through the C ABI (ctypes), against the CPU oracle
+on the same seeded inputs, and against the committed mpmath goldens.
+
+Tolerances (fp64 build, BASELINE.json north_star: 1e-9 relative on per-iteration cost, trajectories, gains):
+  stage outputs  1e-11 norm-wise (max|a-b| / max|b|)
+  full solves    1e-9  norm-wise on per-iteration cost, X, U; 1e-8 on K (its conditioning is that of Quu);
+                 the feed-forward k vanishes at convergence and is compared on the scale of U.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from srbd_horizon_b200.config import DIMS, HESSIAN_GN, MODEL_LIP, MODEL_SRBD, make_config
+from srbd_horizon_b200.ddp import BatchedDDP
+from srbd_horizon_b200.problems import make_batch
+from tests.helpers import golden_cases, random_point, relerr
+
+EX_OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}   # dsrbd_example.py:55-58
+NAMES = ["fx", "fu", "lx", "lu", "lxx", "lux", "luu"]
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("hess", [0, 1])
+def test_stage1_derivatives_vs_golden(golden, hess):
+    for model in (MODEL_SRBD, MODEL_LIP):
+        for mode in ((0, 1) if model == MODEL_SRBD else (0,)):
+            cases = [(k, kind) for k, m, md, kind in golden_cases(golden, model) if md == mode]
+            cfg = make_config(model, 20, 0.05, {"inertia_mode": mode, "hessian_mode": hess})
+            s = BatchedDDP(cfg)
+            x = np.stack([golden[k + "_x"] for k, _ in cases]); u = np.stack([golden[k + "_u"] for k, _ in cases])
+            p = np.stack([golden[k + "_p"] for k, _ in cases]); kind = [kd for _, kd in cases]
+            out = {n: cpu(v) for n, v in s.eval_derivatives(kind, x, u, p).items()}
+            pre = "_gn_" if hess else "_"
+            for i, (k, kd) in enumerate(cases):
+                assert abs(out["l"][i] - float(golden[k + "_L"])) <= 1e-13 * abs(float(golden[k + "_L"]))
+                names = ["lx", "lxx"] if kd == 2 else NAMES
+                if kd != 2:
+                    assert relerr(out["f"][i], golden[k + "_f"]) < 1e-14
+                for n in names:
+                    g = golden[k + (pre if n in ("lxx", "lux", "luu") else "_") + n]
+                    assert relerr(out[n][i], g) < 1e-11, (k, n)
+
+
+@pytest.mark.parametrize("model", [MODEL_SRBD, MODEL_LIP])
+def test_stage1_derivatives_vs_oracle_random(model):
+    rng = np.random.default_rng(7)
+    nx, nu, np_ = DIMS[model]
+    for mode in ((0, 1) if model == MODEL_SRBD else (0,)):
+        cfg = make_config(model, 20, 0.05, {"inertia_mode": mode})
+        s = BatchedDDP(cfg)
+        M = 96
+        pts = [random_point(rng, model) for _ in range(M)]
+        kind = [i % 3 for i in range(M)]
+        out = {n: cpu(v) for n, v in s.eval_derivatives(kind, np.stack([q[0] for q in pts]), np.stack([q[1] for q in pts]),
+                                                        np.stack([q[2] for q in pts])).items()}
+        for i, (x, u, p) in enumerate(pts):
+            d = O.derivs(cfg, kind[i], x, u, p)
+            assert out["l"][i] == pytest.approx(O.cost(cfg, kind[i], x, u, p), rel=1e-13)
+            for n in (["lx", "lxx"] if kind[i] == 2 else NAMES):
+                assert relerr(out[n][i], d[n]) < 1e-11, (i, n)
+            if kind[i] != 2:
+                assert relerr(out["f"][i], O.dynamics(cfg, x, u)) < 1e-14
+
+
+def _setup(model, N, B, opts, x_noise=0.01):
+    cfg = make_config(model, N, 0.05, dict(EX_OPTS, **opts))
+    b = make_batch(model, N, B, x_noise=x_noise if cfg.multiple_shooting else 0.0)
+    return cfg, b, BatchedDDP(cfg)
+
+
+@pytest.mark.parametrize("model,opts", [(MODEL_SRBD, {}), (MODEL_SRBD, {"defect_contraction_rate": 0.5}),
+                                        (MODEL_SRBD, {"inertia_mode": 1}), (MODEL_LIP, {})])
+def test_stages_2_3_4_vs_oracle(model, opts):
+    N, B = 20, 6
+    cfg, b, s = _setup(model, N, B, opts)
+    nx, nu, _ = DIMS[model]
+    X = b["X0"].copy(); X[:, 0] = b["x0"]
+    U = b["U0"] + 0.01
+    # stage 4: defects and total cost
+    D, J = s.defects(X, U, b["params"])
+    D, J = cpu(D), cpu(J)
+    for i in range(B):
+        for k in range(N):
+            assert np.max(np.abs(D[i, k] - (O.dynamics(cfg, X[i, k], U[i, k]) - X[i, k + 1]))) < 1e-14
+        assert J[i] == pytest.approx(O.total_cost(cfg, X[i], U[i], b["params"][i]), rel=1e-13)
+    # stage 2: backward pass (also with regularisation)
+    for mu in (0.0, 1e-2):
+        rc, K, k, dV = (cpu(t) for t in s.backward_pass(X, U, b["params"], D, mu))
+        for i in range(B):
+            rc_o, K_o, k_o, dV_o = O.backward(cfg, X[i], U[i], b["params"][i], D[i], mu)
+            assert rc[i] == rc_o == 0
+            assert relerr(K[i], K_o) < 1e-10 and relerr(k[i], k_o) < 1e-10
+            assert np.max(np.abs(dV[i] - dV_o)) < 1e-9 * np.max(np.abs(dV_o))
+    # stage 3: parallel line search candidates (6 step sizes -> two waves)
+    alphas = np.array([1.0, 0.5, 0.25, 0.125, 0.0625, 0.01])
+    rate = cfg.defect_contraction_rate
+    rhos = np.full(6, rate) if rate > 0 else alphas
+    Jn, Xn, Un = (cpu(t) for t in s.forward_pass(alphas, rhos, b["x0"], X, U, b["params"], D, K, k))
+    for i in range(B):
+        for j, (al, rh) in enumerate(zip(alphas, rhos)):
+            J_o, Xn_o, Un_o = O.forward(cfg, b["x0"][i], X[i], U[i], b["params"][i], D[i], K[i], k[i], al, rh)
+            assert Jn[i, j] == pytest.approx(J_o, rel=1e-11)
+            assert relerr(Xn[i, j], Xn_o) < 1e-11 and relerr(Un[i, j], Un_o) < 1e-11
+
+
+def test_backward_reports_cholesky_failure():
+    """Quu made indefinite through a negative Vxx seed is not reachable from the API; instead check that a huge
+    negative regularisation fails at the last node on both paths."""
+    cfg, b, s = _setup(MODEL_SRBD, 10, 2, {})
+    X = b["X0"].copy(); X[:, 0] = b["x0"]
+    D, _ = s.defects(X, b["U0"], b["params"])
+    rc, *_ = s.backward_pass(X, b["U0"], b["params"], D, -1e9)
+    rc_o, *_ = O.backward(cfg, X[0], b["U0"][0], b["params"][0], cpu(D)[0], -1e9)
+    assert int(cpu(rc)[0]) == rc_o == 10
+
+
+def _compare_solve(cfg, b, r, ro, B):
+    iters, status = cpu(r.iters), cpu(r.status)
+    hist, X, U, K, k, cost = cpu(r.hist), cpu(r.X), cpu(r.U), cpu(r.K), cpu(r.k), cpu(r.cost)
+    np.testing.assert_array_equal(status, ro["status"])
+    np.testing.assert_array_equal(iters, ro["iters"])
+    for i in range(B):
+        n = iters[i]
+        assert relerr(hist[i, :n, 0], ro["hist"][i, :n, 0]) < 1e-9, i        # per-iteration cost
+        np.testing.assert_array_equal(hist[i, :n, 1], ro["hist"][i, :n, 1])   # accepted step sizes (T8)
+        np.testing.assert_array_equal(hist[i, :n, 2], ro["hist"][i, :n, 2])   # regularisation schedule
+        assert relerr(hist[i, :n, 3], ro["hist"][i, :n, 3]) < 1e-9 or np.max(np.abs(hist[i, :n, 3] - ro["hist"][i, :n, 3])) < 1e-15
+        assert relerr(X[i], ro["X"][i]) < 1e-9 and relerr(U[i], ro["U"][i]) < 1e-9, i
+        assert relerr(K[i], ro["K"][i]) < 1e-8, i
+        assert np.max(np.abs(k[i] - ro["k"][i])) < 1e-9 * max(1.0, np.max(np.abs(ro["U"][i]))), i
+        assert cost[i] == pytest.approx(ro["cost"][i], rel=1e-9)
+
+
+@pytest.mark.parametrize("model,N,opts", [
+    (MODEL_SRBD, 20, {}),                                   # dsrbd_example.py configuration
+    (MODEL_SRBD, 50, {}),                                   # batched config (BASELINE configs[2])
+    (MODEL_SRBD, 50, {"defect_contraction_rate": 0.5}),     # fixed defect contraction (configs[3])
+    (MODEL_SRBD, 20, {"defect_contraction_rate": 1.0}),
+    (MODEL_SRBD, 20, {"inertia_mode": 1, "hessian_mode": HESSIAN_GN}),
+    (MODEL_SRBD, 20, {"inertia_mode": 1}),
+    (MODEL_SRBD, 12, {"multiple_shooting": 0}),
+    (MODEL_SRBD, 20, {"mu0": 1e-3}),
+    (MODEL_LIP, 20, {}),                                    # dlip_example.py configuration
+    (MODEL_LIP, 20, {"multiple_shooting": 0}),
+])
+def test_solve_matches_oracle(model, N, opts):
+    B = 24
+    cfg, b, s = _setup(model, N, B, opts)
+    r = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
+    assert (ro["status"] == 0).mean() > 0.7
+    _compare_solve(cfg, b, r, ro, B)
+
+
+def test_solve_host_entry_point_and_ragged_batches():
+    """sddp_solve_batch_host (host buffers) == device entry point; B = 0, 1 and a non-multiple of the grid."""
+    cfg, b, s = _setup(MODEL_SRBD, 20, 5, {})
+    r = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    rh = s.solve_host(b["x0"], b["params"], b["X0"], b["U0"], gains=True, history=True)
+    for name in ("X", "U", "K", "k", "hist", "cost"):
+        np.testing.assert_array_equal(cpu(getattr(r, name)), rh[name])
+    np.testing.assert_array_equal(cpu(r.iters), rh["iters"])
+    r1 = s.solve(b["x0"][:1], b["params"][:1], b["X0"][:1], b["U0"][:1])
+    np.testing.assert_array_equal(cpu(r1.X)[0], cpu(r.X)[0])
+    r0 = s.solve(b["x0"][:0], b["params"][:0], b["X0"][:0], b["U0"][:0])
+    assert r0.X.shape[0] == 0
+    # gains / history are optional outputs
+    r2 = s.solve(b["x0"], b["params"], b["X0"], b["U0"], gains=False, history=False)
+    np.testing.assert_array_equal(cpu(r2.X), cpu(r.X))
+
+
+def test_full_size_properties():
+    """BASELINE-size batch (N=50): properties that need no oracle -- dynamics feasibility of the result
+    (closed defects), cost monotonicity across iterations, cost == re-evaluated cost, determinism."""
+    B, N = 4096, 50
+    cfg, b, s = _setup(MODEL_SRBD, N, B, {}, x_noise=0.0)
+    r = s.solve(b["x0"], b["params"], b["X0"], b["U0"], gains=False)
+    status, iters = cpu(r.status), cpu(r.iters)
+    assert (status == 0).mean() > 0.99
+    D, J = s.defects(r.X, r.U, b["params"])
+    conv = status == 0
+    assert float(D.abs().amax(dim=(1, 2))[torch.as_tensor(conv, device=D.device)].max()) < 1e-7
+    assert relerr(cpu(J), cpu(r.cost)) < 1e-12
+    h = cpu(r.hist)
+    for i in range(0, B, 97):
+        c = h[i, :iters[i], 0]
+        assert c[-1] <= c[0]
+    r2 = s.solve(b["x0"], b["params"], b["X0"], b["U0"], gains=False)
+    assert torch.equal(r.X, r2.X) and torch.equal(r.U, r2.U) and torch.equal(r.iters, r2.iters)
+
+
+def test_error_behaviour():
+    cfg = make_config(MODEL_SRBD, 20, 0.05)
+    s = BatchedDDP(cfg)
+    with pytest.raises(ValueError):
+        s.solve(np.zeros((2, 36)), np.zeros((2, 21, 19)), np.zeros((2, 21, 37)), np.zeros((2, 20, 24)))
+    from srbd_horizon_b200 import _lib
+    with pytest.raises(_lib.SddpError):
+        s.set_options(line_search_decrease_factor=1.5)
+    bad = make_config(MODEL_SRBD, 20, 0.05)
+    bad.N = 0
+    import ctypes
+    h = ctypes.c_void_p()
+    assert _lib.lib().sddp_create(ctypes.byref(bad), ctypes.byref(h)) == -1
