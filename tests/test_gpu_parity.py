@@ -132,8 +132,9 @@ def _compare_solve(cfg, b, r, ro, B):
         np.testing.assert_array_equal(hist[i, :n, 2], ro["hist"][i, :n, 2])   # regularisation schedule
         assert relerr(hist[i, :n, 3], ro["hist"][i, :n, 3]) < 1e-9 or np.max(np.abs(hist[i, :n, 3] - ro["hist"][i, :n, 3])) < 1e-15
         assert relerr(X[i], ro["X"][i]) < 1e-9 and relerr(U[i], ro["U"][i]) < 1e-9, i
-        assert relerr(K[i], ro["K"][i]) < 1e-8, i
-        assert np.max(np.abs(k[i] - ro["k"][i])) < 1e-9 * max(1.0, np.max(np.abs(ro["U"][i]))), i
+        if status[i] != 3:   # REG_FAILED leaves the gains of an aborted backward pass: undefined
+            assert relerr(K[i], ro["K"][i]) < 1e-8, i
+            assert np.max(np.abs(k[i] - ro["k"][i])) < 1e-9 * max(1.0, np.max(np.abs(ro["U"][i]))), i
         assert cost[i] == pytest.approx(ro["cost"][i], rel=1e-9)
 
 

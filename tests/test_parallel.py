@@ -1,0 +1,61 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes shard a batch and all-gather result slabs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from srbd_horizon_b200.parallel import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_covers_batch():
+    for B in (0, 1, 7, 64, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            pieces = [shard_range(B, r, world) for r in range(world)]
+            assert pieces[0][0] == 0 and pieces[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+            sizes = [hi - lo for lo, hi in pieces]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, B, q):
+    sys.path.insert(0, ROOT)
+    from srbd_horizon_b200.ddp import BatchResult
+    from srbd_horizon_b200.parallel import gather_results, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(B, rank, world)
+    idx = torch.arange(lo, hi, dtype=torch.float64)
+    X = idx[:, None, None] * torch.ones(1, 3, 5, dtype=torch.float64)
+    U = -idx[:, None, None] * torch.ones(1, 2, 4, dtype=torch.float64)
+    K = idx[:, None, None, None] * torch.ones(1, 2, 4, 5, dtype=torch.float64)
+    r = BatchResult(X=X, U=U, K=K, k=U.clone(), hist=None, iters=idx.to(torch.int32), status=torch.zeros(hi - lo, dtype=torch.int32), cost=idx * 2)
+    g = gather_results(r, world, B, gains="first")
+    ok = (g["X"].shape == (B, 3, 5) and torch.equal(g["X"][:, 0, 0], torch.arange(B, dtype=torch.float64))
+          and torch.equal(g["cost"], 2 * torch.arange(B, dtype=torch.float64))
+          and torch.equal(g["iters"], torch.arange(B, dtype=torch.int32)) and g["K"].shape == (B, 4, 5)
+          and torch.equal(g["K"][:, 0, 0], torch.arange(B, dtype=torch.float64)))
+    g2 = gather_results(r, world)     # batch size inferred by all-reduce
+    ok = ok and g2["U"].shape == (B, 2, 4)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [8, 7])
+def test_gather_results_gloo_world2(B):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + B
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
