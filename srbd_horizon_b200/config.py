@@ -144,6 +144,7 @@ DEFAULT_OPTS: Dict[str, float] = {
     "defect_ths": 1e-8,
     "inertia_mode": INERTIA_LITERAL,
     "hessian_mode": HESSIAN_EXACT,
+    "dense_backward": 0,                   # 1: generic dense Riccati kernel for SRBD (A/B check of the structured one)
 }
 
 
@@ -164,6 +165,7 @@ def make_config(model: int, N: int, dt: float, opts: Dict | None = None,
     c.hessian_mode = int(o["hessian_mode"])
     c.multiple_shooting = int(o["multiple_shooting"])
     c.max_iters = int(o["max_iters"])
+    c.reserved0 = int(o["dense_backward"])
     c.dt = float(dt)
     c.mass = robot.mass
     c.inertia = (ctypes.c_double * 9)(*robot.inertia)

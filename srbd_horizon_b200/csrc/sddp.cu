@@ -6,13 +6,13 @@
 #include <new>
 
 #include "../../include/sddp.h"
-#include "sddp_solver.cuh"
+#include "sddp_backward_srbd.cuh"
 
 // ===================================================================================== kernels
-template <class M>
-__global__ void __launch_bounds__(NT) solve_kernel(DevCfg c, SolveArgs a) {
+template <class M, class SM, int MINB>
+__global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
     __shared__ int s_prob;
     const int tid = threadIdx.x;
     for (;;) {   // persistent CTA: pull problems from a queue (iteration counts differ per problem)
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(NT) solve_kernel(DevCfg c, SolveArgs a) {
         __syncthreads();
         const int b = s_prob;
         if (b >= a.B) break;
-        solve_one<M>(c, a, S, b, blockIdx.x, tid);
+        solve_one<M, SM>(c, a, S, b, blockIdx.x, tid);
         __syncthreads();
     }
 }
@@ -68,11 +68,11 @@ __global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int*
     }
 }
 
-template <class M>
-__global__ void __launch_bounds__(NT) backward_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, const double* D,
+template <class M, class SM, int MINB>
+__global__ void __launch_bounds__(NT, MINB) backward_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, const double* D,
                                                       double mu, double* K, double* kff, double* dV, int* rc, double* ws_pack) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int tid = threadIdx.x, N = c.N;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -80,19 +80,19 @@ __global__ void __launch_bounds__(NT) backward_kernel(DevCfg c, int B, const dou
         const double* Ub = U + (size_t)b * N * NU;
         double* packs = ws_pack + (size_t)blockIdx.x * N * M::PACK;
         compute_packs<M>(c, Xb, Ub, packs, tid);
-        int r = backward_pass<M>(c, S, Xb, Ub, P + (size_t)b * (N + 1) * NP, D + (size_t)b * N * NX, packs, mu,
-                                 K + (size_t)b * N * NU * NX, kff + (size_t)b * N * NU, &S.red[12], tid);
+        int r = SM::backward(c, S, Xb, Ub, P + (size_t)b * (N + 1) * NP, D + (size_t)b * N * NX, packs, mu,
+                             K + (size_t)b * N * NU * NX, kff + (size_t)b * N * NU, &S.red[12], true, tid);
         if (tid == 0) { rc[b] = r; dV[3 * b] = S.red[12]; dV[3 * b + 1] = S.red[13]; dV[3 * b + 2] = S.red[14]; }
         __syncthreads();
     }
 }
 
-template <class M>
-__global__ void __launch_bounds__(NT) forward_kernel(DevCfg c, int B, int n_alpha, const double* alpha, const double* rho, const double* x0,
+template <class M, class SM, int MINB>
+__global__ void __launch_bounds__(NT, MINB) forward_kernel(DevCfg c, int B, int n_alpha, const double* alpha, const double* rho, const double* x0,
                                                      const double* X, const double* U, const double* P, const double* D, const double* K,
                                                      const double* kff, double* Jn, double* Xn, double* Un, double* ws_xn, double* ws_un) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int tid = threadIdx.x, N = c.N;
     const size_t xsz = (size_t)(N + 1) * NX, usz = (size_t)N * NU;
@@ -104,21 +104,21 @@ __global__ void __launch_bounds__(NT) forward_kernel(DevCfg c, int B, int n_alph
             __syncthreads();
             double* xo = Xn ? Xn + ((size_t)b * n_alpha + base) * xsz : ws_xn + (size_t)blockIdx.x * NCAND * xsz;
             double* uo = Un ? Un + ((size_t)b * n_alpha + base) * usz : ws_un + (size_t)blockIdx.x * NCAND * usz;
-            forward_wave<M>(c, S, x0 + (size_t)b * NX, X + (size_t)b * xsz, U + (size_t)b * usz, P + (size_t)b * (N + 1) * NP,
+            forward_wave<M, SM>(c, S, x0 + (size_t)b * NX, X + (size_t)b * xsz, U + (size_t)b * usz, P + (size_t)b * (N + 1) * NP,
                             D + (size_t)b * N * NX, K + (size_t)b * N * NU * NX, kff + (size_t)b * usz, ncand, xo, xsz, uo, usz, tid);
             if (tid < ncand) Jn[(size_t)b * n_alpha + base + tid] = S.Jc[tid];
         }
     }
 }
 
-template <class M>
-__global__ void __launch_bounds__(NT) defects_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, double* D, double* cost) {
+template <class M, class SM, int MINB>
+__global__ void __launch_bounds__(NT, MINB) defects_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, double* D, double* cost) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int tid = threadIdx.x, N = c.N;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        double J = defects_and_cost<M>(c, S, X + (size_t)b * (N + 1) * NX, U + (size_t)b * N * NU, P + (size_t)b * (N + 1) * NP,
+        double J = defects_and_cost<M, SM>(c, S, X + (size_t)b * (N + 1) * NX, U + (size_t)b * N * NU, P + (size_t)b * (N + 1) * NP,
                                        D ? D + (size_t)b * N * NX : nullptr, tid);
         if (tid == 0 && cost) cost[b] = J;
     }
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 struct SddpHandle {
     SddpConfig cfg;
     DevCfg dc;
-    int device, sms, slots;
-    size_t smem_bytes, ws_bytes;
+    int device, sms, slots, variant;
+    size_t smem_bytes, eval_smem_bytes, ws_bytes;
     double *ws_d, *ws_pack, *ws_xn, *ws_un, *ws_K, *ws_k;
     int* counter;
     // staging for the *_host entry point
@@ -200,18 +200,21 @@ static void make_devcfg(const SddpConfig& s, DevCfg& d) {
     d.mu_min = s.mu_min; d.mu_max = s.mu_max; d.mu_factor = s.mu_factor; d.defect_ths = s.defect_ths;
 }
 
-template <class M> static size_t smem_of() { return sizeof(Smem<M>); }
+// kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.reserved0 = 1), 2 = LIP dense
+constexpr int MINB_FAST = 5, MINB_DENSE = 1;
+static int variant_of(const SddpConfig& c) { return c.model == SDDP_MODEL_LIP ? 2 : (c.reserved0 == 1 ? 1 : 0); }
+static size_t smem_of_variant(int v) { return v == 0 ? sizeof(SmemSrbd) : (v == 1 ? sizeof(Smem<Srbd>) : sizeof(Smem<Lip>)); }
 
-template <class M>
-static cudaError_t set_smem_attr() {
+template <class M, class SM, int MINB>
+static cudaError_t set_smem_attr(int* occ) {
     cudaError_t e;
-    int bytes = (int)sizeof(Smem<M>);
-    if ((e = cudaFuncSetAttribute(solve_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    if ((e = cudaFuncSetAttribute(eval_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    if ((e = cudaFuncSetAttribute(backward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    if ((e = cudaFuncSetAttribute(forward_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    if ((e = cudaFuncSetAttribute(defects_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    return cudaSuccess;
+    int bytes = (int)sizeof(SM);
+    if ((e = cudaFuncSetAttribute(solve_kernel<M, SM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(backward_kernel<M, SM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(forward_kernel<M, SM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(defects_kernel<M, SM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    if ((e = cudaFuncSetAttribute(eval_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<M>)))) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, solve_kernel<M, SM, MINB>, NT, bytes);
 }
 
 static void model_dims(int model, int& nx, int& nu, int& np, int& pack) {
@@ -234,7 +237,7 @@ static WsLayout ws_layout(const SddpConfig& c, int slots) {
     w.total = (w.d + w.pack + w.xn + w.un + w.K + w.k) * sizeof(double) + 256;
     return w;
 }
-static const int kMaxSlotsPerSM = 4;
+static const int kMaxSlotsPerSM = 6;
 
 extern "C" {
 
@@ -279,15 +282,12 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
     CUC(cudaGetDevice(&h->device));
     CUC(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
     int occ = 0;
-    if (cfg->model == SDDP_MODEL_SRBD) {
-        h->smem_bytes = smem_of<Srbd>();
-        CUC(set_smem_attr<Srbd>());
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<Srbd>, NT, h->smem_bytes));
-    } else {
-        h->smem_bytes = smem_of<Lip>();
-        CUC(set_smem_attr<Lip>());
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<Lip>, NT, h->smem_bytes));
-    }
+    h->variant = variant_of(h->cfg);
+    h->smem_bytes = smem_of_variant(h->variant);
+    h->eval_smem_bytes = cfg->model == SDDP_MODEL_SRBD ? sizeof(Smem<Srbd>) : sizeof(Smem<Lip>);
+    if (h->variant == 0) CUC((set_smem_attr<Srbd, SmemSrbd, MINB_FAST>(&occ)));
+    else if (h->variant == 1) CUC((set_smem_attr<Srbd, Smem<Srbd>, MINB_DENSE>(&occ)));
+    else CUC((set_smem_attr<Lip, Smem<Lip>, MINB_DENSE>(&occ)));
     if (occ < 1) { fail(nullptr, SDDP_ECUDA, "%s%s", "solve kernel does not fit on this device", ""); sddp_destroy(h); return SDDP_ECUDA; }
     if (occ > kMaxSlotsPerSM) occ = kMaxSlotsPerSM;
     h->slots = h->sms * occ;
@@ -321,7 +321,8 @@ int sddp_set_config(SddpHandle* h, const SddpConfig* cfg) {
     if (!h) return SDDP_EINVAL;
     int rc = check_config(cfg, h);
     if (rc) return rc;
-    if (cfg->model != h->cfg.model || cfg->N != h->cfg.N) return fail(h, SDDP_EINVAL, "%s%s", "model and N are fixed at create", "");
+    if (cfg->model != h->cfg.model || cfg->N != h->cfg.N || variant_of(*cfg) != h->variant)
+        return fail(h, SDDP_EINVAL, "%s%s", "model, N and the kernel variant are fixed at create", "");
     h->cfg = *cfg;
     make_devcfg(h->cfg, h->dc);
     return 0;
@@ -333,12 +334,13 @@ int sddp_launch_count(const SddpHandle* h, long long* out) {
     return 0;
 }
 
-#define DISPATCH(h, KERNEL, grid, stream, ...)                                                      \
-    do {                                                                                            \
-        if ((h)->cfg.model == SDDP_MODEL_SRBD) KERNEL<Srbd><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__); \
-        else KERNEL<Lip><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);                       \
-        (h)->launches++;                                                                            \
-        CU(cudaGetLastError());                                                                     \
+#define DISPATCH(h, KERNEL, grid, stream, ...)                                                                              \
+    do {                                                                                                                    \
+        if ((h)->variant == 0) KERNEL<Srbd, SmemSrbd, MINB_FAST><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);        \
+        else if ((h)->variant == 1) KERNEL<Srbd, Smem<Srbd>, MINB_DENSE><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__); \
+        else KERNEL<Lip, Smem<Lip>, MINB_DENSE><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);                         \
+        (h)->launches++;                                                                                                    \
+        CU(cudaGetLastError());                                                                                             \
     } while (0)
 
 int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const double* x, const double* u, const double* p,
@@ -349,7 +351,10 @@ int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const doubl
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = M < h->sms * 8 ? M : h->sms * 8;
-    DISPATCH(h, eval_kernel, grid, st, h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
+    if (h->cfg.model == SDDP_MODEL_SRBD) eval_kernel<Srbd><<<grid, NT, h->eval_smem_bytes, st>>>(h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
+    else eval_kernel<Lip><<<grid, NT, h->eval_smem_bytes, st>>>(h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
+    h->launches++;
+    CU(cudaGetLastError());
     return 0;
 }
 

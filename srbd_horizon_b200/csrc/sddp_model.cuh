@@ -373,11 +373,11 @@ struct Srbd {
     }
 
     // Q buffers <- lx, lu, lxx, lux, luu of this node.  Every thread of the block must call.
-    template <class Sync>
+    template <int LDUX = NX, class Sync>
     __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double* pk,
                                   double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync) {
         for (int e = tid; e < NX * NX; e += nthr) Qxx[e] = 0.0;
-        for (int e = tid; e < NU * NX; e += nthr) Qux[e] = 0.0;
+        for (int e = tid; e < NU * LDUX; e += nthr) Qux[e] = 0.0;
         for (int e = tid; e < NU * NU; e += nthr) Quu[e] = 0.0;
         for (int e = tid; e < NX; e += nthr) Qx[e] = 0.0;
         for (int e = tid; e < NU; e += nthr) Qu[e] = 0.0;
@@ -395,7 +395,7 @@ struct Srbd {
                 if (exact) hh += hc(pk, pi, qi);
                 hh *= g2;
                 if (xi >= 0) Qxx[xi * NX + xj] = hh;
-                else if (xj >= 0) Qux[zmap_u(pi) * NX + xj] = hh;
+                else if (xj >= 0) Qux[zmap_u(pi) * LDUX + xj] = hh;
                 else Quu[zmap_u(pi) * NU + zmap_u(qi)] = hh;
             }
             for (int pi = tid; pi < NZ; pi += nthr) {
@@ -557,11 +557,11 @@ struct Lip {
     }
     __device__ static void pack(const DevCfg&, int, const double*, const double*, double*) {}
 
-    template <class Sync>
+    template <int LDUX = NX, class Sync>
     __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double*,
                                   double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync) {
         for (int e = tid; e < NX * NX; e += nthr) Qxx[e] = 0.0;
-        for (int e = tid; e < NU * NX; e += nthr) Qux[e] = 0.0;
+        for (int e = tid; e < NU * LDUX; e += nthr) Qux[e] = 0.0;
         for (int e = tid; e < NU * NU; e += nthr) Quu[e] = 0.0;
         for (int e = tid; e < NX; e += nthr) Qx[e] = 0.0;
         for (int e = tid; e < NU; e += nthr) Qu[e] = 0.0;
@@ -593,12 +593,12 @@ struct Lip {
                 double w2 = 2.0 * c.w_zmp, res = u[k] - csum;   // zmp_tracking, prb.py:393
                 Quu[k * NU + k] += w2; Qu[k] += w2 * res;
                 for (int a = 0; a < 4; a++) {
-                    Qux[k * NX + ci[a]] -= 0.25 * w2; Qx[ci[a]] -= 0.25 * w2 * res;
+                    Qux[k * LDUX + ci[a]] -= 0.25 * w2; Qx[ci[a]] -= 0.25 * w2 * res;
                     for (int b = 0; b < 4; b++) Qxx[ci[a] * NX + ci[b]] += w2 / 16.0;
                 }
                 double e2 = c.eta2, wq = 2.0 * c.gq * e2 * e2;   // min_qddot rddot rows, prb.py:402
                 double acc = e2 * (x[k] - u[k]) - (k == 2 ? c.g : 0.0);
-                Qxx[k * NX + k] += wq; Quu[k * NU + k] += wq; Qux[k * NX + k] -= wq;
+                Qxx[k * NX + k] += wq; Quu[k * NU + k] += wq; Qux[k * LDUX + k] -= wq;
                 Qx[k] += 2.0 * c.gq * e2 * acc; Qu[k] -= 2.0 * c.gq * e2 * acc;
                 if (k == 2)
                     for (int i = 0; i < 4; i++) { Qxx[ci[i] * NX + ci[i]] += 2.0 * c.cw; Qx[ci[i]] += 2.0 * c.cw * (x[ci[i]] - p[3 + 2 * i]); }

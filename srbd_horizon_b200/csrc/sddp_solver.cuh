@@ -33,6 +33,10 @@ struct Smem {
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
     int iflag[4];
+    __device__ static int backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
+                                   const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
+    __device__ double* Kbuf() { return T; }    // forward pass: K of the current node
+    __device__ double* scr() { return fx; }    // per-warp scratch
 };
 enum { R_TOT = 0, R_ACC1 = 1, R_ACC2 = 2, R_G1 = 3, R_G2 = 4, R_YG = 5, R_W0 = 8 };
 
@@ -72,12 +76,12 @@ __device__ double warp_node(const DevCfg& c, int kind, const double* xs, const d
 // ------------------------------------------------------------------------------------------------
 // defects d_k = f(X_k,U_k) - X_{k+1} (if dout) and the total cost; warps stride over nodes.
 // Returns J to every thread.  Uses S.fx as per-warp scratch.
-template <class M>
-__device__ double defects_and_cost(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P,
+template <class M, class SM>
+__device__ double defects_and_cost(const DevCfg& c, SM& S, const double* X, const double* U, const double* P,
                                    double* dout, int tid) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int N = c.N, lane = tid & 31, w = tid >> 5;
-    double* xs = S.fx + w * (2 * NX + NU + NP);
+    double* xs = S.scr() + w * (2 * NX + NU + NP);
     double* us = xs + NX;
     double* ps = us + NU;
     double* xn = ps + NP;
@@ -104,12 +108,12 @@ __device__ double defects_and_cost(const DevCfg& c, Smem<M>& S, const double* X,
 }
 
 // open-loop rollout X_{k+1} = f(X_k, U_k) by warp 0 (single-shooting initialisation)
-template <class M>
-__device__ void open_loop_rollout(const DevCfg& c, Smem<M>& S, double* X, const double* U, int tid) {
+template <class M, class SM>
+__device__ void open_loop_rollout(const DevCfg& c, SM& S, double* X, const double* U, int tid) {
     constexpr int NX = M::NX, NU = M::NU;
     const int lane = tid & 31;
     if (tid < 32) {
-        double* xs = S.fx;
+        double* xs = S.scr();
         double* us = xs + NX;
         double* xn = us + NU;
         for (int i = lane; i < NX; i += 32) xs[i] = X[i];
@@ -319,13 +323,14 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
 // ------------------------------------------------------------------------------------------------
 // Stage 3.  ncand (<= NCAND) candidate step sizes S.alpha[], S.rho[] rolled out in parallel, one warp each.
 // Trial trajectories go to Xn + cand*xn_stride / Un + cand*un_stride (global); costs to S.Jc[].
-template <class M>
-__device__ void forward_wave(const DevCfg& c, Smem<M>& S, const double* x0, const double* X, const double* U, const double* P,
+template <class M, class SM>
+__device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const double* X, const double* U, const double* P,
                              const double* D, const double* Kg, const double* kg, int ncand, double* Xn, size_t xn_stride,
                              double* Un, size_t un_stride, int tid) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int N = c.N, lane = tid & 31, w = tid >> 5;
-    double* xh = S.fx + w * (2 * NX + NU);
+    double* xh = S.scr() + w * (2 * NX + NU);
+    double* Kb = S.Kbuf();
     double* uh = xh + NX;
     double* xn = uh + NU;
     double* Xo = Xn + (size_t)w * xn_stride;
@@ -336,7 +341,7 @@ __device__ void forward_wave(const DevCfg& c, Smem<M>& S, const double* x0, cons
     for (int i = lane; i < NX; i += 32) xh[i] = x0[i];
     for (int k = 0; k < N; k++) {
         __syncthreads();
-        for (int e = tid; e < NU * NX; e += NT) S.T[e] = Kg[(size_t)k * NU * NX + e];
+        for (int e = tid; e < NU * NX; e += NT) Kb[e] = Kg[(size_t)k * NU * NX + e];
         for (int i = tid; i < NU; i += NT) { S.kk[i] = kg[(size_t)k * NU + i]; S.uk[i] = U[(size_t)k * NU + i]; }
         for (int i = tid; i < NX; i += NT) { S.xk[i] = X[(size_t)k * NX + i]; S.cg[i] = (D != nullptr) ? D[(size_t)k * NX + i] : 0.0; }
         for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)k * NP + i];
@@ -344,7 +349,7 @@ __device__ void forward_wave(const DevCfg& c, Smem<M>& S, const double* x0, cons
         if (active) {
             for (int j = lane; j < NU; j += 32) {
                 double t = 0.0;
-                for (int i = 0; i < NX; i++) t += S.T[j * NX + i] * (xh[i] - S.xk[i]);
+                for (int i = 0; i < NX; i++) t += Kb[j * NX + i] * (xh[i] - S.xk[i]);
                 double v = S.uk[j] + alpha * S.kk[j] + t;
                 uh[j] = v;
                 Uo[(size_t)k * NU + j] = v;
@@ -386,8 +391,8 @@ __device__ void compute_packs(const DevCfg& c, const double* X, const double* U,
     __syncthreads();
 }
 
-template <class M>
-__device__ void solve_one(const DevCfg& c, const SolveArgs& a, Smem<M>& S, int b, int slot, int tid) {
+template <class M, class SM>
+__device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int slot, int tid) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int N = c.N;
     const size_t xsz = (size_t)(N + 1) * NX, usz = (size_t)N * NU;
@@ -409,12 +414,12 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, Smem<M>& S, int b
     __syncthreads();
     double J, dmax = 0.0;
     if (!c.ms) {
-        open_loop_rollout<M>(c, S, X, U, tid);
+        open_loop_rollout<M, SM>(c, S, X, U, tid);
         for (int i = tid; i < N * NX; i += NT) d[i] = 0.0;
         __syncthreads();
-        J = defects_and_cost<M>(c, S, X, U, P, nullptr, tid);
+        J = defects_and_cost<M, SM>(c, S, X, U, P, nullptr, tid);
     } else {
-        J = defects_and_cost<M>(c, S, X, U, P, d, tid);
+        J = defects_and_cost<M, SM>(c, S, X, U, P, d, tid);
         double m = 0.0;
         for (int i = tid; i < N * NX; i += NT) { double v = fabs(d[i]); if (v > m || v != v) m = v; }
         m = warp_max(m);
@@ -428,7 +433,7 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, Smem<M>& S, int b
     for (it = 0; it < c.max_iters; it++) {
         compute_packs<M>(c, X, U, packs, tid);
         bool reg_fail = false;
-        while (backward_pass<M>(c, S, X, U, P, d, packs, mu, Kg, kg, &S.red[12], tid)) {
+        while (SM::backward(c, S, X, U, P, d, packs, mu, Kg, kg, &S.red[12], dmax != 0.0, tid)) {
             mu = fmax(mu * c.mu_factor, c.mu_min);
             if (mu > c.mu_max) { reg_fail = true; break; }
         }
@@ -455,7 +460,7 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, Smem<M>& S, int b
             __syncthreads();
             if (tid < NCAND) { S.alpha[tid] = al[tid]; S.rho[tid] = fixed ? c.rho_fixed : al[tid]; }
             __syncthreads();
-            forward_wave<M>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid);
+            forward_wave<M, SM>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid);
             for (int j = 0; j < ncand; j++) {
                 double am = al[j], dJm = C0 + am * D1 + am * am * D2, Jj = S.Jc[j];
                 if (isfinite(Jj) && Jj - J <= dJm + (1.0 - c.beta) * fabs(dJm)) {
@@ -487,4 +492,10 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, Smem<M>& S, int b
     }
     __syncthreads();
     if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
+}
+
+template <class M>
+__device__ int Smem<M>::backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
+                                 const double* packs, double mu, double* Kg, double* kg, double* dV3, bool, int tid) {
+    return backward_pass<M>(c, S, X, U, P, D, packs, mu, Kg, kg, dV3, tid);
 }

@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Aggregate an ncu report's per-instruction warp-stall samples by CUDA source line.
+
+  python tools/ncu_lines.py gpurun_out/prof.ncu-rep solve_kernelI4Srbd [top]
+
+ncu's CSV source page is SASS-only; the line table comes from `nvdisasm -g` on the cubin of the
+in-tree libsddp.so (must be the same build that was profiled)."""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+rep, kernel = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lib = os.path.join(root, "srbd_horizon_b200", "csrc", "libsddp.so")
+tmp = tempfile.mkdtemp()
+subprocess.check_call(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL)
+cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+addr2line, cur, inside = {}, None, False
+for ln in dis:
+    if ln.startswith("\t.section\t.text."):
+        inside = kernel in ln
+    if not inside:
+        continue
+    m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+    if m:
+        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        continue
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);", ln)
+    if m:
+        addr2line[int(m.group(1), 16)] = (cur, m.group(2))
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
+rows = list(csv.reader(out))
+h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+hdr = rows[h]
+ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+base = None
+by_line = collections.Counter(); ex_line = collections.Counter()
+stall_cols = [i for i, c in enumerate(hdr) if c.startswith("stall_") and "Not Issued" not in c]
+stall_by_line = collections.defaultdict(collections.Counter)
+total = 0
+for r in rows[h + 1:]:
+    if len(r) <= isamp:
+        continue
+    a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
+    if base is None:
+        base = a
+    key = addr2line.get(a - base, (None, ""))[0]
+    s = int(r[isamp] or 0)
+    by_line[key] += s; total += s
+    ex_line[key] += int(r[iex] or 0)
+    for i in stall_cols:
+        v = int(r[i] or 0)
+        if v:
+            stall_by_line[key][hdr[i]] += v
+src_cache = {}
+def src(key):
+    if key is None:
+        return ""
+    f, n = key
+    if f not in src_cache:
+        p = os.path.join(root, "srbd_horizon_b200", "csrc", f)
+        src_cache[f] = open(p).read().splitlines() if os.path.exists(p) else []
+    L = src_cache[f]
+    return L[n - 1].strip()[:90] if 0 < n <= len(L) else ""
+print(f"total samples {total}")
+for key, s in by_line.most_common(top):
+    st = ", ".join(f"{k[6:]}={v}" for k, v in stall_by_line[key].most_common(3))
+    print(f"{100.0 * s / total:5.1f}%  inst={ex_line[key]:>11}  {key}  [{st}]  {src(key)}")

@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Small driver for profiling: solves one synthetic SRBD batch (used under ncu)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from srbd_horizon_b200.config import MODEL_SRBD, make_config
+from srbd_horizon_b200.ddp import BatchedDDP
+from srbd_horizon_b200.problems import make_batch
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=1184)
+ap.add_argument("--N", type=int, default=50)
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--no-gains", action="store_true")
+a = ap.parse_args()
+cfg = make_config(MODEL_SRBD, a.N, 0.05, {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3})
+b = make_batch(MODEL_SRBD, a.N, a.batch, enumerate_schedules=True)
+s = BatchedDDP(cfg)
+t = lambda v: torch.as_tensor(v, dtype=torch.float64, device="cuda")
+x0, p, X0, U0 = t(b["x0"]), t(b["params"]), t(b["X0"]), t(b["U0"])
+for _ in range(a.reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = s.solve(x0, p, X0, U0, gains=not a.no_gains, history=False)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"B={a.batch} N={a.N} ms={e0.elapsed_time(e1):.3f} mean_iters={r.iters.double().mean().item():.3f} "
+          f"converged={(r.status == 0).double().mean().item():.4f}")
