@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 #include "../../include/sddp.h"
 #include "sddp_backward_srbd.cuh"
@@ -35,16 +36,21 @@ __global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int*
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int tid = threadIdx.x;
     SyncBlock sync;
+    using NBL = NodeBuf<M>;
+    double* xk = S.nb[0] + NBL::OX;
+    double* uk = S.nb[0] + NBL::OU;
+    double* pk = S.nb[0] + NBL::OP;
+    double* pack = S.nb[0] + NBL::OK;
     for (int m = blockIdx.x; m < npts; m += gridDim.x) {
         const int kd = kind[m];
-        for (int i = tid; i < NX; i += NT) S.xk[i] = x[(size_t)m * NX + i];
-        for (int i = tid; i < NU; i += NT) S.uk[i] = u[(size_t)m * NU + i];
-        for (int i = tid; i < NP; i += NT) S.pk[i] = p[(size_t)m * NP + i];
+        for (int i = tid; i < NX; i += NT) xk[i] = x[(size_t)m * NX + i];
+        for (int i = tid; i < NU; i += NT) uk[i] = u[(size_t)m * NU + i];
+        for (int i = tid; i < NP; i += NT) pk[i] = p[(size_t)m * NP + i];
         __syncthreads();
-        if (tid == 0 && kd != NODE_TERM) M::pack(c, kd, S.xk, S.uk, S.pack);
+        if (tid == 0 && kd != NODE_TERM) M::pack(c, kd, xk, uk, pack);
         __syncthreads();
-        M::expand(c, kd, S.xk, S.uk, S.pk, S.pack, S.Qx, S.Qu, S.Qxx, S.Qux, S.Quu, tid, NT, sync);
-        if (kd != NODE_TERM) M::expand_f(c, S.xk, S.uk, S.pack, S.fx, S.fu, tid, NT, sync);
+        M::expand(c, kd, xk, uk, pk, pack, S.Qx, S.Qu, S.Qxx, S.Qux, S.Quu, tid, NT, sync);
+        if (kd != NODE_TERM) M::expand_f(c, xk, uk, pack, S.fx, S.fu, tid, NT, sync);
         else {
             for (int e = tid; e < NX * NX; e += NT) S.fx[e] = 0.0;
             for (int e = tid; e < NX * NU; e += NT) S.fu[e] = 0.0;
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int*
             __syncthreads();
         }
         if (tid < 32) {
-            double J = warp_node<M>(c, kd, S.xk, S.uk, S.pk, S.vp, nullptr, 0.0, tid);
+            double J = warp_node<M>(c, kd, xk, uk, pk, S.vp, nullptr, 0.0, S.sacc[0], tid);
             if (tid == 0 && l) l[m] = J;
         }
         __syncthreads();
@@ -149,6 +155,7 @@ struct SddpHandle {
     size_t smem_bytes, eval_smem_bytes, ws_bytes;
     double *ws_d, *ws_pack, *ws_xn, *ws_un, *ws_K, *ws_k;
     int* counter;
+    unsigned long long* ztab;
     // staging for the *_host entry point
     void* stage; size_t stage_bytes;
     long long launches;
@@ -198,6 +205,45 @@ static void make_devcfg(const SddpConfig& s, DevCfg& d) {
     d.alpha0 = s.alpha_0; d.alpha_min = s.alpha_converge_threshold; d.ls_factor = s.line_search_decrease_factor;
     d.beta = s.beta; d.cost_ths = s.cost_reduction_ths; d.mu0 = s.mu0; d.rho_fixed = s.defect_contraction_rate;
     d.mu_min = s.mu_min; d.mu_max = s.mu_max; d.mu_factor = s.mu_factor; d.defect_ths = s.defect_ths;
+    d.ztab = nullptr;
+}
+
+// Host mirror of Srbd::zmap_x / zmap_u / hc(): descriptors of the upper-triangular (pi <= qi) entries of the
+// 34 x 34 Hessian block of gq*||wdot||^2, consumed by Srbd::expand (bit layout: sddp_model.cuh ZT_*).
+static void build_ztab(std::vector<unsigned long long>& tab) {
+    const int NZ = Srbd::NZ, ZO = Srbd::ZO, ZC = Srbd::ZC, ZW = Srbd::ZW, ZF = Srbd::ZF;
+    auto zx = [&](int p) { return p < 19 ? p : (p < 22 ? (int)Srbd::XW + (p - 19) : -1); };
+    auto zu = [&](int p) { return 6 * ((p - 22) / 3) + 3 + (p - 22) % 3; };
+    tab.assign((size_t)ZT_ROUNDS * ZT_THREADS, 0ull);
+    int e = 0;
+    for (int pi = 0; pi < NZ; pi++)
+        for (int qi = pi; qi < NZ; qi++, e++) {
+            const int xi = zx(pi), xj = zx(qi);
+            int kind, da, db;
+            if (xi >= 0 && xj >= 0) { kind = 0; da = xi; db = xj; }
+            else if (xi >= 0) { kind = 1; da = zu(qi); db = xi; }
+            else { kind = 2; da = zu(pi); db = zu(qi); }
+            int hs = 0, hoff = 0;   // curvature source: sign * pack[hoff]
+            auto skew = [&](int a, int b, int flip) {      // +-nu[k] of skew(nu)[a][b]
+                if (a == b) return;
+                const int k = 3 - a - b;
+                int neg = ((b - a + 3) % 3 == 1) ? 1 : 0;
+                neg ^= flip;
+                hs = neg ? 2 : 1; hoff = Srbd::PK_NU + k;
+            };
+            if (pi >= ZO && pi < ZC) { hs = 1; hoff = Srbd::PK_HO + (pi - ZO) * NZ + qi; }
+            else if (qi >= ZO && qi < ZC) { hs = 1; hoff = Srbd::PK_HO + (qi - ZO) * NZ + pi; }
+            else if (pi >= ZW && pi < ZF && qi >= ZW && qi < ZF) { hs = 1; hoff = Srbd::PK_HWW + 3 * (pi - ZW) + (qi - ZW); }
+            else if (qi >= ZF) {
+                const int fi = (qi - ZF) / 3, b = (qi - ZF) % 3;
+                if (pi < ZO) skew(pi, b, 0);                                                   // (r_a, f_ib): +skew(nu)[a][b]
+                else if (pi >= ZC && pi < ZW && (pi - ZC) / 3 == fi) skew((pi - ZC) % 3, b, 1);  // (c_ia, f_ib): -skew(nu)[a][b]
+            }
+            unsigned long long d = 1ull | ((unsigned long long)kind << 1) | ((unsigned long long)da << 3) | ((unsigned long long)db << 9) |
+                                   ((unsigned long long)pi << 15) | ((unsigned long long)qi << 21) | ((unsigned long long)hs << 27) |
+                                   ((unsigned long long)hoff << 29);
+            tab[(size_t)(e / ZT_THREADS) * ZT_THREADS + (e % ZT_THREADS)] = d;
+        }
 }
 
 // kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.reserved0 = 1), 2 = LIP dense
@@ -304,6 +350,13 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
     h->ws_k = h->ws_K + w.K;
     h->counter = (int*)(h->ws_k + w.k);
     CUC(cudaMemset(base, 0, w.total));
+    if (cfg->model == SDDP_MODEL_SRBD) {
+        std::vector<unsigned long long> tab;
+        build_ztab(tab);
+        CUC(cudaMalloc((void**)&h->ztab, tab.size() * sizeof(unsigned long long)));
+        CUC(cudaMemcpy(h->ztab, tab.data(), tab.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    h->dc.ztab = h->ztab;
 #undef CUC
     *out = h;
     return 0;
@@ -312,6 +365,7 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
 int sddp_destroy(SddpHandle* h) {
     if (!h) return 0;
     if (h->ws_d) cudaFree(h->ws_d);
+    if (h->ztab) cudaFree(h->ztab);
     if (h->stage) cudaFree(h->stage);
     delete h;
     return 0;
@@ -325,6 +379,7 @@ int sddp_set_config(SddpHandle* h, const SddpConfig* cfg) {
         return fail(h, SDDP_EINVAL, "%s%s", "model, N and the kernel variant are fixed at create", "");
     h->cfg = *cfg;
     make_devcfg(h->cfg, h->dc);
+    h->dc.ztab = h->ztab;
     return 0;
 }
 

@@ -11,35 +11,38 @@
 //   Qxx = lxx + fx^T T,  Qux = lux + fu^T T   one thread per (column, row group)
 //   Quu = luu + fu^T V fu                      one thread per entry of the lower triangle
 // Gains (W-form of sddp_solver.cuh, square-root free):
-//   [Quu_r | Qux | Qu | I] is eliminated column-wise, every thread owning one of the 86 columns in
-//   registers (24 steps, one named barrier each): Quu_r = Lt D Lt^T, frozen rows U = Lt^-1 [Qux Qu],
-//   E = Lt^-1.  With rs = D^-1/2:  Wn = rs.U (= L^-1 [Qux Qu] of the Cholesky form), Es = rs.E
-//   K = -Es^T Wn  (register-tiled matmul over all threads, no substitution chain)
+//   warp 0 factorises Quu_r = Lt D Lt^T (one lane per column held in registers, 24 pivot steps, only
+//   __syncwarp between them, Newton-refined reciprocal instead of a division) WHILE warps 1-3 build
+//   T, Qxx, Qux (they do not depend on the factor).  Then one thread per right-hand side applies
+//   Lt^-1 to [Qux | Qu | I] with no barrier at all: frozen rows U = Lt^-1 [Qux Qu], E = Lt^-1.
+//   With rs = D^-1/2:  Wn = rs.U (= L^-1 [Qux Qu] of the Cholesky form), Es = rs.E
+//   K = -Es^T Wn  (matmul over all threads, no substitution chain)
 //   [Vxx Vx; . |w0|^2] = [sym(Qxx) Qx; . 0] - Wn^T Wn   (3x3 register tiles over the 39x39 product)
+// Node inputs (x, u, p, d, pack) of node k-1 are fetched with cp.async while node k is processed.
 #pragma once
 #include "sddp_solver.cuh"
 
-struct SmemSrbd {
+struct alignas(16) SmemSrbd {
     static constexpr int NX = 37, NU = 24, NP = 19, LDW = 39;
-    double VT[NX * NX];        // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
-    double Qxx[NX * NX];       // forward: K of the current node
+    double VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
+    double Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
     double W[NU * LDW];        // [Qux | w0 | 0] -> Wn
-    double Quu[NU * NU];       // -> Es
-    double Vx[NX], y[NX], Qx[NX], vp[NX], ys[NX], qxy[NX], cg[NX], sv[NX];
-    double Qu[NU], quy[NU], kk[NU];
-    double xk[NX], uk[NU], pk[NP], pack[Srbd::PACK];
-    double mult[2][NU], invp[NU], rs[NU];
+    double Quu[NU * NU];       // Quu -> (strict upper) Lt^T, (lower) Es
+    double Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
+    double Qu[NU], quy[NU], kk[NU], invp[NU], rs[NU];
+    double nb[2][NodeBuf<Srbd>::SIZE];
     double ypart[3][40];
+    double sacc[NWARP][8];
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
     int iflag[4];
-    __device__ double* Kbuf() { return Qxx; }
+    __device__ double* Kbuf(int b) { return Qxx + b * (NU * NX); }
     __device__ double* scr() { return VT; }
     __device__ static int backward(const DevCfg& c, SmemSrbd& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
 };
+static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 39, "forward K double buffer must fit in Qxx + W");
 enum { R_SW = 6 };
-
 // upper-triangular 3x3 tiles of the 39x39 product (13 x 13 tile grid): tile t -> (ti, tj), ti <= tj
 __device__ const unsigned char kTileI[91] = {
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3,
@@ -49,6 +52,18 @@ __device__ const unsigned char kTileJ[91] = {
     4, 5, 6, 7, 8, 9, 10, 11, 12, 5, 6, 7, 8, 9, 10, 11, 12, 6, 7, 8, 9, 10, 11, 12, 7, 8, 9, 10, 11, 12, 8, 9, 10, 11, 12, 9, 10, 11, 12, 10, 11, 12, 11, 12, 12};
 
 SDDP_DEV void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// 1/p by a single-precision seed and two Newton steps (two ulp; the pivot chain is latency critical)
+SDDP_DEV double fast_rcp(double p) {
+    if (!(p > 1e-30 && p < 1e30)) return 1.0 / p;
+    float seed;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"((float)p));
+    double x = (double)seed;
+    double e = fma(-p, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-p, x, 1.0);
+    return fma(x, e, x);
+}
 
 // rows of V that make up row `a` of B^T (.) : cddot(i,k) -> cd_ik ; f(i,k) -> (fs/m) rd_k + G_i[:,k]^T w
 SDDP_DEV int bt_rows(const DevCfg& c, const double* Jac, int a, int* idx, double* coef) {
@@ -78,6 +93,7 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
 __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X, const double* U, const double* P, const double* D,
                                   const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid) {
     using M = Srbd;
+    using NBL = NodeBuf<Srbd>;
     constexpr int NZ = Srbd::NZ;
     const int N = c.N, lane = tid & 31, warp = tid >> 5;
     const bool fixed = c.rho_fixed > 0.0;
@@ -85,34 +101,54 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
     const double dt = c.dt;
     SyncBlock sync;
 
+    auto prefetch = [&](int k) {       // node k -> buffer k & 1
+        double* nb = S.nb[k & 1];
+        for (int i = tid; i < NX; i += NT) {
+            cp_async8(nb + NBL::OX + i, X + (size_t)k * NX + i);
+            if (has_gap) cp_async8(nb + NBL::OD + i, D + (size_t)k * NX + i);
+        }
+        for (int i = tid; i < NU; i += NT) cp_async8(nb + NBL::OU + i, U + (size_t)k * NU + i);
+        for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, P + (size_t)k * NP + i);
+        const double* ps = packs + (size_t)k * M::PACK;
+        if (((((size_t)ps) | ((size_t)(nb + NBL::OK))) & 15) == 0) { for (int i = 2 * tid; i < M::PACK; i += 2 * NT) cp_async16(nb + NBL::OK + i, ps + i); }
+        else { for (int i = tid; i < M::PACK; i += NT) cp_async8(nb + NBL::OK + i, ps + i); }
+        cp_commit();
+    };
+
     // terminal node: Vx = l_Nx, Vxx = l_Nxx (ddp.py:216-226: costs only)
-    for (int i = tid; i < NX; i += NT) S.xk[i] = X[(size_t)N * NX + i];
-    for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)N * NP + i];
+    __syncthreads();
+    {
+        double* nb = S.nb[N & 1];
+        for (int i = tid; i < NX; i += NT) nb[NBL::OX + i] = X[(size_t)N * NX + i];
+        for (int i = tid; i < NP; i += NT) nb[NBL::OP + i] = P[(size_t)N * NP + i];
+    }
+    prefetch(N - 1);
     if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; S.iflag[1] = 0; }
     __syncthreads();
-    M::expand<LDW>(c, NODE_TERM, S.xk, nullptr, S.pk, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync);
+    M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
-    __syncthreads();
 
     for (int k = N - 1; k >= 0; k--) {
         const int kind = node_kind(k, N);
-        for (int i = tid; i < NX; i += NT) {
-            S.xk[i] = X[(size_t)k * NX + i];
-            S.cg[i] = has_gap ? rho_b * D[(size_t)k * NX + i] : 0.0;
-        }
-        for (int i = tid; i < NU; i += NT) S.uk[i] = U[(size_t)k * NU + i];
-        for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)k * NP + i];
-        for (int i = tid; i < M::PACK; i += NT) S.pack[i] = packs[(size_t)k * M::PACK + i];
-        __syncthreads();
-        M::expand<LDW>(c, kind, S.xk, S.uk, S.pk, S.pack, S.Qx, S.Qu, S.Qxx, S.W, S.Quu, tid, NT, sync);
-        const double* Jac = S.pack + M::PK_JAC;
+        double* nb = S.nb[k & 1];
+        const double* xk = nb + NBL::OX;
+        const double* uk = nb + NBL::OU;
+        const double* pk = nb + NBL::OP;
+        double* cg = nb + NBL::OD;
+        const double* pack = nb + NBL::OK;
+        cp_wait_all();
+        __syncthreads();                       // node k landed; everyone is done with node k+1
+        if (k > 0) prefetch(k - 1);
+        if (tid < NX) cg[tid] = has_gap ? rho_b * cg[tid] : 0.0;      // consumed after expand's barriers
+        M::expand<LDW>(c, kind, xk, uk, pk, pack, S.Qx, S.Qu, S.Qxx, S.W, S.Quu, tid, NT, sync);
+        const double* Jac = pack + M::PK_JAC;
 
         // ---- c1: everything that needs Vxx' itself: gap shift, Quu = luu + fu^T Vxx' fu, copies of lx, lu
         if (tid < NX) {
             double s = 0.0;
             if (has_gap) {
 #pragma unroll 4
-                for (int j = 0; j < NX; j++) s += S.VT[tid * NX + j] * S.cg[j];
+                for (int j = 0; j < NX; j++) s += S.VT[tid * NX + j] * cg[j];
             }
             S.sv[tid] = s;
             S.vp[tid] = S.Vx[tid] + s;
@@ -128,156 +164,170 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             int b = e - a * (a + 1) / 2;
             int ia[4], ib[4];
             double ca[4], cb[4];
-            int na = bt_rows(c, Jac, a, ia, ca), nb = bt_rows(c, Jac, b, ib, cb);
+            int na = bt_rows(c, Jac, a, ia, ca), nb_ = bt_rows(c, Jac, b, ib, cb);
             double s = 0.0;
             for (int p = 0; p < na; p++) {
                 double t = 0.0;
-                for (int q = 0; q < nb; q++) t += S.VT[ia[p] * NX + ib[q]] * cb[q];
+                for (int q = 0; q < nb_; q++) t += S.VT[ia[p] * NX + ib[q]] * cb[q];
                 s += ca[p] * t;
             }
-            double v = S.Quu[a * NU + b] + dt * dt * s;
+            double v = S.Quu[a * NU + b] + dt * dt * s + (a == b ? mu : 0.0);
             S.Quu[a * NU + b] = v;
             S.Quu[b * NU + a] = v;
         }
         __syncthreads();
-        if (warp == 0 && has_gap) {   // gap terms of the model
-            double g1 = 0, g2 = 0, yg = 0;
-            for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * S.cg[i]; g2 += S.cg[i] * S.sv[i]; yg += S.y[i] * S.cg[i]; }
-            g1 = warp_sum(g1); g2 = warp_sum(g2); yg = warp_sum(yg);
-            if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
-        } else if (tid == 0) { S.red[R_G1] = 0.0; S.red[R_G2] = 0.0; S.red[R_YG] = 0.0; }
 
-        // ---- c2: T = Vxx' fx = V + dt V A, in place, one thread per row
-        const double* o = S.xk + M::XO;
-        const double* w = S.xk + M::XW;
-        if (tid < NX) {
-            double* row = S.VT + tid * NX;
-            double vr[3], vo[4], vw[3];
+        const double* o = xk + M::XO;
+        const double* w = xk + M::XW;
+        if (warp == 0) {
+            // ---- d1: Quu + mu I = Lt D Lt^T; lane t owns column t.  Row j of Lt^T (the multipliers of step j)
+            //          overwrites the strict upper triangle of S.Quu; D^-1 goes to S.invp.
+            if (has_gap) {   // gap terms of the model (the only use of cg after c1)
+                double g1 = 0, g2 = 0, yg = 0;
+                for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * cg[i]; g2 += cg[i] * S.sv[i]; yg += S.y[i] * cg[i]; }
+                g1 = warp_sum(g1); g2 = warp_sum(g2); yg = warp_sum(yg);
+                if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
+            } else if (lane == 0) { S.red[R_G1] = 0.0; S.red[R_G2] = 0.0; S.red[R_YG] = 0.0; }
+            double a[NU];
+            const int t = lane < NU ? lane : NU - 1;
 #pragma unroll
-            for (int q = 0; q < 3; q++) { vr[q] = row[M::XR + q]; vw[q] = row[M::XW + q]; }
+            for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
+            __syncwarp();
+            bool bad = false;
 #pragma unroll
-            for (int q = 0; q < 4; q++) vo[q] = row[M::XO + q];
-            const double hw[3] = {0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
-            const double ho[4] = {0.5 * dt * o[0], 0.5 * dt * o[1], 0.5 * dt * o[2], 0.5 * dt * o[3]};
-            double to[4], tw[3];
-            contract_Aoo(vo, hw, to);     // (V dt Aoo): o columns
-            contract_Aow(vo, ho, tw);     // (V dt Aow): w columns
-            const double dw0 = dt * vw[0], dw1 = dt * vw[1], dw2 = dt * vw[2];
-            // cd and rd columns first (they read the c and r entries before those are overwritten)
+            for (int j = 0; j < NU; j++) {
+                if (lane == j) {
+                    const double p = a[j];
+                    bad = !(p > 0.0) || !isfinite(p);
+                    const double inv = fast_rcp(p);
+                    S.invp[j] = inv;
 #pragma unroll
-            for (int q = 0; q < 12; q++) row[M::XCD + q] += dt * row[M::XC + q];
-#pragma unroll
-            for (int q = 0; q < 3; q++) row[M::XRD + q] += dt * vr[q];
-#pragma unroll
-            for (int z = 0; z < 19; z++) {        // r, o, c columns: + dt vw . dwdot/dz
-                double v = row[z] + dw0 * Jac[z] + dw1 * Jac[NZ + z] + dw2 * Jac[2 * NZ + z];
-                if (z >= 3 && z < 7) v += to[z - 3];
-                row[z] = v;
-            }
-#pragma unroll
-            for (int q = 0; q < 3; q++)
-                row[M::XW + q] = vw[q] + tw[q] + dw0 * Jac[M::ZW + q] + dw1 * Jac[NZ + M::ZW + q] + dw2 * Jac[2 * NZ + M::ZW + q];
-        }
-        __syncthreads();
-
-        // ---- c3: columns of fx^T (.) and fu^T (.) applied to T (j < 37), v+ (j = 37) and ys (j = 38)
-        if (tid < 39 * 3) {
-            const int j = tid % 39, g = tid / 39;
-            const double* col = (j < NX) ? S.VT + j : (j == NX ? S.vp : S.ys);
-            const int cs = (j < NX) ? NX : 1;      // stride between rows of this "column"
-            double* oxx = (j < NX) ? S.Qxx + j : (j == NX ? S.Qx : S.qxy);
-            const int os = (j < NX) ? NX : 1;
-            const double tw0 = col[(M::XW + 0) * cs], tw1 = col[(M::XW + 1) * cs], tw2 = col[(M::XW + 2) * cs];
-            if (g == 0) {          // rows r, o, rd, w
-                double tov[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) tov[q] = col[(M::XO + q) * cs];
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    oxx[(M::XR + q) * os] += col[(M::XR + q) * cs] + dt * (Jac[M::ZR + q] * tw0 + Jac[NZ + M::ZR + q] * tw1 + Jac[2 * NZ + M::ZR + q] * tw2);
-                    oxx[(M::XRD + q) * os] += col[(M::XRD + q) * cs] + dt * col[(M::XR + q) * cs];
+                    for (int i = j + 1; i < NU; i++) S.Quu[j * NU + i] = a[i] * inv;
                 }
+                __syncwarp();
+                if (lane > j && lane < NU) {
+                    const double aj = a[j];
+#pragma unroll
+                    for (int i = j + 1; i < NU; i++) a[i] -= S.Quu[j * NU + i] * aj;
+                }
+            }
+            if (__any_sync(FULL, bad) && lane == 0) S.iflag[1] = 1;
+            if (lane < NU) S.rs[lane] = sqrt(S.invp[lane]);
+        } else {
+            // ---- c2: T = Vxx' fx = V + dt V A, in place, one thread per row (warps 1-2)
+            const int r_ = tid - 32;
+            if (r_ < NX) {
+                double* row = S.VT + r_ * NX;
+                double vr[3], vo[4], vw[3];
+#pragma unroll
+                for (int q = 0; q < 3; q++) { vr[q] = row[M::XR + q]; vw[q] = row[M::XW + q]; }
+#pragma unroll
+                for (int q = 0; q < 4; q++) vo[q] = row[M::XO + q];
                 const double hw[3] = {0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
                 const double ho[4] = {0.5 * dt * o[0], 0.5 * dt * o[1], 0.5 * dt * o[2], 0.5 * dt * o[3]};
-                double ao[4], aw[3];
-                contract_Aoo(tov, hw, ao);    // (dt Aoo)^T T[o,j]: row o_b = sum_a Aoo[a][b] T[o_a][j]
-                contract_Aow(tov, ho, aw);    // (dt Aow)^T T[o,j]: row w_b
+                double to[4], tw[3];
+                contract_Aoo(vo, hw, to);     // (V dt Aoo): o columns
+                contract_Aow(vo, ho, tw);     // (V dt Aow): w columns
+                const double dw0 = dt * vw[0], dw1 = dt * vw[1], dw2 = dt * vw[2];
+                // cd and rd columns first (they read the c and r entries before those are overwritten)
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    oxx[(M::XO + q) * os] += col[(M::XO + q) * cs] + ao[q] + dt * (Jac[M::ZO + q] * tw0 + Jac[NZ + M::ZO + q] * tw1 + Jac[2 * NZ + M::ZO + q] * tw2);
+                for (int q = 0; q < 12; q++) row[M::XCD + q] += dt * row[M::XC + q];
+#pragma unroll
+                for (int q = 0; q < 3; q++) row[M::XRD + q] += dt * vr[q];
+#pragma unroll
+                for (int z = 0; z < 19; z++) {        // r, o, c columns: + dt vw . dwdot/dz
+                    double v = row[z] + dw0 * Jac[z] + dw1 * Jac[NZ + z] + dw2 * Jac[2 * NZ + z];
+                    if (z >= 3 && z < 7) v += to[z - 3];
+                    row[z] = v;
+                }
 #pragma unroll
                 for (int q = 0; q < 3; q++)
-                    oxx[(M::XW + q) * os] += col[(M::XW + q) * cs] + aw[q] + dt * (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
-            } else if (g == 1) {   // rows c, cd
+                    row[M::XW + q] = vw[q] + tw[q] + dw0 * Jac[M::ZW + q] + dw1 * Jac[NZ + M::ZW + q] + dw2 * Jac[2 * NZ + M::ZW + q];
+            }
+            bar_named(2, 96);
+            // ---- c3: columns of fx^T (.) and fu^T (.) applied to T (j < 37), v+ (j = 37) and ys (j = 38); warps 1-3
+            for (int task = tid - 32; task < 39 * 3; task += 96) {
+                const int j = task % 39, g = task / 39;
+                const double* col = (j < NX) ? S.VT + j : (j == NX ? S.vp : S.ys);
+                const int cs = (j < NX) ? NX : 1;      // stride between rows of this "column"
+                double* oxx = (j < NX) ? S.Qxx + j : (j == NX ? S.Qx : S.qxy);
+                const int os = (j < NX) ? NX : 1;
+                const double tw0 = col[(M::XW + 0) * cs], tw1 = col[(M::XW + 1) * cs], tw2 = col[(M::XW + 2) * cs];
+                if (g == 0) {          // rows r, o, rd, w
+                    double tov[4];
 #pragma unroll
-                for (int q = 0; q < 12; q++) {
-                    double tc = col[(M::XC + q) * cs];
-                    oxx[(M::XC + q) * os] += tc + dt * (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
-                    oxx[(M::XCD + q) * os] += col[(M::XCD + q) * cs] + dt * tc;
-                }
-            } else {               // fu^T (.): rows cddot_i, f_i
-                double* oux = (j < NX) ? S.W + j : (j == NX ? S.Qu : S.quy);
-                const int us = (j < NX) ? LDW : 1;
-                const double trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
-#pragma unroll
-                for (int i = 0; i < 4; i++)
+                    for (int q = 0; q < 4; q++) tov[q] = col[(M::XO + q) * cs];
 #pragma unroll
                     for (int q = 0; q < 3; q++) {
-                        oux[(6 * i + q) * us] += dt * col[(M::XCD + 3 * i + q) * cs];
-                        const int zf = M::ZF + 3 * i + q;
-                        oux[(6 * i + 3 + q) * us] += dt * (trd[q] + Jac[zf] * tw0 + Jac[NZ + zf] * tw1 + Jac[2 * NZ + zf] * tw2);
+                        oxx[(M::XR + q) * os] += col[(M::XR + q) * cs] + dt * (Jac[M::ZR + q] * tw0 + Jac[NZ + M::ZR + q] * tw1 + Jac[2 * NZ + M::ZR + q] * tw2);
+                        oxx[(M::XRD + q) * os] += col[(M::XRD + q) * cs] + dt * col[(M::XR + q) * cs];
                     }
+                    const double hw[3] = {0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
+                    const double ho[4] = {0.5 * dt * o[0], 0.5 * dt * o[1], 0.5 * dt * o[2], 0.5 * dt * o[3]};
+                    double ao[4], aw[3];
+                    contract_Aoo(tov, hw, ao);    // (dt Aoo)^T T[o,j]: row o_b = sum_a Aoo[a][b] T[o_a][j]
+                    contract_Aow(tov, ho, aw);    // (dt Aow)^T T[o,j]: row w_b
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        oxx[(M::XO + q) * os] += col[(M::XO + q) * cs] + ao[q] + dt * (Jac[M::ZO + q] * tw0 + Jac[NZ + M::ZO + q] * tw1 + Jac[2 * NZ + M::ZO + q] * tw2);
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+                        oxx[(M::XW + q) * os] += col[(M::XW + q) * cs] + aw[q] + dt * (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
+                } else if (g == 1) {   // rows c, cd
+#pragma unroll
+                    for (int q = 0; q < 12; q++) {
+                        double tc = col[(M::XC + q) * cs];
+                        oxx[(M::XC + q) * os] += tc + dt * (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
+                        oxx[(M::XCD + q) * os] += col[(M::XCD + q) * cs] + dt * tc;
+                    }
+                } else {               // fu^T (.): rows cddot_i, f_i
+                    double* oux = (j < NX) ? S.W + j : (j == NX ? S.Qu : S.quy);
+                    const int us = (j < NX) ? LDW : 1;
+                    const double trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int q = 0; q < 3; q++) {
+                            oux[(6 * i + q) * us] += dt * col[(M::XCD + 3 * i + q) * cs];
+                            const int zf = M::ZF + 3 * i + q;
+                            oux[(6 * i + 3 + q) * us] += dt * (trd[q] + Jac[zf] * tw0 + Jac[NZ + zf] * tw1 + Jac[2 * NZ + zf] * tw2);
+                        }
+                }
             }
         }
         __syncthreads();
+        if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; cp_wait_all(); __syncthreads(); return k + 1; }
 
-        // ---- d: square-root-free elimination of [Quu + mu I | Qux | Qu | I], one column per thread
-        double a[NU];
-        if (tid < 96) {
+        // ---- d2: Lt^-1 applied to [Qux | Qu | I], one right-hand side per thread, no barriers
+        if (tid < NX + 1 + NU) {
             const int t = tid;
-            if (t < NU) {
+            double a[NU];
+            if (t < NX) {
 #pragma unroll
-                for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t] + (i == t ? mu : 0.0);
-            } else if (t < NU + NX) {
-#pragma unroll
-                for (int i = 0; i < NU; i++) a[i] = S.W[i * LDW + (t - NU)];
-            } else if (t == NU + NX) {
+                for (int i = 0; i < NU; i++) a[i] = S.W[i * LDW + t];
+            } else if (t == NX) {
 #pragma unroll
                 for (int i = 0; i < NU; i++) a[i] = S.Qu[i];
             } else {
 #pragma unroll
-                for (int i = 0; i < NU; i++) a[i] = (i == t - (NU + NX + 1)) ? 1.0 : 0.0;
+                for (int i = 0; i < NU; i++) a[i] = (i == t - (NX + 1)) ? 1.0 : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < NU; j++) {
-                if (t == j) {
-                    const double p = a[j];
-                    if (!(p > 0.0) || !isfinite(p)) S.iflag[1] = 1;
-                    const double inv = 1.0 / p;
-                    S.invp[j] = inv;
+            for (int j = 0; j < NU - 1; j++) {
+                const double aj = a[j];
 #pragma unroll
-                    for (int i = j + 1; i < NU; i++) S.mult[j & 1][i] = a[i] * inv;
-                }
-                bar_named(1, 96);
-                if (t > j) {
-                    const double aj = a[j];
-#pragma unroll
-                    for (int i = j + 1; i < NU; i++) a[i] -= S.mult[j & 1][i] * aj;
-                }
+                for (int i = j + 1; i < NU; i++) a[i] -= S.Quu[j * NU + i] * aj;
             }
-            if (t < NU) S.rs[t] = sqrt(S.invp[t]);
-            bar_named(1, 96);
-            if (t >= NU && t < NU + NX + 1) {          // Wn = rs . frozen rows (column NX is w0)
+            if (t <= NX) {                      // Wn = rs . frozen rows (column NX is w0)
 #pragma unroll
-                for (int l = 0; l < NU; l++) S.W[l * LDW + (t - NU)] = a[l] * S.rs[l];
-            } else if (t >= NU + NX + 1 && t < 2 * NU + NX + 1) {   // Es = rs . Lt^-1 (lower triangular)
-                const int m = t - (NU + NX + 1);
+                for (int l = 0; l < NU; l++) S.W[l * LDW + t] = a[l] * S.rs[l];
+            } else {                            // Es = rs . Lt^-1 -> lower triangle (incl. diagonal) of S.Quu
+                const int m = t - (NX + 1);
 #pragma unroll
-                for (int l = 0; l < NU; l++) S.Quu[l * NU + m] = (l >= m) ? a[l] * S.rs[l] : 0.0;
+                for (int l = 0; l < NU; l++) if (l >= m) S.Quu[l * NU + m] = a[l] * S.rs[l];
             }
         }
         __syncthreads();
-        if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; __syncthreads(); return k + 1; }
 
         // ---- f: [Vxx Vx] = [sym(Qxx) Qx] - Wn^T Wn, 3x3 register tiles of the upper triangle (into VT)
         if (tid < 91) {
@@ -320,7 +370,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 const int i = g + 3 * r8;
                 double s = 0.0;
 #pragma unroll
-                for (int l = 3 * r8; l < NU; l++) s += S.Quu[l * NU + i] * wn[l];   // Es[l][i] = 0 for l < i
+                for (int l = 3 * r8; l < NU; l++) s += (l >= i ? S.Quu[l * NU + i] : 0.0) * wn[l];   // Es is lower triangular
                 const double kv = -s;
                 yp += kv * S.quy[i];
                 if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
@@ -357,8 +407,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             S.red[R_ACC2] += 0.5 * kQk;
             S.red[R_ACC1] += fixed ? (S.red[R_YG] + 0.5 * S.red[R_G2]) : (S.red[R_YG] + sq);
         }
-        __syncthreads();
     }
+    __syncthreads();
     if (tid == 0) {
         double tot = S.red[R_TOT], a1 = S.red[R_ACC1], a2 = S.red[R_ACC2];
         if (fixed) { dV3[2] = a1; dV3[1] = a2; dV3[0] = tot - a1 - a2; }

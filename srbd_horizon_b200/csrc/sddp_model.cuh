@@ -30,7 +30,19 @@ struct DevCfg {
     double w_r, w_rdot, w_w, w_rel, w_fsw, gq, w_minf, w_zmp, cw;
     double drel[2][2];   // drel[pair][axis] = -(foot[pair][axis] - foot[pair+2][axis])   prb.py:153-154
     double alpha0, alpha_min, ls_factor, beta, cost_ths, mu0, rho_fixed, mu_min, mu_max, mu_factor, defect_ths;
+    const unsigned long long* ztab;   // SRBD: descriptors of the 595 upper-triangular entries of the wdot Hessian block
 };
+
+// z-block descriptor bit layout (built on the host, sddp.cu:build_ztab)
+enum { ZT_ROUNDS = 5, ZT_THREADS = 128 };
+#define ZT_VALID(d) ((d) & 1ull)
+#define ZT_KIND(d) (int)(((d) >> 1) & 3)
+#define ZT_DA(d) (int)(((d) >> 3) & 63)
+#define ZT_DB(d) (int)(((d) >> 9) & 63)
+#define ZT_PI(d) (int)(((d) >> 15) & 63)
+#define ZT_QI(d) (int)(((d) >> 21) & 63)
+#define ZT_HSIGN(d) (int)(((d) >> 27) & 3)
+#define ZT_HOFF(d) (int)(((d) >> 29) & 511)
 
 enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2 };
 
@@ -198,9 +210,11 @@ struct Srbd {
 
     // quaternion error rows: quat_prod(o, oref) = E(oref) o        (prb.py:187)
     SDDP_DEV static double E_row(const double* q, int i, int a) {
-        // row i, column a of E
-        const double E[4][4] = {{q[3], q[2], -q[1], q[0]}, {-q[2], q[3], q[0], q[1]}, {q[1], -q[0], q[3], q[2]}, {-q[0], -q[1], -q[2], q[3]}};
-        return E[i][a];
+        // E = [[q3, q2, -q1, q0], [-q2, q3, q0, q1], [q1, -q0, q3, q2], [-q0, -q1, -q2, q3]]
+        if (i == a) return q[3];
+        if (a == 3) return q[i];
+        if (i == 3) return -q[a];
+        return -m3::skew_ab(q, i, a);
     }
 
     SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double* acc) {
@@ -387,6 +401,21 @@ struct Srbd {
             const double* Jac = pk + PK_JAC;
             const double g2 = 2.0 * c.gq;
             const bool exact = c.hessian_mode == 0;
+            if (c.ztab != nullptr && nthr == ZT_THREADS) {
+#pragma unroll
+                for (int r = 0; r < ZT_ROUNDS; r++) {
+                    const unsigned long long d = __ldg(c.ztab + r * ZT_THREADS + tid);
+                    if (!ZT_VALID(d)) continue;
+                    const int pi = ZT_PI(d), qi = ZT_QI(d), da = ZT_DA(d), db = ZT_DB(d), hs = ZT_HSIGN(d);
+                    double hh = Jac[pi] * Jac[qi] + Jac[NZ + pi] * Jac[NZ + qi] + Jac[2 * NZ + pi] * Jac[2 * NZ + qi];
+                    if (exact && hs) { const double v = pk[ZT_HOFF(d)]; hh += (hs == 1) ? v : -v; }
+                    hh *= g2;
+                    const int kd = ZT_KIND(d);
+                    if (kd == 0) { Qxx[da * NX + db] = hh; Qxx[db * NX + da] = hh; }
+                    else if (kd == 1) Qux[da * LDUX + db] = hh;
+                    else { Quu[da * NU + db] = hh; Quu[db * NU + da] = hh; }
+                }
+            } else
             for (int e = tid; e < NZ * NZ; e += nthr) {
                 int pi = e / NZ, qi = e % NZ;
                 int xi = zmap_x(pi), xj = zmap_x(qi);

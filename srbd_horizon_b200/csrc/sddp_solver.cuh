@@ -22,20 +22,40 @@ constexpr int NWARP = NT / 32;
 constexpr int NCAND = NWARP; // line-search candidates evaluated per wave
 constexpr unsigned FULL = 0xffffffffu;
 
+// per-node input buffer: x | u | p | d | (pack in the backward pass, k in the forward pass)
+template <class M>
+struct NodeBuf {
+    static constexpr int OX = 0, OU = M::NX, OP = M::NX + M::NU, OD = M::NX + M::NU + M::NP, OK = (2 * M::NX + M::NU + M::NP + 1) & ~1;
+    static constexpr int TAIL = M::PACK > M::NU ? M::PACK : M::NU;
+    static constexpr int SIZE = (OK + TAIL + 1) & ~1;
+};
+
+SDDP_DEV void cp_async8(double* smem, const double* g) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+}
+SDDP_DEV void cp_async16(double* smem, const double* g) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
+}
+SDDP_DEV void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+SDDP_DEV void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <class M>
 struct Smem {
     static constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     double Vxx[NX * NX], Qxx[NX * NX], Qux[NU * NX], Quu[NU * NU];
     double T[NX * (NX + NU)];            // Vxx [fx fu]; afterwards K of the node (NU*NX); forward: K_k
     double fx[NX * NX], fu[NX * NU];     // dense; forward: per-candidate x^, u^, x^+
-    double Vx[NX], y[NX], Qx[NX], Qu[NU], vp[NX], cg[NX], sv[NX], ys[NX], quy[NU], qxy[NX], kk[NU], w0[NU];
-    double xk[NX], uk[NU], pk[NP], pack[M::PACK];
+    double Vx[NX], y[NX], Qx[NX], Qu[NU], vp[NX], sv[NX], ys[NX], quy[NU], qxy[NX], kk[NU], w0[NU];
+    double nb[2][NodeBuf<M>::SIZE];      // double-buffered per-node inputs (x, u, p, d, pack | k)
+    double sacc[NWARP][8];
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
     int iflag[4];
     __device__ static int backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
-    __device__ double* Kbuf() { return T; }    // forward pass: K of the current node
+    __device__ double* Kbuf(int b) { return T + b * (NU * NX); }   // forward pass: K of node k in buffer k & 1
     __device__ double* scr() { return fx; }    // per-warp scratch
 };
 enum { R_TOT = 0, R_ACC1 = 1, R_ACC2 = 2, R_G1 = 3, R_G2 = 4, R_YG = 5, R_W0 = 8 };
@@ -59,17 +79,25 @@ SDDP_DEV double warp_max(double s) {
 //   xnext = xs + dt*ode(xs,us) - omr*dk
 template <class M>
 __device__ double warp_node(const DevCfg& c, int kind, const double* xs, const double* us, const double* ps,
-                            double* xnext, const double* dk, double omr, int lane) {
-    double acc[M::NACC];
-    if (kind != NODE_TERM) M::accel(c, xs, us, acc);
-    double s = warp_sum(M::cost_lane(c, kind, lane, xs, us, ps, acc));
+                            double* xnext, const double* dk, double omr, double* sacc, int lane) {
+    if (kind != NODE_TERM && M::NACC > 1) {
+        double acc[M::NACC];
+        M::accel(c, xs, us, acc);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < M::NACC; q++) sacc[q] = acc[q];
+        }
+        __syncwarp();
+    }
+    double s = warp_sum(M::cost_lane(c, kind, lane, xs, us, ps, sacc));
     if (xnext != nullptr && kind != NODE_TERM) {
         for (int i = lane; i < M::NX; i += 32) {
-            double v = xs[i] + c.dt * M::xdot_i(c, i, xs, us, acc);
+            double v = xs[i] + c.dt * M::xdot_i(c, i, xs, us, sacc);
             if (dk != nullptr) v -= omr * dk[i];
             xnext[i] = v;
         }
     }
+    __syncwarp();
     return s;
 }
 
@@ -92,7 +120,7 @@ __device__ double defects_and_cost(const DevCfg& c, SM& S, const double* X, cons
         if (k < N) for (int i = lane; i < NU; i += 32) us[i] = U[(size_t)k * NU + i];
         for (int i = lane; i < NP; i += 32) ps[i] = P[(size_t)k * NP + i];
         __syncwarp();
-        part += warp_node<M>(c, kind, xs, us, ps, (dout && k < N) ? xn : nullptr, nullptr, 0.0, lane);
+        part += warp_node<M>(c, kind, xs, us, ps, (dout && k < N) ? xn : nullptr, nullptr, 0.0, S.sacc[w], lane);
         __syncwarp();
         if (dout && k < N)
             for (int i = lane; i < NX; i += 32) dout[(size_t)k * NX + i] = xn[i] - X[(size_t)(k + 1) * NX + i];
@@ -120,9 +148,16 @@ __device__ void open_loop_rollout(const DevCfg& c, SM& S, double* X, const doubl
         for (int k = 0; k < c.N; k++) {
             for (int i = lane; i < NU; i += 32) us[i] = U[(size_t)k * NU + i];
             __syncwarp();
-            double acc[M::NACC];
-            M::accel(c, xs, us, acc);
-            for (int i = lane; i < NX; i += 32) xn[i] = xs[i] + c.dt * M::xdot_i(c, i, xs, us, acc);
+            if (M::NACC > 1) {
+                double acc[M::NACC];
+                M::accel(c, xs, us, acc);
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < M::NACC; q++) S.sacc[0][q] = acc[q];
+                }
+                __syncwarp();
+            }
+            for (int i = lane; i < NX; i += 32) xn[i] = xs[i] + c.dt * M::xdot_i(c, i, xs, us, S.sacc[0]);
             __syncwarp();
             for (int i = lane; i < NX; i += 32) { xs[i] = xn[i]; X[(size_t)(k + 1) * NX + i] = xn[i]; }
             __syncwarp();
@@ -141,33 +176,39 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
     const bool fixed = c.rho_fixed > 0.0;
     const double rho_b = fixed ? c.rho_fixed : 1.0;
     SyncBlock sync;
+    using NBL = NodeBuf<M>;
+    double* xk = S.nb[0] + NBL::OX;
+    double* uk = S.nb[0] + NBL::OU;
+    double* pk = S.nb[0] + NBL::OP;
+    double* cg = S.nb[0] + NBL::OD;
+    double* pack = S.nb[0] + NBL::OK;
 
     // terminal node: Vx = l_Nx, Vxx = l_Nxx (ddp.py:216-226: costs only)
-    for (int i = tid; i < NX; i += NT) S.xk[i] = X[(size_t)N * NX + i];
-    for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)N * NP + i];
+    for (int i = tid; i < NX; i += NT) xk[i] = X[(size_t)N * NX + i];
+    for (int i = tid; i < NP; i += NT) pk[i] = P[(size_t)N * NP + i];
     if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; }
     __syncthreads();
-    M::expand(c, NODE_TERM, S.xk, nullptr, S.pk, nullptr, S.Vx, S.Qu, S.Vxx, S.Qux, S.Quu, tid, NT, sync);
+    M::expand(c, NODE_TERM, xk, nullptr, pk, nullptr, S.Vx, S.Qu, S.Vxx, S.Qux, S.Quu, tid, NT, sync);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
     __syncthreads();
 
     for (int k = N - 1; k >= 0; k--) {
         const int kind = node_kind(k, N);
         for (int i = tid; i < NX; i += NT) {
-            S.xk[i] = X[(size_t)k * NX + i];
-            S.cg[i] = (D != nullptr) ? rho_b * D[(size_t)k * NX + i] : 0.0;
+            xk[i] = X[(size_t)k * NX + i];
+            cg[i] = (D != nullptr) ? rho_b * D[(size_t)k * NX + i] : 0.0;
         }
-        for (int i = tid; i < NU; i += NT) S.uk[i] = U[(size_t)k * NU + i];
-        for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)k * NP + i];
-        for (int i = tid; i < M::PACK; i += NT) S.pack[i] = packs[(size_t)k * M::PACK + i];
+        for (int i = tid; i < NU; i += NT) uk[i] = U[(size_t)k * NU + i];
+        for (int i = tid; i < NP; i += NT) pk[i] = P[(size_t)k * NP + i];
+        for (int i = tid; i < M::PACK; i += NT) pack[i] = packs[(size_t)k * M::PACK + i];
         __syncthreads();
-        M::expand(c, kind, S.xk, S.uk, S.pk, S.pack, S.Qx, S.Qu, S.Qxx, S.Qux, S.Quu, tid, NT, sync);
-        M::expand_f(c, S.xk, S.uk, S.pack, S.fx, S.fu, tid, NT, sync);
+        M::expand(c, kind, xk, uk, pk, pack, S.Qx, S.Qu, S.Qxx, S.Qux, S.Quu, tid, NT, sync);
+        M::expand_f(c, xk, uk, pack, S.fx, S.fu, tid, NT, sync);
 
         // sv = Vxx' c, v+ = Vx' + sv, ys = y' (+ sv)
         if (tid < NX) {
             double s = 0.0;
-            for (int j = 0; j < NX; j++) s += S.Vxx[tid * NX + j] * S.cg[j];
+            for (int j = 0; j < NX; j++) s += S.Vxx[tid * NX + j] * cg[j];
             S.sv[tid] = s;
             S.vp[tid] = S.Vx[tid] + s;
             S.ys[tid] = fixed ? S.y[tid] + s : S.y[tid];
@@ -183,7 +224,7 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
         __syncthreads();
         if (warp == 0) {   // gap terms of the model
             double g1 = 0, g2 = 0, yg = 0;
-            for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * S.cg[i]; g2 += S.cg[i] * S.sv[i]; yg += S.y[i] * S.cg[i]; }
+            for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * cg[i]; g2 += cg[i] * S.sv[i]; yg += S.y[i] * cg[i]; }
             g1 = warp_sum(g1); g2 = warp_sum(g2); yg = warp_sum(yg);
             if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
         }
@@ -328,9 +369,9 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
                              const double* D, const double* Kg, const double* kg, int ncand, double* Xn, size_t xn_stride,
                              double* Un, size_t un_stride, int tid) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
+    using NBL = NodeBuf<M>;
     const int N = c.N, lane = tid & 31, w = tid >> 5;
     double* xh = S.scr() + w * (2 * NX + NU);
-    double* Kb = S.Kbuf();
     double* uh = xh + NX;
     double* xn = uh + NU;
     double* Xo = Xn + (size_t)w * xn_stride;
@@ -338,36 +379,53 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
     const bool active = w < ncand;
     const double alpha = active ? S.alpha[w] : 0.0, omr = active ? 1.0 - S.rho[w] : 0.0;
     double J = 0.0;
+    // node k's inputs (K_k, k_k, X_k, U_k, d_k, p_k) are fetched with cp.async while node k-1 is computed
+    auto prefetch = [&](int k) {
+        double* nb = S.nb[k & 1];
+        double* Kb = S.Kbuf(k & 1);
+        const double* Ks = Kg + (size_t)k * NU * NX;
+        if ((NU * NX) % 2 == 0 && ((((size_t)Kb) | ((size_t)Ks)) & 15) == 0) { for (int e = 2 * tid; e < NU * NX; e += 2 * NT) cp_async16(Kb + e, Ks + e); }
+        else { for (int e = tid; e < NU * NX; e += NT) cp_async8(Kb + e, Ks + e); }
+        for (int i = tid; i < NX; i += NT) { cp_async8(nb + NBL::OX + i, X + (size_t)k * NX + i); cp_async8(nb + NBL::OD + i, D + (size_t)k * NX + i); }
+        for (int i = tid; i < NU; i += NT) { cp_async8(nb + NBL::OU + i, U + (size_t)k * NU + i); cp_async8(nb + NBL::OK + i, kg + (size_t)k * NU + i); }
+        for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, P + (size_t)k * NP + i);
+        cp_commit();
+    };
+    __syncthreads();      // the buffers may still be in use by the caller's previous phase
+    prefetch(0);
     for (int i = lane; i < NX; i += 32) xh[i] = x0[i];
     for (int k = 0; k < N; k++) {
-        __syncthreads();
-        for (int e = tid; e < NU * NX; e += NT) Kb[e] = Kg[(size_t)k * NU * NX + e];
-        for (int i = tid; i < NU; i += NT) { S.kk[i] = kg[(size_t)k * NU + i]; S.uk[i] = U[(size_t)k * NU + i]; }
-        for (int i = tid; i < NX; i += NT) { S.xk[i] = X[(size_t)k * NX + i]; S.cg[i] = (D != nullptr) ? D[(size_t)k * NX + i] : 0.0; }
-        for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)k * NP + i];
-        __syncthreads();
+        cp_wait_all();
+        __syncthreads();                  // node k landed for everyone; everyone is done with node k-1
+        if (k + 1 < N) prefetch(k + 1);
+        else {                            // terminal parameters go to the free buffer
+            double* nb = S.nb[(k + 1) & 1];
+            for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, P + (size_t)N * NP + i);
+            cp_commit();
+        }
         if (active) {
+            const double* nb = S.nb[k & 1];
+            const double* Kb = S.Kbuf(k & 1);
+            const double* xk = nb + NBL::OX;
             for (int j = lane; j < NU; j += 32) {
                 double t = 0.0;
-                for (int i = 0; i < NX; i++) t += Kb[j * NX + i] * (xh[i] - S.xk[i]);
-                double v = S.uk[j] + alpha * S.kk[j] + t;
+                for (int i = 0; i < NX; i++) t += Kb[j * NX + i] * (xh[i] - xk[i]);
+                double v = nb[NBL::OU + j] + alpha * nb[NBL::OK + j] + t;
                 uh[j] = v;
                 Uo[(size_t)k * NU + j] = v;
             }
             for (int i = lane; i < NX; i += 32) Xo[(size_t)k * NX + i] = xh[i];
             __syncwarp();
-            J += warp_node<M>(c, node_kind(k, N), xh, uh, S.pk, xn, S.cg, omr, lane);
-            __syncwarp();
+            J += warp_node<M>(c, node_kind(k, N), xh, uh, nb + NBL::OP, xn, nb + NBL::OD, omr, S.sacc[w], lane);
             for (int i = lane; i < NX; i += 32) xh[i] = xn[i];
             __syncwarp();
         }
     }
-    __syncthreads();
-    for (int i = tid; i < NP; i += NT) S.pk[i] = P[(size_t)N * NP + i];
+    cp_wait_all();
     __syncthreads();
     if (active) {
         for (int i = lane; i < NX; i += 32) Xo[(size_t)N * NX + i] = xh[i];
-        J += warp_node<M>(c, NODE_TERM, xh, nullptr, S.pk, nullptr, nullptr, 0.0, lane);
+        J += warp_node<M>(c, NODE_TERM, xh, nullptr, S.nb[N & 1] + NBL::OP, nullptr, nullptr, 0.0, S.sacc[w], lane);
         if (lane == 0) S.Jc[w] = J;
     }
     __syncthreads();

@@ -72,3 +72,36 @@ print(f"total samples {total}")
 for key, s in by_line.most_common(top):
     st = ", ".join(f"{k[6:]}={v}" for k, v in stall_by_line[key].most_common(3))
     print(f"{100.0 * s / total:5.1f}%  inst={ex_line[key]:>11}  {key}  [{st}]  {src(key)}")
+
+# ---- optional phase buckets: python tools/ncu_lines.py rep kernel top buckets
+if len(sys.argv) > 4:
+    spec = {
+        "forward_wave": [("sddp_solver.cuh", 325, 385)],
+        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 150, 246), ("sddp_solver.cuh", 58, 75)],
+        "init/defects/rollout": [("sddp_solver.cuh", 76, 133)],
+        "pack (thread per node)": [("sddp_model.cuh", 247, 356)],
+        "expand": [("sddp_model.cuh", 357, 470)],
+        "bwd load+c1 (Quu, gap)": [("sddp_backward_srbd.cuh", 88, 150)],
+        "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 151, 182)],
+        "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 183, 232)],
+        "bwd elimination": [("sddp_backward_srbd.cuh", 233, 281)],
+        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 282, 311)],
+        "bwd K matmul": [("sddp_backward_srbd.cuh", 312, 333)],
+        "bwd mu path + model": [("sddp_backward_srbd.cuh", 334, 380)],
+        "solve_one control": [("sddp_solver.cuh", 386, 520)],
+    }
+    tot_b = collections.Counter(); ex_b = collections.Counter(); st_b = collections.defaultdict(collections.Counter)
+    for key, s in by_line.items():
+        name = "other/unattributed"
+        if key is not None:
+            for nm, ranges in spec.items():
+                if any(key[0] == f and lo <= key[1] <= hi for f, lo, hi in ranges):
+                    name = nm
+        tot_b[name] += s; ex_b[name] += ex_line[key]
+        for k2, v in stall_by_line[key].items():
+            st_b[name][k2] += v
+    tot_ex = sum(ex_b.values())
+    print("\nphase buckets: samples%  inst%  top stalls")
+    for nm, s in tot_b.most_common():
+        st = ", ".join(f"{k[6:]}={100.0 * v / max(s, 1):.0f}%" for k, v in st_b[nm].most_common(3))
+        print(f"{100.0 * s / total:5.1f}%  {100.0 * ex_b[nm] / tot_ex:5.1f}%  {nm:32s} [{st}]")
