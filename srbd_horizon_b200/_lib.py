@@ -10,7 +10,7 @@ from .config import SddpConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libsddp.so")
+LIB_PATH = os.environ.get("SDDP_LIB", os.path.join(CSRC, "libsddp.so"))   # SDDP_LIB: A/B builds while tuning
 
 _vp = ctypes.c_void_p
 _ip = ctypes.POINTER(ctypes.c_int)

@@ -15,7 +15,13 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     __shared__ int s_prob;
-    const int tid = threadIdx.x;
+    // Warp w of every resident CTA shares one SM sub-partition (and its 16-lane FP64 pipe).  The solver gives
+    // warps different roles (warp 0 factorises, warps 0-1 own the right-hand sides, ...), so the role index is
+    // rotated per co-resident CTA: otherwise all serial phases of all CTAs pile up on sub-partition 0.
+#ifndef SDDP_ROTATE
+#define SDDP_ROTATE 0
+#endif
+    const int tid = SDDP_ROTATE ? ((threadIdx.x + 32 * ((blockIdx.x / a.sms) & 3)) & (NT - 1)) : threadIdx.x;
     for (;;) {   // persistent CTA: pull problems from a queue (iteration counts differ per problem)
         if (tid == 0) s_prob = atomicAdd(a.counter, 1);
         __syncthreads();
@@ -247,7 +253,10 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
 }
 
 // kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.reserved0 = 1), 2 = LIP dense
-constexpr int MINB_FAST = 5, MINB_DENSE = 1;
+#ifndef SDDP_MINB
+#define SDDP_MINB 4
+#endif
+constexpr int MINB_FAST = SDDP_MINB, MINB_DENSE = 1;
 static int variant_of(const SddpConfig& c) { return c.model == SDDP_MODEL_LIP ? 2 : (c.reserved0 == 1 ? 1 : 0); }
 static size_t smem_of_variant(int v) { return v == 0 ? sizeof(SmemSrbd) : (v == 1 ? sizeof(Smem<Srbd>) : sizeof(Smem<Lip>)); }
 
@@ -426,6 +435,7 @@ int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* param
     a.iters = iters; a.status = status; a.cost = cost;
     a.ws_d = h->ws_d; a.ws_pack = h->ws_pack; a.ws_xn = h->ws_xn; a.ws_un = h->ws_un; a.ws_K = h->ws_K; a.ws_k = h->ws_k;
     a.counter = h->counter;
+    a.sms = h->sms;
     int grid = B < h->slots ? B : h->slots;
     DISPATCH(h, solve_kernel, grid, st, h->dc, a);
     return 0;
@@ -545,5 +555,15 @@ int sddp_fp64_peak_tflops(double* out, void* stream) {
     *out = best;
     return 0;
 }
+
+#ifdef SDDP_PROFILE
+/* developer builds only: cycles accumulated per phase by thread 0 of CTA 0 (see sddp_solver.cuh PROF) */
+int sddp_debug_profile(long long* out32, int reset) {
+    long long z[32] = {0};
+    if (cudaMemcpyFromSymbol(out32, g_prof, sizeof(z)) != cudaSuccess) return SDDP_ECUDA;
+    if (reset && cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return SDDP_ECUDA;
+    return 0;
+}
+#endif
 
 }  // extern "C"

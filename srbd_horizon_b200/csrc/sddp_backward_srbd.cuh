@@ -12,7 +12,7 @@
 //   Quu = luu + fu^T V fu                      one thread per entry of the lower triangle
 // Gains (W-form of sddp_solver.cuh, square-root free):
 //   warp 0 factorises Quu_r = Lt D Lt^T (one lane per column held in registers, 24 pivot steps, only
-//   __syncwarp between them, Newton-refined reciprocal instead of a division) WHILE warps 1-3 build
+//   __syncwarp between them, branch-free updates, Newton-refined reciprocal started one element early) WHILE warps 1-3 build
 //   T, Qxx, Qux (they do not depend on the factor).  Then one thread per right-hand side applies
 //   Lt^-1 to [Qux | Qu | I] with no barrier at all: frozen rows U = Lt^-1 [Qux Qu], E = Lt^-1.
 //   With rs = D^-1/2:  Wn = rs.U (= L^-1 [Qux Qu] of the Cholesky form), Es = rs.E
@@ -27,7 +27,7 @@ struct alignas(16) SmemSrbd {
     double VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
     double Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
     double W[NU * LDW];        // [Qux | w0 | 0] -> Wn
-    double Quu[NU * NU];       // Quu -> (strict upper) Lt^T, (lower) Es
+    double Quu[NU * NU];       // Quu -> (strict upper) D Lt^T = frozen raw columns, (lower) Es
     double Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
     double Qu[NU], quy[NU], kk[NU], invp[NU], rs[NU];
     double nb[2][NodeBuf<Srbd>::SIZE];
@@ -53,12 +53,11 @@ __device__ const unsigned char kTileJ[91] = {
 
 SDDP_DEV void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// 1/p by a single-precision seed and two Newton steps (two ulp; the pivot chain is latency critical)
+// 1/p from the hardware double-precision seed (MUFU.RCP64H, ~20 bits) and two Newton steps (about 2 ulp).
+// The pivot chain of the factorisation is latency critical; a full IEEE division is ~3x longer.
 SDDP_DEV double fast_rcp(double p) {
-    if (!(p > 1e-30 && p < 1e30)) return 1.0 / p;
-    float seed;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"((float)p));
-    double x = (double)seed;
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(p));
     double e = fma(-p, x, 1.0);
     x = fma(x, e, x);
     e = fma(-p, x, 1.0);
@@ -125,7 +124,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
     prefetch(N - 1);
     if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; S.iflag[1] = 0; }
     __syncthreads();
-    M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync);
+    M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, &S.ypart[0][0]);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
 
     for (int k = N - 1; k >= 0; k--) {
@@ -138,10 +137,12 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         const double* pack = nb + NBL::OK;
         cp_wait_all();
         __syncthreads();                       // node k landed; everyone is done with node k+1
-        if (k > 0) prefetch(k - 1);
+        PROF(8);
         if (tid < NX) cg[tid] = has_gap ? rho_b * cg[tid] : 0.0;      // consumed after expand's barriers
-        M::expand<LDW>(c, kind, xk, uk, pk, pack, S.Qx, S.Qu, S.Qxx, S.W, S.Quu, tid, NT, sync);
+        M::expand<LDW>(c, kind, xk, uk, pk, pack, S.Qx, S.Qu, S.Qxx, S.W, S.Quu, tid, NT, sync, &S.ypart[0][0]);
         const double* Jac = pack + M::PK_JAC;
+        PROF(9);
+        if (k > 0) prefetch(k - 1);      // after the zero fill: shared stores queue behind outstanding cp.async
 
         // ---- c1: everything that needs Vxx' itself: gap shift, Quu = luu + fu^T Vxx' fu, copies of lx, lu
         if (tid < NX) {
@@ -156,6 +157,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             S.qxy[tid] = S.Qx[tid];
         } else if (tid >= 64 && tid < 64 + NU) {
             S.quy[tid - 64] = S.Qu[tid - 64];
+        } else if (tid == 127) {
+            S.iflag[2] = 0;            // number of factor columns published by warp 0 (see d1 / d2)
         }
         for (int e = tid; e < NU * (NU + 1) / 2; e += NT) {   // lower triangle (a >= b), mirrored
             int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
@@ -176,6 +179,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             S.Quu[b * NU + a] = v;
         }
         __syncthreads();
+        PROF(10);
 
         const double* o = xk + M::XO;
         const double* w = xk + M::XW;
@@ -188,31 +192,51 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 g1 = warp_sum(g1); g2 = warp_sum(g2); yg = warp_sum(yg);
                 if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
             } else if (lane == 0) { S.red[R_G1] = 0.0; S.red[R_G2] = 0.0; S.red[R_YG] = 0.0; }
+            // Lane t holds column t.  Step j: lane j publishes its (final) column raw, row j of the strict upper
+            // triangle of S.Quu, and 1/pivot; every lane then applies  a[i] -= col_j[i] * (a[j] / pivot_j).
+            // The element that becomes the next pivot (i = j+1) is updated first and its reciprocal started at
+            // once, so the rest of the update overlaps the reciprocal latency.  Lanes <= j update dead values.
             double a[NU];
             const int t = lane < NU ? lane : NU - 1;
 #pragma unroll
             for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
             __syncwarp();
             bool bad = false;
+            double myinv = fast_rcp(a[0]);          // lane 0's pivot
 #pragma unroll
             for (int j = 0; j < NU; j++) {
                 if (lane == j) {
                     const double p = a[j];
                     bad = !(p > 0.0) || !isfinite(p);
-                    const double inv = fast_rcp(p);
-                    S.invp[j] = inv;
+                    S.invp[j] = myinv;
 #pragma unroll
-                    for (int i = j + 1; i < NU; i++) S.Quu[j * NU + i] = a[i] * inv;
+                    for (int i = j + 1; i < NU; i++) S.Quu[j * NU + i] = a[i];
+                    __threadfence_block();
+                    *(volatile int*)&S.iflag[2] = j + 1;      // column j is visible to the right-hand-side warps
                 }
                 __syncwarp();
-                if (lane > j && lane < NU) {
-                    const double aj = a[j];
+                if (j + 1 < NU) {
+                    const double sj = S.invp[j] * a[j];
+                    a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
+                    myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
+                    // the rest of the column in batches of 8: loads first, then the FMAs (keeps the loads in
+                    // flight together without holding a whole second column in registers)
 #pragma unroll
-                    for (int i = j + 1; i < NU; i++) a[i] -= S.Quu[j * NU + i] * aj;
+                    for (int i0 = j + 2; i0 < NU; i0 += 8) {
+                        double col[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (i0 + q < NU) col[q] = S.Quu[j * NU + i0 + q];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (i0 + q < NU) a[i0 + q] -= col[q] * sj;
+                    }
                 }
             }
             if (__any_sync(FULL, bad) && lane == 0) S.iflag[1] = 1;
             if (lane < NU) S.rs[lane] = sqrt(S.invp[lane]);
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) *(volatile int*)&S.iflag[2] = NU + 1;           // rs is visible too
+            PROF_T(14, 0);
         } else {
             // ---- c2: T = Vxx' fx = V + dt V A, in place, one thread per row (warps 1-2)
             const int r_ = tid - 32;
@@ -244,6 +268,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 for (int q = 0; q < 3; q++)
                     row[M::XW + q] = vw[q] + tw[q] + dw0 * Jac[M::ZW + q] + dw1 * Jac[NZ + M::ZW + q] + dw2 * Jac[2 * NZ + M::ZW + q];
             }
+            PROF_T(15, 32);
             bar_named(2, 96);
             // ---- c3: columns of fx^T (.) and fu^T (.) applied to T (j < 37), v+ (j = 37) and ys (j = 38); warps 1-3
             for (int task = tid - 32; task < 39 * 3; task += 96) {
@@ -294,40 +319,53 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                         }
                 }
             }
+            PROF_T(16, 32);
+            // ---- d2: Lt^-1 applied to [Qux | Qu | I], one right-hand side per thread (warps 1-2), trailing the
+            //          factorisation of warp 0 column by column (S.iflag[2] counts the published columns)
+            bar_named(2, 96);                      // Qux, Qu complete
+            const int t = tid - 32;
+            if (t < NX + 1 + NU) {
+                volatile int* published = (volatile int*)&S.iflag[2];
+                double a[NU];
+                if (t < NX) {
+#pragma unroll
+                    for (int i = 0; i < NU; i++) a[i] = S.W[i * LDW + t];
+                } else if (t == NX) {
+#pragma unroll
+                    for (int i = 0; i < NU; i++) a[i] = S.Qu[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NU; i++) a[i] = (i == t - (NX + 1)) ? 1.0 : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < NU - 1; j++) {
+                    while (*published <= j) __nanosleep(40);      // polite wait: spinning warps steal issue slots
+                    asm volatile("" ::: "memory");
+                    const double sj = S.invp[j] * a[j];
+#pragma unroll
+                    for (int i0 = j + 1; i0 < NU; i0 += 8) {
+                        double col[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (i0 + q < NU) col[q] = S.Quu[j * NU + i0 + q];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (i0 + q < NU) a[i0 + q] -= col[q] * sj;
+                    }
+                }
+                while (*published <= NU) __nanosleep(40);
+                asm volatile("" ::: "memory");
+                if (t <= NX) {                      // Wn = rs . frozen rows (column NX is w0)
+#pragma unroll
+                    for (int l = 0; l < NU; l++) S.W[l * LDW + t] = a[l] * S.rs[l];
+                } else {                            // Es = rs . Lt^-1 -> lower triangle (incl. diagonal) of S.Quu
+                    const int m = t - (NX + 1);
+#pragma unroll
+                    for (int l = 0; l < NU; l++) if (l >= m) S.Quu[l * NU + m] = a[l] * S.rs[l];
+                }
+            }
         }
         __syncthreads();
+        PROF(11);
         if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; cp_wait_all(); __syncthreads(); return k + 1; }
-
-        // ---- d2: Lt^-1 applied to [Qux | Qu | I], one right-hand side per thread, no barriers
-        if (tid < NX + 1 + NU) {
-            const int t = tid;
-            double a[NU];
-            if (t < NX) {
-#pragma unroll
-                for (int i = 0; i < NU; i++) a[i] = S.W[i * LDW + t];
-            } else if (t == NX) {
-#pragma unroll
-                for (int i = 0; i < NU; i++) a[i] = S.Qu[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < NU; i++) a[i] = (i == t - (NX + 1)) ? 1.0 : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < NU - 1; j++) {
-                const double aj = a[j];
-#pragma unroll
-                for (int i = j + 1; i < NU; i++) a[i] -= S.Quu[j * NU + i] * aj;
-            }
-            if (t <= NX) {                      // Wn = rs . frozen rows (column NX is w0)
-#pragma unroll
-                for (int l = 0; l < NU; l++) S.W[l * LDW + t] = a[l] * S.rs[l];
-            } else {                            // Es = rs . Lt^-1 -> lower triangle (incl. diagonal) of S.Quu
-                const int m = t - (NX + 1);
-#pragma unroll
-                for (int l = 0; l < NU; l++) if (l >= m) S.Quu[l * NU + m] = a[l] * S.rs[l];
-            }
-        }
-        __syncthreads();
 
         // ---- f: [Vxx Vx] = [sym(Qxx) Qx] - Wn^T Wn, 3x3 register tiles of the upper triangle (into VT)
         if (tid < 91) {
@@ -379,6 +417,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             S.ypart[g][cc] = yp;
         }
         __syncthreads();
+        PROF(13);
         if (tid < NX) S.y[tid] = S.qxy[tid] + (S.ypart[0][tid] + S.ypart[1][tid] + S.ypart[2][tid]);
         if (mu != 0.0) {   // regularised step (rare): Vxx -= mu K^T K, Vx -= mu K^T k, gains re-read from global
             __syncthreads();

@@ -24,6 +24,24 @@
 #pragma once
 #include <math.h>
 
+// Phase timer (developer builds only, -DSDDP_PROFILE): thread 0 of CTA 0 accumulates clock64() deltas per phase
+// into g_prof[]; read back with sddp_debug_profile().  Phases are delimited by block barriers.
+#ifdef SDDP_PROFILE
+__device__ long long g_prof[32];
+__device__ long long g_prof_last;
+#define PROF_DECL
+#define PROF(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long t_ = clock64(); g_prof[i] += t_ - g_prof_last; g_prof_last = t_; } } while (0)
+#define PROF_RESET do { if (threadIdx.x == 0 && blockIdx.x == 0) g_prof_last = clock64(); } while (0)
+#define PROF_T(i, thr) do { if (threadIdx.x == (thr) && blockIdx.x == 0) { g_prof[i] += clock64() - g_prof_last; } } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_RESET
+#define PROF_T(i, thr)
+#endif
+
+
+
 struct DevCfg {
     int model, N, inertia_mode, hessian_mode, ms, max_iters;
     double dt, mscaled, inv_ms, Ib[9], com[3], foot[12], fs, g, eta2;
@@ -47,6 +65,9 @@ enum { ZT_ROUNDS = 5, ZT_THREADS = 128 };
 enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2 };
 
 #define SDDP_DEV __device__ __forceinline__
+#ifndef SDDP_NOINLINE
+#define SDDP_NOINLINE
+#endif
 
 namespace m3 {
 SDDP_DEV void cross(const double* a, const double* b, double* o) {
@@ -259,7 +280,7 @@ struct Srbd {
 
     // ---- single-thread rigid-body pack (see file header) ------------------------------------
     // pk[PK_WD..] wd(3) rdd(3) nu(3) Hww(9) Jac[3][34] Ho[4][34]
-    __device__ static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk) {
+    __device__ SDDP_NOINLINE static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk) {
         if (kind == NODE_TERM) return;
         const double* r = x;
         const double* o = x + XO;
@@ -387,8 +408,155 @@ struct Srbd {
     }
 
     // Q buffers <- lx, lu, lxx, lux, luu of this node.  Every thread of the block must call.
+    // Fast path (128 threads + descriptor table): three barrier-separated passes, each with one or a few
+    // entries per thread and short uniform branches:
+    //   1. zero fill   2. wdot block 2 gq (Jac^T Jac + Hc) through the descriptor table   3. affine residuals
     template <int LDUX = NX, class Sync>
     __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double* pk,
+                                  double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync,
+                                  double* scratch = nullptr) {
+        if (c.ztab == nullptr || nthr != ZT_THREADS || scratch == nullptr) {
+            expand_generic<LDUX>(c, kind, x, u, p, pk, Qx, Qu, Qxx, Qux, Quu, tid, nthr, sync);
+            return;
+        }
+        const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
+        unsigned long long zd[ZT_ROUNDS];
+        if (input) {
+#pragma unroll
+            for (int r = 0; r < ZT_ROUNDS; r++) zd[r] = __ldg(c.ztab + r * ZT_THREADS + tid);    // latency hidden by the zero fill
+        }
+#ifndef SDDP_EXP_SKIP
+#define SDDP_EXP_SKIP 0
+#endif
+        if (SDDP_EXP_SKIP != 3) {
+        for (int e = tid; e < NX * NX; e += ZT_THREADS) Qxx[e] = 0.0;
+        for (int e = tid; e < NU * LDUX; e += ZT_THREADS) Qux[e] = 0.0;
+        for (int e = tid; e < NU * NU; e += ZT_THREADS) Quu[e] = 0.0;
+        }
+        if (tid < NX) Qx[tid] = 0.0;
+        if (tid < NU) Qu[tid] = 0.0;
+        double* Es = scratch;          // E(oref) 4x4, then the four orientation residuals
+        if (track && tid >= 96 && tid < 112) Es[tid - 96] = E_row(p + 15, (tid - 96) >> 2, (tid - 96) & 3);
+        sync();
+        PROF(20);
+        if (track && tid >= 96 && tid < 100) {
+            const int r = tid - 96;
+            const double* o = x + XO;
+            Es[16 + r] = Es[4 * r] * o[0] + Es[4 * r + 1] * o[1] + Es[4 * r + 2] * o[2] + Es[4 * r + 3] * o[3] - (r == 3 ? 1.0 : 0.0);
+        }
+        if (input && SDDP_EXP_SKIP != 1) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc), upper triangle mirrored
+            const double* Jac = pk + PK_JAC;
+            const double g2 = 2.0 * c.gq;
+            const bool exact = c.hessian_mode == 0;
+#pragma unroll
+            for (int r = 0; r < ZT_ROUNDS; r++) {
+                const unsigned long long d = zd[r];
+                if (!ZT_VALID(d)) continue;
+                const int pi = ZT_PI(d), qi = ZT_QI(d), da = ZT_DA(d), db = ZT_DB(d), hs = ZT_HSIGN(d);
+                double hh = Jac[pi] * Jac[qi] + Jac[NZ + pi] * Jac[NZ + qi] + Jac[2 * NZ + pi] * Jac[2 * NZ + qi];
+                if (exact && hs) { const double v = pk[ZT_HOFF(d)]; hh += (hs == 1) ? v : -v; }
+                hh *= g2;
+                const int kd = ZT_KIND(d);
+                if (kd == 0) { Qxx[da * NX + db] = hh; Qxx[db * NX + da] = hh; }
+                else if (kd == 1) Qux[da * LDUX + db] = hh;
+                else { Quu[da * NU + db] = hh; Quu[db * NU + da] = hh; }
+            }
+            if (tid < NZ) {
+                const int pi = tid;
+                const double g = g2 * (Jac[pi] * pk[PK_WD] + Jac[NZ + pi] * pk[PK_WD + 1] + Jac[2 * NZ + pi] * pk[PK_WD + 2]);
+                const int xi = zmap_x(pi);
+                if (xi >= 0) Qx[xi] = g; else Qu[zmap_u(pi)] = g;
+            }
+        }
+        sync();
+        PROF(21);
+        // ---- affine residuals, Hessian: one entry per thread (119 entries)
+        const int t = (SDDP_EXP_SKIP == 2) ? 1000 : tid;
+        if (t < 48) {                                   // rddot rows of min_qddot + min_f + f_active   (prb.py:200-204)
+            if (input) {
+                const int k = t >> 4, i = (t >> 2) & 3, j = t & 3;
+                double v = 2.0 * c.gq * c.inv_ms * c.inv_ms;
+                if (i == j) { const double a = 1.0 - p[8 + 2 * i]; v += 2.0 * (c.w_minf + c.w_fsw * a * a); }
+                Quu[(6 * i + 3 + k) * NU + 6 * j + 3 + k] += v;
+            }
+        } else if (t < 64) {                            // o_tracking_xyz / _w   (prb.py:185-189)
+            if (track) {
+                const int a = (t - 48) >> 2, b = (t - 48) & 3;
+                const double hh = Es[a] * Es[b] + Es[4 + a] * Es[4 + b] + Es[8 + a] * Es[8 + b] + Es[12 + a] * Es[12 + b];
+                Qxx[(XO + a) * NX + XO + b] += 2.0 * p[6] * p[6] * hh;
+            }
+        } else if (t < 80) {                            // rel_pos_*   (prb.py:192-199)
+            if (track) {
+                const int r = (t - 64) >> 2, e = (t - 64) & 3, j = r >> 1, ax = r & 1;
+                const int ia = XC + 3 * j + ax, ib = ia + 6;
+                const int row = (e & 2) ? ib : ia, col = (e & 1) ? ib : ia;
+                Qxx[row * NX + col] += (row == col) ? 2.0 * c.w_rel : -2.0 * c.w_rel;
+            }
+        } else if (t < 96) {                            // relative_vel_* and cdotxy_tracking_*   (prb.py:166-181)
+            if (input) {
+                const int g = (t - 80) >> 2, e = (t - 80) & 3, leg = g >> 1, ax = g & 1;
+                const int ia = XCD + 3 * (2 * leg) + ax, ib = ia + 3;
+                const int row = (e & 2) ? ib : ia, col = (e & 1) ? ib : ia;
+                double v = -2.0 * c.cw;
+                if (row == col) { const double sw = p[8 + 2 * (2 * leg + ((e & 2) ? 1 : 0))]; v = 2.0 * c.cw * (1.0 + sw * sw); }
+                Qxx[row * NX + col] += v;
+            }
+        } else if (t < 108) {                           // cddot rows of min_qddot
+            if (input) { const int i = t - 96, ui = 6 * (i / 3) + i % 3; Quu[ui * NU + ui] += 2.0 * c.gq; }
+        } else if (t < 112) {                           // cz_tracking_i   (prb.py:180)
+            if (input) { const int id = XC + 3 * (t - 108) + 2; Qxx[id * NX + id] += 2.0 * c.cw; }
+        } else if (t < 115) {                           // rdot_tracking   (prb.py:190)
+            if (track) { const int id = XRD + t - 112; Qxx[id * NX + id] += 2.0 * c.w_rdot; }
+        } else if (t < 118) {                           // w_tracking   (prb.py:191)
+            if (track) { const int id = XW + t - 115; Qxx[id * NX + id] += 2.0 * c.w_w; }
+        } else if (t == 118) {                          // rz_tracking   (prb.py:184)
+            if (track) Qxx[2 * NX + 2] += 2.0 * c.w_r;
+        }
+        // ---- affine residuals, gradient: thread t < 24 owns lu[t], thread 32 + i owns lx[i]
+        if (t < NU) {
+            if (input) {
+                const int i = t / 6, r = t % 6;
+                double g;
+                if (r < 3) g = 2.0 * c.gq * u[t];
+                else { const double a = 1.0 - p[8 + 2 * i]; g = 2.0 * c.gq * c.inv_ms * pk[PK_RDD + r - 3] + 2.0 * (c.w_minf + c.w_fsw * a * a) * u[t]; }
+                Qu[t] += g;
+            }
+        } else if (t >= 32 && t < 32 + NX) {
+            const int i = t - 32;
+            double g = 0.0;
+            if (i == 2) { if (track) g = 2.0 * c.w_r * (x[2] - c.com[2]); }
+            else if (i >= XO && i < XC) {
+                if (track) {
+                    const int a = i - XO;
+                    g = 2.0 * p[6] * p[6] * (Es[a] * Es[16] + Es[4 + a] * Es[17] + Es[8 + a] * Es[18] + Es[12 + a] * Es[19]);
+                }
+            } else if (i >= XC && i < XRD) {
+                const int foot = (i - XC) / 3, ax = (i - XC) % 3;
+                if (ax == 2) { if (input) g = 2.0 * c.cw * (x[i] - p[7 + 2 * foot]); }
+                else if (track) {
+                    const int j = foot & 1, ia = XC + 3 * j + ax, ib = ia + 6;
+                    const double res = -x[ia] + x[ib] - c.drel[j][ax];
+                    g = (foot < 2) ? -2.0 * c.w_rel * res : 2.0 * c.w_rel * res;
+                }
+            } else if (i >= XRD && i < XW) { if (track) g = 2.0 * c.w_rdot * (x[i] - p[i - XRD]); }
+            else if (i >= XW && i < XCD) { if (track) g = 2.0 * c.w_w * (x[i] - p[3 + i - XW]); }
+            else if (i >= XCD) {
+                const int foot = (i - XCD) / 3, ax = (i - XCD) % 3;
+                if (ax < 2 && input) {
+                    const int ia = XCD + 3 * (foot & ~1) + ax, ib = ia + 3;
+                    const double res = x[ia] - x[ib], sw = p[8 + 2 * foot];
+                    g = 2.0 * c.cw * (((foot & 1) ? -res : res) + sw * sw * x[i]);
+                }
+            }
+            Qx[i] += g;
+        }
+        sync();
+        PROF(22);
+    }
+
+    // generic fallback (any thread count, no descriptor table)
+    template <int LDUX = NX, class Sync>
+    __device__ static void expand_generic(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double* pk,
                                   double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync) {
         for (int e = tid; e < NX * NX; e += nthr) Qxx[e] = 0.0;
         for (int e = tid; e < NU * LDUX; e += nthr) Qux[e] = 0.0;

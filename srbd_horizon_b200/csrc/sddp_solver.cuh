@@ -78,7 +78,7 @@ SDDP_DEV double warp_max(double s) {
 // cost of one node (all lanes get the sum) and, if xnext != null, the Euler step
 //   xnext = xs + dt*ode(xs,us) - omr*dk
 template <class M>
-__device__ double warp_node(const DevCfg& c, int kind, const double* xs, const double* us, const double* ps,
+__device__ SDDP_NOINLINE double warp_node(const DevCfg& c, int kind, const double* xs, const double* us, const double* ps,
                             double* xnext, const double* dk, double omr, double* sacc, int lane) {
     if (kind != NODE_TERM && M::NACC > 1) {
         double acc[M::NACC];
@@ -440,6 +440,7 @@ struct SolveArgs {
     // workspace, per resident CTA
     double* ws_d; double* ws_pack; double* ws_xn; double* ws_un; double* ws_K; double* ws_k;
     int* counter;
+    int sms;
 };
 
 template <class M>
@@ -489,12 +490,15 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     double mu = c.mu0;
     int status = 1 /*MAX_ITERS*/, it = 0;
     for (it = 0; it < c.max_iters; it++) {
+        PROF_RESET;
         compute_packs<M>(c, X, U, packs, tid);
+        PROF(0);
         bool reg_fail = false;
         while (SM::backward(c, S, X, U, P, d, packs, mu, Kg, kg, &S.red[12], dmax != 0.0, tid)) {
             mu = fmax(mu * c.mu_factor, c.mu_min);
             if (mu > c.mu_max) { reg_fail = true; break; }
         }
+        PROF(1);
         const double D1 = S.red[12], D2 = S.red[13], C0 = S.red[14];
         double* h = hist ? hist + it * 4 : nullptr;
         if (h && tid == 0) { h[0] = J; h[1] = 0.0; h[2] = mu; h[3] = dmax; }
@@ -518,7 +522,9 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
             __syncthreads();
             if (tid < NCAND) { S.alpha[tid] = al[tid]; S.rho[tid] = fixed ? c.rho_fixed : al[tid]; }
             __syncthreads();
+            PROF_RESET;
             forward_wave<M, SM>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid);
+            PROF(2);
             for (int j = 0; j < ncand; j++) {
                 double am = al[j], dJm = C0 + am * D1 + am * am * D2, Jj = S.Jc[j];
                 if (isfinite(Jj) && Jj - J <= dJm + (1.0 - c.beta) * fabs(dJm)) {
@@ -542,6 +548,7 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
             if (mu < c.mu_min) mu = 0.0;
             if (mu < c.mu0) mu = c.mu0;
             __syncthreads();
+            PROF(3);
             if (dJ <= c.cost_ths * (1.0 + fabs(J)) && dmax <= c.defect_ths) { status = 0; it++; break; }
         } else {
             mu = fmax(mu * c.mu_factor, c.mu_min);

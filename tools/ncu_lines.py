@@ -76,19 +76,20 @@ for key, s in by_line.most_common(top):
 # ---- optional phase buckets: python tools/ncu_lines.py rep kernel top buckets
 if len(sys.argv) > 4:
     spec = {
-        "forward_wave": [("sddp_solver.cuh", 325, 385)],
-        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 150, 246), ("sddp_solver.cuh", 58, 75)],
-        "init/defects/rollout": [("sddp_solver.cuh", 76, 133)],
-        "pack (thread per node)": [("sddp_model.cuh", 247, 356)],
-        "expand": [("sddp_model.cuh", 357, 470)],
-        "bwd load+c1 (Quu, gap)": [("sddp_backward_srbd.cuh", 88, 150)],
-        "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 151, 182)],
-        "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 183, 232)],
-        "bwd elimination": [("sddp_backward_srbd.cuh", 233, 281)],
-        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 282, 311)],
-        "bwd K matmul": [("sddp_backward_srbd.cuh", 312, 333)],
-        "bwd mu path + model": [("sddp_backward_srbd.cuh", 334, 380)],
-        "solve_one control": [("sddp_solver.cuh", 386, 520)],
+        "forward_wave": [("sddp_solver.cuh", 368, 434)],
+        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 172, 261), ("sddp_solver.cuh", 81, 104)],
+        "init/defects/rollout": [("sddp_solver.cuh", 105, 169)],
+        "pack (thread per node)": [("sddp_model.cuh", 262, 370)],
+        "expand": [("sddp_model.cuh", 371, 498)],
+        "bwd load+c1 (Quu, gap)": [("sddp_backward_srbd.cuh", 93, 180)],
+        "bwd d1 (warp-0 LDL^T)": [("sddp_backward_srbd.cuh", 181, 215)],
+        "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 216, 246)],
+        "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 247, 297)],
+        "bwd d2 (RHS substitution)": [("sddp_backward_srbd.cuh", 298, 331)],
+        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 332, 360)],
+        "bwd K matmul": [("sddp_backward_srbd.cuh", 361, 380)],
+        "bwd mu path + model": [("sddp_backward_srbd.cuh", 381, 443)],
+        "solve_one control": [("sddp_solver.cuh", 435, 635)],
     }
     tot_b = collections.Counter(); ex_b = collections.Counter(); st_b = collections.defaultdict(collections.Counter)
     for key, s in by_line.items():

@@ -28,5 +28,7 @@ for _ in range(a.reps):
     r = s.solve(x0, p, X0, U0, gains=not a.no_gains, history=False)
     e1.record()
     torch.cuda.synchronize()
-    print(f"B={a.batch} N={a.N} ms={e0.elapsed_time(e1):.3f} mean_iters={r.iters.double().mean().item():.3f} "
-          f"converged={(r.status == 0).double().mean().item():.4f}")
+    ms = e0.elapsed_time(e1)
+    it = r.iters.double()
+    print(f"B={a.batch} N={a.N} ms={ms:.3f} mean_iters={it.mean().item():.3f} max_iters={int(it.max().item())} "
+          f"converged={(r.status == 0).double().mean().item():.4f} us_per_node_iter_of_slowest={1e3 * ms / (it.max().item() * a.N):.2f}")
