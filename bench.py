@@ -36,6 +36,9 @@ EX_OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}   
 # SURVEY.md section 8d / BASELINE.md section 4: dense-equivalent algorithmic work per Riccati node
 F_NODE = 4 * 37 ** 3 + 8 * 37 ** 2 * 24 + 6 * 37 * 24 ** 2 + 24 ** 3 // 3 + 2 * 37 * 24     # 599,716 FLOP
 BYTES_NODE = 15720
+# measured DRAM traffic of solve_kernel per Riccati node-iteration: dram__bytes_read+write of one `ncu --set full`
+# capture (profiles/r1_solve_kernel_full_raw.csv: 27.95 GB for 4736 problems x 4.963 iterations x 50 nodes)
+TRAFFIC_NODE = 27.95e9 / (4736 * 4.963 * 50)
 HBM_PEAK_FALLBACK = 6650.0
 
 
@@ -280,7 +283,8 @@ def main():
     ach_tf = units * F_NODE / t_k / 1e12
     ach_gb = units * BYTES_NODE / t_k / 1e9
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": p64, "unit": "TFLOP/s", "frac": ach_tf / p64 if p64 else None,
-                "traffic": None,
+                "traffic": units * TRAFFIC_NODE,
+                "traffic_note": "bytes per launch = node-iterations x %.0f B measured with ncu --set full at B=4736 (profiles/README.md)" % TRAFFIC_NODE,
                 "note": "dense-equivalent algorithmic FLOP (599,716 per Riccati node-iteration, SURVEY 8d) / CUDA-event duration of "
                         "solve_kernel; peak = FP64 FMA rate measured in this run (sddp_fp64_peak_tflops)",
                 "kernel": "solve_kernel<Srbd>", "kernel_ms": ms_kernel, "node_iterations_per_launch": units,
