@@ -138,9 +138,13 @@ int sddp_defects(SddpHandle *h, int B, const double *X, const double *U, const d
                  double *defect, double *cost, void *stream);
 
 /* Same solve with HOST buffers: copies in, solves, copies out, synchronises.
- * This is what a non-CUDA caller (the reference's Python loop) binds. */
-int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *params, double *X, double *U,
-                          double *K, double *kff, double *hist, int32_t *iters, int32_t *status, double *cost);
+ * This is what a non-CUDA caller (the reference's Python loop) binds.  X0 / U0 are the warm start
+ * (ddp.py:114,117), X / U receive the solution and may alias X0 / U0.  The batch is processed in
+ * chunks so that the host<->device copies of one chunk overlap the solve of another (three streams);
+ * pinned host buffers are needed for that overlap, pageable ones work but serialise. */
+int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *params, const double *X0,
+                          const double *U0, double *X, double *U, double *K, double *kff, double *hist,
+                          int32_t *iters, int32_t *status, double *cost);
 
 /* Measured FP64 FMA rate of the device (microbenchmark, TFLOP/s); used as the roofline peak. */
 int sddp_fp64_peak_tflops(double *out, void *stream);

@@ -2,6 +2,7 @@
 // Built for sm_100a only:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -164,6 +165,8 @@ struct SddpHandle {
     unsigned long long* ztab;
     // staging for the *_host entry point
     void* stage; size_t stage_bytes;
+    cudaStream_t st_in, st_cmp, st_out;
+    int host_chunk;
     long long launches;
     char err[512];
 };
@@ -376,6 +379,9 @@ int sddp_destroy(SddpHandle* h) {
     if (h->ws_d) cudaFree(h->ws_d);
     if (h->ztab) cudaFree(h->ztab);
     if (h->stage) cudaFree(h->stage);
+    if (h->st_in) cudaStreamDestroy(h->st_in);
+    if (h->st_cmp) cudaStreamDestroy(h->st_cmp);
+    if (h->st_out) cudaStreamDestroy(h->st_out);
     delete h;
     return 0;
 }
@@ -475,18 +481,18 @@ int sddp_defects(SddpHandle* h, int B, const double* X, const double* U, const d
     return 0;
 }
 
-int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* params, double* X, double* U, double* K,
-                          double* kff, double* hist, int32_t* iters, int32_t* status, double* cost) {
+int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* params, const double* X0, const double* U0,
+                          double* X, double* U, double* K, double* kff, double* hist, int32_t* iters, int32_t* status, double* cost) {
     if (!h) return SDDP_EINVAL;
-    if (B < 0 || (B > 0 && (!x0 || !params || !X || !U || !iters || !status || !cost)))
-        return fail(h, SDDP_EINVAL, "%s%s", "solve_batch_host: x0, params, X, U, iters, status, cost are required", "");
+    if (B < 0 || (B > 0 && (!x0 || !params || !X0 || !U0 || !X || !U || !iters || !status || !cost)))
+        return fail(h, SDDP_EINVAL, "%s%s", "solve_batch_host: x0, params, X0, U0, X, U, iters, status, cost are required", "");
     if (B == 0) return 0;
     int nx, nu, np, pack;
     model_dims(h->cfg.model, nx, nu, np, pack);
     const size_t N = (size_t)h->cfg.N, Bz = (size_t)B;
-    const size_t n_x0 = Bz * nx, n_p = Bz * (N + 1) * np, n_X = Bz * (N + 1) * nx, n_U = Bz * N * nu;
-    const size_t n_K = K ? Bz * N * nu * nx : 0, n_k = kff ? n_U : 0, n_h = hist ? Bz * h->cfg.max_iters * SDDP_HIST : 0;
-    const size_t n_d = n_x0 + n_p + n_X + n_U + n_K + n_k + n_h + Bz;
+    const size_t s_x0 = nx, s_p = (N + 1) * np, s_X = (N + 1) * nx, s_U = N * nu;              // doubles per problem
+    const size_t s_K = K ? N * nu * nx : 0, s_k = kff ? s_U : 0, s_h = hist ? (size_t)h->cfg.max_iters * SDDP_HIST : 0;
+    const size_t n_d = Bz * (s_x0 + s_p + s_X + s_U + s_K + s_k + s_h + 1);
     const size_t bytes = n_d * sizeof(double) + 2 * Bz * sizeof(int32_t);
     if (bytes > h->stage_bytes) {
         if (h->stage) cudaFree(h->stage);
@@ -495,32 +501,65 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         if (e != cudaSuccess) return fail(h, SDDP_ENOMEM, "cudaMalloc(staging): %s%s", cudaGetErrorString(e), "");
         h->stage_bytes = bytes;
     }
+    if (!h->st_in) {
+        CU(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->st_cmp, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
+        h->host_chunk = 16384;
+        const char* env = getenv("SDDP_HOST_CHUNK");
+        if (env && atoi(env) > 0) h->host_chunk = atoi(env);
+    }
     double* d_x0 = (double*)h->stage;
-    double* d_p = d_x0 + n_x0;
-    double* d_X = d_p + n_p;
-    double* d_U = d_X + n_X;
-    double* d_K = d_U + n_U;
-    double* d_k = d_K + n_K;
-    double* d_h = d_k + n_k;
-    double* d_c = d_h + n_h;
+    double* d_p = d_x0 + Bz * s_x0;
+    double* d_X = d_p + Bz * s_p;
+    double* d_U = d_X + Bz * s_X;
+    double* d_K = d_U + Bz * s_U;
+    double* d_k = d_K + Bz * s_K;
+    double* d_h = d_k + Bz * s_k;
+    double* d_c = d_h + Bz * s_h;
     int32_t* d_it = (int32_t*)(d_c + Bz);
     int32_t* d_st = d_it + Bz;
-    cudaStream_t st = 0;
-    CU(cudaMemcpyAsync(d_x0, x0, n_x0 * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_p, params, n_p * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_X, X, n_X * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_U, U, n_U * 8, cudaMemcpyHostToDevice, st));
-    int rc = sddp_solve_batch(h, B, d_x0, d_p, d_X, d_U, K ? d_K : nullptr, kff ? d_k : nullptr, hist ? d_h : nullptr, d_it, d_st, d_c, st);
+    const int chunk = h->host_chunk;
+    const int nchunk = (B + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev_in(nchunk), ev_cmp(nchunk);
+    int rc = 0;
+    for (int c = 0; c < nchunk; c++) {
+        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_cmp[c], cudaEventDisableTiming);
+    }
+    for (int c = 0; c < nchunk && rc == 0; c++) {
+        const size_t o = (size_t)c * chunk, n = (size_t)((B - (int)o) < chunk ? (B - (int)o) : chunk);
+        cudaError_t e = cudaSuccess;
+        auto cp = [&](void* dst, const void* src, size_t nbytes, cudaMemcpyKind kind, cudaStream_t st) {
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, nbytes, kind, st);
+        };
+        cp(d_x0 + o * s_x0, x0 + o * s_x0, n * s_x0 * 8, cudaMemcpyHostToDevice, h->st_in);
+        cp(d_p + o * s_p, params + o * s_p, n * s_p * 8, cudaMemcpyHostToDevice, h->st_in);
+        cp(d_X + o * s_X, X0 + o * s_X, n * s_X * 8, cudaMemcpyHostToDevice, h->st_in);
+        cp(d_U + o * s_U, U0 + o * s_U, n * s_U * 8, cudaMemcpyHostToDevice, h->st_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_in[c], h->st_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->st_cmp, ev_in[c], 0);
+        if (e != cudaSuccess) { rc = fail(h, SDDP_ECUDA, "solve_batch_host (copy in): %s%s", cudaGetErrorString(e), ""); break; }
+        rc = sddp_solve_batch(h, (int)n, d_x0 + o * s_x0, d_p + o * s_p, d_X + o * s_X, d_U + o * s_U, K ? d_K + o * s_K : nullptr,
+                              kff ? d_k + o * s_k : nullptr, hist ? d_h + o * s_h : nullptr, d_it + o, d_st + o, d_c + o, h->st_cmp);
+        if (rc) break;
+        e = cudaEventRecord(ev_cmp[c], h->st_cmp);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->st_out, ev_cmp[c], 0);
+        cp(X + o * s_X, d_X + o * s_X, n * s_X * 8, cudaMemcpyDeviceToHost, h->st_out);
+        cp(U + o * s_U, d_U + o * s_U, n * s_U * 8, cudaMemcpyDeviceToHost, h->st_out);
+        if (K) cp(K + o * s_K, d_K + o * s_K, n * s_K * 8, cudaMemcpyDeviceToHost, h->st_out);
+        if (kff) cp(kff + o * s_k, d_k + o * s_k, n * s_k * 8, cudaMemcpyDeviceToHost, h->st_out);
+        if (hist) cp(hist + o * s_h, d_h + o * s_h, n * s_h * 8, cudaMemcpyDeviceToHost, h->st_out);
+        cp(cost + o, d_c + o, n * 8, cudaMemcpyDeviceToHost, h->st_out);
+        cp(iters + o, d_it + o, n * 4, cudaMemcpyDeviceToHost, h->st_out);
+        cp(status + o, d_st + o, n * 4, cudaMemcpyDeviceToHost, h->st_out);
+        if (e != cudaSuccess) rc = fail(h, SDDP_ECUDA, "solve_batch_host (copy out): %s%s", cudaGetErrorString(e), "");
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->st_in), e2 = cudaStreamSynchronize(h->st_cmp), e3 = cudaStreamSynchronize(h->st_out);
+    for (int c = 0; c < nchunk; c++) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_cmp[c]); }
     if (rc) return rc;
-    CU(cudaMemcpyAsync(X, d_X, n_X * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(U, d_U, n_U * 8, cudaMemcpyDeviceToHost, st));
-    if (K) CU(cudaMemcpyAsync(K, d_K, n_K * 8, cudaMemcpyDeviceToHost, st));
-    if (kff) CU(cudaMemcpyAsync(kff, d_k, n_k * 8, cudaMemcpyDeviceToHost, st));
-    if (hist) CU(cudaMemcpyAsync(hist, d_h, n_h * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(cost, d_c, Bz * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(iters, d_it, Bz * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(status, d_st, Bz * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(h, SDDP_ECUDA, "solve_batch_host (sync): %s%s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)), "");
     return 0;
 }
 

@@ -120,22 +120,33 @@ class BatchedDDP:
         return BatchResult(X, U, K, k, hist, iters, status, cost)
 
     def solve_host(self, x0: np.ndarray, params: np.ndarray, X0: np.ndarray, U0: np.ndarray, gains: bool = False,
-                   history: bool = False) -> Dict[str, np.ndarray]:
-        """Same solve on HOST numpy buffers through `sddp_solve_batch_host` (copies inside the call)."""
+                   history: bool = False, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """Same solve on HOST numpy buffers through `sddp_solve_batch_host` (chunked copies overlap the solves).
+        `out` may hold preallocated (pinned) X, U, iters, status, cost [, K, k, hist] arrays to reuse."""
         B = x0.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
-        x0 = np.ascontiguousarray(x0, dtype=np.float64); params = np.ascontiguousarray(params, dtype=np.float64)
-        assert x0.shape == (B, nx) and params.shape == (B, N + 1, np_)
-        X = np.array(X0, dtype=np.float64, order="C", copy=True); U = np.array(U0, dtype=np.float64, order="C", copy=True)
-        assert X.shape == (B, N + 1, nx) and U.shape == (B, N, nu)
-        K = np.empty((B, N, nu, nx)) if gains else None
-        k = np.empty((B, N, nu)) if gains else None
-        hist = np.empty((B, self.cfg.max_iters, HIST)) if history else None
-        iters = np.empty(B, dtype=np.int32); status = np.empty(B, dtype=np.int32); cost = np.empty(B)
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x0, params, X0, U0 = c(x0), c(params), c(X0), c(U0)
+        if x0.shape != (B, nx) or params.shape != (B, N + 1, np_) or X0.shape != (B, N + 1, nx) or U0.shape != (B, N, nu):
+            raise ValueError("solve_host: bad input shapes")
+        out = dict(out) if out else {}
+        def buf(name, shape, dtype=np.float64):
+            a = out.get(name)
+            if a is None or a.shape != tuple(shape) or a.dtype != dtype or not a.flags.c_contiguous:
+                a = np.empty(shape, dtype=dtype)
+            out[name] = a
+            return a
+        X, U = buf("X", (B, N + 1, nx)), buf("U", (B, N, nu))
+        K = buf("K", (B, N, nu, nx)) if gains else None
+        k = buf("k", (B, N, nu)) if gains else None
+        hist = buf("hist", (B, self.cfg.max_iters, HIST)) if history else None
+        iters, status, cost = buf("iters", (B,), np.int32), buf("status", (B,), np.int32), buf("cost", (B,))
         with torch.cuda.device(self.device):
-            _lib.check(self.L.sddp_solve_batch_host(self.h, B, _np_ptr(x0), _np_ptr(params), _np_ptr(X), _np_ptr(U), _np_ptr(K),
-                                                    _np_ptr(k), _np_ptr(hist), _np_ptr(iters), _np_ptr(status), _np_ptr(cost)), self.h)
-        return dict(X=X, U=U, K=K, k=k, hist=hist, iters=iters, status=status, cost=cost)
+            _lib.check(self.L.sddp_solve_batch_host(self.h, B, _np_ptr(x0), _np_ptr(params), _np_ptr(X0), _np_ptr(U0), _np_ptr(X),
+                                                    _np_ptr(U), _np_ptr(K), _np_ptr(k), _np_ptr(hist), _np_ptr(iters), _np_ptr(status),
+                                                    _np_ptr(cost)), self.h)
+        out.update(K=K, k=k, hist=hist)
+        return out
 
     # -- stage entry points (used by the stage parity tests) ------------------------------------
     def eval_derivatives(self, kind, x, u, p):
