@@ -1,0 +1,71 @@
+"""BASELINE configs[0] and configs[1]: the reference's example loops (dlip_example.py, dsrbd_example.py) driven through
+the drop-in DDPSolver on the GPU, tick by tick against the CPU oracle solving the same problem from the same warm start."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from srbd_horizon_b200 import prb as P
+from srbd_horizon_b200 import wpg
+from srbd_horizon_b200.config import MODEL_LIP, MODEL_SRBD
+from srbd_horizon_b200.ddp import DDPSolver
+from srbd_horizon_b200.mpc import mpc_tick_references, plant_step
+from tests.helpers import relerr
+
+OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}     # dsrbd_example.py:55-58
+
+
+def _loop(model, ticks):
+    ns, T = 20, 1.0                                                             # dsrbd_example.py:30-31
+    if model == MODEL_SRBD:
+        prob = P.SRBDProblem(); prob.createSRBDProblem(ns, T)
+        w_ref, otg = prob.w_ref, prob.orientation_tracking_gain
+    else:
+        prob = P.LIPProblem(); prob.createLIPProblem(ns, T)
+        dummy = P.SRBDProblem(); dummy.createSRBDProblem(ns, T)                 # dlip_example.py:33-36, 85
+        w_ref, otg = dummy.w_ref, dummy.orientation_tracking_gain
+    solver = DDPSolver(prob.prb, dict(OPTS))
+    gen = wpg.steps_phase(getattr(prob, "f", None), prob.c, prob.cdot, float(prob.initial_foot_position[0][2]), prob.c_ref, w_ref,
+                          otg, prob.cdot_switch, ns, number_of_legs=2, contact_model=prob.contact_model)
+    state = prob.getInitialState()
+    solver.set_u_warmstart(np.tile(prob.getStaticInput()[:, None], (1, ns)))
+    cfg = solver.cfg
+    Xw = np.tile(state, (ns + 1, 1)); Uw = np.tile(prob.getStaticInput(), (ns, 1))
+    worst = 0.0
+    for tick in range(ticks):
+        solver.setInitialState(state)
+        walking = tick >= 5
+        mpc_tick_references(prob, [0.5 if walking else 0.0, 0.0, 0.0])          # dsrbd_example.py:102-122
+        gen.set("step" if walking else "standing")                              # :126-131
+        params = solver.get_params_value()
+        ok = solver.solve()                                                     # :135
+        ro = O.solve_batch(cfg, state[None], params[None], Xw[None], Uw[None])
+        sol = solver.getSolutionDict()
+        assert ok == (ro["status"][0] == 0)
+        assert solver.last["iters"] == ro["iters"][0]
+        ex, eu = relerr(sol["x_opt"].T, ro["X"][0]), relerr(sol["u_opt"].T, ro["U"][0])
+        worst = max(worst, ex, eu)
+        assert ex < 1e-9 and eu < 1e-9, (tick, ex, eu)
+        # the solution dict has the reference's keys and shapes (ddp.py:125-151)
+        assert sol["r"].shape == (3, ns + 1) and sol["c3"].shape == (3, ns + 1) and sol["u_opt"].shape[1] == ns
+        if model == MODEL_SRBD:
+            assert sol["o"].shape == (4, ns + 1) and sol["f2"].shape == (3, ns) and sol["cddot0"].shape == (3, ns)
+        else:
+            assert sol["z"].shape == (3, ns)
+        Xw, Uw = ro["X"][0], ro["U"][0]          # both sides warm start from their own previous solution
+        state = plant_step(solver.ddp_solver, state, sol["u_opt"][:, 0])        # :158-160
+        ref = O.dynamics(cfg, solver._x0, sol["u_opt"][:, 0])
+        if model == MODEL_SRBD:
+            ref[3:7] /= np.linalg.norm(ref[3:7])
+        assert np.max(np.abs(state - ref)) < 1e-13
+    return worst
+
+
+def test_config0_dlip_example_closed_loop():
+    assert _loop(MODEL_LIP, 30) < 1e-9
+
+
+def test_config1_dsrbd_example_closed_loop():
+    assert _loop(MODEL_SRBD, 30) < 1e-9

@@ -39,6 +39,8 @@ rows = list(csv.reader(out))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]
 ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+iwf = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
+wf_line = collections.Counter()
 base = None
 by_line = collections.Counter(); ex_line = collections.Counter()
 stall_cols = [i for i, c in enumerate(hdr) if c.startswith("stall_") and "Not Issued" not in c]
@@ -54,6 +56,8 @@ for r in rows[h + 1:]:
     s = int(r[isamp] or 0)
     by_line[key] += s; total += s
     ex_line[key] += int(r[iex] or 0)
+    if iwf is not None:
+        wf_line[key] += int(float(r[iwf] or 0))
     for i in stall_cols:
         v = int(r[i] or 0)
         if v:
@@ -77,32 +81,33 @@ for key, s in by_line.most_common(top):
 if len(sys.argv) > 4:
     spec = {
         "forward_wave": [("sddp_solver.cuh", 368, 434)],
-        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 172, 261), ("sddp_solver.cuh", 81, 104)],
+        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 193, 282), ("sddp_solver.cuh", 80, 104)],
         "init/defects/rollout": [("sddp_solver.cuh", 105, 169)],
-        "pack (thread per node)": [("sddp_model.cuh", 262, 370)],
-        "expand": [("sddp_model.cuh", 371, 498)],
-        "bwd load+c1 (Quu, gap)": [("sddp_backward_srbd.cuh", 93, 180)],
-        "bwd d1 (warp-0 LDL^T)": [("sddp_backward_srbd.cuh", 181, 215)],
-        "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 216, 246)],
-        "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 247, 297)],
-        "bwd d2 (RHS substitution)": [("sddp_backward_srbd.cuh", 298, 331)],
-        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 332, 360)],
-        "bwd K matmul": [("sddp_backward_srbd.cuh", 361, 380)],
-        "bwd mu path + model": [("sddp_backward_srbd.cuh", 381, 443)],
+        "pack (thread per node)": [("sddp_model.cuh", 283, 391)],
+        "expand": [("sddp_model.cuh", 392, 664)],
+        "bwd load+c1 (Quu, gap)": [("sddp_backward_srbd.cuh", 92, 184)],
+        "bwd d1 (warp-0 LDL^T)": [("sddp_backward_srbd.cuh", 185, 239)],
+        "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 240, 271)],
+        "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 272, 320)],
+        "bwd d2 (RHS substitution)": [("sddp_backward_srbd.cuh", 321, 365)],
+        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 366, 398)],
+        "bwd K matmul": [("sddp_backward_srbd.cuh", 399, 419)],
+        "bwd mu path + model": [("sddp_backward_srbd.cuh", 420, 482)],
         "solve_one control": [("sddp_solver.cuh", 435, 635)],
     }
-    tot_b = collections.Counter(); ex_b = collections.Counter(); st_b = collections.defaultdict(collections.Counter)
+    tot_b = collections.Counter(); ex_b = collections.Counter(); wf_b = collections.Counter(); st_b = collections.defaultdict(collections.Counter)
     for key, s in by_line.items():
         name = "other/unattributed"
         if key is not None:
             for nm, ranges in spec.items():
                 if any(key[0] == f and lo <= key[1] <= hi for f, lo, hi in ranges):
                     name = nm
-        tot_b[name] += s; ex_b[name] += ex_line[key]
+        tot_b[name] += s; ex_b[name] += ex_line[key]; wf_b[name] += wf_line[key]
         for k2, v in stall_by_line[key].items():
             st_b[name][k2] += v
     tot_ex = sum(ex_b.values())
-    print("\nphase buckets: samples%  inst%  top stalls")
+    tot_wf = max(1, sum(wf_b.values()))
+    print("\nphase buckets: samples%  inst%  smem-wavefronts%  top stalls")
     for nm, s in tot_b.most_common():
         st = ", ".join(f"{k[6:]}={100.0 * v / max(s, 1):.0f}%" for k, v in st_b[nm].most_common(3))
-        print(f"{100.0 * s / total:5.1f}%  {100.0 * ex_b[nm] / tot_ex:5.1f}%  {nm:32s} [{st}]")
+        print(f"{100.0 * s / total:5.1f}%  {100.0 * ex_b[nm] / tot_ex:5.1f}%  {100.0 * wf_b[nm] / tot_wf:5.1f}%  {nm:32s} [{st}]")
