@@ -146,6 +146,20 @@ int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *
                           const double *U0, double *X, double *U, double *K, double *kff, double *hist,
                           int32_t *iters, int32_t *status, double *cost);
 
+/* ---- receding-horizon glue on the device (the caller side of the path: dsrbd_example.py:102-131,158-160, wpg.py:68-101) ----
+ * gait tables of wpg.steps_phase (wpg.py:19-64): four arrays of 21 entries, l_cycle, l_switch, r_cycle, r_switch (host pointers) */
+int sddp_set_gait_tables(SddpHandle *h, const double *l_cycle, const double *l_switch, const double *r_cycle,
+                         const double *r_switch);
+/* One MPC tick of the parameter schedule for B problems: every per-node parameter moves one node back
+ * (dsrbd_example.py:102-106, wpg.py:74-77), node N receives rdot_ref_cmd[b] and, per action[b]
+ * (0 "step", 1 stance, 2 "jump"), the gait entries of wpg.py:80-99 at ref_id = step_counter[b] % 20;
+ * step_counter[b] is incremented.  params[B][N+1][np], action/step_counter int32[B], rdot_ref_cmd[B][3]. */
+int sddp_mpc_advance(SddpHandle *h, int B, double *params, const int32_t *action, int32_t *step_counter,
+                     const double *rdot_ref_cmd, void *stream);
+/* Plant step of the examples: state[b] <- EULER(state[b], u[b*u_stride .. +nu], dt), SRBD quaternion renormalised
+ * (dsrbd_example.py:158-160, dlip_example.py:161-162).  state[B][nx] in place; u_stride in doubles (N*nu to use U[b][0]). */
+int sddp_plant_step(SddpHandle *h, int B, double *state, const double *u, long long u_stride, void *stream);
+
 /* Measured FP64 FMA rate of the device (microbenchmark, TFLOP/s); used as the roofline peak. */
 int sddp_fp64_peak_tflops(double *out, void *stream);
 

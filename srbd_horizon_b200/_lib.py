@@ -31,6 +31,9 @@ SYMBOLS = {
     "sddp_forward_pass": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int] + [_vp] * 12 + [_vp]),
     "sddp_defects": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sddp_solve_batch_host": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 12),
+    "sddp_set_gait_tables": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "sddp_mpc_advance": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "sddp_plant_step": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_longlong, _vp]),
     "sddp_fp64_peak_tflops": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), _vp]),
     "sddp_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
 }

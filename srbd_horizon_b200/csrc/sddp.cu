@@ -137,6 +137,54 @@ __global__ void __launch_bounds__(NT, MINB) defects_kernel(DevCfg c, int B, cons
     }
 }
 
+// ---- receding-horizon glue: schedule shift + gait fill, plant step
+template <class M>
+__global__ void mpc_advance_kernel(DevCfg c, int B, double* params, const int* action, int* counter, const double* cmd,
+                                   const double* tab /* l_cycle, l_switch, r_cycle, r_switch: 4 x 21 */) {
+    constexpr int NP = M::NP;
+    const int N = c.N;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B * NP) return;
+    const int b = g / NP, p = g % NP;
+    double* P = params + (size_t)b * (N + 1) * NP;
+    for (int j = 1; j <= N; j++) P[(size_t)(j - 1) * NP + p] = P[(size_t)j * NP + p];      // one node back
+    const int act = action[b], ref_id = counter[b] % 20;                                     // wpg.py:71
+    double* last = P + (size_t)N * NP;
+    constexpr bool srbd = (M::NP == 19);
+    constexpr int base = srbd ? 7 : 3;            // first (c_ref, cdot_switch) pair
+    if (p < 3) last[p] = cmd[3 * b + p];                                                     // dsrbd_example.py:115-122
+    else if (srbd && p < 6) last[p] = 0.0;                                                   // w_ref, wpg.py:81,90,95
+    else if (srbd && p == 6) last[p] = (act == 2) ? 0.0 : 1e2;                               // wpg.py:82,91,96
+    else if (p >= base && p < base + 8) {
+        const int i = (p - base) >> 1, is_sw = (p - base) & 1;
+        const bool left = i < 2;                                                             // contact_model = 2
+        if (act == 0) last[p] = tab[(left ? 0 : 42) + (is_sw ? 21 : 0) + ref_id];            // wpg.py:83-88
+        else if (act == 2) { if (is_sw) last[p] = 0.0; }                                     // wpg.py:92-93 (c_ref untouched)
+        else last[p] = is_sw ? 1.0 : 0.0;                                                    // wpg.py:97-99
+    }
+}
+__global__ void counter_inc_kernel(int B, int* counter) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) counter[b] += 1;                                                              // wpg.py:101
+}
+
+template <class M>
+__global__ void plant_step_kernel(DevCfg c, int B, double* state, const double* u, long long u_stride) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double x[NX], uu[NU], acc[M::NACC < 6 ? 6 : M::NACC], xn[NX];
+    for (int i = 0; i < NX; i++) x[i] = state[(size_t)b * NX + i];
+    for (int i = 0; i < NU; i++) uu[i] = u[(size_t)b * u_stride + i];
+    M::accel(c, x, uu, acc);
+    for (int i = 0; i < NX; i++) xn[i] = x[i] + c.dt * M::xdot_i(c, i, x, uu, acc);
+    if (M::NP == 19) {      // SRBD: state[3:7] /= norm (dsrbd_example.py:160)
+        const double n = sqrt(xn[3] * xn[3] + xn[4] * xn[4] + xn[5] * xn[5] + xn[6] * xn[6]);
+        for (int i = 3; i < 7; i++) xn[i] /= n;
+    }
+    for (int i = 0; i < NX; i++) state[(size_t)b * NX + i] = xn[i];
+}
+
 // FP64 FMA-rate microbenchmark: 8 independent chains per thread
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
     double v[8];
@@ -163,6 +211,7 @@ struct SddpHandle {
     double *ws_d, *ws_pack, *ws_xn, *ws_un, *ws_K, *ws_k;
     int* counter;
     unsigned long long* ztab;
+    double* gait;        // device copy of the four 21-entry wpg tables
     // staging for the *_host entry point
     void* stage; size_t stage_bytes;
     cudaStream_t st_in, st_cmp, st_out;
@@ -378,6 +427,7 @@ int sddp_destroy(SddpHandle* h) {
     if (!h) return 0;
     if (h->ws_d) cudaFree(h->ws_d);
     if (h->ztab) cudaFree(h->ztab);
+    if (h->gait) cudaFree(h->gait);
     if (h->stage) cudaFree(h->stage);
     if (h->st_in) cudaStreamDestroy(h->st_in);
     if (h->st_cmp) cudaStreamDestroy(h->st_cmp);
@@ -560,6 +610,47 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(h, SDDP_ECUDA, "solve_batch_host (sync): %s%s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)), "");
+    return 0;
+}
+
+int sddp_set_gait_tables(SddpHandle* h, const double* l_cycle, const double* l_switch, const double* r_cycle, const double* r_switch) {
+    if (!h) return SDDP_EINVAL;
+    if (!l_cycle || !l_switch || !r_cycle || !r_switch) return fail(h, SDDP_EINVAL, "%s%s", "set_gait_tables: four tables are required", "");
+    double tab[84];
+    for (int i = 0; i < 21; i++) { tab[i] = l_cycle[i]; tab[21 + i] = l_switch[i]; tab[42 + i] = r_cycle[i]; tab[63 + i] = r_switch[i]; }
+    if (!h->gait) CU(cudaMalloc((void**)&h->gait, sizeof(tab)));
+    CU(cudaMemcpy(h->gait, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int sddp_mpc_advance(SddpHandle* h, int B, double* params, const int32_t* action, int32_t* step_counter, const double* rdot_ref_cmd,
+                     void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (B < 0 || (B > 0 && (!params || !action || !step_counter || !rdot_ref_cmd))) return fail(h, SDDP_EINVAL, "%s%s", "mpc_advance: bad arguments", "");
+    if (!h->gait) return fail(h, SDDP_EINVAL, "%s%s", "mpc_advance: call sddp_set_gait_tables first", "");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int nx, nu, np, pack;
+    model_dims(h->cfg.model, nx, nu, np, pack);
+    const int threads = 128, grid = (B * np + threads - 1) / threads;
+    if (h->cfg.model == SDDP_MODEL_SRBD) mpc_advance_kernel<Srbd><<<grid, threads, 0, st>>>(h->dc, B, params, action, step_counter, rdot_ref_cmd, h->gait);
+    else mpc_advance_kernel<Lip><<<grid, threads, 0, st>>>(h->dc, B, params, action, step_counter, rdot_ref_cmd, h->gait);
+    counter_inc_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(B, step_counter);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int sddp_plant_step(SddpHandle* h, int B, double* state, const double* u, long long u_stride, void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (B < 0 || (B > 0 && (!state || !u))) return fail(h, SDDP_EINVAL, "%s%s", "plant_step: bad arguments", "");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 64, grid = (B + threads - 1) / threads;
+    if (h->cfg.model == SDDP_MODEL_SRBD) plant_step_kernel<Srbd><<<grid, threads, 0, st>>>(h->dc, B, state, u, u_stride);
+    else plant_step_kernel<Lip><<<grid, threads, 0, st>>>(h->dc, B, state, u, u_stride);
+    h->launches++;
+    CU(cudaGetLastError());
     return 0;
 }
 

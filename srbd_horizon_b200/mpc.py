@@ -36,3 +36,66 @@ def plant_step(ddp_solver, state: np.ndarray, u: np.ndarray) -> np.ndarray:
     if ddp_solver.cfg.model == MODEL_SRBD:
         f[3:7] /= np.linalg.norm(f[3:7])
     return f
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-side closed loop for a batch of robots (SURVEY.md section 8f, N1 + N2): the tick of the example
+# loops -- shift the schedule, write the gait entries of node N, solve, plant step -- without host round trips.
+ACTION_STEP, ACTION_STANCE, ACTION_JUMP = 0, 1, 2
+
+
+class BatchedMPC:
+    """B independent MPC loops on one GPU.  Per tick (dsrbd_example.py:84-160):
+    x0 <- state; references / contact plan one node back and node N filled from the gait tables
+    (`sddp_mpc_advance`, wpg.py:68-101); `sddp_solve_batch` warm-started from the previous solution;
+    state <- EULER(state, u_0) with the SRBD quaternion renormalised (`sddp_plant_step`)."""
+
+    def __init__(self, solver, x0, params, U0=None):
+        import ctypes
+
+        import torch
+
+        from . import _lib
+        from .wpg import gait_tables
+        self._ct, self._torch, self._lib = ctypes, torch, _lib
+        self.solver = solver
+        dev = solver.device
+        t = lambda a, dt=torch.float64: torch.as_tensor(a, dtype=dt, device=dev).contiguous()
+        self.state = t(x0).clone()
+        B = self.state.shape[0]
+        self.B = B
+        self.params = t(params).clone()
+        N, nx, nu = solver.N, solver.nx, solver.nu
+        self.X = self.state[:, None, :].repeat(1, N + 1, 1).contiguous()
+        self.U = t(U0).clone() if U0 is not None else torch.zeros((B, N, nu), dtype=torch.float64, device=dev)
+        self.step_counter = torch.zeros(B, dtype=torch.int32, device=dev)
+        c_init_z = float(solver.cfg.foot[2])
+        tabs = [np.ascontiguousarray(a, dtype=np.float64) for a in gait_tables(c_init_z)]
+        _lib.check(solver.L.sddp_set_gait_tables(solver.h, *[a.ctypes.data_as(ctypes.c_void_p) for a in tabs]), solver.h)
+        self.last = None
+
+    def _p(self, t):
+        return self._ct.c_void_p(t.data_ptr())
+
+    def advance_schedule(self, actions, rdot_ref_cmd):
+        torch = self._torch
+        s = self.solver
+        a = torch.as_tensor(actions, dtype=torch.int32, device=s.device).contiguous()
+        cmd = torch.as_tensor(rdot_ref_cmd, dtype=torch.float64, device=s.device).contiguous()
+        assert a.shape == (self.B,) and cmd.shape == (self.B, 3)
+        with torch.cuda.device(s.device):
+            self._lib.check(s.L.sddp_mpc_advance(s.h, self.B, self._p(self.params), self._p(a), self._p(self.step_counter),
+                                                 self._p(cmd), s._stream()), s.h)
+
+    def plant_step(self):
+        torch = self._torch
+        s = self.solver
+        with torch.cuda.device(s.device):
+            self._lib.check(s.L.sddp_plant_step(s.h, self.B, self._p(self.state), self._p(self.U), s.N * s.nu, s._stream()), s.h)
+
+    def tick(self, actions, rdot_ref_cmd, gains: bool = False):
+        """One closed-loop tick for all B robots; returns the BatchResult of the solve (X, U alias the warm start)."""
+        self.advance_schedule(actions, rdot_ref_cmd)
+        self.last = self.solver.solve(self.state, self.params, self.X, self.U, gains=gains, history=False, inplace=True)
+        self.plant_step()
+        return self.last
