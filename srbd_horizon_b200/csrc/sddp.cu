@@ -551,6 +551,9 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         if (e != cudaSuccess) return fail(h, SDDP_ENOMEM, "cudaMalloc(staging): %s%s", cudaGetErrorString(e), "");
         h->stage_bytes = bytes;
     }
+    // The handle's workspace serves one solve at a time; this entry point runs on its own streams, so work the
+    // caller queued earlier on other streams with the same handle must finish first.
+    CU(cudaDeviceSynchronize());
     if (!h->st_in) {
         CU(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->st_cmp, cudaStreamNonBlocking));

@@ -17,6 +17,9 @@
 #pragma once
 #include "sddp_model.cuh"
 
+#ifndef SDDP_FIRST_WAVE_SINGLE
+#define SDDP_FIRST_WAVE_SINGLE 1
+#endif
 constexpr int NT = 128;      // threads per CTA
 constexpr int NWARP = NT / 32;
 constexpr int NCAND = NWARP; // line-search candidates evaluated per wave
@@ -511,13 +514,21 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
         bool accepted = false;
         double alpha = a0, Jn = J, alpha_acc = 0.0, rho_acc = 0.0;
         int sel = 0;
+        bool first_wave = true;
         while (!accepted && alpha >= c.alpha_min) {
+            // The first wave tries alpha_0 alone: it is accepted in the vast majority of iterations, and the three
+            // spared rollouts leave issue slots and shared-memory bandwidth to the co-resident CTAs.  Later waves
+            // evaluate NCAND candidates in parallel; the accepted step is the same as with sequential backtracking.
+            const int wave = (first_wave && SDDP_FIRST_WAVE_SINGLE) ? 1 : NCAND;
+            first_wave = false;
             int ncand = 0;
             double al[NCAND];
             for (int j = 0; j < NCAND; j++) {
                 al[j] = alpha;
-                if (alpha >= c.alpha_min) ncand++;
-                alpha *= c.ls_factor;
+                if (j < wave) {
+                    if (alpha >= c.alpha_min) ncand++;
+                    alpha *= c.ls_factor;
+                }
             }
             __syncthreads();
             if (tid < NCAND) { S.alpha[tid] = al[tid]; S.rho[tid] = fixed ? c.rho_fixed : al[tid]; }
