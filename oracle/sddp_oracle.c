@@ -642,23 +642,37 @@ int orc_backward(const OrcConfig *c, const double *X, const double *U, const dou
         tot += g1 + 0.5 * g2;
         for (int i = 0; i < nx; i++) ys[i] = fixed_rho ? y[i] + s[i] : y[i];
         if (fixed_rho) acc1 += yg + 0.5 * g2;
-        /* T = Vxx' fx, Tu = Vxx' fu */
+        /* T = Vxx' fx, Tu = Vxx' fu   (loops ordered i-l-j: unit-stride inner loop, same summation order over l) */
         for (int i = 0; i < nx; i++) {
-            for (int j = 0; j < nx; j++) { double t = 0; for (int l = 0; l < nx; l++) t += Vxx[i * nx + l] * fx[l * nx + j]; T[i * nx + j] = t; }
-            for (int j = 0; j < nu; j++) { double t = 0; for (int l = 0; l < nx; l++) t += Vxx[i * nx + l] * fu[l * nu + j]; Tu[i * nu + j] = t; }
+            for (int j = 0; j < nx; j++) T[i * nx + j] = 0.0;
+            for (int j = 0; j < nu; j++) Tu[i * nu + j] = 0.0;
+            for (int l = 0; l < nx; l++) {
+                const double v = Vxx[i * nx + l];
+                for (int j = 0; j < nx; j++) T[i * nx + j] += v * fx[l * nx + j];
+                for (int j = 0; j < nu; j++) Tu[i * nu + j] += v * fu[l * nu + j];
+            }
         }
         for (int i = 0; i < nx; i++) {
             double t = lx[i];
             for (int l = 0; l < nx; l++) t += fx[l * nx + i] * vp[l];
             Qx[i] = t;
-            for (int j = 0; j < nx; j++) { double q = lxx[i * nx + j]; for (int l = 0; l < nx; l++) q += fx[l * nx + i] * T[l * nx + j]; Qxx[i * nx + j] = q; }
+            for (int j = 0; j < nx; j++) Qxx[i * nx + j] = lxx[i * nx + j];
+            for (int l = 0; l < nx; l++) {
+                const double v = fx[l * nx + i];
+                for (int j = 0; j < nx; j++) Qxx[i * nx + j] += v * T[l * nx + j];
+            }
         }
         for (int i = 0; i < nu; i++) {
             double t = lu[i];
             for (int l = 0; l < nx; l++) t += fu[l * nu + i] * vp[l];
             Qu[i] = t;
-            for (int j = 0; j < nx; j++) { double q = lux[i * nx + j]; for (int l = 0; l < nx; l++) q += fu[l * nu + i] * T[l * nx + j]; Qux[i * nx + j] = q; }
-            for (int j = 0; j < nu; j++) { double q = luu[i * nu + j]; for (int l = 0; l < nx; l++) q += fu[l * nu + i] * Tu[l * nu + j]; Quu[i * nu + j] = q; }
+            for (int j = 0; j < nx; j++) Qux[i * nx + j] = lux[i * nx + j];
+            for (int j = 0; j < nu; j++) Quu[i * nu + j] = luu[i * nu + j];
+            for (int l = 0; l < nx; l++) {
+                const double v = fu[l * nu + i];
+                for (int j = 0; j < nx; j++) Qux[i * nx + j] += v * T[l * nx + j];
+                for (int j = 0; j < nu; j++) Quu[i * nu + j] += v * Tu[l * nu + j];
+            }
         }
         for (int i = 0; i < nu; i++) for (int j = 0; j < i; j++) { /* symmetrise Quu */
             double m_ = 0.5 * (Quu[i * nu + j] + Quu[j * nu + i]);
@@ -699,14 +713,19 @@ int orc_backward(const OrcConfig *c, const double *X, const double *U, const dou
         }
         /* Tu(reuse as QuuK: nu x nx) */
         double *QuuK = Tu;
-        for (int i = 0; i < nu; i++) for (int j = 0; j < nx; j++) {
-            double t = 0; for (int l = 0; l < nu; l++) t += Quu[i * nu + l] * Kk[l * nx + j];
-            QuuK[i * nx + j] = t;
+        for (int i = 0; i < nu; i++) {
+            for (int j = 0; j < nx; j++) QuuK[i * nx + j] = 0.0;
+            for (int l = 0; l < nu; l++) {
+                const double v = Quu[i * nu + l];
+                for (int j = 0; j < nx; j++) QuuK[i * nx + j] += v * Kk[l * nx + j];
+            }
         }
-        for (int i = 0; i < nx; i++) for (int j = 0; j < nx; j++) {
-            double t = Qxx[i * nx + j];
-            for (int l = 0; l < nu; l++) t += Kk[l * nx + i] * (QuuK[l * nx + j] + Qux[l * nx + j]) + Qux[l * nx + i] * Kk[l * nx + j];
-            T[i * nx + j] = t;
+        for (int i = 0; i < nx; i++) {
+            for (int j = 0; j < nx; j++) T[i * nx + j] = Qxx[i * nx + j];
+            for (int l = 0; l < nu; l++) {
+                const double ki = Kk[l * nx + i], qi = Qux[l * nx + i];
+                for (int j = 0; j < nx; j++) T[i * nx + j] += ki * (QuuK[l * nx + j] + Qux[l * nx + j]) + qi * Kk[l * nx + j];
+            }
         }
         for (int i = 0; i < nx; i++) for (int j = 0; j < nx; j++) Vxx[i * nx + j] = 0.5 * (T[i * nx + j] + T[j * nx + i]);
     }

@@ -1,0 +1,108 @@
+"""Edge cases of the CUDA path against the oracle: shortest and long horizons, tiny batches, iteration caps,
+non-finite inputs, and BASELINE configs[3] (multiple shooting with a fixed defect contraction rate) at full size."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from srbd_horizon_b200.config import DIMS, MODEL_LIP, MODEL_SRBD, STATUS_MAX_ITERS, make_config
+from srbd_horizon_b200.ddp import BatchedDDP
+from srbd_horizon_b200.problems import make_batch
+from tests.helpers import relerr
+
+EX = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}
+cpu = lambda t: t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("model", [MODEL_SRBD, MODEL_LIP])
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 64])
+def test_horizon_lengths(model, N):
+    B = 3
+    cfg = make_config(model, N, 0.05, EX)
+    b = make_batch(model, N, B, x_noise=0.01)
+    r = BatchedDDP(cfg).solve(b["x0"], b["params"], b["X0"], b["U0"])
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"])
+    np.testing.assert_array_equal(cpu(r.iters), ro["iters"])
+    np.testing.assert_array_equal(cpu(r.status), ro["status"])
+    assert relerr(cpu(r.X), ro["X"]) < 1e-9 and relerr(cpu(r.U), ro["U"]) < 1e-9
+    assert relerr(cpu(r.cost), ro["cost"]) < 1e-9
+
+
+def test_iteration_cap_and_alpha_threshold():
+    """max_iters = 1 / 2 stops with MAX_ITERS exactly like the oracle; the adapter's default threshold 1e-1 (ddp.py:23)
+    gives four candidate step sizes -- one wave."""
+    for opts in ({"max_iters": 1}, {"max_iters": 2}, {"max_iters": 3, "alpha_converge_threshold": 1e-1, "beta": 1e-4}):
+        cfg = make_config(MODEL_SRBD, 20, 0.05, opts)
+        b = make_batch(MODEL_SRBD, 20, 4, x_noise=0.01)
+        r = BatchedDDP(cfg).solve(b["x0"], b["params"], b["X0"], b["U0"])
+        ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"])
+        np.testing.assert_array_equal(cpu(r.status), ro["status"])
+        np.testing.assert_array_equal(cpu(r.iters), ro["iters"])
+        assert (ro["status"] == STATUS_MAX_ITERS).any()
+        assert relerr(cpu(r.X), ro["X"]) < 1e-9 and relerr(cpu(r.hist)[..., 0], ro["hist"][..., 0]) < 1e-9
+
+
+def test_non_finite_problem_does_not_poison_the_batch():
+    """A NaN initial state fails its own problem (status != 0) and leaves its neighbours bit-identical."""
+    cfg = make_config(MODEL_SRBD, 20, 0.05, EX)
+    b = make_batch(MODEL_SRBD, 20, 6)
+    s = BatchedDDP(cfg)
+    good = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    x0 = b["x0"].copy(); X0 = b["X0"].copy()
+    x0[2, 0] = np.nan; X0[2, :, 0] = np.nan
+    bad = s.solve(x0, b["params"], X0, b["U0"])
+    st = cpu(bad.status)
+    assert st[2] != 0
+    keep = [0, 1, 3, 4, 5]
+    assert (st[keep] == 0).all()
+    np.testing.assert_array_equal(cpu(bad.X)[keep], cpu(good.X)[keep])
+    ro = O.solve_batch(cfg, x0, b["params"], X0, b["U0"])
+    assert ro["status"][2] == st[2]
+
+
+def test_line_search_beyond_the_first_wave():
+    """A poor warm start (large input noise) needs step sizes below 1: later waves of four candidates must pick the
+    same alpha as the oracle's sequential backtracking (T8)."""
+    cfg = make_config(MODEL_SRBD, 20, 0.05, dict(EX, multiple_shooting=0))
+    b = make_batch(MODEL_SRBD, 20, 16)
+    rng = np.random.default_rng(0)
+    U0 = b["U0"] + rng.normal(0, 0.05, b["U0"].shape)
+    r = BatchedDDP(cfg).solve(b["x0"], b["params"], b["X0"], U0)
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], U0, nthreads=4)
+    h, ho = cpu(r.hist), ro["hist"]
+    np.testing.assert_array_equal(cpu(r.iters), ro["iters"])
+    np.testing.assert_array_equal(h[..., 1], ho[..., 1])
+    assert ((ho[..., 1] > 0) & (ho[..., 1] < 1)).any(), "the case must exercise alpha < 1"
+    ok = ro["status"] != 3
+    assert relerr(cpu(r.X)[ok], ro["X"][ok]) < 1e-9
+
+
+def test_config3_fixed_contraction_full_size_properties():
+    """BASELINE configs[3]: multiple shooting, fixed defect contraction rate, SRBD, batch 16K, N = 50.  Without an
+    oracle at this size: after k accepted steps every defect is (1 - rho)^k times its initial value, and the first
+    512 problems agree with the oracle."""
+    B, N, rho = 16384, 50, 0.5
+    cfg = make_config(MODEL_SRBD, N, 0.05, dict(EX, defect_contraction_rate=rho))
+    b = make_batch(MODEL_SRBD, N, B, x_noise=0.01)
+    s = BatchedDDP(cfg)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")
+    x0, p, X0, U0 = t(b["x0"]), t(b["params"]), t(b["X0"]), t(b["U0"])
+    X0[:, 0] = x0
+    D0, _ = s.defects(X0, U0, p)
+    r = s.solve(x0, p, X0, U0, gains=False)
+    iters, status = cpu(r.iters), cpu(r.status)
+    assert (status == 0).mean() > 0.99
+    hist = cpu(r.hist)
+    d0 = cpu(D0.abs().amax(dim=(1, 2)))
+    for i in range(0, B, 257):
+        n = iters[i]
+        steps = np.cumsum(hist[i, :n, 1] > 0)
+        np.testing.assert_allclose(hist[i, :n, 3], d0[i] * (1 - rho) ** steps, rtol=1e-12, atol=1e-300)
+    D, J = s.defects(r.X, r.U, p)
+    conv = torch.as_tensor(status == 0, device="cuda")
+    assert float(D.abs().amax(dim=(1, 2))[conv].max()) <= cfg.defect_ths * 1.0001
+    ro = O.solve_batch(cfg, b["x0"][:512], b["params"][:512], b["X0"][:512], b["U0"][:512], nthreads=16)
+    np.testing.assert_array_equal(iters[:512], ro["iters"])
+    assert relerr(cpu(r.X)[:512], ro["X"]) < 1e-9 and relerr(cpu(r.U)[:512], ro["U"]) < 1e-9
