@@ -63,20 +63,18 @@ def test_non_finite_problem_does_not_poison_the_batch():
 
 
 def test_line_search_beyond_the_first_wave():
-    """A poor warm start (large input noise) needs step sizes below 1: later waves of four candidates must pick the
-    same alpha as the oracle's sequential backtracking (T8)."""
-    cfg = make_config(MODEL_SRBD, 20, 0.05, dict(EX, multiple_shooting=0))
-    b = make_batch(MODEL_SRBD, 20, 16)
-    rng = np.random.default_rng(0)
-    U0 = b["U0"] + rng.normal(0, 0.05, b["U0"].shape)
-    r = BatchedDDP(cfg).solve(b["x0"], b["params"], b["X0"], U0)
-    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], U0, nthreads=4)
+    """A poor warm start (10 cm / 0.1 m/s noise on the state guess) needs step sizes down to 1/32: the later waves of
+    four candidates must pick the same alpha as the oracle's sequential backtracking (T8)."""
+    cfg = make_config(MODEL_SRBD, 20, 0.05, EX)
+    b = make_batch(MODEL_SRBD, 20, 16, x_noise=0.1)
+    r = BatchedDDP(cfg).solve(b["x0"], b["params"], b["X0"], b["U0"])
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=4)
     h, ho = cpu(r.hist), ro["hist"]
     np.testing.assert_array_equal(cpu(r.iters), ro["iters"])
     np.testing.assert_array_equal(h[..., 1], ho[..., 1])
-    assert ((ho[..., 1] > 0) & (ho[..., 1] < 1)).any(), "the case must exercise alpha < 1"
-    ok = ro["status"] != 3
-    assert relerr(cpu(r.X)[ok], ro["X"][ok]) < 1e-9
+    small = ho[..., 1][(ho[..., 1] > 0) & (ho[..., 1] < 1)]
+    assert small.size >= 5 and small.min() <= 1.0 / 16, "the case must exercise several waves"
+    assert relerr(cpu(r.X), ro["X"]) < 1e-9 and relerr(cpu(r.U), ro["U"]) < 1e-9
 
 
 def test_config3_fixed_contraction_full_size_properties():
