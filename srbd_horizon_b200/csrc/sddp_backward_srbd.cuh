@@ -16,17 +16,19 @@
 //   T, Qxx, Qux (they do not depend on the factor).  Then one thread per right-hand side applies
 //   Lt^-1 to [Qux | Qu | I] with no barrier at all: frozen rows U = Lt^-1 [Qux Qu], E = Lt^-1.
 //   With rs = D^-1/2:  Wn = rs.U (= L^-1 [Qux Qu] of the Cholesky form), Es = rs.E
-//   K = -Es^T Wn  (matmul over all threads, no substitution chain)
-//   [Vxx Vx; . |w0|^2] = [sym(Qxx) Qx; . 0] - Wn^T Wn   (3x3 register tiles over the 39x39 product)
+//   K = -Es^T Wn  and  [Vxx Vx; . |w0|^2] = [sym(Qxx) Qx; . 0] - Wn^T Wn  on the FP64 tensor cores
+//   (mma.sync m8n8k4 f64, 8x8 tiles, fragments straight from shared memory: two 8-byte loads feed 256 FMA,
+//   where a 3x3 register tile needs six loads for nine -- these products were shared-memory-bandwidth bound)
 // Node inputs (x, u, p, d, pack) of node k-1 are fetched with cp.async while node k is processed.
 #pragma once
 #include "sddp_solver.cuh"
 
 struct alignas(16) SmemSrbd {
-    static constexpr int NX = 37, NU = 24, NP = 19, LDW = 39;
+    static constexpr int NX = 37, NU = 24, NP = 19;
+    static constexpr int LDW = 44;   // row pitch of W: 88 words = 24 mod 32, so the 4 x 8 DMMA fragment loads are conflict free
     double VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
     double Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
-    double W[NU * LDW];        // [Qux | w0 | 0] -> Wn
+    double W[NU * LDW];        // [Qux | w0 | 0 ...] -> Wn
     double Quu[NU * NU];       // Quu -> (strict upper) D Lt^T = frozen raw columns, (lower) Es
     double Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
     double Qu[NU], quy[NU], kk[NU], invp[NU], rs[NU];
@@ -41,17 +43,15 @@ struct alignas(16) SmemSrbd {
     __device__ static int backward(const DevCfg& c, SmemSrbd& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
 };
-static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 39, "forward K double buffer must fit in Qxx + W");
+static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 44, "forward K double buffer must fit in Qxx + W");
 enum { R_SW = 6 };
-// upper-triangular 3x3 tiles of the 39x39 product (13 x 13 tile grid): tile t -> (ti, tj), ti <= tj
-__device__ const unsigned char kTileI[91] = {
-    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3,
-    4, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 9, 9, 9, 9, 10, 10, 10, 11, 11, 12};
-__device__ const unsigned char kTileJ[91] = {
-    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12,
-    4, 5, 6, 7, 8, 9, 10, 11, 12, 5, 6, 7, 8, 9, 10, 11, 12, 6, 7, 8, 9, 10, 11, 12, 7, 8, 9, 10, 11, 12, 8, 9, 10, 11, 12, 9, 10, 11, 12, 10, 11, 12, 11, 12, 12};
-
 SDDP_DEV void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Fragments (PTX ISA, m8n8k4 .f64): lane holds
+// A[lane/4][lane%4], B[lane%4][lane/4], C[lane/4][2*(lane%4) + {0,1}].
+SDDP_DEV void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // 1/p from the hardware double-precision seed (MUFU.RCP64H, ~20 bits) and two Newton steps (about 2 ulp).
 // The pivot chain of the factorisation is latency critical; a full IEEE division is ~3x longer.
@@ -367,54 +367,62 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         PROF(11);
         if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; cp_wait_all(); __syncthreads(); return k + 1; }
 
-        // ---- f: [Vxx Vx] = [sym(Qxx) Qx] - Wn^T Wn, 3x3 register tiles of the upper triangle (into VT)
-        if (tid < 91) {
-            const int ti = kTileI[tid], tj = kTileJ[tid];
-            double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll 4
-            for (int l = 0; l < NU; l++) {
-                const double* r = S.W + l * LDW;
-                const double u0 = r[3 * ti], u1 = r[3 * ti + 1], u2 = r[3 * ti + 2];
-                const double v0 = r[3 * tj], v1 = r[3 * tj + 1], v2 = r[3 * tj + 2];
-                acc[0][0] += u0 * v0; acc[0][1] += u0 * v1; acc[0][2] += u0 * v2;
-                acc[1][0] += u1 * v0; acc[1][1] += u1 * v1; acc[1][2] += u1 * v2;
-                acc[2][0] += u2 * v0; acc[2][1] += u2 * v1; acc[2][2] += u2 * v2;
-            }
+        // ---- f: [Vxx Vx] = [sym(Qxx) Qx] - Wn^T Wn: upper-triangular 8x8 tiles of the 40x40 product, K = 24 in six
+        //         DMMA steps; warp w takes tiles w, w+4, ...  Results go to VT (T is dead), Vx and red[R_SW] = |w0|^2.
+        {
+            const int fr = lane >> 2, fc = lane & 3;       // fragment row / column of this lane
+            for (int t = warp; t < 15; t += NWARP) {
+                int I = 0, rem = t;
+                while (rem >= 5 - I) { rem -= 5 - I; I++; }
+                const int J = I + rem;
+                double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-            for (int p = 0; p < 3; p++)
+                for (int k0 = 0; k0 < NU; k0 += 4) {
+                    const double* r = S.W + (k0 + fc) * LDW + fr;
+                    dmma884(c0, c1, r[8 * I], r[8 * J]);
+                }
+                const int gi = 8 * I + fr;
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    const int gi = 3 * ti + p, gj = 3 * tj + q;
+                for (int e = 0; e < 2; e++) {
+                    const int gj = 8 * J + 2 * fc + e;
+                    const double acc = e ? c1 : c0;
                     if (gj < gi) continue;
                     if (gj < NX) {
-                        const double v = 0.5 * (S.Qxx[gi * NX + gj] + S.Qxx[gj * NX + gi]) - acc[p][q];
+                        const double v = 0.5 * (S.Qxx[gi * NX + gj] + S.Qxx[gj * NX + gi]) - acc;
                         S.VT[gi * NX + gj] = v;
                         S.VT[gj * NX + gi] = v;
                     } else if (gj == NX) {
-                        if (gi < NX) S.Vx[gi] = S.Qx[gi] - acc[p][q];
-                        else S.red[R_SW] = acc[p][q];            // |w0|^2
+                        if (gi < NX) S.Vx[gi] = S.Qx[gi] - acc;
+                        else S.red[R_SW] = acc;            // |w0|^2
                     }
                 }
-        }
-        // ---- g: K = -Es^T Wn (column c of [K | k], interleaved row groups), y partial sums
-        if (tid < 38 * 3) {
-            const int cc = tid % 38, g = tid / 38;
-            double wn[NU];
-#pragma unroll
-            for (int l = 0; l < NU; l++) wn[l] = S.W[l * LDW + cc];
-            double yp = 0.0;
-#pragma unroll
-            for (int r8 = 0; r8 < 8; r8++) {
-                const int i = g + 3 * r8;
-                double s = 0.0;
-#pragma unroll
-                for (int l = 3 * r8; l < NU; l++) s += (l >= i ? S.Quu[l * NU + i] : 0.0) * wn[l];   // Es is lower triangular
-                const double kv = -s;
-                yp += kv * S.quy[i];
-                if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
-                else { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
             }
-            S.ypart[g][cc] = yp;
+            // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
+            //         at k0 = 8 I and entries above the diagonal are masked (that part of S.Quu holds the raw factor).
+            for (int t = warp; t < 15; t += NWARP) {
+                const int I = t / 5, J = t % 5;
+                const int i = 8 * I + fr;
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < NU; k0 += 4) {
+                    if (k0 < 8 * I) continue;
+                    const int l = k0 + fc;
+                    const double a = (l >= i) ? S.Quu[l * NU + i] : 0.0;
+                    dmma884(c0, c1, a, S.W[l * LDW + 8 * J + fr]);
+                }
+                const double q = S.quy[i];
+                double y0 = -c0 * q, y1 = -c1 * q;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int cc = 8 * J + 2 * fc + e;
+                    const double kv = e ? -c1 : -c0;
+                    if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
+                    else if (cc == NX) { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) { y0 += __shfl_xor_sync(FULL, y0, o); y1 += __shfl_xor_sync(FULL, y1, o); }
+                if (fr == 0) { S.ypart[I][8 * J + 2 * fc] = y0; S.ypart[I][8 * J + 2 * fc + 1] = y1; }
+            }
         }
         __syncthreads();
         PROF(13);
