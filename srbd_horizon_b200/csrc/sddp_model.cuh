@@ -214,19 +214,16 @@ struct Srbd {
     }
 
     SDDP_DEV static double xdot_i(const DevCfg& c, int i, const double* x, const double* u, const double* acc) {
-        if (i < 3) return x[XRD + i];
-        if (i < 7) {   // odot = quat_prod([w/2, 0], o)
-            const double* o = x + XO;
-            const double* w = x + XW;
-            if (i == 6) return -0.5 * (w[0] * o[0] + w[1] * o[1] + w[2] * o[2]);
-            int a = i - 3, b = (a + 1) % 3, d = (a + 2) % 3;
-            return 0.5 * (o[3] * w[a] + (w[b] * o[d] - w[d] * o[b]));
-        }
-        if (i < 19) return x[i + 18];
-        if (i < 22) return acc[3 + (i - 19)];
-        if (i < 25) return acc[i - 22];
-        int j = (i - 25) / 3, k = (i - 25) % 3;
-        return u[6 * j + k];
+        if (i < 3 || (i >= XC && i < XRD)) return x[i + (i < 3 ? XRD : XCD - XC)];        // rdot, cdot_j
+        if (i >= XRD && i < XCD) return acc[i < XW ? i - XRD + 3 : i - XW];               // rddot, wdot
+        if (i >= XCD) { const int j = (i - XCD) / 3; return u[i - XCD + 3 * j]; }          // cddot_j = u[6 j + k]
+        // odot = quat_prod([w/2, 0], o)  (world-aligned angular velocity, prb.py:107-108)
+        const double* o = x + XO;
+        const double* w = x + XW;
+        const int a = i - XO;
+        if (a == 3) return -0.5 * (w[0] * o[0] + w[1] * o[1] + w[2] * o[2]);
+        const int b2 = a == 2 ? 0 : a + 1, d = a == 0 ? 2 : a - 1;
+        return 0.5 * (o[3] * w[a] + (w[b2] * o[d] - w[d] * o[b2]));
     }
 
     // quaternion error rows: quat_prod(o, oref) = E(oref) o        (prb.py:187)
@@ -238,42 +235,58 @@ struct Srbd {
         return -m3::skew_ab(q, i, a);
     }
 
-    SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double* acc) {
+    // parts: 1 = terms indexed by the state, 2 = terms indexed by the input, 4 = rddot / wdot terms (need accel)
+    SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double* acc,
+                                     int parts = 7) {
         double s = 0.0;
-        for (int i = lane; i < NX; i += 32) {
-            if (kind != NODE_FIRST) {   // nodes 1..N: prb.py:184-199
-                if (i == 2) { double r = x[2] - c.com[2]; s += c.w_r * r * r; }
-                else if (i >= 3 && i < 7) {
-                    const double* q = p + 15;
-                    const double* o = x + XO;
-                    int a = i - 3;
-                    double r = E_row(q, a, 0) * o[0] + E_row(q, a, 1) * o[1] + E_row(q, a, 2) * o[2] + E_row(q, a, 3) * o[3] - (a == 3 ? 1.0 : 0.0);
-                    s += p[6] * p[6] * r * r;
-                } else if (i >= 7 && i < 13 && (i - 7) % 3 < 2) {
-                    int j = (i - 7) / 3, ax = (i - 7) % 3;
-                    double r = -x[i] + x[i + 6] - c.drel[j][ax];
-                    s += c.w_rel * r * r;
-                } else if (i >= 19 && i < 22) { double r = x[i] - p[i - 19]; s += c.w_rdot * r * r; }
-                else if (i >= 22 && i < 25) { double r = x[i] - p[3 + i - 22]; s += c.w_w * r * r; }
-            }
-            if (kind != NODE_TERM) {    // equality constraints on nodes 0..N-1: prb.py:166-181, ddp.py:191-196
-                if (i >= 7 && i < 19 && (i - 7) % 3 == 2) { double r = x[i] - p[7 + 2 * ((i - 7) / 3)]; s += c.cw * r * r; }
-                else if (i >= 25 && (i - 25) % 3 < 2) {
-                    int j = (i - 25) / 3;
-                    double r = p[8 + 2 * j] * x[i];
-                    s += c.cw * r * r;
-                    if (j == 0 || j == 2) { double r2 = x[i] - x[i + 3]; s += c.cw * r2 * r2; }
+        if (parts & 1) {
+            const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
+            for (int i = lane; i < NX; i += 32) {
+                if (i == 2 || (i >= XRD && i < XCD)) {                     // rz / rdot / w tracking (prb.py:184,190-191)
+                    if (track) {
+                        const double ref = (i == 2) ? c.com[2] : p[i - XRD];            // rdot_ref = p[0:3], w_ref = p[3:6]
+                        const double wg = (i == 2) ? c.w_r : (i < XW ? c.w_rdot : c.w_w);
+                        const double r = x[i] - ref;
+                        s += wg * r * r;
+                    }
+                } else if (i >= XO && i < XC) {                            // otg * (quat_prod(o, oref) - [0,0,0,1])  (prb.py:185-189)
+                    if (track) {
+                        const double* q = p + 15;
+                        const double* o = x + XO;
+                        const int a = i - XO;
+                        double r;
+                        if (a == 3) r = o[3] * q[3] - (o[0] * q[0] + o[1] * q[1] + o[2] * q[2]) - 1.0;
+                        else {
+                            const int b2 = a == 2 ? 0 : a + 1, d = a == 0 ? 2 : a - 1;
+                            r = o[3] * q[a] + q[3] * o[a] + (o[b2] * q[d] - o[d] * q[b2]);
+                        }
+                        s += p[6] * p[6] * r * r;
+                    }
+                } else if (i >= XC) {                                      // contact points and their velocities
+                    const bool vel = i >= XCD;
+                    const int e = i - (vel ? XCD : XC), foot = e / 3, ax = e - 3 * foot;
+                    if (!vel && ax == 2) {                                 // cz_tracking (prb.py:180)
+                        if (input) { const double r = x[i] - p[7 + 2 * foot]; s += c.cw * r * r; }
+                    } else if (ax < 2) {
+                        if (vel && input) { const double r = p[8 + 2 * foot] * x[i]; s += c.cw * r * r; }      // cdotxy_tracking (:181)
+                        // pair terms: rel_pos (c_j, c_j+2), j < 2 (prb.py:192-199) / relative_vel (cdot_0,1), (cdot_2,3) (:166-170)
+                        const bool pair = vel ? ((foot & 1) == 0 && input) : (foot < 2 && track);
+                        if (pair) {
+                            const double r = x[i + (vel ? 3 : 6)] - x[i] - (vel ? 0.0 : c.drel[foot][ax]);
+                            s += (vel ? c.cw : c.w_rel) * r * r;
+                        }
+                    }
                 }
             }
         }
         if (kind != NODE_TERM) {        // nodes 0..N-1: prb.py:200-204
-            if (lane < NU) {
+            if ((parts & 2) && lane < NU) {
                 int i = lane / 6, r = lane % 6;
                 double v = u[lane];
                 if (r < 3) s += c.gq * v * v;
                 else { double a = 1.0 - p[8 + 2 * i]; s += (c.w_minf + c.w_fsw * a * a) * v * v; }
             }
-            if (lane < 3) s += c.gq * (acc[lane] * acc[lane] + acc[3 + lane] * acc[3 + lane]);
+            if ((parts & 4) && lane < 3) s += c.gq * (acc[lane] * acc[lane] + acc[3 + lane] * acc[3 + lane]);
         }
         return s;
     }
@@ -719,9 +732,10 @@ struct Lip {
         if (i < 18) { int k = i - 15; return c.eta2 * (x[k] - u[k]) - (k == 2 ? c.g : 0.0); }   // prb.py:317-318
         return u[3 + i - 18];
     }
-    SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double*) {
+    SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double*,
+                                     int parts = 7) {
         double s = 0.0;
-        if (lane < NX) {
+        if ((parts & 1) && lane < NX) {
             int i = lane;
             if (kind != NODE_FIRST) {   // prb.py:390-392, 394-401
                 if (i == 2) { double r = x[2] - c.com[2]; s += c.w_r * r * r; }
@@ -742,7 +756,7 @@ struct Lip {
                 }
             }
         }
-        if (kind != NODE_TERM && lane < NU) {   // prb.py:393, 402
+        if ((parts & 2) && kind != NODE_TERM && lane < NU) {   // prb.py:393, 402
             if (lane < 3) {
                 int k = lane;
                 double r = u[k] - 0.25 * (x[3 + k] + x[6 + k] + x[9 + k] + x[12 + k]);

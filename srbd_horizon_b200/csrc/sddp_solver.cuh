@@ -396,6 +396,71 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
     };
     __syncthreads();      // the buffers may still be in use by the caller's previous phase
     prefetch(0);
+    if (ncand == 1) {
+        // One candidate (the usual first wave): its work is spread over the warps instead of leaving three idle.
+        // Per node: warp 0 forms u = U + alpha k + K dx; then warp 0 integrates (accel, Euler step) while warp 1 sums
+        // the state-indexed cost terms and warp 2 the input-indexed ones.  Two block barriers per node.
+        double* xb[2] = {S.scr(), S.scr() + NX};       // x^_k ping-pong
+        double* ub = S.scr() + 2 * NX;
+        for (int i = tid; i < NX; i += NT) xb[0][i] = x0[i];
+        double Jw = 0.0;
+        for (int k = 0; k < N; k++) {
+            cp_wait_all();
+            __syncthreads();                  // node k landed; everyone is done with node k-1
+            if (k + 1 < N) prefetch(k + 1);
+            else {
+                double* nbt = S.nb[(k + 1) & 1];
+                for (int i = tid; i < NP; i += NT) cp_async8(nbt + NBL::OP + i, P + (size_t)N * NP + i);
+                cp_commit();
+            }
+            const double* nb = S.nb[k & 1];
+            const double* xc = xb[k & 1];
+            if (w == 0) {
+                const double* Kb = S.Kbuf(k & 1);
+                const double* xk = nb + NBL::OX;
+                for (int j = lane; j < NU; j += 32) {
+                    double t = 0.0;
+                    for (int i = 0; i < NX; i++) t += Kb[j * NX + i] * (xc[i] - xk[i]);
+                    const double v = nb[NBL::OU + j] + alpha * nb[NBL::OK + j] + t;
+                    ub[j] = v;
+                    Un[(size_t)k * NU + j] = v;
+                }
+                for (int i = lane; i < NX; i += 32) Xn[(size_t)k * NX + i] = xc[i];
+            }
+            __syncthreads();                  // u^_k visible
+            const int kind = node_kind(k, N);
+            if (w == 0) {
+                double* xn_ = xb[(k + 1) & 1];
+                if (M::NACC > 1) {
+                    double acc[M::NACC];
+                    M::accel(c, xc, ub, acc);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < M::NACC; q++) S.sacc[0][q] = acc[q];
+                    }
+                    __syncwarp();
+                }
+                Jw += M::cost_lane(c, kind, lane, xc, ub, nb + NBL::OP, S.sacc[0], 4);
+                for (int i = lane; i < NX; i += 32)
+                    xn_[i] = xc[i] + c.dt * M::xdot_i(c, i, xc, ub, S.sacc[0]) - omr * nb[NBL::OD + i];
+            } else if (w == 1) {
+                Jw += M::cost_lane(c, kind, lane, xc, ub, nb + NBL::OP, S.sacc[0], 1);
+            } else if (w == 2) {
+                Jw += M::cost_lane(c, kind, lane, xc, ub, nb + NBL::OP, S.sacc[0], 2);
+            }
+        }
+        cp_wait_all();
+        __syncthreads();
+        const double* xT = xb[N & 1];
+        if (w == 0) for (int i = lane; i < NX; i += 32) Xn[(size_t)N * NX + i] = xT[i];
+        if (w == 1) Jw += M::cost_lane(c, NODE_TERM, lane, xT, nullptr, S.nb[N & 1] + NBL::OP, S.sacc[0], 1);
+        Jw = warp_sum(Jw);
+        if (lane == 0) S.red[R_W0 + w] = Jw;
+        __syncthreads();
+        if (tid == 0) S.Jc[0] = S.red[R_W0] + S.red[R_W0 + 1] + S.red[R_W0 + 2];
+        __syncthreads();
+        return;
+    }
     for (int i = lane; i < NX; i += 32) xh[i] = x0[i];
     for (int k = 0; k < N; k++) {
         cp_wait_all();

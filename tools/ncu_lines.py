@@ -90,9 +90,9 @@ if len(sys.argv) > 4:
         "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 240, 271)],
         "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 272, 320)],
         "bwd d2 (RHS substitution)": [("sddp_backward_srbd.cuh", 321, 365)],
-        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 366, 398)],
-        "bwd K matmul": [("sddp_backward_srbd.cuh", 399, 419)],
-        "bwd mu path + model": [("sddp_backward_srbd.cuh", 420, 482)],
+        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 366, 399)],
+        "bwd K matmul": [("sddp_backward_srbd.cuh", 400, 427)],
+        "bwd mu path + model": [("sddp_backward_srbd.cuh", 428, 490)],
         "solve_one control": [("sddp_solver.cuh", 435, 635)],
     }
     tot_b = collections.Counter(); ex_b = collections.Counter(); wf_b = collections.Counter(); st_b = collections.defaultdict(collections.Counter)
