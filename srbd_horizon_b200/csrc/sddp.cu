@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) 
 #ifndef SDDP_ROTATE
 #define SDDP_ROTATE 0
 #endif
-    const int tid = SDDP_ROTATE ? ((threadIdx.x + 32 * ((blockIdx.x / a.sms) & 3)) & (NT - 1)) : threadIdx.x;
+    const int rot_ = SDDP_ROTATE == 1 ? ((blockIdx.x / a.sms) & 3) : (SDDP_ROTATE == 2 ? (blockIdx.x & 3) : 0);
+    const int tid = (threadIdx.x + 32 * rot_) & (NT - 1);
     for (;;) {   // persistent CTA: pull problems from a queue (iteration counts differ per problem)
         if (tid == 0) s_prob = atomicAdd(a.counter, 1);
         __syncthreads();

@@ -80,20 +80,20 @@ for key, s in by_line.most_common(top):
 # ---- optional phase buckets: python tools/ncu_lines.py rep kernel top buckets
 if len(sys.argv) > 4:
     spec = {
-        "forward_wave": [("sddp_solver.cuh", 368, 434)],
-        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 193, 282), ("sddp_solver.cuh", 80, 104)],
-        "init/defects/rollout": [("sddp_solver.cuh", 105, 169)],
-        "pack (thread per node)": [("sddp_model.cuh", 283, 391)],
-        "expand": [("sddp_model.cuh", 392, 664)],
+        "forward_wave": [("sddp_solver.cuh", 371, 502)],
+        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 193, 295), ("sddp_solver.cuh", 83, 107)],
+        "init/defects/rollout": [("sddp_solver.cuh", 108, 172)],
+        "pack (thread per node)": [("sddp_model.cuh", 296, 404)],
+        "expand": [("sddp_model.cuh", 405, 677)],
         "bwd load+c1 (Quu, gap)": [("sddp_backward_srbd.cuh", 92, 184)],
         "bwd d1 (warp-0 LDL^T)": [("sddp_backward_srbd.cuh", 185, 239)],
         "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 240, 271)],
         "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 272, 320)],
         "bwd d2 (RHS substitution)": [("sddp_backward_srbd.cuh", 321, 365)],
-        "bwd syrk (Vxx)": [("sddp_backward_srbd.cuh", 366, 399)],
-        "bwd K matmul": [("sddp_backward_srbd.cuh", 400, 427)],
+        "bwd syrk (DMMA)": [("sddp_backward_srbd.cuh", 366, 399)],
+        "bwd K matmul (DMMA)": [("sddp_backward_srbd.cuh", 400, 427)],
         "bwd mu path + model": [("sddp_backward_srbd.cuh", 428, 490)],
-        "solve_one control": [("sddp_solver.cuh", 435, 635)],
+        "solve_one control": [("sddp_solver.cuh", 503, 703)],
     }
     tot_b = collections.Counter(); ex_b = collections.Counter(); wf_b = collections.Counter(); st_b = collections.defaultdict(collections.Counter)
     for key, s in by_line.items():
