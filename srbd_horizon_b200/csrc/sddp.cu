@@ -275,9 +275,11 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
     auto zu = [&](int p) { return 6 * ((p - 22) / 3) + 3 + (p - 22) % 3; };
     tab.assign((size_t)ZT_ROUNDS * ZT_THREADS, 0ull);
     int e = 0;
+    for (int pass = 0; pass < 2; pass++)      // xx and ux entries first (ZT_NXX_NUX of them), then uu
     for (int pi = 0; pi < NZ; pi++)
-        for (int qi = pi; qi < NZ; qi++, e++) {
+        for (int qi = pi; qi < NZ; qi++) {
             const int xi = zx(pi), xj = zx(qi);
+            if ((pass == 0) != (xi >= 0)) continue;
             int kind, da, db;
             if (xi >= 0 && xj >= 0) { kind = 0; da = xi; db = xj; }
             else if (xi >= 0) { kind = 1; da = zu(qi); db = xi; }
@@ -301,8 +303,9 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
             unsigned long long d = 1ull | ((unsigned long long)kind << 1) | ((unsigned long long)da << 3) | ((unsigned long long)db << 9) |
                                    ((unsigned long long)pi << 15) | ((unsigned long long)qi << 21) | ((unsigned long long)hs << 27) |
                                    ((unsigned long long)hoff << 29);
-            tab[(size_t)(e / ZT_THREADS) * ZT_THREADS + (e % ZT_THREADS)] = d;
+            tab[e++] = d;
         }
+    if (e != NZ * (NZ + 1) / 2) abort();
 }
 
 // kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.reserved0 = 1), 2 = LIP dense
@@ -697,6 +700,12 @@ int sddp_debug_profile(long long* out32, int reset) {
     if (cudaMemcpyFromSymbol(out32, g_prof, sizeof(z)) != cudaSuccess) return SDDP_ECUDA;
     if (reset && cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return SDDP_ECUDA;
     return 0;
+}
+#endif
+
+#ifdef SDDP_STAMP
+int sddp_debug_stamps(long long* out64) {
+    return cudaMemcpyFromSymbol(out64, g_stamp, sizeof(long long) * 64) == cudaSuccess ? 0 : SDDP_ECUDA;
 }
 #endif
 

@@ -28,12 +28,12 @@ struct alignas(16) SmemSrbd {
     static constexpr int LDW = 44;   // row pitch of W: 88 words = 24 mod 32, so the 4 x 8 DMMA fragment loads are conflict free
     double VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
     double Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
-    double W[NU * LDW];        // [Qux | w0 | 0 ...] -> Wn
+    double W[NU * LDW];        // B = [Qux | Qu | quy | .] -> Wn = Es B  (quy: lu + fu^T ys of the y recursion)
     double Quu[NU * NU];       // Quu -> (strict upper) D Lt^T = frozen raw columns, (lower) Es
     double Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
-    double Qu[NU], quy[NU], kk[NU], invp[NU], rs[NU];
+    double Qu[NU], kk[NU], invp[NU], rs[NU];
     double nb[2][NodeBuf<Srbd>::SIZE];
-    double ypart[3][40];
+    double escr[24];           // expand scratch: E(oref) and the orientation residuals
     double sacc[NWARP][8];
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
@@ -44,8 +44,9 @@ struct alignas(16) SmemSrbd {
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
 };
 static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 44, "forward K double buffer must fit in Qxx + W");
-enum { R_SW = 6 };
+enum { R_SW = 6, R_SQ = 7 };
 SDDP_DEV void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+struct Bar96 { __device__ void operator()() const { bar_named(2, 96); } };      // warps 1-3
 
 // D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Fragments (PTX ISA, m8n8k4 .f64): lane holds
 // A[lane/4][lane%4], B[lane%4][lane/4], C[lane/4][2*(lane%4) + {0,1}].
@@ -64,15 +65,52 @@ SDDP_DEV double fast_rcp(double p) {
     return fma(x, e, x);
 }
 
-// rows of V that make up row `a` of B^T (.) : cddot(i,k) -> cd_ik ; f(i,k) -> (fs/m) rd_k + G_i[:,k]^T w
-SDDP_DEV int bt_rows(const DevCfg& c, const double* Jac, int a, int* idx, double* coef) {
-    int i = a / 6, r = a % 6;
-    if (r < 3) { idx[0] = Srbd::XCD + 3 * i + r; coef[0] = 1.0; return 1; }
-    int k = r - 3;
-    idx[0] = Srbd::XRD + k; coef[0] = c.inv_ms;
+#ifndef SDDP_ROW128
+#define SDDP_ROW128 0
+#endif
+// a[i] -= row[i] * s for lo <= i < n; `lo` is a compile-time constant after unrolling.  Every thread of a warp reads
+// the same addresses (broadcast).  Loads first, then the FMAs, in batches of 8 (keeps the loads in flight together
+// without holding a whole second column in registers).  SDDP_ROW128: 128-bit loads (`row` is 16-byte aligned).
+template <int n>
+SDDP_DEV void axpy_row(double* a, const double* row, int lo, double s) {
+    static_assert(n % 8 == 0, "row length");
+#if SDDP_ROW128
 #pragma unroll
-    for (int q = 0; q < 3; q++) { idx[1 + q] = Srbd::XW + q; coef[1 + q] = Jac[q * Srbd::NZ + Srbd::ZF + 3 * i + k]; }
-    return 4;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        double2 c[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (i0 + 2 * q + 1 >= lo) c[q] = *reinterpret_cast<const double2*>(row + i0 + 2 * q);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + 2 * q;
+            if (i >= lo) a[i] -= c[q].x * s;
+            if (i + 1 >= lo) a[i + 1] -= c[q].y * s;
+        }
+    }
+#else
+#pragma unroll
+    for (int i0 = lo; i0 < n; i0 += 8) {
+        double col[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (i0 + q < n) col[q] = row[i0 + q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (i0 + q < n) a[i0 + q] -= col[q] * s;
+    }
+#endif
+}
+// row[i] = a[i] for lo <= i < n
+template <int n>
+SDDP_DEV void store_row(double* row, const double* a, int lo) {
+#if SDDP_ROW128
+#pragma unroll
+    for (int i = 0; i < n; i += 2) {
+        if (i >= lo) *reinterpret_cast<double2*>(row + i) = make_double2(a[i], a[i + 1]);
+        else if (i + 1 >= lo) row[i + 1] = a[i + 1];
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < n; i++) if (i >= lo) row[i] = a[i];
+#endif
 }
 
 // out[b] = sum_a v[a] * (dt Aoo)[a][b],  Aoo = d odot / d o = [[skew(w)/2, w/2], [-w^T/2, 0]];  hw = dt w / 2
@@ -124,7 +162,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
     prefetch(N - 1);
     if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; S.iflag[1] = 0; }
     __syncthreads();
-    M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, &S.ypart[0][0]);
+    M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, S.escr);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
 
     for (int k = N - 1; k >= 0; k--) {
@@ -135,50 +173,86 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         const double* pk = nb + NBL::OP;
         double* cg = nb + NBL::OD;
         const double* pack = nb + NBL::OK;
+        STAMP(0);
         cp_wait_all();
         __syncthreads();                       // node k landed; everyone is done with node k+1
+        STAMP(1);
         PROF(8);
-        if (tid < NX) cg[tid] = has_gap ? rho_b * cg[tid] : 0.0;      // consumed after expand's barriers
-        M::expand<LDW>(c, kind, xk, uk, pk, pack, S.Qx, S.Qu, S.Qxx, S.W, S.Quu, tid, NT, sync, &S.ypart[0][0]);
         const double* Jac = pack + M::PK_JAC;
         PROF(9);
-        if (k > 0) prefetch(k - 1);      // after the zero fill: shared stores queue behind outstanding cp.async
-
-        // ---- c1: everything that needs Vxx' itself: gap shift, Quu = luu + fu^T Vxx' fu, copies of lx, lu
+        // ---- c1: everything that needs Vxx' itself: gap shift, Quu = luu + fu^T Vxx' fu + mu I (written whole: luu of
+        //          the wdot block is 2 gq Jac_f^T Jac_f, of the affine residuals a few constants, prb.py:200-204)
         if (tid < NX) {
             double s = 0.0;
             if (has_gap) {
 #pragma unroll 4
                 for (int j = 0; j < NX; j++) s += S.VT[tid * NX + j] * cg[j];
+                s *= rho_b;
             }
             S.sv[tid] = s;
             S.vp[tid] = S.Vx[tid] + s;
             S.ys[tid] = fixed ? S.y[tid] + s : S.y[tid];
-            S.qxy[tid] = S.Qx[tid];
-        } else if (tid >= 64 && tid < 64 + NU) {
-            S.quy[tid - 64] = S.Qu[tid - 64];
-        } else if (tid == 127) {
-            S.iflag[2] = 0;            // number of factor columns published by warp 0 (see d1 / d2)
         }
-        for (int e = tid; e < NU * (NU + 1) / 2; e += NT) {   // lower triangle (a >= b), mirrored
-            int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-            while ((a + 1) * (a + 2) / 2 <= e) a++;
-            while (a * (a + 1) / 2 > e) a--;
-            int b = e - a * (a + 1) / 2;
-            int ia[4], ib[4];
-            double ca[4], cb[4];
-            int na = bt_rows(c, Jac, a, ia, ca), nb_ = bt_rows(c, Jac, b, ib, cb);
-            double s = 0.0;
-            for (int p = 0; p < na; p++) {
-                double t = 0.0;
-                for (int q = 0; q < nb_; q++) t += S.VT[ia[p] * NX + ib[q]] * cb[q];
-                s += ca[p] * t;
+        {
+            // u = (cddot_i, f_i) x 4: "c" index ci = 3 i + r -> u index 6 i + r, "f" index fj = 3 j + k -> 6 j + 3 + k.
+            // B^T rows: cddot -> e(cd); f_jk -> (fs/m) e(rd_k) + sum_q G_j[q][k] e(w_q),  G_j[q][k] = Jac[q][ZF + fj].
+            // Threads 0..77 take one (f, f) entry each (16 products), threads 78..127 the 144 (cddot, f) and the 78
+            // (cddot, cddot) entries (4 or 1 products, 4-5 entries each): one balanced round.
+            const double dt2 = dt * dt, g2 = 2.0 * c.gq;
+            auto tri = [](int e, int& hi, int& lo) {       // e = hi (hi + 1) / 2 + lo, lo <= hi
+                int h = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                while ((h + 1) * (h + 2) / 2 <= e) h++;
+                while (h * (h + 1) / 2 > e) h--;
+                hi = h; lo = e - h * (h + 1) / 2;
+            };
+            if (tid < 78) {
+                int fa, fb;
+                tri(tid, fa, fb);
+                const int ka = fa % 3, kb = fb % 3;
+                const double* Ga = Jac + M::ZF + fa;
+                const double* Gb = Jac + M::ZF + fb;
+                const double a1 = Ga[0], a2 = Ga[NZ], a3 = Ga[2 * NZ], b1 = Gb[0], b2 = Gb[NZ], b3 = Gb[2 * NZ], im = c.inv_ms;
+                const double* Vr = S.VT + (M::XRD + ka) * NX;
+                const double* Vw = S.VT + M::XW * NX;
+                const int cr = M::XRD + kb, cw = M::XW;
+                const double t0 = Vr[cr] * im + Vr[cw] * b1 + Vr[cw + 1] * b2 + Vr[cw + 2] * b3;
+                const double t1 = Vw[cr] * im + Vw[cw] * b1 + Vw[cw + 1] * b2 + Vw[cw + 2] * b3;
+                const double t2 = Vw[NX + cr] * im + Vw[NX + cw] * b1 + Vw[NX + cw + 1] * b2 + Vw[NX + cw + 2] * b3;
+                const double t3 = Vw[2 * NX + cr] * im + Vw[2 * NX + cw] * b1 + Vw[2 * NX + cw + 1] * b2 + Vw[2 * NX + cw + 2] * b3;
+                double v = dt2 * (im * t0 + a1 * t1 + a2 * t2 + a3 * t3) + g2 * (a1 * b1 + a2 * b2 + a3 * b3);
+                if (ka == kb) {                       // rddot rows of min_qddot; min_f and f_active on the diagonal
+                    v += g2 * im * im;
+                    if (fa == fb) { const double sw1 = 1.0 - pk[8 + 2 * (fa / 3)]; v += 2.0 * (c.w_minf + c.w_fsw * sw1 * sw1) + mu; }
+                }
+                const int ua = 6 * (fa / 3) + 3 + ka, ub = 6 * (fb / 3) + 3 + kb;
+                S.Quu[ua * NU + ub] = v;
+                S.Quu[ub * NU + ua] = v;
+            } else {
+                for (int e = tid - 78; e < 144 + 78; e += NT - 78) {
+                    int ua, ub;
+                    double v;
+                    if (e < 144) {
+                        const int ci = e / 12, fj = e % 12, kb = fj % 3;
+                        const double* G = Jac + M::ZF + fj;
+                        const double* Vc = S.VT + (M::XCD + ci) * NX;
+                        v = dt2 * (Vc[M::XRD + kb] * c.inv_ms + Vc[M::XW] * G[0] + Vc[M::XW + 1] * G[NZ] + Vc[M::XW + 2] * G[2 * NZ]);
+                        ua = 6 * (ci / 3) + ci % 3; ub = 6 * (fj / 3) + 3 + kb;
+                    } else {
+                        int ca, cb;
+                        tri(e - 144, ca, cb);
+                        v = dt2 * S.VT[(M::XCD + ca) * NX + M::XCD + cb];
+                        if (ca == cb) v += g2 + mu;      // cddot rows of min_qddot
+                        ua = 6 * (ca / 3) + ca % 3; ub = 6 * (cb / 3) + cb % 3;
+                    }
+                    S.Quu[ua * NU + ub] = v;
+                    S.Quu[ub * NU + ua] = v;
+                }
             }
-            double v = S.Quu[a * NU + b] + dt * dt * s + (a == b ? mu : 0.0);
-            S.Quu[a * NU + b] = v;
-            S.Quu[b * NU + a] = v;
         }
+        if (k > 0) prefetch(k - 1);
+        STAMP(2);
         __syncthreads();
+        STAMP(3);
         PROF(10);
 
         const double* o = xk + M::XO;
@@ -189,13 +263,15 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             if (has_gap) {   // gap terms of the model (the only use of cg after c1)
                 double g1 = 0, g2 = 0, yg = 0;
                 for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * cg[i]; g2 += cg[i] * S.sv[i]; yg += S.y[i] * cg[i]; }
-                g1 = warp_sum(g1); g2 = warp_sum(g2); yg = warp_sum(yg);
+                g1 = rho_b * warp_sum(g1); g2 = rho_b * warp_sum(g2); yg = rho_b * warp_sum(yg);
                 if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
             } else if (lane == 0) { S.red[R_G1] = 0.0; S.red[R_G2] = 0.0; S.red[R_YG] = 0.0; }
             // Lane t holds column t.  Step j: lane j publishes its (final) column raw, row j of the strict upper
-            // triangle of S.Quu, and 1/pivot; every lane then applies  a[i] -= col_j[i] * (a[j] / pivot_j).
+            // triangle of S.Quu, and 1/pivot; every lane then applies  a[i] -= col_j[i] * (a[j] / pivot_j),  i > j.
             // The element that becomes the next pivot (i = j+1) is updated first and its reciprocal started at
-            // once, so the rest of the update overlaps the reciprocal latency.  Lanes <= j update dead values.
+            // once, so the rest of the update overlaps the reciprocal latency.
+            // A lane whose column is published restarts as column j of the identity: the very same updates then
+            // build E = Lt^-1 in the lanes the factorisation no longer needs (lane t ends with column t of E).
             double a[NU];
             const int t = lane < NU ? lane : NU - 1;
 #pragma unroll
@@ -209,34 +285,28 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     const double p = a[j];
                     bad = !(p > 0.0) || !isfinite(p);
                     S.invp[j] = myinv;
+                    store_row<NU>(S.Quu + j * NU, a, j + 1);
+                    a[j] = 1.0;
 #pragma unroll
-                    for (int i = j + 1; i < NU; i++) S.Quu[j * NU + i] = a[i];
-                    __threadfence_block();
-                    *(volatile int*)&S.iflag[2] = j + 1;      // column j is visible to the right-hand-side warps
+                    for (int i = j + 1; i < NU; i++) a[i] = 0.0;
                 }
                 __syncwarp();
                 if (j + 1 < NU) {
                     const double sj = S.invp[j] * a[j];
                     a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
                     myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
-                    // the rest of the column in batches of 8: loads first, then the FMAs (keeps the loads in
-                    // flight together without holding a whole second column in registers)
-#pragma unroll
-                    for (int i0 = j + 2; i0 < NU; i0 += 8) {
-                        double col[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) if (i0 + q < NU) col[q] = S.Quu[j * NU + i0 + q];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) if (i0 + q < NU) a[i0 + q] -= col[q] * sj;
-                    }
+                    if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
                 }
             }
             if (__any_sync(FULL, bad) && lane == 0) S.iflag[1] = 1;
             if (lane < NU) S.rs[lane] = sqrt(S.invp[lane]);
             __syncwarp();
-            __threadfence_block();
-            if (lane == 0) *(volatile int*)&S.iflag[2] = NU + 1;           // rs is visible too
+            if (lane < NU) {                        // Es = rs . E -> lower triangle (incl. diagonal) of S.Quu
+#pragma unroll
+                for (int i = 0; i < NU; i++) if (i >= lane) S.Quu[i * NU + lane] = a[i] * S.rs[i];
+            }
             PROF_T(14, 0);
+            STAMP(4); STAMP(5); STAMP(6); STAMP(7);
         } else {
             // ---- c2: T = Vxx' fx = V + dt V A, in place, one thread per row (warps 1-2)
             const int r_ = tid - 32;
@@ -268,9 +338,12 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 for (int q = 0; q < 3; q++)
                     row[M::XW + q] = vw[q] + tw[q] + dw0 * Jac[M::ZW + q] + dw1 * Jac[NZ + M::ZW + q] + dw2 * Jac[2 * NZ + M::ZW + q];
             }
+            else if (r_ >= 64 && r_ < 80 && kind != NODE_FIRST) M::prep_E(pk, S.escr, r_ - 64);
             PROF_T(15, 32);
+            STAMP(4);
             bar_named(2, 96);
-            // ---- c3: columns of fx^T (.) and fu^T (.) applied to T (j < 37), v+ (j = 37) and ys (j = 38); warps 1-3
+            // ---- c3: columns of fx^T (.) and fu^T (.) applied to T (j < 37), v+ (j = 37) and ys (j = 38); warps 1-3.
+            //          Plain stores: lxx, lux, lx, lu are added afterwards (expand MODE 1)
             for (int task = tid - 32; task < 39 * 3; task += 96) {
                 const int j = task % 39, g = task / 39;
                 const double* col = (j < NX) ? S.VT + j : (j == NX ? S.vp : S.ys);
@@ -284,8 +357,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     for (int q = 0; q < 4; q++) tov[q] = col[(M::XO + q) * cs];
 #pragma unroll
                     for (int q = 0; q < 3; q++) {
-                        oxx[(M::XR + q) * os] += col[(M::XR + q) * cs] + dt * (Jac[M::ZR + q] * tw0 + Jac[NZ + M::ZR + q] * tw1 + Jac[2 * NZ + M::ZR + q] * tw2);
-                        oxx[(M::XRD + q) * os] += col[(M::XRD + q) * cs] + dt * col[(M::XR + q) * cs];
+                        oxx[(M::XR + q) * os] = col[(M::XR + q) * cs] + dt * (Jac[M::ZR + q] * tw0 + Jac[NZ + M::ZR + q] * tw1 + Jac[2 * NZ + M::ZR + q] * tw2);
+                        oxx[(M::XRD + q) * os] = col[(M::XRD + q) * cs] + dt * col[(M::XR + q) * cs];
                     }
                     const double hw[3] = {0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
                     const double ho[4] = {0.5 * dt * o[0], 0.5 * dt * o[1], 0.5 * dt * o[2], 0.5 * dt * o[3]};
@@ -294,98 +367,122 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     contract_Aow(tov, ho, aw);    // (dt Aow)^T T[o,j]: row w_b
 #pragma unroll
                     for (int q = 0; q < 4; q++)
-                        oxx[(M::XO + q) * os] += col[(M::XO + q) * cs] + ao[q] + dt * (Jac[M::ZO + q] * tw0 + Jac[NZ + M::ZO + q] * tw1 + Jac[2 * NZ + M::ZO + q] * tw2);
+                        oxx[(M::XO + q) * os] = col[(M::XO + q) * cs] + ao[q] + dt * (Jac[M::ZO + q] * tw0 + Jac[NZ + M::ZO + q] * tw1 + Jac[2 * NZ + M::ZO + q] * tw2);
 #pragma unroll
                     for (int q = 0; q < 3; q++)
-                        oxx[(M::XW + q) * os] += col[(M::XW + q) * cs] + aw[q] + dt * (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
+                        oxx[(M::XW + q) * os] = col[(M::XW + q) * cs] + aw[q] + dt * (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
                 } else if (g == 1) {   // rows c, cd
 #pragma unroll
                     for (int q = 0; q < 12; q++) {
                         double tc = col[(M::XC + q) * cs];
-                        oxx[(M::XC + q) * os] += tc + dt * (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
-                        oxx[(M::XCD + q) * os] += col[(M::XCD + q) * cs] + dt * tc;
+                        oxx[(M::XC + q) * os] = tc + dt * (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
+                        oxx[(M::XCD + q) * os] = col[(M::XCD + q) * cs] + dt * tc;
                     }
                 } else {               // fu^T (.): rows cddot_i, f_i
-                    double* oux = (j < NX) ? S.W + j : (j == NX ? S.Qu : S.quy);
-                    const int us = (j < NX) ? LDW : 1;
+                    double* oux = S.W + j;           // columns NX, NX+1 of W: Qu = lu + fu^T v+ and quy = lu + fu^T ys
+                    const int us = LDW;
                     const double trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int q = 0; q < 3; q++) {
-                            oux[(6 * i + q) * us] += dt * col[(M::XCD + 3 * i + q) * cs];
+                            oux[(6 * i + q) * us] = dt * col[(M::XCD + 3 * i + q) * cs];
                             const int zf = M::ZF + 3 * i + q;
-                            oux[(6 * i + 3 + q) * us] += dt * (trd[q] + Jac[zf] * tw0 + Jac[NZ + zf] * tw1 + Jac[2 * NZ + zf] * tw2);
+                            oux[(6 * i + 3 + q) * us] = dt * (trd[q] + Jac[zf] * tw0 + Jac[NZ + zf] * tw1 + Jac[2 * NZ + zf] * tw2);
                         }
                 }
             }
             PROF_T(16, 32);
-            // ---- d2: Lt^-1 applied to [Qux | Qu | I], one right-hand side per thread (warps 1-2), trailing the
-            //          factorisation of warp 0 column by column (S.iflag[2] counts the published columns)
-            bar_named(2, 96);                      // Qux, Qu complete
-            const int t = tid - 32;
-            if (t < NX + 1 + NU) {
-                volatile int* published = (volatile int*)&S.iflag[2];
-                double a[NU];
-                if (t < NX) {
-#pragma unroll
-                    for (int i = 0; i < NU; i++) a[i] = S.W[i * LDW + t];
-                } else if (t == NX) {
-#pragma unroll
-                    for (int i = 0; i < NU; i++) a[i] = S.Qu[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NU; i++) a[i] = (i == t - (NX + 1)) ? 1.0 : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < NU - 1; j++) {
-                    while (*published <= j) __nanosleep(40);      // polite wait: spinning warps steal issue slots
-                    asm volatile("" ::: "memory");
-                    const double sj = S.invp[j] * a[j];
-#pragma unroll
-                    for (int i0 = j + 1; i0 < NU; i0 += 8) {
-                        double col[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) if (i0 + q < NU) col[q] = S.Quu[j * NU + i0 + q];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) if (i0 + q < NU) a[i0 + q] -= col[q] * sj;
-                    }
-                }
-                while (*published <= NU) __nanosleep(40);
-                asm volatile("" ::: "memory");
-                if (t <= NX) {                      // Wn = rs . frozen rows (column NX is w0)
-#pragma unroll
-                    for (int l = 0; l < NU; l++) S.W[l * LDW + t] = a[l] * S.rs[l];
-                } else {                            // Es = rs . Lt^-1 -> lower triangle (incl. diagonal) of S.Quu
-                    const int m = t - (NX + 1);
-#pragma unroll
-                    for (int l = 0; l < NU; l++) if (l >= m) S.Quu[l * NU + m] = a[l] * S.rs[l];
-                }
-            }
+            STAMP(5);
+            bar_named(2, 96);
+            // ---- e: + lx, lu, lxx, lux of the node (two barrier-separated passes among warps 1-3)
+            M::expand<LDW, 1>(c, kind, xk, uk, pk, pack, S.Qx, S.W + NX, S.Qxx, S.W, nullptr, tid - 32, 96, Bar96(), S.escr, S.qxy, S.W + NX + 1);
+            PROF_T(17, 32);
+            STAMP(6);
         }
+        if (warp != 0) STAMP(7);
         __syncthreads();
+        STAMP(8);
         PROF(11);
         if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; cp_wait_all(); __syncthreads(); return k + 1; }
 
-        // ---- f: [Vxx Vx] = [sym(Qxx) Qx] - Wn^T Wn: upper-triangular 8x8 tiles of the 40x40 product, K = 24 in six
-        //         DMMA steps; warp w takes tiles w, w+4, ...  Results go to VT (T is dead), Vx and red[R_SW] = |w0|^2.
+        // ---- h: Wn = Es B (B = [Qux | Qu | quy], 24 x 40 in S.W; Es lower triangular in S.Quu, entries above the
+        //         diagonal masked: that part holds the raw factor).  In place: a warp owns whole 8-column blocks
+        //         (warp 0: blocks 0 and 4) and reads all of a block before it writes; the three row tiles of a block
+        //         are independent DMMA chains of 2, 4 and 6 steps.
         {
-            const int fr = lane >> 2, fc = lane & 3;       // fragment row / column of this lane
-            for (int t = warp; t < 15; t += NWARP) {
-                int I = 0, rem = t;
-                while (rem >= 5 - I) { rem -= 5 - I; I++; }
-                const int J = I + rem;
-                double c0 = 0.0, c1 = 0.0;
+            const int fr = lane >> 2, fc = lane & 3;
+            for (int J = warp; J < 5; J += NWARP) {
+                double h0[3] = {0, 0, 0}, h1[3] = {0, 0, 0};
 #pragma unroll
                 for (int k0 = 0; k0 < NU; k0 += 4) {
-                    const double* r = S.W + (k0 + fc) * LDW + fr;
-                    dmma884(c0, c1, r[8 * I], r[8 * J]);
+                    const int l = k0 + fc;
+                    const double bv = S.W[l * LDW + 8 * J + fr];
+#pragma unroll
+                    for (int I = 0; I < 3; I++) {
+                        if (k0 > 8 * I + 7) continue;
+                        const int i = 8 * I + fr;
+                        const double av = (l <= i) ? S.Quu[i * NU + l] : 0.0;
+                        dmma884(h0[I], h1[I], av, bv);
+                    }
                 }
-                const int gi = 8 * I + fr;
+                __syncwarp();
+#pragma unroll
+                for (int I = 0; I < 3; I++)
+                    *reinterpret_cast<double2*>(S.W + (8 * I + fr) * LDW + 8 * J + 2 * fc) = make_double2(h0[I], h1[I]);
+            }
+        }
+        STAMP(11);
+        __syncthreads();
+        // ---- f: [Vxx Vx y] = [sym(Qxx) Qx qxy] - Wn^T Wn: upper-triangular 8x8 tiles of the 40x40 product, K = 24 in
+        //         six DMMA steps.  Results go to VT (T is dead), Vx, y (column 38 = Wn^T Es quy = -K^T quy),
+        //         red[R_SW] = |w0|^2 and red[R_SQ] = quy . k.
+        // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
+        //         at k0 = 8 I and entries above the diagonal are masked (that part of S.Quu holds the raw factor).
+        // Warp w takes tiles w, w+4, w+8, w+12 of each product and runs their accumulation chains interleaved (a
+        // single chain of six dependent DMMAs is latency bound); slot 3 of warp 3 is a dummy.
+        {
+            const int fr = lane >> 2, fc = lane & 3;       // fragment row / column of this lane
+            int fI[4], fJ[4], gI[4], gJ[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int t = min(warp + 4 * q, 14);
+                int I = 0, rem = t;
+                while (rem >= 5 - I) { rem -= 5 - I; I++; }
+                fI[q] = I; fJ[q] = I + rem;
+                gI[q] = t / 5; gJ[q] = t % 5;
+            }
+            double fc0[4] = {0, 0, 0, 0}, fc1[4] = {0, 0, 0, 0}, gc0[4] = {0, 0, 0, 0}, gc1[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int k0 = 0; k0 < NU; k0 += 4) {
+                const double* r = S.W + (k0 + fc) * LDW + fr;
+                double av[4], bv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) { av[q] = r[8 * fI[q]]; bv[q] = r[8 * fJ[q]]; }
+#pragma unroll
+                for (int q = 0; q < 4; q++) dmma884(fc0[q], fc1[q], av[q], bv[q]);
+            }
+#pragma unroll
+            for (int k0 = 0; k0 < NU; k0 += 4) {
+                const int l = k0 + fc;
+                double av[4], bv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = 8 * gI[q] + fr;
+                    av[q] = (l >= i) ? S.Quu[l * NU + i] : 0.0;
+                    bv[q] = S.W[l * LDW + 8 * gJ[q] + fr];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (k0 >= 8 * gI[q]) dmma884(gc0[q], gc1[q], av[q], bv[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (warp + 4 * q >= 15) continue;
+                const int gi = 8 * fI[q] + fr;
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const int gj = 8 * J + 2 * fc + e;
-                    const double acc = e ? c1 : c0;
+                    const int gj = 8 * fJ[q] + 2 * fc + e;
+                    const double acc = e ? fc1[q] : fc0[q];
                     if (gj < gi) continue;
                     if (gj < NX) {
                         const double v = 0.5 * (S.Qxx[gi * NX + gj] + S.Qxx[gj * NX + gi]) - acc;
@@ -394,39 +491,29 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     } else if (gj == NX) {
                         if (gi < NX) S.Vx[gi] = S.Qx[gi] - acc;
                         else S.red[R_SW] = acc;            // |w0|^2
+                    } else if (gj == NX + 1) {
+                        if (gi < NX) S.y[gi] = S.qxy[gi] - acc;
+                        else if (gi == NX) S.red[R_SQ] = -acc;
                     }
                 }
             }
-            // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
-            //         at k0 = 8 I and entries above the diagonal are masked (that part of S.Quu holds the raw factor).
-            for (int t = warp; t < 15; t += NWARP) {
-                const int I = t / 5, J = t % 5;
-                const int i = 8 * I + fr;
-                double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-                for (int k0 = 0; k0 < NU; k0 += 4) {
-                    if (k0 < 8 * I) continue;
-                    const int l = k0 + fc;
-                    const double a = (l >= i) ? S.Quu[l * NU + i] : 0.0;
-                    dmma884(c0, c1, a, S.W[l * LDW + 8 * J + fr]);
-                }
-                const double q = S.quy[i];
-                double y0 = -c0 * q, y1 = -c1 * q;
+            for (int q = 0; q < 4; q++) {
+                if (warp + 4 * q >= 15) continue;
+                const int J = gJ[q], i = 8 * gI[q] + fr;
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int cc = 8 * J + 2 * fc + e;
-                    const double kv = e ? -c1 : -c0;
+                    const double kv = e ? -gc1[q] : -gc0[q];
                     if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
                     else if (cc == NX) { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
                 }
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) { y0 += __shfl_xor_sync(FULL, y0, o); y1 += __shfl_xor_sync(FULL, y1, o); }
-                if (fr == 0) { S.ypart[I][8 * J + 2 * fc] = y0; S.ypart[I][8 * J + 2 * fc + 1] = y1; }
             }
         }
+        STAMP(9);
         __syncthreads();
+        STAMP(10);
         PROF(13);
-        if (tid < NX) S.y[tid] = S.qxy[tid] + (S.ypart[0][tid] + S.ypart[1][tid] + S.ypart[2][tid]);
         if (mu != 0.0) {   // regularised step (rare): Vxx -= mu K^T K, Vx -= mu K^T k, gains re-read from global
             __syncthreads();
             for (int e = tid; e < NX * NX + NX; e += NT) {
@@ -448,7 +535,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             const double sw = S.red[R_SW];
             double sk = 0.0;
             if (mu != 0.0) for (int i = 0; i < NU; i++) sk += S.kk[i] * S.kk[i];
-            const double sq = S.ypart[0][NX] + S.ypart[1][NX] + S.ypart[2][NX];      // quy . k
+            const double sq = S.red[R_SQ];      // quy . k
             const double kQk = sw - mu * sk;
             S.red[R_TOT] += S.red[R_G1] + 0.5 * S.red[R_G2] + (-sw) + 0.5 * kQk;
             S.red[R_ACC2] += 0.5 * kQk;

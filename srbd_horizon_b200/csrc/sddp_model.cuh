@@ -42,6 +42,15 @@ __device__ long long g_prof_last;
 
 
 
+// Per-warp timeline of one backward node of CTA 0 (developer builds only, -DSDDP_STAMP): lane 0 of every warp stores
+// clock64() at each stamp (no read-modify-write, so the probes do not stall the warps); sddp_debug_stamps() reads them.
+#ifdef SDDP_STAMP
+__device__ long long g_stamp[16 * 4];
+#define STAMP(id) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && k == 10) g_stamp[(id) * 4 + (threadIdx.x >> 5)] = clock64(); } while (0)
+#else
+#define STAMP(id)
+#endif
+
 struct DevCfg {
     int model, N, inertia_mode, hessian_mode, ms, max_iters;
     double dt, mscaled, inv_ms, Ib[9], com[3], foot[12], fs, g, eta2;
@@ -52,7 +61,7 @@ struct DevCfg {
 };
 
 // z-block descriptor bit layout (built on the host, sddp.cu:build_ztab)
-enum { ZT_ROUNDS = 5, ZT_THREADS = 128 };
+enum { ZT_ROUNDS = 5, ZT_THREADS = 128, ZT_NXX_NUX = 517, ZT_LAZY_THREADS = 96, ZT_LAZY_ROUNDS = 6 };   // 595 entries: 253 xx + 264 ux first, then 78 uu
 #define ZT_VALID(d) ((d) & 1ull)
 #define ZT_KIND(d) (int)(((d) >> 1) & 3)
 #define ZT_DA(d) (int)(((d) >> 3) & 63)
@@ -424,45 +433,50 @@ struct Srbd {
     // Fast path (128 threads + descriptor table): three barrier-separated passes, each with one or a few
     // entries per thread and short uniform branches:
     //   1. zero fill   2. wdot block 2 gq (Jac^T Jac + Hc) through the descriptor table   3. affine residuals
-    template <int LDUX = NX, class Sync>
+    // MODE 1 (structured backward pass, ZT_LAZY_THREADS threads, tid 0..95): the caller has already written the
+    // fx / fu products into Qx, Qu (and their copies Qx2, Qu2), Qxx, Qux and owns Quu; this call ADDS lx, lu, lxx,
+    // lux to them (no zero fill, no luu), so that the expansion runs in the shadow of the factorisation.  Qu and Qu2
+    // are columns of the Qux buffer there (stride LDUX).  The caller runs prep_E() and a barrier first.
+    SDDP_DEV static void prep_E(const double* p, double* scratch, int t) {   // t in [0, 16)
+        scratch[t] = E_row(p + 15, t >> 2, t & 3);
+    }
+    template <int LDUX = NX, int MODE = 0, class Sync>
     __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double* pk,
                                   double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync,
-                                  double* scratch = nullptr) {
-        if (c.ztab == nullptr || nthr != ZT_THREADS || scratch == nullptr) {
+                                  double* scratch = nullptr, double* Qx2 = nullptr, double* Qu2 = nullptr) {
+        if (MODE == 0 && (c.ztab == nullptr || nthr != ZT_THREADS || scratch == nullptr)) {
             expand_generic<LDUX>(c, kind, x, u, p, pk, Qx, Qu, Qxx, Qux, Quu, tid, nthr, sync);
             return;
         }
+        constexpr int NTH = MODE ? ZT_LAZY_THREADS : ZT_THREADS, ROUNDS = MODE ? ZT_LAZY_ROUNDS : ZT_ROUNDS, EB = NTH - 32;
         const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
-        unsigned long long zd[ZT_ROUNDS];
-        if (input) {
+        unsigned long long zd[ROUNDS];
+        if (input) {      // MODE 0: latency hidden by the zero fill.  MODE 1: the table lists the xx / ux entries first
 #pragma unroll
-            for (int r = 0; r < ZT_ROUNDS; r++) zd[r] = __ldg(c.ztab + r * ZT_THREADS + tid);    // latency hidden by the zero fill
+            for (int r = 0; r < ROUNDS; r++) zd[r] = (MODE == 0 || r * NTH + tid < ZT_NXX_NUX) ? __ldg(c.ztab + r * NTH + tid) : 0ull;
         }
-#ifndef SDDP_EXP_SKIP
-#define SDDP_EXP_SKIP 0
-#endif
-        if (SDDP_EXP_SKIP != 3) {
-        for (int e = tid; e < NX * NX; e += ZT_THREADS) Qxx[e] = 0.0;
-        for (int e = tid; e < NU * LDUX; e += ZT_THREADS) Qux[e] = 0.0;
-        for (int e = tid; e < NU * NU; e += ZT_THREADS) Quu[e] = 0.0;
-        }
-        if (tid < NX) Qx[tid] = 0.0;
-        if (tid < NU) Qu[tid] = 0.0;
         double* Es = scratch;          // E(oref) 4x4, then the four orientation residuals
-        if (track && tid >= 96 && tid < 112) Es[tid - 96] = E_row(p + 15, (tid - 96) >> 2, (tid - 96) & 3);
-        sync();
+        if (MODE == 0) {
+            for (int e = tid; e < NX * NX; e += NTH) Qxx[e] = 0.0;
+            for (int e = tid; e < NU * LDUX; e += NTH) Qux[e] = 0.0;
+            for (int e = tid; e < NU * NU; e += NTH) Quu[e] = 0.0;
+            if (tid < NX) Qx[tid] = 0.0;
+            if (tid < NU) Qu[tid] = 0.0;
+            if (track && tid >= EB && tid < EB + 16) prep_E(p, Es, tid - EB);
+            sync();
+        }
         PROF(20);
-        if (track && tid >= 96 && tid < 100) {
-            const int r = tid - 96;
+        if (track && tid >= EB && tid < EB + 4) {
+            const int r = tid - EB;
             const double* o = x + XO;
             Es[16 + r] = Es[4 * r] * o[0] + Es[4 * r + 1] * o[1] + Es[4 * r + 2] * o[2] + Es[4 * r + 3] * o[3] - (r == 3 ? 1.0 : 0.0);
         }
-        if (input && SDDP_EXP_SKIP != 1) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc), upper triangle mirrored
+        if (input) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc), upper triangle mirrored
             const double* Jac = pk + PK_JAC;
             const double g2 = 2.0 * c.gq;
             const bool exact = c.hessian_mode == 0;
 #pragma unroll
-            for (int r = 0; r < ZT_ROUNDS; r++) {
+            for (int r = 0; r < ROUNDS; r++) {
                 const unsigned long long d = zd[r];
                 if (!ZT_VALID(d)) continue;
                 const int pi = ZT_PI(d), qi = ZT_QI(d), da = ZT_DA(d), db = ZT_DB(d), hs = ZT_HSIGN(d);
@@ -470,21 +484,31 @@ struct Srbd {
                 if (exact && hs) { const double v = pk[ZT_HOFF(d)]; hh += (hs == 1) ? v : -v; }
                 hh *= g2;
                 const int kd = ZT_KIND(d);
-                if (kd == 0) { Qxx[da * NX + db] = hh; Qxx[db * NX + da] = hh; }
-                else if (kd == 1) Qux[da * LDUX + db] = hh;
-                else { Quu[da * NU + db] = hh; Quu[db * NU + da] = hh; }
+                if (MODE) {
+                    if (kd == 0) { Qxx[da * NX + db] += hh; if (da != db) Qxx[db * NX + da] += hh; }
+                    else if (kd == 1) Qux[da * LDUX + db] += hh;
+                } else {
+                    if (kd == 0) { Qxx[da * NX + db] = hh; Qxx[db * NX + da] = hh; }
+                    else if (kd == 1) Qux[da * LDUX + db] = hh;
+                    else { Quu[da * NU + db] = hh; Quu[db * NU + da] = hh; }
+                }
             }
             if (tid < NZ) {
                 const int pi = tid;
                 const double g = g2 * (Jac[pi] * pk[PK_WD] + Jac[NZ + pi] * pk[PK_WD + 1] + Jac[2 * NZ + pi] * pk[PK_WD + 2]);
                 const int xi = zmap_x(pi);
-                if (xi >= 0) Qx[xi] = g; else Qu[zmap_u(pi)] = g;
+                if (MODE) {
+                    if (xi >= 0) { Qx[xi] += g; Qx2[xi] += g; } else { const int ui = zmap_u(pi) * LDUX; Qu[ui] += g; Qu2[ui] += g; }
+                } else {
+                    if (xi >= 0) Qx[xi] = g; else Qu[zmap_u(pi)] = g;
+                }
             }
         }
         sync();
         PROF(21);
-        // ---- affine residuals, Hessian: one entry per thread (119 entries)
-        const int t = (SDDP_EXP_SKIP == 2) ? 1000 : tid;
+        if (MODE) PROF_T(18, 32);
+        // ---- affine residuals, Hessian: one entry per thread (119 entries; MODE 1 skips the luu entries 0..47, 96..107)
+        const int t = MODE ? (tid < 48 ? tid + 48 : tid + 60) : tid;
         if (t < 48) {                                   // rddot rows of min_qddot + min_f + f_active   (prb.py:200-204)
             if (input) {
                 const int k = t >> 4, i = (t >> 2) & 3, j = t & 3;
@@ -525,17 +549,19 @@ struct Srbd {
         } else if (t == 118) {                          // rz_tracking   (prb.py:184)
             if (track) Qxx[2 * NX + 2] += 2.0 * c.w_r;
         }
-        // ---- affine residuals, gradient: thread t < 24 owns lu[t], thread 32 + i owns lx[i]
-        if (t < NU) {
+        // ---- affine residuals, gradient: thread tg < 24 owns lu[tg], thread 32 + i owns lx[i]
+        const int tg = tid;
+        if (tg < NU) {
             if (input) {
-                const int i = t / 6, r = t % 6;
+                const int i = tg / 6, r = tg % 6;
                 double g;
-                if (r < 3) g = 2.0 * c.gq * u[t];
-                else { const double a = 1.0 - p[8 + 2 * i]; g = 2.0 * c.gq * c.inv_ms * pk[PK_RDD + r - 3] + 2.0 * (c.w_minf + c.w_fsw * a * a) * u[t]; }
-                Qu[t] += g;
+                if (r < 3) g = 2.0 * c.gq * u[tg];
+                else { const double a = 1.0 - p[8 + 2 * i]; g = 2.0 * c.gq * c.inv_ms * pk[PK_RDD + r - 3] + 2.0 * (c.w_minf + c.w_fsw * a * a) * u[tg]; }
+                if (MODE) { Qu[tg * LDUX] += g; Qu2[tg * LDUX] += g; }
+                else Qu[tg] += g;
             }
-        } else if (t >= 32 && t < 32 + NX) {
-            const int i = t - 32;
+        } else if (tg >= 32 && tg < 32 + NX) {
+            const int i = tg - 32;
             double g = 0.0;
             if (i == 2) { if (track) g = 2.0 * c.w_r * (x[2] - c.com[2]); }
             else if (i >= XO && i < XC) {
@@ -562,6 +588,7 @@ struct Srbd {
                 }
             }
             Qx[i] += g;
+            if (MODE) Qx2[i] += g;
         }
         sync();
         PROF(22);

@@ -18,7 +18,7 @@ s = BatchedDDP(cfg)
 L = _lib.lib()
 out = (ctypes.c_longlong * 32)()
 names = {0: "packs", 1: "backward total", 2: "forward wave", 3: "accept/copy", 8: "bwd: wait+sync (top)", 9: "bwd: expand", 10: "bwd: c1 (Quu, gap)",
-         11: "bwd: d1 || c2,c3", 12: "bwd: d2 (RHS subst)", 13: "bwd: f,g (syrk, K)", 14: "  d1 alone (thread 0, since c1 end)", 15: "  c2 alone (thread 32)", 16: "  c2+c3 (thread 32)", 20: "  expand: zero fill + sync", 21: "  expand: z-block + sync", 22: "  expand: affine + sync"}
+         11: "bwd: d1 || c2,c3", 12: "bwd: d2 (RHS subst)", 13: "bwd: f,g (syrk, K)", 14: "  d1 alone (thread 0, since c1 end)", 15: "  c2 alone (thread 32)", 16: "  c2+c3 (thread 32)", 18: "  c2+c3+e phase 1 (thread 32)", 17: "  c2+c3+e (thread 32)", 20: "  expand: zero fill + sync", 21: "  expand: z-block + sync", 22: "  expand: affine + sync"}
 for rep in range(2):
     L.sddp_debug_profile(out, 1)
     r = s.solve(b["x0"], b["params"], b["X0"], b["U0"], gains=False, history=False)

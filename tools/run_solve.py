@@ -22,6 +22,7 @@ b = make_batch(MODEL_SRBD, a.N, a.batch, enumerate_schedules=True)
 s = BatchedDDP(cfg)
 t = lambda v: torch.as_tensor(v, dtype=torch.float64, device="cuda")
 x0, p, X0, U0 = t(b["x0"]), t(b["params"]), t(b["X0"]), t(b["U0"])
+times = []
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -29,6 +30,10 @@ for _ in range(a.reps):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    times.append(ms)
     it = r.iters.double()
     print(f"B={a.batch} N={a.N} ms={ms:.3f} mean_iters={it.mean().item():.3f} max_iters={int(it.max().item())} "
           f"converged={(r.status == 0).double().mean().item():.4f} us_per_node_iter_of_slowest={1e3 * ms / (it.max().item() * a.N):.2f}")
+if len(times) > 2:
+    ts = sorted(times[1:])
+    print(f"SUMMARY B={a.batch} median_ms={ts[len(ts) // 2]:.3f} min_ms={ts[0]:.3f} (first rep excluded, {len(ts)} reps)")
