@@ -273,7 +273,7 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
     const int NZ = Srbd::NZ, ZO = Srbd::ZO, ZC = Srbd::ZC, ZW = Srbd::ZW, ZF = Srbd::ZF;
     auto zx = [&](int p) { return p < 19 ? p : (p < 22 ? (int)Srbd::XW + (p - 19) : -1); };
     auto zu = [&](int p) { return 6 * ((p - 22) / 3) + 3 + (p - 22) % 3; };
-    tab.assign((size_t)ZT_ROUNDS * ZT_THREADS, 0ull);
+    tab.assign((size_t)ZT_TOTAL, 0ull);
     int e = 0;
     for (int pass = 0; pass < 2; pass++)      // xx and ux entries first (ZT_NXX_NUX of them), then uu
     for (int pi = 0; pi < NZ; pi++)
@@ -306,6 +306,24 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
             tab[e++] = d;
         }
     if (e != NZ * (NZ + 1) / 2) abort();
+    // Quu work table (sddp_backward_srbd.cuh, phase c1).  Types: 1 (f_a, f_b) a >= b, 2 (cddot_a, f_b), 3 (cddot_a, cddot_b) a >= b.
+    auto desc = [](int type, int i1, int i2) { return (unsigned long long)(type | (i1 << 2) | (i2 << 6)); };
+    std::vector<unsigned long long> light;
+    for (int a = 0; a < 12; a++) for (int b = 0; b < 12; b++) light.push_back(desc(2, a, b));
+    std::vector<unsigned long long> cc;
+    for (int a = 0; a < 12; a++) for (int b = 0; b <= a; b++) cc.push_back(desc(3, a, b));
+    int t = 0;
+    for (int a = 0; a < 12; a++) for (int b = 0; b <= a; b++, t++) {      // threads 0..77: one heavy entry + one (c, c) entry
+        unsigned long long d = desc(1, a, b);
+        if (!cc.empty() && t < 72) { d |= cc.back() << 16; cc.pop_back(); }
+        tab[ZT_C1OFF + t] = d;
+    }
+    for (auto v : cc) light.push_back(v);
+    for (size_t i = 0; i < light.size(); i++) {                            // threads 78..127: three entries each
+        const size_t th = 78 + i % 50, sl = 1 + i / 50;
+        if (sl > 3) abort();
+        tab[ZT_C1OFF + th] |= light[i] << (16 * sl);
+    }
 }
 
 // kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.reserved0 = 1), 2 = LIP dense

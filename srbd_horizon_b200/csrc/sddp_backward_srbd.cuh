@@ -66,7 +66,7 @@ SDDP_DEV double fast_rcp(double p) {
 }
 
 #ifndef SDDP_ROW128
-#define SDDP_ROW128 0
+#define SDDP_ROW128 1
 #endif
 // a[i] -= row[i] * s for lo <= i < n; `lo` is a compile-time constant after unrolling.  Every thread of a warp reads
 // the same addresses (broadcast).  Loads first, then the FMAs, in batches of 8 (keeps the loads in flight together
@@ -165,6 +165,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
     M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, S.escr);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
 
+    const unsigned long long c1d = __ldg(c.ztab + ZT_C1OFF + tid);     // this thread's Quu entries (see c1)
     for (int k = N - 1; k >= 0; k--) {
         const int kind = node_kind(k, N);
         double* nb = S.nb[k & 1];
@@ -196,18 +197,12 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         {
             // u = (cddot_i, f_i) x 4: "c" index ci = 3 i + r -> u index 6 i + r, "f" index fj = 3 j + k -> 6 j + 3 + k.
             // B^T rows: cddot -> e(cd); f_jk -> (fs/m) e(rd_k) + sum_q G_j[q][k] e(w_q),  G_j[q][k] = Jac[q][ZF + fj].
-            // Threads 0..77 take one (f, f) entry each (16 products), threads 78..127 the 144 (cddot, f) and the 78
-            // (cddot, cddot) entries (4 or 1 products, 4-5 entries each): one balanced round.
+            // Threads 0..77 take one (f, f) entry (16 products) and one (cddot, cddot) entry, threads 78..127 three of
+            // the remaining (cddot, f) / (cddot, cddot) entries (4 or 1 products): the assignment is a host-built
+            // table (sddp.cu:build_ztab), four 16-bit descriptors per thread.
             const double dt2 = dt * dt, g2 = 2.0 * c.gq;
-            auto tri = [](int e, int& hi, int& lo) {       // e = hi (hi + 1) / 2 + lo, lo <= hi
-                int h = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-                while ((h + 1) * (h + 2) / 2 <= e) h++;
-                while (h * (h + 1) / 2 > e) h--;
-                hi = h; lo = e - h * (h + 1) / 2;
-            };
             if (tid < 78) {
-                int fa, fb;
-                tri(tid, fa, fb);
+                const int fa = C1_I1(c1d), fb = C1_I2(c1d);
                 const int ka = fa % 3, kb = fb % 3;
                 const double* Ga = Jac + M::ZF + fa;
                 const double* Gb = Jac + M::ZF + fb;
@@ -227,26 +222,27 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 const int ua = 6 * (fa / 3) + 3 + ka, ub = 6 * (fb / 3) + 3 + kb;
                 S.Quu[ua * NU + ub] = v;
                 S.Quu[ub * NU + ua] = v;
-            } else {
-                for (int e = tid - 78; e < 144 + 78; e += NT - 78) {
-                    int ua, ub;
-                    double v;
-                    if (e < 144) {
-                        const int ci = e / 12, fj = e % 12, kb = fj % 3;
-                        const double* G = Jac + M::ZF + fj;
-                        const double* Vc = S.VT + (M::XCD + ci) * NX;
-                        v = dt2 * (Vc[M::XRD + kb] * c.inv_ms + Vc[M::XW] * G[0] + Vc[M::XW + 1] * G[NZ] + Vc[M::XW + 2] * G[2 * NZ]);
-                        ua = 6 * (ci / 3) + ci % 3; ub = 6 * (fj / 3) + 3 + kb;
-                    } else {
-                        int ca, cb;
-                        tri(e - 144, ca, cb);
-                        v = dt2 * S.VT[(M::XCD + ca) * NX + M::XCD + cb];
-                        if (ca == cb) v += g2 + mu;      // cddot rows of min_qddot
-                        ua = 6 * (ca / 3) + ca % 3; ub = 6 * (cb / 3) + cb % 3;
-                    }
-                    S.Quu[ua * NU + ub] = v;
-                    S.Quu[ub * NU + ua] = v;
+            }
+#pragma unroll 1
+            for (int sl = 1; sl < 4; sl++) {
+                const unsigned d = (unsigned)(c1d >> (16 * sl)) & 0xffffu;
+                const int ty = C1_TYPE(d), i1 = C1_I1(d), i2 = C1_I2(d);
+                if (ty == 0) continue;
+                int ua, ub;
+                double v;
+                if (ty == 2) {                        // (cddot ci, f fj)
+                    const int kb = i2 % 3;
+                    const double* G = Jac + M::ZF + i2;
+                    const double* Vc = S.VT + (M::XCD + i1) * NX;
+                    v = dt2 * (Vc[M::XRD + kb] * c.inv_ms + Vc[M::XW] * G[0] + Vc[M::XW + 1] * G[NZ] + Vc[M::XW + 2] * G[2 * NZ]);
+                    ua = 6 * (i1 / 3) + i1 % 3; ub = 6 * (i2 / 3) + 3 + kb;
+                } else {                              // (cddot ca, cddot cb)
+                    v = dt2 * S.VT[(M::XCD + i1) * NX + M::XCD + i2];
+                    if (i1 == i2) v += g2 + mu;      // cddot rows of min_qddot
+                    ua = 6 * (i1 / 3) + i1 % 3; ub = 6 * (i2 / 3) + i2 % 3;
                 }
+                S.Quu[ua * NU + ub] = v;
+                S.Quu[ub * NU + ua] = v;
             }
         }
         if (k > 0) prefetch(k - 1);
@@ -267,11 +263,12 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
             } else if (lane == 0) { S.red[R_G1] = 0.0; S.red[R_G2] = 0.0; S.red[R_YG] = 0.0; }
             // Lane t holds column t.  Step j: lane j publishes its (final) column raw, row j of the strict upper
-            // triangle of S.Quu, and 1/pivot; every lane then applies  a[i] -= col_j[i] * (a[j] / pivot_j),  i > j.
+            // triangle of S.Quu, and 1/pivot; every other lane then applies  a[i] -= col_j[i] * (a[j] / pivot_j),  i > j.
             // The element that becomes the next pivot (i = j+1) is updated first and its reciprocal started at
             // once, so the rest of the update overlaps the reciprocal latency.
-            // A lane whose column is published restarts as column j of the identity: the very same updates then
-            // build E = Lt^-1 in the lanes the factorisation no longer needs (lane t ends with column t of E).
+            // Lane j skips step j and keeps taking part afterwards: its registers then carry -pivot_j times column j
+            // of E = Lt^-1 (E[:,j] starts as -col_j / pivot_j and obeys the same linear recurrence), so the inverse
+            // factor costs no extra arithmetic in lanes the factorisation no longer needs.
             double a[NU];
             const int t = lane < NU ? lane : NU - 1;
 #pragma unroll
@@ -279,31 +276,37 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             __syncwarp();
             bool bad = false;
             double myinv = fast_rcp(a[0]);          // lane 0's pivot
+            double pinv = 0.0;                      // 1 / pivot of this lane's column
 #pragma unroll
             for (int j = 0; j < NU; j++) {
                 if (lane == j) {
                     const double p = a[j];
                     bad = !(p > 0.0) || !isfinite(p);
+                    pinv = myinv;
                     S.invp[j] = myinv;
                     store_row<NU>(S.Quu + j * NU, a, j + 1);
-                    a[j] = 1.0;
-#pragma unroll
-                    for (int i = j + 1; i < NU; i++) a[i] = 0.0;
                 }
                 __syncwarp();
                 if (j + 1 < NU) {
-                    const double sj = S.invp[j] * a[j];
+                    const double sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
                     a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
                     myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
                     if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
                 }
             }
             if (__any_sync(FULL, bad) && lane == 0) S.iflag[1] = 1;
-            if (lane < NU) S.rs[lane] = sqrt(S.invp[lane]);
+            if (lane < NU) S.rs[lane] = sqrt(pinv);
             __syncwarp();
-            if (lane < NU) {                        // Es = rs . E -> lower triangle (incl. diagonal) of S.Quu
+            {   // Es = rs . E -> S.Quu, zeros above the diagonal (the raw columns are dead).  Branch free: selects and
+                // one predicated pair of stores per row pair (a divergent branch per entry costs ~10x more).
+                const double np = -pinv;
 #pragma unroll
-                for (int i = 0; i < NU; i++) if (i >= lane) S.Quu[i * NU + lane] = a[i] * S.rs[i];
+                for (int i = 0; i < NU; i += 2) {
+                    const double2 r = *reinterpret_cast<const double2*>(S.rs + i);
+                    const double v0 = (i > t) ? np * a[i] * r.x : (i == t ? r.x : 0.0);
+                    const double v1 = (i + 1 > t) ? np * a[i + 1] * r.y : (i + 1 == t ? r.y : 0.0);
+                    if (lane < NU) { S.Quu[i * NU + lane] = v0; S.Quu[(i + 1) * NU + lane] = v1; }
+                }
             }
             PROF_T(14, 0);
             STAMP(4); STAMP(5); STAMP(6); STAMP(7);
@@ -407,7 +410,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; cp_wait_all(); __syncthreads(); return k + 1; }
 
         // ---- h: Wn = Es B (B = [Qux | Qu | quy], 24 x 40 in S.W; Es lower triangular in S.Quu, entries above the
-        //         diagonal masked: that part holds the raw factor).  In place: a warp owns whole 8-column blocks
+        //         diagonal are zero).  In place: a warp owns whole 8-column blocks
         //         (warp 0: blocks 0 and 4) and reads all of a block before it writes; the three row tiles of a block
         //         are independent DMMA chains of 2, 4 and 6 steps.
         {
@@ -422,7 +425,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     for (int I = 0; I < 3; I++) {
                         if (k0 > 8 * I + 7) continue;
                         const int i = 8 * I + fr;
-                        const double av = (l <= i) ? S.Quu[i * NU + l] : 0.0;
+                        const double av = S.Quu[i * NU + l];
                         dmma884(h0[I], h1[I], av, bv);
                     }
                 }
@@ -438,7 +441,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         //         six DMMA steps.  Results go to VT (T is dead), Vx, y (column 38 = Wn^T Es quy = -K^T quy),
         //         red[R_SW] = |w0|^2 and red[R_SQ] = quy . k.
         // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
-        //         at k0 = 8 I and entries above the diagonal are masked (that part of S.Quu holds the raw factor).
+        //         at k0 = 8 I.
         // Warp w takes tiles w, w+4, w+8, w+12 of each product and runs their accumulation chains interleaved (a
         // single chain of six dependent DMMAs is latency bound); slot 3 of warp 3 is a dummy.
         {
@@ -469,7 +472,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int i = 8 * gI[q] + fr;
-                    av[q] = (l >= i) ? S.Quu[l * NU + i] : 0.0;
+                    av[q] = S.Quu[l * NU + i];
                     bv[q] = S.W[l * LDW + 8 * gJ[q] + fr];
                 }
 #pragma unroll

@@ -62,6 +62,11 @@ struct DevCfg {
 
 // z-block descriptor bit layout (built on the host, sddp.cu:build_ztab)
 enum { ZT_ROUNDS = 5, ZT_THREADS = 128, ZT_NXX_NUX = 517, ZT_LAZY_THREADS = 96, ZT_LAZY_ROUNDS = 6 };   // 595 entries: 253 xx + 264 ux first, then 78 uu
+// Quu work table of the structured backward pass: ztab[ZT_C1OFF + tid] = four 16-bit descriptors type | i1 << 2 | i2 << 6
+enum { ZT_C1OFF = 640, ZT_TOTAL = 640 + 128 };
+#define C1_TYPE(d) (int)((d) & 3)
+#define C1_I1(d) (int)(((d) >> 2) & 15)
+#define C1_I2(d) (int)(((d) >> 6) & 15)
 #define ZT_VALID(d) ((d) & 1ull)
 #define ZT_KIND(d) (int)(((d) >> 1) & 3)
 #define ZT_DA(d) (int)(((d) >> 3) & 63)
