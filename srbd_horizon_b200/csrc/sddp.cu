@@ -275,11 +275,11 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
     auto zu = [&](int p) { return 6 * ((p - 22) / 3) + 3 + (p - 22) % 3; };
     tab.assign((size_t)ZT_TOTAL, 0ull);
     int e = 0;
-    for (int pass = 0; pass < 2; pass++)      // xx and ux entries first (ZT_NXX_NUX of them), then uu
+    for (int pass = 0; pass < 3; pass++)      // xx entries first, then ux (ZT_NXX_NUX together), then uu: warps see one kind
     for (int pi = 0; pi < NZ; pi++)
         for (int qi = pi; qi < NZ; qi++) {
             const int xi = zx(pi), xj = zx(qi);
-            if ((pass == 0) != (xi >= 0)) continue;
+            if (pass != ((xi >= 0 && xj >= 0) ? 0 : (xi >= 0 ? 1 : 2))) continue;
             int kind, da, db;
             if (xi >= 0 && xj >= 0) { kind = 0; da = xi; db = xj; }
             else if (xi >= 0) { kind = 1; da = zu(qi); db = xi; }
@@ -303,6 +303,8 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
             unsigned long long d = 1ull | ((unsigned long long)kind << 1) | ((unsigned long long)da << 3) | ((unsigned long long)db << 9) |
                                    ((unsigned long long)pi << 15) | ((unsigned long long)qi << 21) | ((unsigned long long)hs << 27) |
                                    ((unsigned long long)hoff << 29);
+            if (kind == 0) d |= ((unsigned long long)(da * Srbd::NX + db) << 38) | ((unsigned long long)(db * Srbd::NX + da) << 50);
+            if (kind == 1) d |= ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 38) | ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 50);
             tab[e++] = d;
         }
     if (e != NZ * (NZ + 1) / 2) abort();

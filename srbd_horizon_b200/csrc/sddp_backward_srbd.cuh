@@ -21,6 +21,7 @@
 //   where a 3x3 register tile needs six loads for nine -- these products were shared-memory-bandwidth bound)
 // Node inputs (x, u, p, d, pack) of node k-1 are fetched with cp.async while node k is processed.
 #pragma once
+#include <cstddef>
 #include "sddp_solver.cuh"
 
 struct alignas(16) SmemSrbd {
@@ -44,7 +45,7 @@ struct alignas(16) SmemSrbd {
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
 };
 static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 44, "forward K double buffer must fit in Qxx + W");
-enum { R_SW = 6, R_SQ = 7 };
+static_assert(offsetof(SmemSrbd, W) - offsetof(SmemSrbd, Qxx) == ZT_QUX_OFF * sizeof(double) && SmemSrbd::LDW == ZT_LDUX, "descriptor table destinations (sddp.cu:build_ztab)");
 SDDP_DEV void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 struct Bar96 { __device__ void operator()() const { bar_named(2, 96); } };      // warps 1-3
 
@@ -160,7 +161,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         for (int i = tid; i < NP; i += NT) nb[NBL::OP + i] = P[(size_t)N * NP + i];
     }
     prefetch(N - 1);
-    if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; S.iflag[1] = 0; }
+    if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; S.iflag[1] = 0; S.Qx[NX] = 0.0; S.qxy[NX] = 0.0; }
     __syncthreads();
     M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, S.escr);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
@@ -439,7 +440,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         __syncthreads();
         // ---- f: [Vxx Vx y] = [sym(Qxx) Qx qxy] - Wn^T Wn: upper-triangular 8x8 tiles of the 40x40 product, K = 24 in
         //         six DMMA steps.  Results go to VT (T is dead), Vx, y (column 38 = Wn^T Es quy = -K^T quy),
-        //         red[R_SW] = |w0|^2 and red[R_SQ] = quy . k.
+        //         Vx[37] = -|w0|^2 and y[37] = quy . k.
         // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
         //         at k0 = 8 I.
         // Warp w takes tiles w, w+4, w+8, w+12 of each product and runs their accumulation chains interleaved (a
@@ -484,20 +485,20 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 const int gi = 8 * fI[q] + fr;
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
+                    // Branch free (a divergent branch per case costs more than the work): columns 37 / 38 use the
+                    // vectors Qx -> Vx and qxy -> y as one more row / column of the matrices, whose spare entry 37 is
+                    // kept zero, so Vx[37] = -|w0|^2 and y[37] = quy . k; inactive lanes hit dummy addresses.
                     const int gj = 8 * fJ[q] + 2 * fc + e;
                     const double acc = e ? fc1[q] : fc0[q];
-                    if (gj < gi) continue;
-                    if (gj < NX) {
-                        const double v = 0.5 * (S.Qxx[gi * NX + gj] + S.Qxx[gj * NX + gi]) - acc;
-                        S.VT[gi * NX + gj] = v;
-                        S.VT[gj * NX + gi] = v;
-                    } else if (gj == NX) {
-                        if (gi < NX) S.Vx[gi] = S.Qx[gi] - acc;
-                        else S.red[R_SW] = acc;            // |w0|^2
-                    } else if (gj == NX + 1) {
-                        if (gi < NX) S.y[gi] = S.qxy[gi] - acc;
-                        else if (gi == NX) S.red[R_SQ] = -acc;
-                    }
+                    const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
+                    const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
+                    const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
+                    double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
+                    double* d2 = m ? S.VT + gj * NX + gi : d1;
+                    if (!ok) { s1 = s2 = S.Qx + NX; d1 = d2 = S.escr + 23; }
+                    const double v = 0.5 * (*s1 + *s2) - acc;
+                    *d1 = v;
+                    *d2 = v;
                 }
             }
 #pragma unroll
@@ -509,7 +510,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     const int cc = 8 * J + 2 * fc + e;
                     const double kv = e ? -gc1[q] : -gc0[q];
                     if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
-                    else if (cc == NX) { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
+                    if (cc == NX) S.kk[i] = kv;
+                    if (cc == NX) kg[(size_t)k * NU + i] = kv;
                 }
             }
         }
@@ -535,10 +537,10 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             }
         }
         if (tid == 0) {   // model accumulators
-            const double sw = S.red[R_SW];
+            const double sw = -S.Vx[NX];        // |w0|^2 (see f)
             double sk = 0.0;
             if (mu != 0.0) for (int i = 0; i < NU; i++) sk += S.kk[i] * S.kk[i];
-            const double sq = S.red[R_SQ];      // quy . k
+            const double sq = S.y[NX];          // quy . k
             const double kQk = sw - mu * sk;
             S.red[R_TOT] += S.red[R_G1] + 0.5 * S.red[R_G2] + (-sw) + 0.5 * kQk;
             S.red[R_ACC2] += 0.5 * kQk;

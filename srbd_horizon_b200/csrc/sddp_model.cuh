@@ -75,6 +75,9 @@ enum { ZT_C1OFF = 640, ZT_TOTAL = 640 + 128 };
 #define ZT_QI(d) (int)(((d) >> 21) & 63)
 #define ZT_HSIGN(d) (int)(((d) >> 27) & 3)
 #define ZT_HOFF(d) (int)(((d) >> 29) & 511)
+#define ZT_DST1(d) (int)(((d) >> 38) & 4095)
+#define ZT_DST2(d) (int)(((d) >> 50) & 4095)
+enum { ZT_QUX_OFF = 37 * 37 + 1, ZT_LDUX = 44 };   // layout of SmemSrbd (static_assert there)
 
 enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2 };
 
@@ -489,9 +492,10 @@ struct Srbd {
                 if (exact && hs) { const double v = pk[ZT_HOFF(d)]; hh += (hs == 1) ? v : -v; }
                 hh *= g2;
                 const int kd = ZT_KIND(d);
-                if (MODE) {
-                    if (kd == 0) { Qxx[da * NX + db] += hh; if (da != db) Qxx[db * NX + da] += hh; }
-                    else if (kd == 1) Qux[da * LDUX + db] += hh;
+                if (MODE) {        // destinations as offsets from Qxx (Qux = Qxx + ZT_QUX_OFF, pitch ZT_LDUX): no branch on the kind
+                    const int o1 = ZT_DST1(d), o2 = ZT_DST2(d);
+                    Qxx[o1] += hh;
+                    if (o2 != o1) Qxx[o2] += hh;
                 } else {
                     if (kd == 0) { Qxx[da * NX + db] = hh; Qxx[db * NX + da] = hh; }
                     else if (kd == 1) Qux[da * LDUX + db] = hh;
@@ -514,47 +518,54 @@ struct Srbd {
         if (MODE) PROF_T(18, 32);
         // ---- affine residuals, Hessian: one entry per thread (119 entries; MODE 1 skips the luu entries 0..47, 96..107)
         const int t = MODE ? (tid < 48 ? tid + 48 : tid + 60) : tid;
+        // (each case only computes the destination and the value; one read-modify-write at the end keeps the cases
+        //  short enough to be predicated instead of branched over)
+        int hdst = -1;
+        bool huu = false;
+        double hval = 0.0;
         if (t < 48) {                                   // rddot rows of min_qddot + min_f + f_active   (prb.py:200-204)
             if (input) {
                 const int k = t >> 4, i = (t >> 2) & 3, j = t & 3;
-                double v = 2.0 * c.gq * c.inv_ms * c.inv_ms;
-                if (i == j) { const double a = 1.0 - p[8 + 2 * i]; v += 2.0 * (c.w_minf + c.w_fsw * a * a); }
-                Quu[(6 * i + 3 + k) * NU + 6 * j + 3 + k] += v;
+                hval = 2.0 * c.gq * c.inv_ms * c.inv_ms;
+                if (i == j) { const double a = 1.0 - p[8 + 2 * i]; hval += 2.0 * (c.w_minf + c.w_fsw * a * a); }
+                hdst = (6 * i + 3 + k) * NU + 6 * j + 3 + k; huu = true;
             }
         } else if (t < 64) {                            // o_tracking_xyz / _w   (prb.py:185-189)
             if (track) {
                 const int a = (t - 48) >> 2, b = (t - 48) & 3;
                 const double hh = Es[a] * Es[b] + Es[4 + a] * Es[4 + b] + Es[8 + a] * Es[8 + b] + Es[12 + a] * Es[12 + b];
-                Qxx[(XO + a) * NX + XO + b] += 2.0 * p[6] * p[6] * hh;
+                hdst = (XO + a) * NX + XO + b; hval = 2.0 * p[6] * p[6] * hh;
             }
         } else if (t < 80) {                            // rel_pos_*   (prb.py:192-199)
             if (track) {
                 const int r = (t - 64) >> 2, e = (t - 64) & 3, j = r >> 1, ax = r & 1;
                 const int ia = XC + 3 * j + ax, ib = ia + 6;
                 const int row = (e & 2) ? ib : ia, col = (e & 1) ? ib : ia;
-                Qxx[row * NX + col] += (row == col) ? 2.0 * c.w_rel : -2.0 * c.w_rel;
+                hdst = row * NX + col; hval = (row == col) ? 2.0 * c.w_rel : -2.0 * c.w_rel;
             }
         } else if (t < 96) {                            // relative_vel_* and cdotxy_tracking_*   (prb.py:166-181)
             if (input) {
                 const int g = (t - 80) >> 2, e = (t - 80) & 3, leg = g >> 1, ax = g & 1;
                 const int ia = XCD + 3 * (2 * leg) + ax, ib = ia + 3;
                 const int row = (e & 2) ? ib : ia, col = (e & 1) ? ib : ia;
-                double v = -2.0 * c.cw;
-                if (row == col) { const double sw = p[8 + 2 * (2 * leg + ((e & 2) ? 1 : 0))]; v = 2.0 * c.cw * (1.0 + sw * sw); }
-                Qxx[row * NX + col] += v;
+                const double sw = p[8 + 2 * (2 * leg + ((e & 2) ? 1 : 0))];
+                hdst = row * NX + col; hval = (row == col) ? 2.0 * c.cw * (1.0 + sw * sw) : -2.0 * c.cw;
             }
         } else if (t < 108) {                           // cddot rows of min_qddot
-            if (input) { const int i = t - 96, ui = 6 * (i / 3) + i % 3; Quu[ui * NU + ui] += 2.0 * c.gq; }
+            if (input) { const int i = t - 96, ui = 6 * (i / 3) + i % 3; hdst = ui * NU + ui; hval = 2.0 * c.gq; huu = true; }
         } else if (t < 112) {                           // cz_tracking_i   (prb.py:180)
-            if (input) { const int id = XC + 3 * (t - 108) + 2; Qxx[id * NX + id] += 2.0 * c.cw; }
+            if (input) { const int id = XC + 3 * (t - 108) + 2; hdst = id * NX + id; hval = 2.0 * c.cw; }
         } else if (t < 115) {                           // rdot_tracking   (prb.py:190)
-            if (track) { const int id = XRD + t - 112; Qxx[id * NX + id] += 2.0 * c.w_rdot; }
+            if (track) { const int id = XRD + t - 112; hdst = id * NX + id; hval = 2.0 * c.w_rdot; }
         } else if (t < 118) {                           // w_tracking   (prb.py:191)
-            if (track) { const int id = XW + t - 115; Qxx[id * NX + id] += 2.0 * c.w_w; }
+            if (track) { const int id = XW + t - 115; hdst = id * NX + id; hval = 2.0 * c.w_w; }
         } else if (t == 118) {                          // rz_tracking   (prb.py:184)
-            if (track) Qxx[2 * NX + 2] += 2.0 * c.w_r;
+            if (track) { hdst = 2 * NX + 2; hval = 2.0 * c.w_r; }
         }
-        // ---- affine residuals, gradient: thread tg < 24 owns lu[tg], thread 32 + i owns lx[i]
+        if (hdst >= 0) {
+            if (MODE == 0 && huu) Quu[hdst] += hval; else Qxx[hdst] += hval;
+        }
+        // ---- affine residuals, gradient: thread tg < 24 owns lu[tg], thread 32 + i owns lx[i] (MODE 0)
         const int tg = tid;
         if (tg < NU) {
             if (input) {
@@ -565,8 +576,9 @@ struct Srbd {
                 if (MODE) { Qu[tg * LDUX] += g; Qu2[tg * LDUX] += g; }
                 else Qu[tg] += g;
             }
-        } else if (tg >= 32 && tg < 32 + NX) {
-            const int i = tg - 32;
+        } else if (MODE ? (tg >= 64 || tg < NU + 5) : (tg >= 32 && tg < 32 + NX)) {
+            // MODE 1: lx[0..31] on the third warp (the only one without Hessian entries above), lx[32..36] on threads 24..28
+            const int i = MODE ? (tg >= 64 ? tg - 64 : 32 + tg - NU) : tg - 32;
             double g = 0.0;
             if (i == 2) { if (track) g = 2.0 * c.w_r * (x[2] - c.com[2]); }
             else if (i >= XO && i < XC) {

@@ -22,7 +22,7 @@ for rep in range(2):
     torch.cuda.synchronize()
 L.sddp_debug_stamps(out)
 names = ["node top", "after top sync", "c1 done", "after c1 sync", "w0: d1 done | w1-3: c2 done", "w1-3: c3 done", "w1-3: e done",
-         "w1-3: d2 done", "after d sync", "f,g done", "after f,g sync"]
+         "end of d phase", "after d sync", "f,g done", "after f,g sync", "h done"]
 t0 = out[1 * 4 + 0]
 print(f"batch={a.batch}: cycles since warp 0 passed the top barrier of node 10 (last iteration of the last problem of CTA 0)")
 print(f"{'':30s}" + "".join(f"{'warp ' + str(w):>10s}" for w in range(4)))
