@@ -415,16 +415,29 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             }
             const double* nb = S.nb[k & 1];
             const double* xc = xb[k & 1];
-            if (w == 0) {
+            constexpr int MV = (4 * NU + 31) & ~31;       // whole warps take part in the shuffles
+            static_assert(MV <= NT - 32, "the last warp copies x^");
+            if (tid < MV) {                    // u^ = U + alpha k + K dx: four threads per row of K, partial sums by shuffle
                 const double* Kb = S.Kbuf(k & 1);
                 const double* xk = nb + NBL::OX;
-                for (int j = lane; j < NU; j += 32) {
-                    double t = 0.0;
-                    for (int i = 0; i < NX; i++) t += Kb[j * NX + i] * (xc[i] - xk[i]);
-                    const double v = nb[NBL::OU + j] + alpha * nb[NBL::OK + j] + t;
+                const int j = tid >> 2, part = tid & 3;
+                constexpr int CH = (NX + 3) / 4;
+                double t = 0.0;
+                if (j < NU) {
+#pragma unroll
+                    for (int q = 0; q < CH; q++) {
+                        const int i = part * CH + q;
+                        if (i < NX) t += Kb[j * NX + i] * (xc[i] - xk[i]);
+                    }
+                }
+                t += __shfl_xor_sync(FULL, t, 1);
+                t += __shfl_xor_sync(FULL, t, 2);
+                if (j < NU && part == 0) {
+                    const double v = nb[NBL::OU + j] + S.alpha[0] * nb[NBL::OK + j] + t;      // (`alpha` is per warp = per candidate)
                     ub[j] = v;
                     Un[(size_t)k * NU + j] = v;
                 }
+            } else if (w == NWARP - 1) {
                 for (int i = lane; i < NX; i += 32) Xn[(size_t)k * NX + i] = xc[i];
             }
             __syncthreads();                  // u^_k visible
