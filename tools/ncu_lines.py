@@ -42,6 +42,7 @@ ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instru
 iwf = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
 wf_line = collections.Counter()
 base = None
+ex_addr = {}
 by_line = collections.Counter(); ex_line = collections.Counter()
 stall_cols = [i for i, c in enumerate(hdr) if c.startswith("stall_") and "Not Issued" not in c]
 stall_by_line = collections.defaultdict(collections.Counter)
@@ -55,6 +56,7 @@ for r in rows[h + 1:]:
     key = addr2line.get(a - base, (None, ""))[0]
     s = int(r[isamp] or 0)
     by_line[key] += s; total += s
+    ex_addr[a - base] = int(r[iex] or 0)
     ex_line[key] += int(r[iex] or 0)
     if iwf is not None:
         wf_line[key] += int(float(r[iwf] or 0))
@@ -79,22 +81,33 @@ for key, s in by_line.most_common(top):
 
 # ---- optional phase buckets: python tools/ncu_lines.py rep kernel top buckets
 if len(sys.argv) > 4:
-    spec = {
-        "forward_wave": [("sddp_solver.cuh", 371, 502)],
-        "node eval (accel/cost/xdot)": [("sddp_model.cuh", 193, 295), ("sddp_solver.cuh", 83, 107)],
-        "init/defects/rollout": [("sddp_solver.cuh", 108, 172)],
-        "pack (thread per node)": [("sddp_model.cuh", 296, 404)],
-        "expand": [("sddp_model.cuh", 405, 677)],
-        "bwd load+c1 (Quu, gap)": [("sddp_backward_srbd.cuh", 92, 184)],
-        "bwd d1 (warp-0 LDL^T)": [("sddp_backward_srbd.cuh", 185, 239)],
-        "bwd c2 (T=V fx)": [("sddp_backward_srbd.cuh", 240, 271)],
-        "bwd c3 (Qxx,Qux cols)": [("sddp_backward_srbd.cuh", 272, 320)],
-        "bwd d2 (RHS substitution)": [("sddp_backward_srbd.cuh", 321, 365)],
-        "bwd syrk (DMMA)": [("sddp_backward_srbd.cuh", 366, 399)],
-        "bwd K matmul (DMMA)": [("sddp_backward_srbd.cuh", 400, 427)],
-        "bwd mu path + model": [("sddp_backward_srbd.cuh", 428, 490)],
-        "solve_one control": [("sddp_solver.cuh", 503, 703)],
-    }
+    # phase buckets are delimited by marker strings in the sources (first match), so they follow the code
+    csrc = os.path.join(root, "srbd_horizon_b200", "csrc")
+    def ln(f, marker, nth=1):
+        n = 0
+        for i, l in enumerate(open(os.path.join(csrc, f)), 1):
+            if marker in l:
+                n += 1
+                if n == nth:
+                    return i
+        raise SystemExit(f"marker not found: {f}: {marker}")
+    B, Mo, So = "sddp_backward_srbd.cuh", "sddp_model.cuh", "sddp_solver.cuh"
+    marks = [("bwd load + top", ln(B, "__device__ int SmemSrbd::backward(")), ("bwd c1 (Quu, gap)", ln(B, "// ---- c1:")),
+             ("bwd d1 (warp-0 LDL^T, E)", ln(B, "// ---- d1:")), ("bwd c2 (T = V fx)", ln(B, "// ---- c2:")),
+             ("bwd c3 (fx^T T, fu^T T)", ln(B, "// ---- c3:")), ("bwd e call", ln(B, "// ---- e:")),
+             ("bwd h (Wn = Es B, DMMA)", ln(B, "// ---- h:")), ("bwd f,g (syrk + gains, DMMA)", ln(B, "// ---- f:")),
+             ("bwd mu path + model", ln(B, "if (mu != 0.0) {   // regularised step")), ("", 10 ** 9)]
+    spec = {name: [(B, lo, marks[i + 1][1] - 1)] for i, (name, lo) in enumerate(marks[:-1])}
+    spec["bwd row helpers (axpy/store, in d1)"] = [(B, ln(B, "SDDP_DEV void axpy_row"), ln(B, "// out[b] = sum_a v[a] * (dt Aoo)") - 1)]
+    spec["bwd dmma/rcp/contract helpers"] = [(B, ln(B, "SDDP_DEV void dmma884"), ln(B, "#ifndef SDDP_ROW128") - 1),
+                                             (B, ln(B, "// out[b] = sum_a v[a] * (dt Aoo)"), ln(B, "__device__ int SmemSrbd::backward(") - 1)]
+    srbd0, lip0 = ln(Mo, "struct Srbd {"), ln(Mo, "struct Lip {")
+    spec["model: accel/xdot/cost lanes"] = [(Mo, ln(Mo, "SDDP_DEV static void accel("), ln(Mo, "static void pack(") - 1)]
+    spec["model: pack (thread per node)"] = [(Mo, ln(Mo, "static void pack("), ln(Mo, "SDDP_DEV static int zmap_x") - 1)]
+    spec["model: expand (lx, lxx, lux terms)"] = [(Mo, ln(Mo, "SDDP_DEV static int zmap_x"), lip0 - 1)]
+    spec["model: m3 / inertia helpers"] = [(Mo, 1, ln(Mo, "SDDP_DEV static void accel(") - 1)]
+    spec["forward_wave"] = [(So, ln(So, "__device__ void forward_wave("), ln(So, "struct SolveArgs") - 1)]
+    spec["solve_one control, packs loop, defects"] = [(So, ln(So, "struct SolveArgs"), 10 ** 9), (So, 1, ln(So, "__device__ void forward_wave(") - 1)]
     tot_b = collections.Counter(); ex_b = collections.Counter(); wf_b = collections.Counter(); st_b = collections.defaultdict(collections.Counter)
     for key, s in by_line.items():
         name = "other/unattributed"
@@ -107,7 +120,19 @@ if len(sys.argv) > 4:
             st_b[name][k2] += v
     tot_ex = sum(ex_b.values())
     tot_wf = max(1, sum(wf_b.values()))
-    print("\nphase buckets: samples%  inst%  smem-wavefronts%  top stalls")
+    size_b = collections.Counter(); hot_b = collections.Counter()
+    mx = max(ex_addr.values()) if ex_addr else 1
+    for a_, (key, _) in addr2line.items():
+        name = "other/unattributed"
+        if key is not None:
+            for nm, ranges in spec.items():
+                if any(key[0] == f and lo <= key[1] <= hi for f, lo, hi in ranges):
+                    name = nm
+        size_b[name] += 16
+        if ex_addr.get(a_, 0) > 0.003 * mx:
+            hot_b[name] += 16
+    print(f"\nstatic SASS {sum(size_b.values()) / 1024:.0f} KB, executed often (> 0.3 % of the hottest instruction) {sum(hot_b.values()) / 1024:.0f} KB")
+    print("\nphase buckets: samples%  inst%  smem-wavefronts%  SASS KB (hot KB)  top stalls")
     for nm, s in tot_b.most_common():
         st = ", ".join(f"{k[6:]}={100.0 * v / max(s, 1):.0f}%" for k, v in st_b[nm].most_common(3))
-        print(f"{100.0 * s / total:5.1f}%  {100.0 * ex_b[nm] / tot_ex:5.1f}%  {100.0 * wf_b[nm] / tot_wf:5.1f}%  {nm:32s} [{st}]")
+        print(f"{100.0 * s / total:5.1f}%  {100.0 * ex_b[nm] / tot_ex:5.1f}%  {100.0 * wf_b[nm] / tot_wf:5.1f}%  {size_b[nm] / 1024:5.1f} ({hot_b[nm] / 1024:4.1f})  {nm:38s} [{st}]")
