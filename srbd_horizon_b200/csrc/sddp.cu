@@ -274,7 +274,7 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
     auto zx = [&](int p) { return p < 19 ? p : (p < 22 ? (int)Srbd::XW + (p - 19) : -1); };
     auto zu = [&](int p) { return 6 * ((p - 22) / 3) + 3 + (p - 22) % 3; };
     tab.assign((size_t)ZT_TOTAL, 0ull);
-    int e = 0;
+    int e = 0, nc = 0;
     for (int pass = 0; pass < 3; pass++)      // xx entries first, then ux (ZT_NXX_NUX together), then uu: warps see one kind
     for (int pi = 0; pi < NZ; pi++)
         for (int qi = pi; qi < NZ; qi++) {
@@ -306,6 +306,7 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
             if (kind == 0) d |= ((unsigned long long)(da * Srbd::NX + db) << 38) | ((unsigned long long)(db * Srbd::NX + da) << 50);
             if (kind == 1) d |= ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 38) | ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 50);
             tab[e++] = d;
+            if (kind != 2 && hs != 0) { if (nc >= ZT_CROUNDS * ZT_LAZY_THREADS) abort(); tab[ZT_COFF + nc++] = d; }   // curvature-only list
         }
     if (e != NZ * (NZ + 1) / 2) abort();
     // Quu work table (sddp_backward_srbd.cuh, phase c1).  Types: 1 (f_a, f_b) a >= b, 2 (cddot_a, f_b), 3 (cddot_a, cddot_b) a >= b.

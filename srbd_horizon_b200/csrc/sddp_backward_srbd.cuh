@@ -66,6 +66,14 @@ SDDP_DEV double fast_rcp(double p) {
     return fma(x, e, x);
 }
 
+// unroll depth of the two long loops of c3 (instruction-cache footprint vs load batching)
+#ifndef SDDP_C3_UNROLL
+#define SDDP_C3_UNROLL 12
+#endif
+#ifndef SDDP_C3_UNROLL_I
+#define SDDP_C3_UNROLL_I 4
+#endif
+constexpr int C3U = SDDP_C3_UNROLL, C3UI = SDDP_C3_UNROLL_I;
 #ifndef SDDP_ROW128
 #define SDDP_ROW128 1
 #endif
@@ -354,14 +362,19 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 const int cs = (j < NX) ? NX : 1;      // stride between rows of this "column"
                 double* oxx = (j < NX) ? S.Qxx + j : (j == NX ? S.Qx : S.qxy);
                 const int os = (j < NX) ? NX : 1;
-                const double tw0 = col[(M::XW + 0) * cs], tw1 = col[(M::XW + 1) * cs], tw2 = col[(M::XW + 2) * cs];
+                // tw = dt T[w, j] (+ 2 gq Jac[:, z_j] when column j is one of the wdot arguments r, o, c, w): the second
+                // term makes  Jac[:, z]^T tw  deliver the 2 gq Jac^T Jac part of lxx / lux on top of dt A^T T, so that
+                // only the curvature entries of the wdot block are left for the descriptor table (phase e)
+                const int zj = (j < M::XRD) ? j : ((j >= M::XW && j < M::XCD) ? j - 3 : -1);
+                double tw0 = dt * col[(M::XW + 0) * cs], tw1 = dt * col[(M::XW + 1) * cs], tw2 = dt * col[(M::XW + 2) * cs];
+                if (zj >= 0) { const double g2 = 2.0 * c.gq; tw0 += g2 * Jac[zj]; tw1 += g2 * Jac[NZ + zj]; tw2 += g2 * Jac[2 * NZ + zj]; }
                 if (g == 0) {          // rows r, o, rd, w
                     double tov[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) tov[q] = col[(M::XO + q) * cs];
 #pragma unroll
                     for (int q = 0; q < 3; q++) {
-                        oxx[(M::XR + q) * os] = col[(M::XR + q) * cs] + dt * (Jac[M::ZR + q] * tw0 + Jac[NZ + M::ZR + q] * tw1 + Jac[2 * NZ + M::ZR + q] * tw2);
+                        oxx[(M::XR + q) * os] = col[(M::XR + q) * cs] + (Jac[M::ZR + q] * tw0 + Jac[NZ + M::ZR + q] * tw1 + Jac[2 * NZ + M::ZR + q] * tw2);
                         oxx[(M::XRD + q) * os] = col[(M::XRD + q) * cs] + dt * col[(M::XR + q) * cs];
                     }
                     const double hw[3] = {0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
@@ -371,28 +384,28 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     contract_Aow(tov, ho, aw);    // (dt Aow)^T T[o,j]: row w_b
 #pragma unroll
                     for (int q = 0; q < 4; q++)
-                        oxx[(M::XO + q) * os] = col[(M::XO + q) * cs] + ao[q] + dt * (Jac[M::ZO + q] * tw0 + Jac[NZ + M::ZO + q] * tw1 + Jac[2 * NZ + M::ZO + q] * tw2);
+                        oxx[(M::XO + q) * os] = col[(M::XO + q) * cs] + ao[q] + (Jac[M::ZO + q] * tw0 + Jac[NZ + M::ZO + q] * tw1 + Jac[2 * NZ + M::ZO + q] * tw2);
 #pragma unroll
                     for (int q = 0; q < 3; q++)
-                        oxx[(M::XW + q) * os] = col[(M::XW + q) * cs] + aw[q] + dt * (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
+                        oxx[(M::XW + q) * os] = col[(M::XW + q) * cs] + aw[q] + (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
                 } else if (g == 1) {   // rows c, cd
-#pragma unroll
+#pragma unroll C3U
                     for (int q = 0; q < 12; q++) {
                         double tc = col[(M::XC + q) * cs];
-                        oxx[(M::XC + q) * os] = tc + dt * (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
+                        oxx[(M::XC + q) * os] = tc + (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
                         oxx[(M::XCD + q) * os] = col[(M::XCD + q) * cs] + dt * tc;
                     }
                 } else {               // fu^T (.): rows cddot_i, f_i
                     double* oux = S.W + j;           // columns NX, NX+1 of W: Qu = lu + fu^T v+ and quy = lu + fu^T ys
                     const int us = LDW;
                     const double trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
-#pragma unroll
+#pragma unroll C3UI
                     for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int q = 0; q < 3; q++) {
                             oux[(6 * i + q) * us] = dt * col[(M::XCD + 3 * i + q) * cs];
                             const int zf = M::ZF + 3 * i + q;
-                            oux[(6 * i + 3 + q) * us] = dt * (trd[q] + Jac[zf] * tw0 + Jac[NZ + zf] * tw1 + Jac[2 * NZ + zf] * tw2);
+                            oux[(6 * i + 3 + q) * us] = dt * trd[q] + (Jac[zf] * tw0 + Jac[NZ + zf] * tw1 + Jac[2 * NZ + zf] * tw2);
                         }
                 }
             }

@@ -61,9 +61,9 @@ struct DevCfg {
 };
 
 // z-block descriptor bit layout (built on the host, sddp.cu:build_ztab)
-enum { ZT_ROUNDS = 5, ZT_THREADS = 128, ZT_NXX_NUX = 517, ZT_LAZY_THREADS = 96, ZT_LAZY_ROUNDS = 6 };   // 595 entries: 253 xx + 264 ux first, then 78 uu
+enum { ZT_ROUNDS = 5, ZT_THREADS = 128, ZT_NXX_NUX = 517, ZT_LAZY_THREADS = 96 };   // 595 entries: 253 xx + 264 ux first, then 78 uu
 // Quu work table of the structured backward pass: ztab[ZT_C1OFF + tid] = four 16-bit descriptors type | i1 << 2 | i2 << 6
-enum { ZT_C1OFF = 640, ZT_TOTAL = 640 + 128 };
+enum { ZT_C1OFF = 640, ZT_COFF = 768, ZT_CROUNDS = 2, ZT_TOTAL = 768 + 2 * 96 };   // ZT_COFF: the xx / ux entries that have a curvature term
 #define C1_TYPE(d) (int)((d) & 3)
 #define C1_I1(d) (int)(((d) >> 2) & 15)
 #define C1_I2(d) (int)(((d) >> 6) & 15)
@@ -456,12 +456,14 @@ struct Srbd {
             expand_generic<LDUX>(c, kind, x, u, p, pk, Qx, Qu, Qxx, Qux, Quu, tid, nthr, sync);
             return;
         }
-        constexpr int NTH = MODE ? ZT_LAZY_THREADS : ZT_THREADS, ROUNDS = MODE ? ZT_LAZY_ROUNDS : ZT_ROUNDS, EB = NTH - 32;
+        constexpr int NTH = MODE ? ZT_LAZY_THREADS : ZT_THREADS, ROUNDS = MODE ? ZT_CROUNDS : ZT_ROUNDS, EB = NTH - 32;
         const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
+        // MODE 1: the caller has already added the 2 gq Jac^T Jac part (it rides on its fx^T / fu^T products), so only the
+        // entries with a curvature term are left: the compact list at ZT_COFF, nothing at all for the Gauss-Newton Hessian
         unsigned long long zd[ROUNDS];
-        if (input) {      // MODE 0: latency hidden by the zero fill.  MODE 1: the table lists the xx / ux entries first
+        if (input) {      // MODE 0: latency hidden by the zero fill
 #pragma unroll
-            for (int r = 0; r < ROUNDS; r++) zd[r] = (MODE == 0 || r * NTH + tid < ZT_NXX_NUX) ? __ldg(c.ztab + r * NTH + tid) : 0ull;
+            for (int r = 0; r < ROUNDS; r++) zd[r] = MODE ? __ldg(c.ztab + ZT_COFF + r * NTH + tid) : __ldg(c.ztab + r * NTH + tid);
         }
         double* Es = scratch;          // E(oref) 4x4, then the four orientation residuals
         if (MODE == 0) {
@@ -487,20 +489,23 @@ struct Srbd {
             for (int r = 0; r < ROUNDS; r++) {
                 const unsigned long long d = zd[r];
                 if (!ZT_VALID(d)) continue;
+                if (MODE) {        // destinations as offsets from Qxx (Qux = Qxx + ZT_QUX_OFF, pitch ZT_LDUX): no branch on the kind
+                    if (exact) {
+                        const double v = pk[ZT_HOFF(d)], hv = (ZT_HSIGN(d) == 1) ? g2 * v : -g2 * v;
+                        const int o1 = ZT_DST1(d), o2 = ZT_DST2(d);
+                        Qxx[o1] += hv;
+                        if (o2 != o1) Qxx[o2] += hv;
+                    }
+                    continue;
+                }
                 const int pi = ZT_PI(d), qi = ZT_QI(d), da = ZT_DA(d), db = ZT_DB(d), hs = ZT_HSIGN(d);
                 double hh = Jac[pi] * Jac[qi] + Jac[NZ + pi] * Jac[NZ + qi] + Jac[2 * NZ + pi] * Jac[2 * NZ + qi];
                 if (exact && hs) { const double v = pk[ZT_HOFF(d)]; hh += (hs == 1) ? v : -v; }
                 hh *= g2;
                 const int kd = ZT_KIND(d);
-                if (MODE) {        // destinations as offsets from Qxx (Qux = Qxx + ZT_QUX_OFF, pitch ZT_LDUX): no branch on the kind
-                    const int o1 = ZT_DST1(d), o2 = ZT_DST2(d);
-                    Qxx[o1] += hh;
-                    if (o2 != o1) Qxx[o2] += hh;
-                } else {
-                    if (kd == 0) { Qxx[da * NX + db] = hh; Qxx[db * NX + da] = hh; }
-                    else if (kd == 1) Qux[da * LDUX + db] = hh;
-                    else { Quu[da * NU + db] = hh; Quu[db * NU + da] = hh; }
-                }
+                if (kd == 0) { Qxx[da * NX + db] = hh; Qxx[db * NX + da] = hh; }
+                else if (kd == 1) Qux[da * LDUX + db] = hh;
+                else { Quu[da * NU + db] = hh; Quu[db * NU + da] = hh; }
             }
             if (tid < NZ) {
                 const int pi = tid;
