@@ -207,11 +207,19 @@ struct Srbd {
     }
 
     // acc[0:3] = wdot, acc[3:6] = rddot      (kin_dyn.fSRBD as called at prb.py:99)
-    SDDP_DEV static void accel(const DevCfg& c, const double* x, const double* u, double* acc) {
-        double R[9], J[9], M[9];
+    // The part of the accelerations that depends on the state only: pre[0:9] = I_w^-1, pre[9:12] = w x I_w w.
+    // (The forward pass computes it for x^_k on an idle warp while u^_k is still being formed.)
+    static constexpr int NPRE = 12;
+    SDDP_DEV static void accel_pre(const DevCfg& c, const double* x, double* pre) {
+        double R[9], J[9];
         quat_R(x + XO, R);
         inertia(c, R, J);
-        m3::inv(J, M);
+        m3::inv(J, pre);
+        double Jw[3];
+        m3::mv(J, x + XW, Jw);
+        m3::cross(x + XW, Jw, pre + 9);
+    }
+    SDDP_DEV static void accel_post(const DevCfg& c, const double* x, const double* u, const double* pre, double* acc) {
         double tau[3] = {0, 0, 0}, fsum[3] = {0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -222,14 +230,15 @@ struct Srbd {
             tau[0] += t[0]; tau[1] += t[1]; tau[2] += t[2];
             fsum[0] += fi[0]; fsum[1] += fi[1]; fsum[2] += fi[2];
         }
-        double Jw[3], wJw[3];
-        m3::mv(J, x + XW, Jw);
-        m3::cross(x + XW, Jw, wJw);
-        double h[3] = {tau[0] - wJw[0], tau[1] - wJw[1], tau[2] - wJw[2]};
-        m3::mv(M, h, acc);
+        double h[3] = {tau[0] - pre[9], tau[1] - pre[10], tau[2] - pre[11]};
+        m3::mv(pre, h, acc);
         acc[3] = fsum[0] * c.inv_ms; acc[4] = fsum[1] * c.inv_ms; acc[5] = fsum[2] * c.inv_ms - c.g;
     }
-
+    SDDP_DEV static void accel(const DevCfg& c, const double* x, const double* u, double* acc) {
+        double pre[NPRE];
+        accel_pre(c, x, pre);
+        accel_post(c, x, u, pre, acc);
+    }
     SDDP_DEV static double xdot_i(const DevCfg& c, int i, const double* x, const double* u, const double* acc) {
         if (i < 3 || (i >= XC && i < XRD)) return x[i + (i < 3 ? XRD : XCD - XC)];        // rdot, cdot_j
         if (i >= XRD && i < XCD) return acc[i < XW ? i - XRD + 3 : i - XW];               // rddot, wdot
@@ -252,13 +261,15 @@ struct Srbd {
         return -m3::skew_ab(q, i, a);
     }
 
-    // parts: 1 = terms indexed by the state, 2 = terms indexed by the input, 4 = rddot / wdot terms (need accel)
+    // parts: 1 = terms indexed by the state (8: those of the contact-point velocities, split off for load balance),
+    //        2 = terms indexed by the input, 4 = rddot / wdot terms (need accel)
     SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double* acc,
-                                     int parts = 7) {
+                                     int parts = 15) {
         double s = 0.0;
-        if (parts & 1) {
+        if (parts & 9) {
             const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
             for (int i = lane; i < NX; i += 32) {
+                if (!(parts & (i < XCD ? 1 : 8))) continue;
                 if (i == 2 || (i >= XRD && i < XCD)) {                     // rz / rdot / w tracking (prb.py:184,190-191)
                     if (track) {
                         const double ref = (i == 2) ? c.com[2] : p[i - XRD];            // rdot_ref = p[0:3], w_ref = p[3:6]
@@ -775,14 +786,17 @@ struct Lip {
     // x: r[0:3] c_i[3+3i] rdot[15:18] cdot_i[18+3i];  u: z[0:3] cddot_i[3+3i];  p: rdot_ref[0:3] (c_ref_i, sw_i)[3+2i, 4+2i]
     enum { XR = 0, XC = 3, XRD = 15, XCD = 18 };
 
+    static constexpr int NPRE = 1;
     SDDP_DEV static void accel(const DevCfg&, const double*, const double*, double*) {}
+    SDDP_DEV static void accel_pre(const DevCfg&, const double*, double*) {}
+    SDDP_DEV static void accel_post(const DevCfg&, const double*, const double*, const double*, double*) {}
     SDDP_DEV static double xdot_i(const DevCfg& c, int i, const double* x, const double* u, const double*) {
         if (i < 15) return x[i + 15];
         if (i < 18) { int k = i - 15; return c.eta2 * (x[k] - u[k]) - (k == 2 ? c.g : 0.0); }   // prb.py:317-318
         return u[3 + i - 18];
     }
     SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double*,
-                                     int parts = 7) {
+                                     int parts = 15) {
         double s = 0.0;
         if ((parts & 1) && lane < NX) {
             int i = lane;

@@ -413,10 +413,12 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
                 for (int i = tid; i < NP; i += NT) cp_async8(nbt + NBL::OP + i, P + (size_t)N * NP + i);
                 cp_commit();
             }
+            STAMP(12);
             const double* nb = S.nb[k & 1];
             const double* xc = xb[k & 1];
             constexpr int MV = (4 * NU + 31) & ~31;       // whole warps take part in the shuffles
             static_assert(MV <= NT - 32, "the last warp copies x^");
+            static_assert(M::NPRE <= 2 * 8, "accel_pre result lives in rows 2-3 of sacc");
             if (tid < MV) {                    // u^ = U + alpha k + K dx: four threads per row of K, partial sums by shuffle
                 const double* Kb = S.Kbuf(k & 1);
                 const double* xk = nb + NBL::OX;
@@ -437,16 +439,26 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
                     ub[j] = v;
                     Un[(size_t)k * NU + j] = v;
                 }
-            } else if (w == NWARP - 1) {
+            } else if (w == NWARP - 1) {       // meanwhile: copy x^ out, and the state-only part of the accelerations
                 for (int i = lane; i < NX; i += 32) Xn[(size_t)k * NX + i] = xc[i];
+                if (M::NACC > 1) {
+                    double pre[M::NPRE];
+                    M::accel_pre(c, xc, pre);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < M::NPRE; q++) (&S.sacc[0][0])[16 + q] = pre[q];      // rows 2-3 of sacc (unused on this path)
+                    }
+                }
             }
+            STAMP(13);
             __syncthreads();                  // u^_k visible
+            STAMP(14);
             const int kind = node_kind(k, N);
             if (w == 0) {
                 double* xn_ = xb[(k + 1) & 1];
                 if (M::NACC > 1) {
                     double acc[M::NACC];
-                    M::accel(c, xc, ub, acc);
+                    M::accel_post(c, xc, ub, &S.sacc[0][0] + 16, acc);
                     if (lane == 0) {
 #pragma unroll
                         for (int q = 0; q < M::NACC; q++) S.sacc[0][q] = acc[q];
@@ -460,7 +472,10 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
                 Jw += M::cost_lane(c, kind, lane, xc, ub, nb + NBL::OP, S.sacc[0], 1);
             } else if (w == 2) {
                 Jw += M::cost_lane(c, kind, lane, xc, ub, nb + NBL::OP, S.sacc[0], 2);
+            } else {
+                Jw += M::cost_lane(c, kind, lane, xc, ub, nb + NBL::OP, S.sacc[0], 8);
             }
+            STAMP(15);
         }
         cp_wait_all();
         __syncthreads();
@@ -470,7 +485,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         Jw = warp_sum(Jw);
         if (lane == 0) S.red[R_W0 + w] = Jw;
         __syncthreads();
-        if (tid == 0) S.Jc[0] = S.red[R_W0] + S.red[R_W0 + 1] + S.red[R_W0 + 2];
+        if (tid == 0) S.Jc[0] = S.red[R_W0] + S.red[R_W0 + 1] + S.red[R_W0 + 2] + S.red[R_W0 + 3];
         __syncthreads();
         return;
     }

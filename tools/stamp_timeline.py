@@ -22,9 +22,10 @@ for rep in range(2):
     torch.cuda.synchronize()
 L.sddp_debug_stamps(out)
 names = ["node top", "after top sync", "c1 done", "after c1 sync", "w0: d1 done | w1-3: c2 done", "w1-3: c3 done", "w1-3: e done",
-         "end of d phase", "after d sync", "f,g done", "after f,g sync", "h done"]
+         "end of d phase", "after d sync", "f,g done", "after f,g sync", "h done", "fwd: node top (after sync)", "fwd: u^ done", "fwd: after sync", "fwd: integrate / cost done"]
 t0 = out[1 * 4 + 0]
 print(f"batch={a.batch}: cycles since warp 0 passed the top barrier of node 10 (last iteration of the last problem of CTA 0)")
 print(f"{'':30s}" + "".join(f"{'warp ' + str(w):>10s}" for w in range(4)))
 for i, n in enumerate(names):
-    print(f"{n:30s}" + "".join(f"{out[i * 4 + w] - t0:10d}" for w in range(4)))
+    tb = out[12 * 4 + 0] if i >= 12 else t0      # forward-pass stamps are relative to their own node top
+    print(f"{n:30s}" + "".join(f"{out[i * 4 + w] - tb:10d}" for w in range(4)))
