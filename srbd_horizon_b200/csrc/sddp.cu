@@ -16,14 +16,9 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     __shared__ int s_prob;
-    // Warp w of every resident CTA shares one SM sub-partition (and its 16-lane FP64 pipe).  The solver gives
-    // warps different roles (warp 0 factorises, warps 0-1 own the right-hand sides, ...), so the role index is
-    // rotated per co-resident CTA: otherwise all serial phases of all CTAs pile up on sub-partition 0.
-#ifndef SDDP_ROTATE
-#define SDDP_ROTATE 0
-#endif
-    const int rot_ = SDDP_ROTATE == 1 ? ((blockIdx.x / a.sms) & 3) : (SDDP_ROTATE == 2 ? (blockIdx.x & 3) : 0);
-    const int tid = (threadIdx.x + 32 * rot_) & (NT - 1);
+    // (Warp w of every resident CTA shares one SM sub-partition.  Rotating the warp roles per co-resident CTA was
+    //  measured slower: same-role warps share their code in the sub-partition's instruction cache.)
+    const int tid = threadIdx.x;
     for (;;) {   // persistent CTA: pull problems from a queue (iteration counts differ per problem)
         if (tid == 0) s_prob = atomicAdd(a.counter, 1);
         __syncthreads();

@@ -66,14 +66,6 @@ SDDP_DEV double fast_rcp(double p) {
     return fma(x, e, x);
 }
 
-// unroll depth of the two long loops of c3 (instruction-cache footprint vs load batching)
-#ifndef SDDP_C3_UNROLL
-#define SDDP_C3_UNROLL 12
-#endif
-#ifndef SDDP_C3_UNROLL_I
-#define SDDP_C3_UNROLL_I 4
-#endif
-constexpr int C3U = SDDP_C3_UNROLL, C3UI = SDDP_C3_UNROLL_I;
 #ifndef SDDP_ROW128
 #define SDDP_ROW128 1
 #endif
@@ -389,7 +381,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     for (int q = 0; q < 3; q++)
                         oxx[(M::XW + q) * os] = col[(M::XW + q) * cs] + aw[q] + (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
                 } else if (g == 1) {   // rows c, cd
-#pragma unroll C3U
+#pragma unroll
                     for (int q = 0; q < 12; q++) {
                         double tc = col[(M::XC + q) * cs];
                         oxx[(M::XC + q) * os] = tc + (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
@@ -399,7 +391,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     double* oux = S.W + j;           // columns NX, NX+1 of W: Qu = lu + fu^T v+ and quy = lu + fu^T ys
                     const int us = LDW;
                     const double trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
-#pragma unroll C3UI
+#pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int q = 0; q < 3; q++) {
