@@ -37,8 +37,8 @@ EX_OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}   
 F_NODE = 4 * 37 ** 3 + 8 * 37 ** 2 * 24 + 6 * 37 * 24 ** 2 + 24 ** 3 // 3 + 2 * 37 * 24     # 599,716 FLOP
 BYTES_NODE = 15720
 # measured DRAM traffic of solve_kernel per Riccati node-iteration: dram__bytes_read+write of one `ncu --set full`
-# capture (profiles/r1_solve_kernel_full_raw.csv: 26.08 GB for 4736 problems x 4.963 iterations x 50 nodes)
-TRAFFIC_NODE = 26.08e9 / (4736 * 4.963 * 50)
+# capture (profiles/r1_solve_kernel_full_raw.csv: 26.14 GB for 4736 problems x 4.963 iterations x 50 nodes)
+TRAFFIC_NODE = 26.14e9 / (4736 * 4.963 * 50)
 HBM_PEAK_FALLBACK = 6650.0
 
 
@@ -154,7 +154,7 @@ def run_reference(args, rank, world):
 def workload_config(args, sample_note=None):
     c = {"workload": "BASELINE configs[4]: SRBD DDP batch %d (N=%d, dt=%.2f, nx=37 nu=24 np=19), all 60 wpg gait schedules "
                      "round-robin, seeds default_rng(12345+b), multiple shooting from X=x0 repeated / U=static input" % (args.batch, N_HORIZON, DT),
-         "batch": args.batch, "horizon": N_HORIZON, "opts": EX_OPTS, "sharding": "contiguous batch slices per rank, results all-gathered (NCCL)",
+         "batch": args.batch, "horizon": N_HORIZON, "opts": EX_OPTS, "sharding": "contiguous batch slices per rank, solved in two pieces, results all-gathered (NCCL) while the next piece is solved",
          "cache": "inputs larger than L2 (%.1f GB per step), no L2 flush" % (args.batch * (51 * 37 + 50 * 24 + 51 * 19 + 37) * 8 / 1e9)}
     if sample_note:
         c["sample"] = sample_note
@@ -184,7 +184,7 @@ def main():
     import torch
     import torch.distributed as dist
     from srbd_horizon_b200.ddp import BatchedDDP, DDPSolver, fp64_peak_tflops
-    from srbd_horizon_b200.parallel import gather_results, shard_range
+    from srbd_horizon_b200.parallel import shard_range, solve_sharded
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -204,11 +204,17 @@ def main():
     x0, params, X0, U0 = t(batch["x0"]), t(batch["params"]), t(batch["X0"]), t(batch["U0"])
     gains = not args.no_gains
 
+    last = {}
+
+    def solve_piece(x0c, pc, Xc, Uc):
+        last["r"] = solver.solve(x0c, pc, Xc, Uc, gains=gains, history=False, inplace=True)
+        return last["r"]
+
     def step():
-        r = solver.solve(x0, params, X0, U0, gains=gains, history=False)
-        if world > 1:
-            gather_results(r, world)
-        return r
+        if world > 1:      # two pieces per rank: the all-gather of the first overlaps the solve of the second
+            solve_sharded(solve_piece, x0, params, X0.clone(), U0.clone(), world, args.batch, rank, chunks=2)
+            return last["r"]
+        return solver.solve(x0, params, X0, U0, gains=gains, history=False)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -229,10 +235,12 @@ def main():
             ev[s][0].record()
             Xc, Uc = X0.clone(), U0.clone()
             kev[s][0].record()
-            r = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True)
-            kev[s][1].record()
             if world > 1:
-                gather_results(r, world)
+                gathered = solve_sharded(solve_piece, x0, params, Xc, Uc, world, args.batch, rank, chunks=2)
+                r = last["r"]
+            else:
+                r = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True)
+            kev[s][1].record()
             ev[s][1].record()
         sync_all()
         t_wall = time.perf_counter() - t_wall0
@@ -243,11 +251,10 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_dev, ms_kernel = float(tt[0]), float(tt[1])
-    iters_sum = r.iters.sum().to(torch.float64)
-    conv = (r.status == 0).sum().to(torch.float64)
-    agg = torch.stack([iters_sum, conv])
-    if world > 1:
-        dist.all_reduce(agg)
+    if world > 1:      # every rank holds the whole gathered batch
+        agg = torch.stack([gathered["iters"].sum().to(torch.float64), (gathered["status"] == 0).sum().to(torch.float64)])
+    else:
+        agg = torch.stack([r.iters.sum().to(torch.float64), (r.status == 0).sum().to(torch.float64)])
     mean_iters = float(agg[0]) / args.batch
     conv_frac = float(agg[1]) / args.batch
     ms_per_step = ms_dev / args.steps

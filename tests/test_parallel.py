@@ -26,7 +26,7 @@ def test_shard_range_covers_batch():
 def _worker(rank, world, port, B, q):
     sys.path.insert(0, ROOT)
     from srbd_horizon_b200.ddp import BatchResult
-    from srbd_horizon_b200.parallel import gather_results, shard_range
+    from srbd_horizon_b200.parallel import gather_results, shard_range, solve_sharded
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -43,6 +43,16 @@ def _worker(rank, world, port, B, q):
           and torch.equal(g["K"][:, 0, 0], torch.arange(B, dtype=torch.float64)))
     g2 = gather_results(r, world)     # batch size inferred by all-reduce
     ok = ok and g2["U"].shape == (B, 2, 4)
+    # chunked solve with the gathers of one piece overlapping the next solve: original problem order, any chunk count
+    def fake_solve(x0c, pc, Xc, Uc):
+        i = x0c[:, 0]
+        return BatchResult(X=i[:, None, None] * torch.ones(1, 3, 5, dtype=torch.float64), U=-i[:, None, None] * torch.ones(1, 2, 4, dtype=torch.float64),
+                           K=None, k=None, hist=None, iters=i.to(torch.int32), status=torch.zeros(i.shape[0], dtype=torch.int32), cost=2 * i)
+    x0 = idx[:, None].clone()
+    for chunks in (1, 2, 3):
+        g3 = solve_sharded(fake_solve, x0, x0, x0, x0, world, B, rank, chunks=chunks)
+        ok = ok and (torch.equal(g3["X"][:, 0, 0], torch.arange(B, dtype=torch.float64)) and g3["U"].shape == (B, 2, 4)
+                     and torch.equal(g3["iters"], torch.arange(B, dtype=torch.int32)) and torch.equal(g3["cost"], 2 * torch.arange(B, dtype=torch.float64)))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
