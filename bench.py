@@ -154,7 +154,7 @@ def run_reference(args, rank, world):
 def workload_config(args, sample_note=None):
     c = {"workload": "BASELINE configs[4]: SRBD DDP batch %d (N=%d, dt=%.2f, nx=37 nu=24 np=19), all 60 wpg gait schedules "
                      "round-robin, seeds default_rng(12345+b), multiple shooting from X=x0 repeated / U=static input" % (args.batch, N_HORIZON, DT),
-         "batch": args.batch, "horizon": N_HORIZON, "opts": EX_OPTS, "sharding": "contiguous batch slices per rank, solved in two pieces, results all-gathered (NCCL) while the next piece is solved",
+         "batch": args.batch, "horizon": N_HORIZON, "opts": EX_OPTS, "sharding": "contiguous batch slices per rank, results all-gathered (NCCL)",
          "cache": "inputs larger than L2 (%.1f GB per step), no L2 flush" % (args.batch * (51 * 37 + 50 * 24 + 51 * 19 + 37) * 8 / 1e9)}
     if sample_note:
         c["sample"] = sample_note
@@ -184,7 +184,7 @@ def main():
     import torch
     import torch.distributed as dist
     from srbd_horizon_b200.ddp import BatchedDDP, DDPSolver, fp64_peak_tflops
-    from srbd_horizon_b200.parallel import shard_range, solve_sharded
+    from srbd_horizon_b200.parallel import gather_results, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -204,17 +204,11 @@ def main():
     x0, params, X0, U0 = t(batch["x0"]), t(batch["params"]), t(batch["X0"]), t(batch["U0"])
     gains = not args.no_gains
 
-    last = {}
-
-    def solve_piece(x0c, pc, Xc, Uc):
-        last["r"] = solver.solve(x0c, pc, Xc, Uc, gains=gains, history=False, inplace=True)
-        return last["r"]
-
     def step():
-        if world > 1:      # two pieces per rank: the all-gather of the first overlaps the solve of the second
-            solve_sharded(solve_piece, x0, params, X0.clone(), U0.clone(), world, args.batch, rank, chunks=2)
-            return last["r"]
-        return solver.solve(x0, params, X0, U0, gains=gains, history=False)
+        r = solver.solve(x0, params, X0, U0, gains=gains, history=False)
+        if world > 1:
+            gather_results(r, world, args.batch)
+        return r
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -235,12 +229,10 @@ def main():
             ev[s][0].record()
             Xc, Uc = X0.clone(), U0.clone()
             kev[s][0].record()
-            if world > 1:
-                gathered = solve_sharded(solve_piece, x0, params, Xc, Uc, world, args.batch, rank, chunks=2)
-                r = last["r"]
-            else:
-                r = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True)
+            r = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True)
             kev[s][1].record()
+            if world > 1:      # (solving in two pieces to overlap the gather with the second solve was measured slower:
+                gathered = gather_results(r, world, args.batch)      #  parallel.solve_sharded, 99.5 vs 92.1 ms at 8 GPUs)
             ev[s][1].record()
         sync_all()
         t_wall = time.perf_counter() - t_wall0
