@@ -6,6 +6,7 @@
 //   V2: columns broadcast by warp shuffles (no shared-memory column traffic, no divergent publish)
 //   V3: V0 without the E trick (lanes <= j update dead values; reference for the cost of the chain alone)
 //   V4: V0 with the pivot chain through shuffles (1/pivot and col_j[j+1]) and the column through shared memory
+//   V10: by symmetry col_j[t] is lane t's own a[j]: every lane stores one entry, nobody publishes a column
 #include <cstdio>
 #include <cuda_runtime.h>
 #define FULL 0xffffffffu
@@ -83,6 +84,20 @@ __device__ __forceinline__ void ldlt(Sm& S, int lane) {
                 a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
                 myinv = fast_rcp(a[j + 1]);
                 if (j + 2 < NU) axpy_row<W>(a, S.Quu + j * NU, j + 2, sj);
+            }
+        }
+    } else if (V == 10) {      // every lane publishes its own entry of row j (= col_j[lane] by symmetry): no divergent publish
+#pragma unroll
+        for (int j = 0; j < NU; j++) {
+            if (lane < NU) S.Quu[j * NU + lane] = a[j];
+            if (lane == j) S.invp[j] = myinv;
+            pinv = (lane == j) ? myinv : pinv;
+            __syncwarp();
+            if (j + 1 < NU) {
+                const double sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
+                a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
+                myinv = fast_rcp(a[j + 1]);
+                if (j + 2 < NU) axpy_row<true>(a, S.Quu + j * NU, j + 2, sj);
             }
         }
     } else if (V >= 5 && V <= 8) {      // timing probes of V0 (wrong results): 5 no reciprocal, 6 no warp sync, 7 chain only, 8 no chain
@@ -230,5 +245,6 @@ int main() {
     run<7>("V7 = V0 pivot chain only (timing)", dQ, dout, dcyc, ref);
     run<8>("V8 = V0 column updates only (timing)", dQ, dout, dcyc, ref);
     run<9>("V9 = V0 with a branch per entry in the Es write", dQ, dout, dcyc, ref);
+    run<10>("V10 every lane publishes its row-j entry", dQ, dout, dcyc, ref);
     return 0;
 }
