@@ -264,7 +264,8 @@ static void make_devcfg(const SddpConfig& s, DevCfg& d) {
 
 // Host mirror of Srbd::zmap_x / zmap_u / hc(): descriptors of the upper-triangular (pi <= qi) entries of the
 // 34 x 34 Hessian block of gq*||wdot||^2, consumed by Srbd::expand (bit layout: sddp_model.cuh ZT_*).
-static void build_ztab(std::vector<unsigned long long>& tab) {
+// returns false if the tables do not fit their slots (a programming error caught at sddp_create, never at run time)
+static bool build_ztab(std::vector<unsigned long long>& tab) {
     const int NZ = Srbd::NZ, ZO = Srbd::ZO, ZC = Srbd::ZC, ZW = Srbd::ZW, ZF = Srbd::ZF;
     auto zx = [&](int p) { return p < 19 ? p : (p < 22 ? (int)Srbd::XW + (p - 19) : -1); };
     auto zu = [&](int p) { return 6 * ((p - 22) / 3) + 3 + (p - 22) % 3; };
@@ -301,9 +302,9 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
             if (kind == 0) d |= ((unsigned long long)(da * Srbd::NX + db) << 38) | ((unsigned long long)(db * Srbd::NX + da) << 50);
             if (kind == 1) d |= ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 38) | ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 50);
             tab[e++] = d;
-            if (kind != 2 && hs != 0) { if (nc >= ZT_CROUNDS * ZT_LAZY_THREADS) abort(); tab[ZT_COFF + nc++] = d; }   // curvature-only list
+            if (kind != 2 && hs != 0) { if (nc >= ZT_CROUNDS * ZT_LAZY_THREADS) return false; tab[ZT_COFF + nc++] = d; }   // curvature-only list
         }
-    if (e != NZ * (NZ + 1) / 2) abort();
+    if (e != NZ * (NZ + 1) / 2) return false;
     // Quu work table (sddp_backward_srbd.cuh, phase c1).  Types: 1 (f_a, f_b) a >= b, 2 (cddot_a, f_b), 3 (cddot_a, cddot_b) a >= b.
     auto desc = [](int type, int i1, int i2) { return (unsigned long long)(type | (i1 << 2) | (i2 << 6)); };
     std::vector<unsigned long long> light;
@@ -319,9 +320,10 @@ static void build_ztab(std::vector<unsigned long long>& tab) {
     for (auto v : cc) light.push_back(v);
     for (size_t i = 0; i < light.size(); i++) {                            // threads 78..127: three entries each
         const size_t th = 78 + i % 50, sl = 1 + i / 50;
-        if (sl > 3) abort();
+        if (sl > 3) return false;
         tab[ZT_C1OFF + th] |= light[i] << (16 * sl);
     }
+    return true;
 }
 
 // kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.reserved0 = 1), 2 = LIP dense
@@ -433,7 +435,7 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
     CUC(cudaMemset(base, 0, w.total));
     if (cfg->model == SDDP_MODEL_SRBD) {
         std::vector<unsigned long long> tab;
-        build_ztab(tab);
+        if (!build_ztab(tab)) { sddp_destroy(h); return fail(nullptr, SDDP_EINVAL, "%s%s", "internal: descriptor tables do not fit", ""); }
         CUC(cudaMalloc((void**)&h->ztab, tab.size() * sizeof(unsigned long long)));
         CUC(cudaMemcpy(h->ztab, tab.data(), tab.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
