@@ -146,6 +146,15 @@ int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *
                           const double *U0, double *X, double *U, double *K, double *kff, double *hist,
                           int32_t *iters, int32_t *status, double *cost);
 
+/* Dispatch order of the next solves (scheduling only: results do not depend on it).  The persistent CTAs take
+ * problems order[0], order[1], ... instead of 0, 1, ...; `order` must be a permutation of 0..n-1 and applies to
+ * solves of exactly n problems.  Problems that behave alike (same contact schedule, similar iteration counts)
+ * should be neighbours: co-resident CTAs then run the same phases at the same time and share their instructions
+ * in the SM's instruction cache (about 10 % on BASELINE configs[4]).  on_host = 0: `order` is a DEVICE array the
+ * caller keeps alive, used by sddp_solve_batch; on_host = 1: HOST array, copied, used by sddp_solve_batch_host
+ * (checked to be a permutation).  order = NULL clears.  The reference has no counterpart (one problem per process). */
+int sddp_set_dispatch_order(SddpHandle *h, const int32_t *order, int n, int on_host);
+
 /* ---- receding-horizon glue on the device (the caller side of the path: dsrbd_example.py:102-131,158-160, wpg.py:68-101) ----
  * gait tables of wpg.steps_phase (wpg.py:19-64): four arrays of 21 entries, l_cycle, l_switch, r_cycle, r_switch (host pointers) */
 int sddp_set_gait_tables(SddpHandle *h, const double *l_cycle, const double *l_switch, const double *r_cycle,

@@ -35,6 +35,7 @@ SYMBOLS = {
     "sddp_mpc_advance": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
     "sddp_plant_step": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_longlong, _vp]),
     "sddp_fp64_peak_tflops": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), _vp]),
+    "sddp_set_dispatch_order": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
     "sddp_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
 }
 

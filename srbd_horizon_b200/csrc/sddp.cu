@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) 
     for (;;) {   // persistent CTA: pull problems from a queue (iteration counts differ per problem)
         if (tid == 0) s_prob = atomicAdd(a.counter, 1);
         __syncthreads();
-        const int b = s_prob;
-        if (b >= a.B) break;
+        if (s_prob >= a.B) break;
+        const int b = a.order ? a.order[s_prob] : s_prob;
         solve_one<M, SM>(c, a, S, b, blockIdx.x, tid);
         __syncthreads();
     }
@@ -213,6 +213,8 @@ struct SddpHandle {
     cudaStream_t st_in, st_cmp, st_out;
     int host_chunk;
     long long launches;
+    const int32_t* order_dev; int order_n;      // caller-owned device permutation for sddp_solve_batch
+    std::vector<int32_t> order_host;            // copy of the host permutation for sddp_solve_batch_host
     char err[512];
 };
 static char g_create_err[512] = "";
@@ -402,7 +404,6 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
         return fail(nullptr, SDDP_ECUDA, "no CUDA device (%s); this library has no CPU path%s", cudaGetErrorString(e), "");
     SddpHandle* hh = new (std::nothrow) SddpHandle();
     if (!hh) return fail(nullptr, SDDP_ENOMEM, "%s%s", "host allocation failed", "");
-    memset(hh, 0, sizeof(*hh));
     h = hh;
     h->cfg = *cfg;
     make_devcfg(h->cfg, h->dc);
@@ -513,6 +514,7 @@ int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* param
     a.iters = iters; a.status = status; a.cost = cost;
     a.ws_d = h->ws_d; a.ws_pack = h->ws_pack; a.ws_xn = h->ws_xn; a.ws_un = h->ws_un; a.ws_K = h->ws_K; a.ws_k = h->ws_k;
     a.counter = h->counter;
+    a.order = (h->order_dev && h->order_n == B) ? h->order_dev : nullptr;
     a.sms = h->sms;
     int grid = B < h->slots ? B : h->slots;
     DISPATCH(h, solve_kernel, grid, st, h->dc, a);
@@ -565,7 +567,7 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     const size_t s_x0 = nx, s_p = (N + 1) * np, s_X = (N + 1) * nx, s_U = N * nu;              // doubles per problem
     const size_t s_K = K ? N * nu * nx : 0, s_k = kff ? s_U : 0, s_h = hist ? (size_t)h->cfg.max_iters * SDDP_HIST : 0;
     const size_t n_d = Bz * (s_x0 + s_p + s_X + s_U + s_K + s_k + s_h + 1);
-    const size_t bytes = n_d * sizeof(double) + 2 * Bz * sizeof(int32_t);
+    const size_t bytes = n_d * sizeof(double) + 3 * Bz * sizeof(int32_t);
     if (bytes > h->stage_bytes) {
         if (h->stage) cudaFree(h->stage);
         h->stage = nullptr; h->stage_bytes = 0;
@@ -594,8 +596,20 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     double* d_c = d_h + Bz * s_h;
     int32_t* d_it = (int32_t*)(d_c + Bz);
     int32_t* d_st = d_it + Bz;
+    int32_t* d_ord = d_st + Bz;
     const int chunk = h->host_chunk;
     const int nchunk = (B + chunk - 1) / chunk;
+    // dispatch order: the global permutation restricted to each chunk, as chunk-local indices (same relative order)
+    const bool ordered = h->order_host.size() == Bz;
+    std::vector<int32_t> ordl;
+    if (ordered) {
+        std::vector<size_t> fill(nchunk);
+        for (int c = 0; c < nchunk; c++) fill[c] = (size_t)c * chunk;
+        ordl.resize(Bz);
+        for (size_t i = 0; i < Bz; i++) { const int g = h->order_host[i], c = g / chunk; ordl[fill[c]++] = g - c * chunk; }
+    }
+    const int32_t* saved_order = h->order_dev;
+    const int saved_n = h->order_n;
     std::vector<cudaEvent_t> ev_in(nchunk), ev_cmp(nchunk);
     int rc = 0;
     for (int c = 0; c < nchunk; c++) {
@@ -612,9 +626,11 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         cp(d_p + o * s_p, params + o * s_p, n * s_p * 8, cudaMemcpyHostToDevice, h->st_in);
         cp(d_X + o * s_X, X0 + o * s_X, n * s_X * 8, cudaMemcpyHostToDevice, h->st_in);
         cp(d_U + o * s_U, U0 + o * s_U, n * s_U * 8, cudaMemcpyHostToDevice, h->st_in);
+        if (ordered) cp(d_ord + o, ordl.data() + o, n * 4, cudaMemcpyHostToDevice, h->st_in);
         if (e == cudaSuccess) e = cudaEventRecord(ev_in[c], h->st_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->st_cmp, ev_in[c], 0);
         if (e != cudaSuccess) { rc = fail(h, SDDP_ECUDA, "solve_batch_host (copy in): %s%s", cudaGetErrorString(e), ""); break; }
+        h->order_dev = ordered ? d_ord + o : nullptr; h->order_n = (int)n;
         rc = sddp_solve_batch(h, (int)n, d_x0 + o * s_x0, d_p + o * s_p, d_X + o * s_X, d_U + o * s_U, K ? d_K + o * s_K : nullptr,
                               kff ? d_k + o * s_k : nullptr, hist ? d_h + o * s_h : nullptr, d_it + o, d_st + o, d_c + o, h->st_cmp);
         if (rc) break;
@@ -630,11 +646,27 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         cp(status + o, d_st + o, n * 4, cudaMemcpyDeviceToHost, h->st_out);
         if (e != cudaSuccess) rc = fail(h, SDDP_ECUDA, "solve_batch_host (copy out): %s%s", cudaGetErrorString(e), "");
     }
+    h->order_dev = saved_order; h->order_n = saved_n;
     cudaError_t e1 = cudaStreamSynchronize(h->st_in), e2 = cudaStreamSynchronize(h->st_cmp), e3 = cudaStreamSynchronize(h->st_out);
     for (int c = 0; c < nchunk; c++) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_cmp[c]); }
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(h, SDDP_ECUDA, "solve_batch_host (sync): %s%s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)), "");
+    return 0;
+}
+
+int sddp_set_dispatch_order(SddpHandle* h, const int32_t* order, int n, int on_host) {
+    if (!h) return SDDP_EINVAL;
+    if (n < 0 || (order && n == 0)) return fail(h, SDDP_EINVAL, "%s%s", "set_dispatch_order: bad length", "");
+    if (!on_host) { h->order_dev = order; h->order_n = order ? n : 0; return 0; }
+    h->order_host.clear();
+    if (!order) return 0;
+    std::vector<char> seen((size_t)n, 0);
+    for (int i = 0; i < n; i++) {
+        if (order[i] < 0 || order[i] >= n || seen[order[i]]) return fail(h, SDDP_EINVAL, "%s%s", "set_dispatch_order: not a permutation of 0..n-1", "");
+        seen[order[i]] = 1;
+    }
+    h->order_host.assign(order, order + n);
     return 0;
 }
 

@@ -536,6 +536,7 @@ struct SolveArgs {
     // workspace, per resident CTA
     double* ws_d; double* ws_pack; double* ws_xn; double* ws_un; double* ws_K; double* ws_k;
     int* counter;
+    const int* order;     // dispatch order (permutation of 0..B-1) or nullptr
     int sms;
 };
 

@@ -96,8 +96,26 @@ class BatchedDDP:
         return n.value
 
     # -- the solve ----------------------------------------------------------------------------
-    def solve(self, x0, params, X0, U0, gains: bool = True, history: bool = True, inplace: bool = False) -> BatchResult:
-        """x0[B,nx], params[B,N+1,np], warm starts X0[B,N+1,nx], U0[B,N,nu] (device tensors)."""
+    # columns of the per-node parameter vector that hold the contact switches (prb.py:159-163 / 372-376)
+    _SWITCH_COLS = {MODEL_SRBD: (8, 10, 12, 14), MODEL_LIP: (4, 6, 8, 10)}
+
+    def dispatch_order(self, params, nodes: int = 24):
+        """Dispatch order that puts problems with the same contact schedule next to each other (a hash of the switch
+        pattern over the first `nodes` nodes, stable argsort).  Scheduling only: co-resident CTAs then stay in step and
+        share their instructions in the SM's instruction cache.  Works on a device tensor or a numpy array."""
+        cols = list(self._SWITCH_COLS[self.cfg.model])
+        n = min(nodes, params.shape[1])
+        sl = slice(cols[0], cols[-1] + 1, cols[1] - cols[0])          # the switch columns as a strided view (no copy)
+        if isinstance(params, np.ndarray):
+            w = (1.0 + np.arange(n * len(cols), dtype=np.float64).reshape(n, len(cols))) ** 2
+            key = np.einsum("bnc,nc->b", params[:, :n, sl], w)
+            return np.argsort(key, kind="stable").astype(np.int32)
+        w = (1.0 + torch.arange(n * len(cols), dtype=torch.float64, device=params.device).reshape(n, len(cols))) ** 2
+        return torch.argsort((params[:, :n, sl] * w).sum(dim=(1, 2)), stable=True).to(torch.int32)
+
+    def solve(self, x0, params, X0, U0, gains: bool = True, history: bool = True, inplace: bool = False, order=None) -> BatchResult:
+        """x0[B,nx], params[B,N+1,np], warm starts X0[B,N+1,nx], U0[B,N,nu] (device tensors).
+        order: None (natural dispatch order), "schedule" (`dispatch_order(params)`) or an int32 device permutation."""
         x0 = torch.as_tensor(x0, dtype=torch.float64, device=self.device).contiguous()
         B = x0.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
@@ -114,13 +132,29 @@ class BatchedDDP:
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         status = torch.empty(B, dtype=torch.int32, device=dev)
         cost = torch.empty(B, dtype=torch.float64, device=dev)
+        if isinstance(order, str):
+            if order != "schedule":
+                raise ValueError("order: None, 'schedule' or a permutation")
+            order = self.dispatch_order(params) if B > 1 else None
+        if order is not None:
+            order = torch.as_tensor(order, dtype=torch.int32, device=dev).contiguous()
+            if order.shape != (B,):
+                raise ValueError("order must have one entry per problem")
         with torch.cuda.device(dev):
-            _lib.check(self.L.sddp_solve_batch(self.h, B, _ptr(x0), _ptr(params), _ptr(X), _ptr(U), _ptr(K), _ptr(k),
-                                               _ptr(hist), _ptr(iters), _ptr(status), _ptr(cost), self._stream()), self.h)
-        return BatchResult(X, U, K, k, hist, iters, status, cost)
+            if order is not None:
+                _lib.check(self.L.sddp_set_dispatch_order(self.h, _ptr(order), B, 0), self.h)
+            try:
+                _lib.check(self.L.sddp_solve_batch(self.h, B, _ptr(x0), _ptr(params), _ptr(X), _ptr(U), _ptr(K), _ptr(k),
+                                                   _ptr(hist), _ptr(iters), _ptr(status), _ptr(cost), self._stream()), self.h)
+            finally:
+                if order is not None:
+                    self.L.sddp_set_dispatch_order(self.h, None, 0, 0)
+        r = BatchResult(X, U, K, k, hist, iters, status, cost)
+        r._keepalive = order      # the kernel reads the permutation asynchronously
+        return r
 
     def solve_host(self, x0: np.ndarray, params: np.ndarray, X0: np.ndarray, U0: np.ndarray, gains: bool = False,
-                   history: bool = False, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+                   history: bool = False, out: Optional[Dict[str, np.ndarray]] = None, order=None) -> Dict[str, np.ndarray]:
         """Same solve on HOST numpy buffers through `sddp_solve_batch_host` (chunked copies overlap the solves).
         `out` may hold preallocated (pinned) X, U, iters, status, cost [, K, k, hist] arrays to reuse."""
         B = x0.shape[0]
@@ -141,10 +175,24 @@ class BatchedDDP:
         k = buf("k", (B, N, nu)) if gains else None
         hist = buf("hist", (B, self.cfg.max_iters, HIST)) if history else None
         iters, status, cost = buf("iters", (B,), np.int32), buf("status", (B,), np.int32), buf("cost", (B,))
+        if isinstance(order, str):
+            if order != "schedule":
+                raise ValueError("order: None, 'schedule' or a permutation")
+            order = self.dispatch_order(params) if B > 1 else None
+        if order is not None:
+            order = np.ascontiguousarray(order, dtype=np.int32)
+            if order.shape != (B,):
+                raise ValueError("order must have one entry per problem")
         with torch.cuda.device(self.device):
-            _lib.check(self.L.sddp_solve_batch_host(self.h, B, _np_ptr(x0), _np_ptr(params), _np_ptr(X0), _np_ptr(U0), _np_ptr(X),
-                                                    _np_ptr(U), _np_ptr(K), _np_ptr(k), _np_ptr(hist), _np_ptr(iters), _np_ptr(status),
-                                                    _np_ptr(cost)), self.h)
+            if order is not None:
+                _lib.check(self.L.sddp_set_dispatch_order(self.h, _np_ptr(order), B, 1), self.h)
+            try:
+                _lib.check(self.L.sddp_solve_batch_host(self.h, B, _np_ptr(x0), _np_ptr(params), _np_ptr(X0), _np_ptr(U0), _np_ptr(X),
+                                                        _np_ptr(U), _np_ptr(K), _np_ptr(k), _np_ptr(hist), _np_ptr(iters), _np_ptr(status),
+                                                        _np_ptr(cost)), self.h)
+            finally:
+                if order is not None:
+                    self.L.sddp_set_dispatch_order(self.h, None, 0, 1)
         out.update(K=K, k=k, hist=hist)
         return out
 

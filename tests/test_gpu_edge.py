@@ -1,5 +1,7 @@
 """Edge cases of the CUDA path against the oracle: shortest and long horizons, tiny batches, iteration caps,
 non-finite inputs, and BASELINE configs[3] (multiple shooting with a fixed defect contraction rate) at full size."""
+import os
+
 import numpy as np
 import pytest
 
@@ -104,3 +106,41 @@ def test_config3_fixed_contraction_full_size_properties():
     ro = O.solve_batch(cfg, b["x0"][:512], b["params"][:512], b["X0"][:512], b["U0"][:512], nthreads=16)
     np.testing.assert_array_equal(iters[:512], ro["iters"])
     assert relerr(cpu(r.X)[:512], ro["X"]) < 1e-9 and relerr(cpu(r.U)[:512], ro["U"]) < 1e-9
+
+
+def test_dispatch_order_changes_nothing_but_the_schedule():
+    """sddp_set_dispatch_order: any permutation (random, or grouped by contact schedule) gives bit-identical results,
+    on the device entry point and on the chunked host entry point; a non-permutation is rejected."""
+    import ctypes
+    from srbd_horizon_b200 import _lib
+    B, N = 700, 20
+    cfg = make_config(MODEL_SRBD, N, 0.05, EX)
+    b = make_batch(MODEL_SRBD, N, B, enumerate_schedules=True)
+    s = BatchedDDP(cfg)
+    r0 = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).to(torch.int32)
+    for order in (perm, "schedule"):
+        r = s.solve(b["x0"], b["params"], b["X0"], b["U0"], order=order)
+        for f in ("X", "U", "K", "k", "cost", "iters", "status", "hist"):
+            assert torch.equal(getattr(r, f), getattr(r0, f)), (f, order if isinstance(order, str) else "perm")
+    o = s.dispatch_order(torch.as_tensor(b["params"], device="cuda"))
+    assert sorted(o.tolist()) == list(range(B))
+    assert np.array_equal(cpu(o), s.dispatch_order(b["params"]))          # device and host versions agree
+    os.environ.pop("SDDP_HOST_CHUNK", None)
+    rh0 = s.solve_host(b["x0"], b["params"], b["X0"], b["U0"])
+    for order in (perm.numpy(), "schedule"):
+        rh = s.solve_host(b["x0"], b["params"], b["X0"], b["U0"], order=order)
+        for f in ("X", "U", "cost", "iters", "status"):
+            np.testing.assert_array_equal(rh[f], rh0[f])
+            np.testing.assert_array_equal(rh[f], cpu(getattr(r0, f)))
+    os.environ["SDDP_HOST_CHUNK"] = "256"           # three chunks: the permutation is split into chunk-local orders
+    try:
+        s2 = BatchedDDP(cfg)
+        rh2 = s2.solve_host(b["x0"], b["params"], b["X0"], b["U0"], order=perm.numpy())
+    finally:
+        os.environ.pop("SDDP_HOST_CHUNK", None)
+    for f in ("X", "U", "cost", "iters", "status"):
+        np.testing.assert_array_equal(rh2[f], rh0[f])
+    bad = np.zeros(B, dtype=np.int32)
+    rc = s.L.sddp_set_dispatch_order(s.h, bad.ctypes.data_as(ctypes.c_void_p), B, 1)
+    assert rc == -1 and b"permutation" in s.L.sddp_last_error(s.h)
