@@ -101,7 +101,7 @@ class BatchedDDP:
 
     def dispatch_order(self, params, nodes: int = 24):
         """Dispatch order that puts problems with the same contact schedule next to each other (a hash of the switch
-        pattern over the first `nodes` nodes, stable argsort).  Scheduling only: co-resident CTAs then stay in step and
+        pattern over the first `nodes` nodes), the fastest commanded velocities first inside a schedule.  Scheduling only: co-resident CTAs then stay in step and
         share their instructions in the SM's instruction cache.  Works on a device tensor or a numpy array."""
         cols = list(self._SWITCH_COLS[self.cfg.model])
         n = min(nodes, params.shape[1])
@@ -109,9 +109,20 @@ class BatchedDDP:
         if isinstance(params, np.ndarray):
             w = (1.0 + np.arange(n * len(cols), dtype=np.float64).reshape(n, len(cols))) ** 2
             key = np.einsum("bnc,nc->b", params[:, :n, sl], w)
-            return np.argsort(key, kind="stable").astype(np.int32)
+            return self.order_from_keys(key, (params[:, -1, 0:3] ** 2).sum(axis=1))
         w = (1.0 + torch.arange(n * len(cols), dtype=torch.float64, device=params.device).reshape(n, len(cols))) ** 2
-        return torch.argsort((params[:, :n, sl] * w).sum(dim=(1, 2)), stable=True).to(torch.int32)
+        return self.order_from_keys((params[:, :n, sl] * w).sum(dim=(1, 2)), (params[:, -1, 0:3] ** 2).sum(dim=1))
+
+    @staticmethod
+    def order_from_keys(group, effort):
+        """Permutation that sorts by `group` (ascending) and, inside a group, by `effort` (descending).  `effort` is a
+        guess of how many iterations a problem needs -- by default the commanded velocity |rdot_ref| (p[0:3] of the last
+        node, prb.py:74), which correlates +0.5 with the iteration count inside a schedule (tools/iters_features.py)."""
+        if isinstance(group, np.ndarray):
+            o1 = np.argsort(-np.asarray(effort), kind="stable")
+            return o1[np.argsort(np.asarray(group)[o1], kind="stable")].astype(np.int32)
+        o1 = torch.argsort(effort, descending=True, stable=True)
+        return o1[torch.argsort(group[o1], stable=True)].to(torch.int32)
 
     def solve(self, x0, params, X0, U0, gains: bool = True, history: bool = True, inplace: bool = False, order=None) -> BatchResult:
         """x0[B,nx], params[B,N+1,np], warm starts X0[B,N+1,nx], U0[B,N,nu] (device tensors).
