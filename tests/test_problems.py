@@ -63,3 +63,20 @@ def test_batch_is_seeded_and_sliceable():
     m = make_batch(MODEL_SRBD, 20, 3, x_noise=0.01)
     assert np.abs(m["X0"][:, 1:, 0:3] - m["x0"][:, None, 0:3]).max() > 0
     np.testing.assert_array_equal(m["X0"][:, 0], m["x0"])
+
+
+def test_dispatch_order_from_keys_groups_and_sorts():
+    """BatchedDDP.order_from_keys (host version, no GPU): groups ascending, inside a group the effort key descending,
+    stable, always a permutation; the torch version gives the same permutation."""
+    import torch
+    from srbd_horizon_b200.ddp import BatchedDDP
+    rng = np.random.default_rng(0)
+    g = rng.integers(0, 7, size=500)
+    e = rng.random(500)
+    o = BatchedDDP.order_from_keys(g, e)
+    assert o.dtype == np.int32 and sorted(o.tolist()) == list(range(500))
+    assert (np.diff(g[o]) >= 0).all()
+    for k in range(7):
+        assert (np.diff(e[o][g[o] == k]) <= 0).all()
+    ot = BatchedDDP.order_from_keys(torch.as_tensor(g), torch.as_tensor(e))
+    assert np.array_equal(ot.numpy(), o)
