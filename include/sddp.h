@@ -141,7 +141,9 @@ int sddp_defects(SddpHandle *h, int B, const double *X, const double *U, const d
  * This is what a non-CUDA caller (the reference's Python loop) binds.  X0 / U0 are the warm start
  * (ddp.py:114,117), X / U receive the solution and may alias X0 / U0.  The batch is processed in
  * chunks so that the host<->device copies of one chunk overlap the solve of another (three streams);
- * pinned host buffers are needed for that overlap, pageable ones work but serialise. */
+ * pinned host buffers are needed for that overlap, pageable ones work but serialise.  Small batches (one chunk,
+ * < 4 MB, the reference's one-problem use) take a single-stream path with one copy in and one copy out through a
+ * pinned staging buffer of the handle. */
 int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *params, const double *X0,
                           const double *U0, double *X, double *U, double *K, double *kff, double *hist,
                           int32_t *iters, int32_t *status, double *cost);

@@ -210,6 +210,7 @@ struct SddpHandle {
     double* gait;        // device copy of the four 21-entry wpg tables
     // staging for the *_host entry point
     void* stage; size_t stage_bytes;
+    void* hstage; size_t hstage_bytes;       // pinned host staging of the small-batch path
     cudaStream_t st_in, st_cmp, st_out;
     int host_chunk;
     long long launches;
@@ -452,6 +453,7 @@ int sddp_destroy(SddpHandle* h) {
     if (h->ztab) cudaFree(h->ztab);
     if (h->gait) cudaFree(h->gait);
     if (h->stage) cudaFree(h->stage);
+    if (h->hstage) cudaFreeHost(h->hstage);
     if (h->st_in) cudaStreamDestroy(h->st_in);
     if (h->st_cmp) cudaStreamDestroy(h->st_cmp);
     if (h->st_out) cudaStreamDestroy(h->st_out);
@@ -599,6 +601,43 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     int32_t* d_ord = d_st + Bz;
     const int chunk = h->host_chunk;
     const int nchunk = (B + chunk - 1) / chunk;
+    // Small batches (the reference's own use: one problem per call): one pinned staging buffer, one copy in, one copy
+    // out, one stream, no events -- the latency of a single solve is mostly launch and copy overhead otherwise.
+    const size_t in_bytes = Bz * (s_x0 + s_p + s_X + s_U) * sizeof(double);
+    const size_t out_bytes = bytes - Bz * (s_x0 + s_p) * sizeof(double) - Bz * sizeof(int32_t);      // X .. status
+    if (nchunk == 1 && in_bytes + out_bytes <= ((size_t)4 << 20) && h->order_host.empty()) {
+        if (in_bytes + out_bytes > h->hstage_bytes) {
+            if (h->hstage) cudaFreeHost(h->hstage);
+            h->hstage = nullptr; h->hstage_bytes = 0;
+            cudaError_t e = cudaHostAlloc(&h->hstage, in_bytes + out_bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) return fail(h, SDDP_ENOMEM, "cudaHostAlloc(staging): %s%s", cudaGetErrorString(e), "");
+            h->hstage_bytes = in_bytes + out_bytes;
+        }
+        double* hi = (double*)h->hstage;
+        memcpy(hi, x0, Bz * s_x0 * 8);
+        memcpy(hi + Bz * s_x0, params, Bz * s_p * 8);
+        memcpy(hi + Bz * (s_x0 + s_p), X0, Bz * s_X * 8);
+        memcpy(hi + Bz * (s_x0 + s_p + s_X), U0, Bz * s_U * 8);
+        CU(cudaMemcpyAsync(d_x0, hi, in_bytes, cudaMemcpyHostToDevice, h->st_cmp));
+        int rc1 = sddp_solve_batch(h, B, d_x0, d_p, d_X, d_U, K ? d_K : nullptr, kff ? d_k : nullptr, hist ? d_h : nullptr, d_it, d_st, d_c, h->st_cmp);
+        if (rc1) return rc1;
+        char* ho = (char*)h->hstage + in_bytes;
+        CU(cudaMemcpyAsync(ho, d_X, out_bytes, cudaMemcpyDeviceToHost, h->st_cmp));
+        CU(cudaStreamSynchronize(h->st_cmp));
+        const double* o = (const double*)ho;
+        memcpy(X, o, Bz * s_X * 8); o += Bz * s_X;
+        memcpy(U, o, Bz * s_U * 8); o += Bz * s_U;
+        if (K) memcpy(K, o, Bz * s_K * 8);
+        o += Bz * s_K;
+        if (kff) memcpy(kff, o, Bz * s_k * 8);
+        o += Bz * s_k;
+        if (hist) memcpy(hist, o, Bz * s_h * 8);
+        o += Bz * s_h;
+        memcpy(cost, o, Bz * 8); o += Bz;
+        memcpy(iters, o, Bz * 4);
+        memcpy(status, (const int32_t*)o + Bz, Bz * 4);
+        return 0;
+    }
     // dispatch order: the global permutation restricted to each chunk, as chunk-local indices (same relative order)
     const bool ordered = h->order_host.size() == Bz;
     std::vector<int32_t> ordl;
