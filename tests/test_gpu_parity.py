@@ -212,3 +212,30 @@ def test_error_behaviour():
     import ctypes
     h = ctypes.c_void_p()
     assert _lib.lib().sddp_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_solve_matches_oracle_random_configurations(seed):
+    """Fuzz over what the fixed cases above hold constant: horizon, time step, robot constants, cost gains, modes.
+    The structured SRBD kernel must follow the oracle iteration by iteration for each of them."""
+    from srbd_horizon_b200.config import Gains, RobotConstants
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(4, 41))
+    dt = float(rng.choice([0.02, 0.04, 0.05, 0.08]))
+    sc = lambda v, lo=0.4, hi=2.5: float(v * np.exp(rng.uniform(np.log(lo), np.log(hi))))
+    inertia = np.diag([sc(2.0), sc(1.8), sc(0.5)]) + 0.02 * rng.uniform(-1, 1) * (np.ones((3, 3)) - np.eye(3))
+    hw, hl = sc(0.10, 0.6, 1.6), sc(0.10, 0.6, 1.6)
+    robot = RobotConstants(mass=sc(40.0), inertia=tuple(inertia.reshape(-1)), com=(0.0, 0.0, sc(0.88, 0.8, 1.2)),
+                           foot=(hl, hw, 0.0, -hl, hw, 0.0, hl, -hw, 0.0, -hl, -hw, 0.0))
+    gains = Gains(r_tracking_gain=sc(1e3), rdot_tracking_gain=sc(1e4), w_tracking_gain=sc(1e4), rel_position_gain=sc(1e4),
+                  force_switch_weight=sc(1e2), min_qddot_gain=sc(1.0), min_f_gain=sc(1e-2), constraint_weight=sc(1e6, 0.1, 1.0))
+    opts = dict(EX_OPTS, inertia_mode=(seed // 2) % 2, hessian_mode=seed % 2,
+                defect_contraction_rate=float(rng.choice([0.0, 0.0, 0.5])), mu0=float(rng.choice([0.0, 0.0, 1e-4])))
+    cfg = make_config(MODEL_SRBD, N, dt, opts, robot=robot, gains=gains)
+    B = 12
+    b = make_batch(MODEL_SRBD, N, B, seed=500 + seed, x_noise=0.01, robot=robot)
+    s = BatchedDDP(cfg)
+    r = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
+    assert (ro["status"] == 0).mean() > 0.5, (N, dt, opts)
+    _compare_solve(cfg, b, r, ro, B)
