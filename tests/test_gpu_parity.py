@@ -120,22 +120,22 @@ def test_backward_reports_cholesky_failure():
     assert int(cpu(rc)[0]) == rc_o == 10
 
 
-def _compare_solve(cfg, b, r, ro, B):
+def _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9, sol_tol=1e-9):
     iters, status = cpu(r.iters), cpu(r.status)
     hist, X, U, K, k, cost = cpu(r.hist), cpu(r.X), cpu(r.U), cpu(r.K), cpu(r.k), cpu(r.cost)
     np.testing.assert_array_equal(status, ro["status"])
     np.testing.assert_array_equal(iters, ro["iters"])
     for i in range(B):
         n = iters[i]
-        assert relerr(hist[i, :n, 0], ro["hist"][i, :n, 0]) < 1e-9, i        # per-iteration cost
+        assert relerr(hist[i, :n, 0], ro["hist"][i, :n, 0]) < hist_tol, i    # per-iteration cost
         np.testing.assert_array_equal(hist[i, :n, 1], ro["hist"][i, :n, 1])   # accepted step sizes (T8)
         np.testing.assert_array_equal(hist[i, :n, 2], ro["hist"][i, :n, 2])   # regularisation schedule
-        assert relerr(hist[i, :n, 3], ro["hist"][i, :n, 3]) < 1e-9 or np.max(np.abs(hist[i, :n, 3] - ro["hist"][i, :n, 3])) < 1e-15
-        assert relerr(X[i], ro["X"][i]) < 1e-9 and relerr(U[i], ro["U"][i]) < 1e-9, i
+        assert relerr(hist[i, :n, 3], ro["hist"][i, :n, 3]) < hist_tol or np.max(np.abs(hist[i, :n, 3] - ro["hist"][i, :n, 3])) < 1e-15
+        assert relerr(X[i], ro["X"][i]) < sol_tol and relerr(U[i], ro["U"][i]) < sol_tol, i
         if status[i] != 3:   # REG_FAILED leaves the gains of an aborted backward pass: undefined
-            assert relerr(K[i], ro["K"][i]) < 1e-8, i
-            assert np.max(np.abs(k[i] - ro["k"][i])) < 1e-9 * max(1.0, np.max(np.abs(ro["U"][i]))), i
-        assert cost[i] == pytest.approx(ro["cost"][i], rel=1e-9)
+            assert relerr(K[i], ro["K"][i]) < 10 * sol_tol, i
+            assert np.max(np.abs(k[i] - ro["k"][i])) < sol_tol * max(1.0, np.max(np.abs(ro["U"][i]))), i
+        assert cost[i] == pytest.approx(ro["cost"][i], rel=max(1e-9, 1e-3 * sol_tol))
 
 
 @pytest.mark.parametrize("model,N,opts", [
@@ -239,3 +239,29 @@ def test_solve_matches_oracle_random_configurations(seed):
     ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
     assert (ro["status"] == 0).mean() > 0.5, (N, dt, opts)
     _compare_solve(cfg, b, r, ro, B)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_lip_and_rough_warm_starts_match_oracle_random_configurations(seed):
+    """Same fuzz for the LIP model (generic dense kernel) and for SRBD started far from the solution (x_noise = 0.1:
+    line searches that go beyond the first wave, regularisation failures in single shooting).  Far from the solution
+    the iteration map amplifies rounding differences (costs fall from 1e7 to 3e4 over up to 17 iterations) and the
+    solve stops on the cost-reduction test, not at full convergence: every discrete decision (status, iteration
+    count, accepted step sizes, regularisation schedule) still agrees exactly and 29 of the 30 SRBD problems agree
+    to 1e-12, but one 17-iteration problem only to 1e-8 in the final trajectory and 8e-8 in the intermediate costs --
+    for the structured kernel and the generic dense kernel alike (1.0e-8 / 1.5e-8), so it is the conditioning of
+    that instance, not a kernel.  Tolerances here: 1e-6 (solution) and 1e-5 (history); 1e-9 everywhere else."""
+    from srbd_horizon_b200.config import Gains, RobotConstants
+    rng = np.random.default_rng(2000 + seed)
+    sc = lambda v, lo=0.5, hi=2.0: float(v * np.exp(rng.uniform(np.log(lo), np.log(hi))))
+    for model, x_noise in ((MODEL_LIP, 0.01), (MODEL_SRBD, 0.1)):
+        N = int(rng.integers(5, 31))
+        dt = float(rng.choice([0.03, 0.05]))
+        robot = RobotConstants(mass=sc(40.0), com=(0.0, 0.0, sc(0.88, 0.9, 1.1)))
+        gains = Gains(r_tracking_gain=sc(1e3), rdot_tracking_gain=sc(1e4), rel_position_gain=sc(1e4), zmp_tracking_gain=sc(1e3))
+        cfg = make_config(model, N, dt, dict(EX_OPTS, multiple_shooting=int(seed != 2)), robot=robot, gains=gains)
+        B = 10
+        b = make_batch(model, N, B, seed=700 + seed, x_noise=x_noise if cfg.multiple_shooting else 0.0, robot=robot)
+        r = BatchedDDP(cfg).solve(b["x0"], b["params"], b["X0"], b["U0"])
+        ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
+        _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9 if model == MODEL_LIP else 1e-5, sol_tol=1e-9 if model == MODEL_LIP else 1e-6)
