@@ -239,17 +239,21 @@ struct Srbd {
         accel_pre(c, x, pre);
         accel_post(c, x, u, pre, acc);
     }
+    // Branch free: lanes of a warp own different components, and a divergent branch per component kind costs more
+    // than the work.  Every component but the quaternion rate is a copy from one of the arrays.
     SDDP_DEV static double xdot_i(const DevCfg& c, int i, const double* x, const double* u, const double* acc) {
-        if (i < 3 || (i >= XC && i < XRD)) return x[i + (i < 3 ? XRD : XCD - XC)];        // rdot, cdot_j
-        if (i >= XRD && i < XCD) return acc[i < XW ? i - XRD + 3 : i - XW];               // rddot, wdot
-        if (i >= XCD) { const int j = (i - XCD) / 3; return u[i - XCD + 3 * j]; }          // cddot_j = u[6 j + k]
+        const double* src = x;                                                              // rdot, cdot_j
+        int idx = (i < 3) ? XRD + i : XCD + (i - XC);
+        if (i >= XRD) { src = acc; idx = (i < XW) ? i - XRD + 3 : i - XW; }                 // rddot, wdot
+        if (i >= XCD) { src = u; const int e = i - XCD; idx = e + 3 * (e / 3); }            // cddot_j = u[6 j + k]
+        const double v = src[idx];
         // odot = quat_prod([w/2, 0], o)  (world-aligned angular velocity, prb.py:107-108)
         const double* o = x + XO;
         const double* w = x + XW;
-        const int a = i - XO;
-        if (a == 3) return -0.5 * (w[0] * o[0] + w[1] * o[1] + w[2] * o[2]);
-        const int b2 = a == 2 ? 0 : a + 1, d = a == 0 ? 2 : a - 1;
-        return 0.5 * (o[3] * w[a] + (w[b2] * o[d] - w[d] * o[b2]));
+        const int a = min(max(i - XO, 0), 3), a3 = min(a, 2);
+        const int b2 = a3 == 2 ? 0 : a3 + 1, d = a3 == 0 ? 2 : a3 - 1;
+        const double qv = (a == 3) ? -0.5 * (w[0] * o[0] + w[1] * o[1] + w[2] * o[2]) : 0.5 * (o[3] * w[a3] + (w[b2] * o[d] - w[d] * o[b2]));
+        return (i >= XO && i < XC) ? qv : v;
     }
 
     // quaternion error rows: quat_prod(o, oref) = E(oref) o        (prb.py:187)
