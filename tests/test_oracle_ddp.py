@@ -134,3 +134,20 @@ def test_srbd_batch_converges_and_decreases():
         # dynamics feasibility of the returned trajectory
         for k in range(0, N, 7):
             assert np.max(np.abs(O.dynamics(cfg, r["X"][i, k], r["U"][i, k]) - r["X"][i, k + 1])) < 1e-7
+
+
+def test_history_logging_helpers():
+    """srbd_horizon_b200.log on an oracle solve (same hist layout as the CUDA path): rows, text table, batch summary."""
+    from srbd_horizon_b200 import log
+    from srbd_horizon_b200.config import MODEL_LIP, make_config
+    from srbd_horizon_b200.problems import make_batch
+    cfg = make_config(MODEL_LIP, 10, 0.05, {"max_iters": 20})
+    b = make_batch(MODEL_LIP, 10, 3, x_noise=0.01)
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=2)
+    rows = log.history_rows(ro["hist"], ro["iters"], problem=1)
+    assert len(rows) == ro["iters"][1] and rows[0]["cost"] == ro["hist"][1, 0, 0] and rows[0]["alpha"] in (0.0, 1.0)
+    assert np.isnan(rows[-1]["cost_change"]) and all(r["cost_change"] <= 1e-9 * abs(r["cost"]) for r in rows[:-1]) or cfg.multiple_shooting
+    txt = log.format_history(ro["hist"], ro["iters"], ro["status"], problem=1)
+    assert "status: converged" in txt and txt.count("\n") == len(rows) + 1
+    s = log.batch_summary(ro["iters"], ro["status"])
+    assert s["problems"] == 3 and s["converged"] == 3 and s["max_iters"] == 0 and s["iters_max"] >= s["iters_mean"] >= 1
