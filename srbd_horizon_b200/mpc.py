@@ -96,6 +96,13 @@ class BatchedMPC:
     def tick(self, actions, rdot_ref_cmd, gains: bool = False):
         """One closed-loop tick for all B robots; returns the BatchResult of the solve (X, U alias the warm start)."""
         self.advance_schedule(actions, rdot_ref_cmd)
-        self.last = self.solver.solve(self.state, self.params, self.X, self.U, gains=gains, history=False, inplace=True)
+        # Dispatch hint (scheduling only): robots that needed many iterations at the previous tick go first, the rest
+        # grouped by contact schedule -- consecutive ticks of a receding-horizon loop solve nearly the same problems.
+        order = None
+        if self.state.shape[0] >= 1024:
+            order = self.solver.dispatch_order(self.params)
+            if self.last is not None and self.last.iters.shape[0] == self.state.shape[0]:
+                order = self.solver.order_from_keys(-self.last.iters.to(self.params.dtype), (self.params[:, -1, 0:3] ** 2).sum(dim=1))
+        self.last = self.solver.solve(self.state, self.params, self.X, self.U, gains=gains, history=False, inplace=True, order=order)
         self.plant_step()
         return self.last

@@ -104,3 +104,30 @@ def test_plant_step_matches_example():
             if model == MODEL_SRBD:
                 ref[3:7] /= np.linalg.norm(ref[3:7])
             assert np.max(np.abs(out[b] - ref)) < 1e-14
+
+
+def test_large_fleet_ticks_use_the_dispatch_hint_and_change_nothing():
+    """B >= 1024 robots: BatchedMPC.tick dispatches the solve by the previous tick's iteration counts / the contact
+    schedule; the closed loop must be bit-identical to the same ticks solved in index order."""
+    from srbd_horizon_b200.problems import make_batch
+    ns, B, ticks = 12, 1500, 3
+    cfg = make_config(MODEL_SRBD, ns, 0.05, OPTS)
+    b = make_batch(MODEL_SRBD, ns, B, enumerate_schedules=True)
+    rng = np.random.default_rng(5)
+    acts = rng.choice(3, size=(ticks, B), p=[0.7, 0.2, 0.1])
+    cmd = np.tile([0.3, 0.0, 0.0], (B, 1))
+    runs = []
+    for hinted in (True, False):
+        s = BatchedDDP(cfg)
+        mpc = BatchedMPC(s, b["x0"], b["params"], b["U0"])
+        if not hinted:      # same ticks, index order: call the pieces of tick() by hand
+            for t in range(ticks):
+                mpc.advance_schedule(acts[t], cmd)
+                mpc.last = s.solve(mpc.state, mpc.params, mpc.X, mpc.U, gains=False, history=False, inplace=True)
+                mpc.plant_step()
+        else:
+            for t in range(ticks):
+                mpc.tick(acts[t], cmd)
+        runs.append((mpc.state.clone(), mpc.X.clone(), mpc.U.clone(), mpc.last.iters.clone()))
+    for a, c in zip(runs[0], runs[1]):
+        assert torch.equal(a, c)
