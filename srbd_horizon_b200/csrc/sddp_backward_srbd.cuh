@@ -165,6 +165,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
     __syncthreads();
     M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, S.escr);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
+    cp_wait_all();
+    __syncthreads();                           // node N-1 landed
 
     const unsigned long long c1d = __ldg(c.ztab + ZT_C1OFF + tid);     // this thread's Quu entries (see c1)
     for (int k = N - 1; k >= 0; k--) {
@@ -175,10 +177,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         const double* pk = nb + NBL::OP;
         double* cg = nb + NBL::OD;
         const double* pack = nb + NBL::OK;
-        STAMP(0);
-        cp_wait_all();
-        __syncthreads();                       // node k landed; everyone is done with node k+1
-        STAMP(1);
+        STAMP(0);                              // node k has landed and everyone is done with node k+1: see the barrier that
+        STAMP(1);                              // ends the f / g phase (and the one in front of the loop)
         PROF(8);
         const double* Jac = pack + M::PK_JAC;
         PROF(9);
@@ -521,7 +521,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             }
         }
         STAMP(9);
-        __syncthreads();
+        cp_wait_all();                         // the prefetch of node k-1 (issued in c1) is long done: this barrier also
+        __syncthreads();                       // publishes it, so the next node starts without one of its own
         STAMP(10);
         PROF(13);
         if (mu != 0.0) {   // regularised step (rare): Vxx -= mu K^T K, Vx -= mu K^T k, gains re-read from global
@@ -540,6 +541,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     S.Vx[j] -= mu * t;
                 }
             }
+            __syncthreads();                   // the next node reads Vxx, Vx right away
         }
         if (tid == 0) {   // model accumulators
             const double sw = -S.Vx[NX];        // |w0|^2 (see f)

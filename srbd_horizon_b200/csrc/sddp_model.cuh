@@ -627,7 +627,7 @@ struct Srbd {
             Qx[i] += g;
             if (MODE) Qx2[i] += g;
         }
-        sync();
+        if (MODE == 0) sync();      // MODE 1: the caller's block barrier at the end of the phase follows immediately
         PROF(22);
     }
 
