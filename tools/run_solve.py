@@ -16,6 +16,7 @@ ap.add_argument("--batch", type=int, default=1184)
 ap.add_argument("--N", type=int, default=50)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--no-gains", action="store_true")
+ap.add_argument("--order", default="schedule", choices=["schedule", "index"], help="dispatch order (see sddp_set_dispatch_order)")
 a = ap.parse_args()
 cfg = make_config(MODEL_SRBD, a.N, 0.05, {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3})
 b = make_batch(MODEL_SRBD, a.N, a.batch, enumerate_schedules=True)
@@ -26,7 +27,7 @@ times = []
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    r = s.solve(x0, p, X0, U0, gains=not a.no_gains, history=False)
+    r = s.solve(x0, p, X0, U0, gains=not a.no_gains, history=False, order=None if a.order == "index" else "schedule")
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
