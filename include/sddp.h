@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SDDP_ABI_VERSION 1
+#define SDDP_ABI_VERSION 2
 
 enum { SDDP_MODEL_SRBD = 0, SDDP_MODEL_LIP = 1 };
 enum { SDDP_INERTIA_LITERAL = 0, SDDP_INERTIA_ROTATED = 1 };   /* prb.py:99 as written / README.md:2 intent */
@@ -88,6 +88,14 @@ typedef struct SddpConfig {
     double defect_contraction_rate;      /* README.md:6; <= 0: rho = alpha */
     double mu_min, mu_max, mu_factor;
     double defect_ths;
+    /* Inequality handling: the friction cone the reference computes and drops (prb.py:173-177), as the
+     * exponential barrier its adapter sketches (ddp.py:197-203): on nodes 0..N-1
+     *   L += friction_cone_weight * sum_feet sum_rows exp(friction_cone_sharpness * g_row(f_i)),
+     * g = (f_x - mu f_z, -f_x - mu f_z, f_y - mu f_z, -f_y - mu f_z, -f_z) <= 0 (linearised cone, world frame).
+     * weight = 0 (default) reproduces the reference: no inequality terms.  SRBD only. */
+    double friction_cone_weight;
+    double friction_cone_mu;          /* prb.py:174 friction_cone_coefficient, default 0.8 */
+    double friction_cone_sharpness;   /* ddp.py:182 exp_parameter, default 6.0 */
 } SddpConfig;
 
 typedef struct SddpHandle SddpHandle;

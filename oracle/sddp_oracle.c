@@ -429,6 +429,29 @@ static void srbd_cost(const OrcConfig *c, int kind, const double *x, const doubl
             acc_single(a, fs * fs * c->min_f_gain, nx + SU_F(i) + k, u[SU_F(i) + k]);
             acc_single(a, fs * fs * c->force_switch_weight * (1.0 - sw) * (1.0 - sw), nx + SU_F(i) + k, u[SU_F(i) + k]);
         }
+        /* Friction cone as an exponential barrier (extension, off by default): the reference builds the linearised cone
+         * (prb.py:173-177) and drops it; its adapter sketches  cost += exp_parameter * exp(g)  for g <= 0
+         * (ddp.py:197-203).  Here  L += w sum_rows exp(kappa g_row(f_i)),  g = A f,
+         * A = [1 0 -mu; -1 0 -mu; 0 1 -mu; 0 -1 -mu; 0 0 -1]  (stance frame = world frame, prb.py:175). */
+        if (c->friction_cone_weight != 0.0) {
+            const double w = c->friction_cone_weight, kap = c->friction_cone_sharpness, fm = c->friction_cone_mu;
+            const double A[5][3] = {{1, 0, -fm}, {-1, 0, -fm}, {0, 1, -fm}, {0, -1, -fm}, {0, 0, -1}};
+            for (int i = 0; i < 4; i++) {
+                const double *f = u + SU_F(i);
+                for (int r = 0; r < 5; r++) {
+                    double g = A[r][0] * f[0] + A[r][1] * f[1] + A[r][2] * f[2];
+                    double e = w * exp(kap * g);
+                    a->cost += e;
+                    if (a->derivs) {
+                        for (int k = 0; k < 3; k++) {
+                            a->lu[SU_F(i) + k] += kap * e * A[r][k];
+                            for (int l = 0; l < 3; l++)
+                                a->luu[(SU_F(i) + k) * a->nu + SU_F(i) + l] += kap * kap * e * A[r][k] * A[r][l];
+                        }
+                    }
+                }
+            }
+        }
         /* equality constraints, weight 1e6 (ddp.py:181,191-196); prb.py:166-181 */
         double cw = c->constraint_weight;
         for (int leg = 0; leg < 2; leg++) for (int ax = 0; ax < 2; ax++) { /* relative_vel_left_1 / right_3 */

@@ -62,6 +62,9 @@ typedef struct OrcConfig {
     double defect_contraction_rate;      /* README.md:6; <=0 means rho = alpha */
     double mu_min, mu_max, mu_factor;    /* regularisation schedule */
     double defect_ths;                   /* MS convergence: max |defect| */
+    double friction_cone_weight;         /* 0 = reference behaviour (cone dropped, prb.py:173-177); see include/sddp.h */
+    double friction_cone_mu;             /* prb.py:174 */
+    double friction_cone_sharpness;      /* ddp.py:182 exp_parameter */
 } OrcConfig;
 
 enum { ORC_HIST = 4 };   /* per-iteration record: cost, alpha, mu, max|defect| */

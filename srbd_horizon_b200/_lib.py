@@ -11,6 +11,8 @@ from .config import SddpConfig
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("SDDP_LIB", os.path.join(CSRC, "libsddp.so"))   # SDDP_LIB: A/B builds while tuning
+# second build of the same sources with the friction-cone barrier compiled in (csrc/Makefile); loaded on demand
+CONE_LIB_PATH = os.environ.get("SDDP_LIB_CONE", os.path.join(CSRC, "libsddp_cone.so"))
 
 _vp = ctypes.c_void_p
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -39,42 +41,44 @@ SYMBOLS = {
     "sddp_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
 }
 
-_lib = None
+_libs = {}
 
 
 def build(force: bool = False) -> str:
-    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("sddp.cu", "sddp_solver.cuh", "sddp_model.cuh")]
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU): both libraries, in parallel."""
+    srcs = [os.path.join(CSRC, f) for f in ("sddp.cu", "sddp_solver.cuh", "sddp_backward_srbd.cuh", "sddp_model.cuh", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "sddp.h"))
-    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    outs = [os.path.join(CSRC, "libsddp.so"), os.path.join(CSRC, "libsddp_cone.so")]
+    stale = any((not os.path.exists(o)) or any(os.path.getmtime(s) > os.path.getmtime(o) for s in srcs) for o in outs)
     if force or stale:
-        subprocess.check_call(["make", "-C", CSRC, "-B", "libsddp.so"])
+        subprocess.check_call(["make", "-C", CSRC, "-B", "-j2", "all"])
     return LIB_PATH
 
 
-def lib() -> ctypes.CDLL:
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+def lib(cone: bool = False) -> ctypes.CDLL:
+    """The product library, or (cone=True) the build with the friction-cone barrier."""
+    path = CONE_LIB_PATH if cone else LIB_PATH
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.sddp_abi_version() != 1:
-            raise RuntimeError("libsddp.so ABI version mismatch")
+        if L.sddp_abi_version() != 2:
+            raise RuntimeError(f"{os.path.basename(path)} ABI version mismatch")
         if L.sddp_config_size() != ctypes.sizeof(SddpConfig):
             raise RuntimeError("SddpConfig layout mismatch between config.py and include/sddp.h")
-        _lib = L
-    return _lib
+        _libs[path] = L
+    return _libs[path]
 
 
 class SddpError(RuntimeError):
     pass
 
 
-def check(rc: int, handle=None) -> None:
+def check(rc: int, handle=None, L=None) -> None:
     if rc != 0:
-        msg = lib().sddp_last_error(handle)
+        msg = (L or lib()).sddp_last_error(handle)
         raise SddpError(f"sddp error {rc}: {msg.decode() if msg else '?'}")

@@ -80,6 +80,9 @@ class SddpConfig(ctypes.Structure):
         ("mu_max", ctypes.c_double),
         ("mu_factor", ctypes.c_double),
         ("defect_ths", ctypes.c_double),
+        ("friction_cone_weight", ctypes.c_double),
+        ("friction_cone_mu", ctypes.c_double),
+        ("friction_cone_sharpness", ctypes.c_double),
     ]
 
     def copy(self) -> "SddpConfig":
@@ -145,6 +148,10 @@ DEFAULT_OPTS: Dict[str, float] = {
     "inertia_mode": INERTIA_LITERAL,
     "hessian_mode": HESSIAN_EXACT,
     "dense_backward": 0,                   # 1: generic dense Riccati kernel for SRBD (A/B check of the structured one)
+    # inequality handling: exponential barrier on the linearised friction cone; 0 = dropped as in the reference
+    "friction_cone_weight": 0.0,
+    "friction_cone_mu": 0.8,               # prb.py:174
+    "friction_cone_sharpness": 6.0,        # ddp.py:182
 }
 
 
@@ -180,7 +187,7 @@ def make_config(model: int, N: int, dt: float, opts: Dict | None = None,
         setattr(c, name, float(getattr(gains, name)))
     for name in ("alpha_0", "alpha_converge_threshold", "line_search_decrease_factor", "beta",
                  "cost_reduction_ths", "mu0", "defect_contraction_rate", "mu_min", "mu_max",
-                 "mu_factor", "defect_ths"):
+                 "mu_factor", "defect_ths", "friction_cone_weight", "friction_cone_mu", "friction_cone_sharpness"):
         setattr(c, name, float(o[name]))
     if c.N < 1 or c.max_iters < 1:
         raise ValueError("N and max_iters must be >= 1")

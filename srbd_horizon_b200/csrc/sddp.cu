@@ -242,6 +242,12 @@ static int check_config(const SddpConfig* c, SddpHandle* h) {
     if (!(c->alpha_converge_threshold > 0.0)) return fail(h, SDDP_EINVAL, "%s%s", "alpha_converge_threshold must be > 0", "");
     if (!(c->mu_factor > 1.0)) return fail(h, SDDP_EINVAL, "%s%s", "mu_factor must be > 1", "");
     if (c->defect_contraction_rate > 1.0) return fail(h, SDDP_EINVAL, "%s%s", "defect_contraction_rate must be <= 1", "");
+    if (!(c->friction_cone_weight >= 0.0) || !(c->friction_cone_mu >= 0.0) || !(c->friction_cone_sharpness >= 0.0))
+        return fail(h, SDDP_EINVAL, "%s%s", "friction_cone_weight, _mu and _sharpness must be >= 0", "");
+#ifdef SDDP_NO_CONE
+    if (c->friction_cone_weight != 0.0)
+        return fail(h, SDDP_EINVAL, "%s%s", "friction_cone_weight > 0 needs the build with inequality support (libsddp_cone.so)", "");
+#endif
     return 0;
 }
 
@@ -262,6 +268,7 @@ static void make_devcfg(const SddpConfig& s, DevCfg& d) {
     d.alpha0 = s.alpha_0; d.alpha_min = s.alpha_converge_threshold; d.ls_factor = s.line_search_decrease_factor;
     d.beta = s.beta; d.cost_ths = s.cost_reduction_ths; d.mu0 = s.mu0; d.rho_fixed = s.defect_contraction_rate;
     d.mu_min = s.mu_min; d.mu_max = s.mu_max; d.mu_factor = s.mu_factor; d.defect_ths = s.defect_ths;
+    d.w_cone = s.model == SDDP_MODEL_SRBD ? s.friction_cone_weight : 0.0; d.cone_mu = s.friction_cone_mu; d.cone_k = s.friction_cone_sharpness;
     d.ztab = nullptr;
 }
 

@@ -202,6 +202,13 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             // the remaining (cddot, f) / (cddot, cddot) entries (4 or 1 products): the assignment is a host-built
             // table (sddp.cu:build_ztab), four 16-bit descriptors per thread.
             const double dt2 = dt * dt, g2 = 2.0 * c.gq;
+            if (SDDP_CONE_ON(c)) {          // friction-cone barrier (extension, off by default): 3 x 3 Hessian per foot -> escr
+                if (tid < 4) {
+                    double val, cg[3];
+                    M::cone_terms_cold(c, uk + 6 * tid + 3, val, cg, S.escr + 6 * tid);
+                }
+                __syncthreads();
+            }
             if (tid < 78) {
                 const int fa = C1_I1(c1d), fb = C1_I2(c1d);
                 const int ka = fa % 3, kb = fb % 3;
@@ -220,6 +227,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     v += g2 * im * im;
                     if (fa == fb) { const double sw1 = 1.0 - pk[8 + 2 * (fa / 3)]; v += 2.0 * (c.w_minf + c.w_fsw * sw1 * sw1) + mu; }
                 }
+                if (SDDP_CONE_ON(c) && fa / 3 == fb / 3) v += S.escr[6 * (fa / 3) + M::cone_hidx(ka, kb)];      // friction-cone barrier
                 const int ua = 6 * (fa / 3) + 3 + ka, ub = 6 * (fb / 3) + 3 + kb;
                 S.Quu[ua * NU + ub] = v;
                 S.Quu[ub * NU + ua] = v;

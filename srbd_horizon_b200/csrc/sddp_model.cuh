@@ -51,10 +51,19 @@ __device__ long long g_stamp[16 * 4];
 #define STAMP(id)
 #endif
 
+// The friction-cone barrier (include/sddp.h) is off unless SddpConfig.friction_cone_weight > 0.  -DSDDP_NO_CONE compiles
+// it out (A/B builds); -DSDDP_CONE_INLINE inlines the five exp() at every call site instead of one out-of-line copy.
+#ifdef SDDP_NO_CONE
+#define SDDP_CONE_ON(c) false
+#else
+#define SDDP_CONE_ON(c) ((c).w_cone != 0.0)
+#endif
+
 struct DevCfg {
     int model, N, inertia_mode, hessian_mode, ms, max_iters;
     double dt, mscaled, inv_ms, Ib[9], com[3], foot[12], fs, g, eta2;
     double w_r, w_rdot, w_w, w_rel, w_fsw, gq, w_minf, w_zmp, cw;
+    double w_cone, cone_mu, cone_k;   // friction-cone barrier (include/sddp.h); w_cone = 0: off
     double drel[2][2];   // drel[pair][axis] = -(foot[pair][axis] - foot[pair+2][axis])   prb.py:153-154
     double alpha0, alpha_min, ls_factor, beta, cost_ths, mu0, rho_fixed, mu_min, mu_max, mu_factor, defect_ths;
     const unsigned long long* ztab;   // SRBD: descriptors of the 595 upper-triangular entries of the wdot Hessian block
@@ -265,6 +274,32 @@ struct Srbd {
         return -m3::skew_ab(q, i, a);
     }
 
+    // Exponential barrier on the linearised friction cone of one foot (include/sddp.h, extension, off by default):
+    // value, gradient (3) and Hessian (xx, xy, xz, yy, yz, zz) with respect to the foot's force f.
+    SDDP_DEV static void cone_terms(const DevCfg& c, const double* f, double& val, double* g, double* h) {
+        const double k = c.cone_k, m = c.cone_mu, kz = k * m * f[2];
+        const double e1 = c.w_cone * exp(k * f[0] - kz), e2 = c.w_cone * exp(-k * f[0] - kz);
+        const double e3 = c.w_cone * exp(k * f[1] - kz), e4 = c.w_cone * exp(-k * f[1] - kz), e5 = c.w_cone * exp(-k * f[2]);
+        const double s4 = (e1 + e2) + (e3 + e4);
+        val = s4 + e5;
+        g[0] = k * (e1 - e2); g[1] = k * (e3 - e4); g[2] = -k * (m * s4 + e5);
+        h[0] = k * k * (e1 + e2); h[1] = 0.0; h[2] = -k * k * m * (e1 - e2);
+        h[3] = k * k * (e3 + e4); h[4] = -k * k * m * (e3 - e4); h[5] = k * k * (m * m * s4 + e5);
+    }
+    // Out-of-line copy for the call sites inside hot loops (forward-pass cost, node expansion): with the barrier off they
+    // cost one predicated call instead of five inlined exp().
+#ifdef SDDP_CONE_INLINE
+    SDDP_DEV static void cone_terms_cold(const DevCfg& c, const double* f, double& val, double* g, double* h) { cone_terms(c, f, val, g, h); }
+#else
+    __device__ __noinline__ static void cone_terms_cold(const DevCfg& c, const double* f, double& val, double* g, double* h) {
+        cone_terms(c, f, val, g, h);
+    }
+#endif
+    SDDP_DEV static int cone_hidx(int a, int b) {      // index of (a, b) in (xx, xy, xz, yy, yz, zz)
+        const int lo = min(a, b), hi = max(a, b);
+        return lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+    }
+
     // parts: 1 = terms indexed by the state (8: those of the contact-point velocities, split off for load balance),
     //        2 = terms indexed by the input, 4 = rddot / wdot terms (need accel)
     SDDP_DEV static double cost_lane(const DevCfg& c, int kind, int lane, const double* x, const double* u, const double* p, const double* acc,
@@ -319,6 +354,11 @@ struct Srbd {
                 else { double a = 1.0 - p[8 + 2 * i]; s += (c.w_minf + c.w_fsw * a * a) * v * v; }
             }
             if ((parts & 4) && lane < 3) s += c.gq * (acc[lane] * acc[lane] + acc[3 + lane] * acc[3 + lane]);
+            if ((parts & 2) && SDDP_CONE_ON(c) && lane < 4) {      // friction-cone barrier of foot `lane`
+                double val, g[3], h[6];
+                cone_terms_cold(c, u + 6 * lane + 3, val, g, h);
+                s += val;
+            }
         }
         return s;
     }
@@ -592,7 +632,11 @@ struct Srbd {
                 const int i = tg / 6, r = tg % 6;
                 double g;
                 if (r < 3) g = 2.0 * c.gq * u[tg];
-                else { const double a = 1.0 - p[8 + 2 * i]; g = 2.0 * c.gq * c.inv_ms * pk[PK_RDD + r - 3] + 2.0 * (c.w_minf + c.w_fsw * a * a) * u[tg]; }
+                else {
+                    const double a = 1.0 - p[8 + 2 * i];
+                    g = 2.0 * c.gq * c.inv_ms * pk[PK_RDD + r - 3] + 2.0 * (c.w_minf + c.w_fsw * a * a) * u[tg];
+                    if (SDDP_CONE_ON(c)) { double val, cg[3], ch[6]; cone_terms_cold(c, u + 6 * i + 3, val, cg, ch); g += cg[r - 3]; }
+                }
                 if (MODE) { Qu[tg * LDUX] += g; Qu2[tg * LDUX] += g; }
                 else Qu[tg] += g;
             }
@@ -626,6 +670,15 @@ struct Srbd {
             }
             Qx[i] += g;
             if (MODE) Qx2[i] += g;
+        }
+        if (MODE == 0 && input && SDDP_CONE_ON(c)) {      // luu of the friction-cone barrier (MODE 1: the caller builds Quu itself)
+            sync();
+            if (tid < 36) {
+                const int i = tid / 9, ka = (tid % 9) / 3, kb = tid % 3;
+                double val, cg[3], ch[6];
+                cone_terms_cold(c, u + 6 * i + 3, val, cg, ch);
+                Quu[(6 * i + 3 + ka) * NU + 6 * i + 3 + kb] += ch[cone_hidx(ka, kb)];
+            }
         }
         if (MODE == 0) sync();      // MODE 1: the caller's block barrier at the end of the phase follows immediately
         PROF(22);
@@ -737,6 +790,17 @@ struct Srbd {
             Qx[ia] += w2 * (res + sa * sa * x[ia]); Qx[ib] += w2 * (-res + sb * sb * x[ib]);
         }
         sync();
+        if (input && SDDP_CONE_ON(c)) {       // friction-cone barrier (extension): gradient and 3 x 3 Hessian per foot
+            if (tid < 4) {
+                double val, cg[3], ch[6];
+                cone_terms_cold(c, u + 6 * tid + 3, val, cg, ch);
+                for (int a = 0; a < 3; a++) {
+                    Qu[6 * tid + 3 + a] += cg[a];
+                    for (int b = 0; b < 3; b++) Quu[(6 * tid + 3 + a) * NU + 6 * tid + 3 + b] += ch[cone_hidx(a, b)];
+                }
+            }
+            sync();
+        }
     }
 
     // dense fx = I + dt A, fu = dt B.  Every thread of the block must call.

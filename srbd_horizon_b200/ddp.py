@@ -51,14 +51,14 @@ class BatchedDDP:
     def __init__(self, cfg: SddpConfig, device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("srbd_horizon_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.L = _lib.lib()
+        self.L = _lib.lib(cone=cfg.friction_cone_weight != 0.0)      # inequality support is a separate build (csrc/Makefile)
         self.cfg = cfg.copy()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.nx, self.nu, self.np = DIMS[cfg.model]
         self.N = cfg.N
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(self.L.sddp_create(ctypes.byref(self.cfg), ctypes.byref(h)))
+            _lib.check(self.L.sddp_create(ctypes.byref(self.cfg), ctypes.byref(h)), None, self.L)
         self.h = h
 
     def close(self):

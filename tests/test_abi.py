@@ -19,13 +19,26 @@ def _header_functions():
     return sorted(set(re.findall(r"\b(sddp_[a-z0-9_]+)\s*\(", src)))
 
 
-def test_library_exports_every_declared_symbol():
-    L = _lib.lib()
+@pytest.mark.parametrize("cone", [False, True])
+def test_library_exports_every_declared_symbol(cone):
+    """libsddp.so and libsddp_cone.so (the build with the friction-cone barrier) export the whole header."""
+    L = _lib.lib(cone=cone)
     declared = _header_functions()
     assert len(declared) >= 15
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(_lib.SYMBOLS) == declared
+    assert L.sddp_abi_version() == 2 and L.sddp_config_size() == ctypes.sizeof(SddpConfig)
+
+
+def test_inequality_option_needs_the_build_that_has_it():
+    """The product library is built without the barrier code (it costs the hot path 3 %); it must say so instead of
+    silently ignoring friction_cone_weight.  (No GPU needed: the config check comes first.)"""
+    cfg = make_config(MODEL_SRBD, 10, 0.05, {"friction_cone_weight": 1.0})
+    assert _lib.lib().sddp_workspace_bytes(ctypes.byref(cfg)) == 0
+    assert _lib.lib(cone=True).sddp_workspace_bytes(ctypes.byref(cfg)) > 0
+    cfg.friction_cone_mu = -1.0
+    assert _lib.lib(cone=True).sddp_workspace_bytes(ctypes.byref(cfg)) == 0
 
 
 def test_config_layout_matches_header_and_oracle():

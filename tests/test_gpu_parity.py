@@ -265,3 +265,34 @@ def test_lip_and_rough_warm_starts_match_oracle_random_configurations(seed):
         r = BatchedDDP(cfg).solve(b["x0"], b["params"], b["X0"], b["U0"])
         ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
         _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9 if model == MODEL_LIP else 1e-5, sol_tol=1e-9 if model == MODEL_LIP else 1e-6)
+
+
+@pytest.mark.parametrize("dense", [0, 1])
+def test_friction_cone_barrier_matches_oracle(dense):
+    """Inequality handling (off by default): stage-1 derivatives and whole solves with the friction-cone barrier, on
+    the structured and on the generic dense kernel."""
+    opts = dict(EX_OPTS, friction_cone_weight=5.0, friction_cone_sharpness=8.0, friction_cone_mu=0.7, dense_backward=dense)
+    cfg = make_config(MODEL_SRBD, 20, 0.05, opts)
+    s = BatchedDDP(cfg)
+    rng = np.random.default_rng(9)
+    M = 24
+    kind = np.array([0, 1, 2] * 8, dtype=np.int32)
+    pts = [random_point(rng, MODEL_SRBD) for _ in range(M)]
+    x, u, p = (np.stack([q[i] for q in pts]) for i in range(3))
+    out = s.eval_derivatives(kind, x, u, p)
+    for m in range(M):
+        ref = O.derivs(cfg, int(kind[m]), x[m], u[m], p[m])
+        ref["l"] = np.array(O.cost(cfg, int(kind[m]), x[m], u[m], p[m]))
+        for name in ("l", "lu", "luu", "lx", "lxx", "lux"):
+            if kind[m] == 2 and name in ("lu", "luu", "lux"):
+                continue                                   # terminal node: no input terms
+            a = cpu(out[name][m])
+            assert np.max(np.abs(a - ref[name])) <= 1e-11 * max(1.0, np.max(np.abs(ref[name]))), (m, name)
+    B = 16
+    b = make_batch(MODEL_SRBD, 20, B, x_noise=0.01)
+    r = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
+    r0 = BatchedDDP(make_config(MODEL_SRBD, 20, 0.05, dict(EX_OPTS, dense_backward=dense))).solve(b["x0"], b["params"], b["X0"], b["U0"])
+    assert not torch.equal(r.U, r0.U)            # the barrier does change the solution
+    assert (ro["status"] == 0).mean() > 0.7
+    _compare_solve(cfg, b, r, ro, B)

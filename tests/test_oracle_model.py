@@ -80,3 +80,33 @@ def test_T5_cost_bookkeeping():
     # static cost at the nominal point: only min_f (1e4 |f|^2) is non-zero
     fz = RobotConstants().mass * 9.81 / 1000 / 4
     assert base == pytest.approx(4 * 1e4 * fz * fz, rel=1e-12)
+
+
+def test_friction_cone_barrier_derivatives_by_finite_differences():
+    """Inequality handling (off by default): the exponential barrier on the linearised friction cone adds
+    to L, lu and the per-foot 3x3 blocks of luu; gradient and Hessian against central differences of the oracle's own
+    cost, and nothing changes when the weight is 0 (the reference drops the cone, prb.py:173-177)."""
+    from oracle import oracle as O
+    from srbd_horizon_b200.config import MODEL_SRBD, make_config
+    from srbd_horizon_b200.problems import nominal
+    cfg0 = make_config(MODEL_SRBD, 10, 0.05, {})
+    cfg = make_config(MODEL_SRBD, 10, 0.05, {"friction_cone_weight": 2.0, "friction_cone_sharpness": 4.0, "friction_cone_mu": 0.6})
+    rng = np.random.default_rng(3)
+    x, u = nominal(MODEL_SRBD)
+    x = x + 0.01 * rng.standard_normal(37); u = u + 0.02 * rng.standard_normal(24)
+    p = np.zeros(19); p[8:15:2] = 1.0; p[18] = 1.0; p[6] = 10.0
+    d, d0 = O.derivs(cfg, 1, x, u, p), O.derivs(cfg0, 1, x, u, p)
+    assert O.cost(cfg, 1, x, u, p) > O.cost(cfg0, 1, x, u, p)
+    assert O.cost(cfg, 2, x, u, p) == O.cost(cfg0, 2, x, u, p)          # terminal node: no input terms
+    for name in ("lx", "lxx", "lux"):
+        np.testing.assert_array_equal(d[name], d0[name])
+    eps = 1e-6
+    lu_fd = np.array([(O.cost(cfg, 1, x, u + eps * e, p) - O.cost(cfg, 1, x, u - eps * e, p)) / (2 * eps) for e in np.eye(24)])
+    assert np.abs(lu_fd - d["lu"]).max() < 1e-8 * np.abs(d["lu"]).max()
+    luu_fd = np.array([(O.derivs(cfg, 1, x, u + eps * e, p)["lu"] - O.derivs(cfg, 1, x, u - eps * e, p)["lu"]) / (2 * eps) for e in np.eye(24)])
+    assert np.abs(luu_fd - d["luu"]).max() < 1e-8 * np.abs(d["luu"]).max()
+    dd = d["luu"] - d0["luu"]
+    mask = np.zeros((24, 24), bool)
+    for i in range(4):
+        mask[6 * i + 3:6 * i + 6, 6 * i + 3:6 * i + 6] = True
+    assert np.all(dd[~mask] == 0) and np.all(np.linalg.eigvalsh(dd) > -1e-9)
