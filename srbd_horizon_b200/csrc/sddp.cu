@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -19,9 +20,11 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) 
     // (Warp w of every resident CTA shares one SM sub-partition.  Rotating the warp roles per co-resident CTA was
     //  measured slower: same-role warps share their code in the sub-partition's instruction cache.)
     const int tid = threadIdx.x;
+    PROF_RESET;
     for (;;) {   // persistent CTA: pull problems from a queue (iteration counts differ per problem)
         if (tid == 0) s_prob = atomicAdd(a.counter, 1);
         __syncthreads();
+        PROF(7);
         if (s_prob >= a.B) break;
         const int b = a.order ? a.order[s_prob] : s_prob;
         solve_one<M, SM>(c, a, S, b, blockIdx.x, tid);
@@ -212,6 +215,7 @@ struct SddpHandle {
     void* stage; size_t stage_bytes;
     void* hstage; size_t hstage_bytes;       // pinned host staging of the small-batch path
     cudaStream_t st_in, st_cmp, st_out;
+    cudaEvent_t ev_last; bool ev_last_valid;   // recorded after the last launch that uses the workspace
     int host_chunk;
     long long launches;
     const int32_t* order_dev; int order_n;      // caller-owned device permutation for sddp_solve_batch
@@ -231,6 +235,15 @@ static int fail(SddpHandle* h, int code, const char* fmt, const char* a, const c
         if (e_ != cudaSuccess) return fail(h, SDDP_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// The handle's workspace serves one solve at a time: remember the end of the last launch that used it.
+static cudaError_t mark_last(SddpHandle* h, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    if (!h->ev_last && (e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming)) != cudaSuccess) return e;
+    e = cudaEventRecord(h->ev_last, st);
+    h->ev_last_valid = (e == cudaSuccess);
+    return e;
+}
+
 static int check_config(const SddpConfig* c, SddpHandle* h) {
     if (!c) return fail(h, SDDP_EINVAL, "%s%s", "config is NULL", "");
     if (c->model != SDDP_MODEL_SRBD && c->model != SDDP_MODEL_LIP) return fail(h, SDDP_EINVAL, "%s%s", "unknown model", "");
@@ -240,7 +253,16 @@ static int check_config(const SddpConfig* c, SddpHandle* h) {
     if (!(c->line_search_decrease_factor > 0.0 && c->line_search_decrease_factor < 1.0))
         return fail(h, SDDP_EINVAL, "%s%s", "line_search_decrease_factor must be in (0,1)", "");
     if (!(c->alpha_converge_threshold > 0.0)) return fail(h, SDDP_EINVAL, "%s%s", "alpha_converge_threshold must be > 0", "");
-    if (!(c->mu_factor > 1.0)) return fail(h, SDDP_EINVAL, "%s%s", "mu_factor must be > 1", "");
+    if (!(c->mu_factor > 1.0) || !std::isfinite(c->mu_factor)) return fail(h, SDDP_EINVAL, "%s%s", "mu_factor must be finite and > 1", "");
+    // the in-kernel regularisation and line-search loops terminate only for these (sddp_solver.cuh solve_one)
+    if (!std::isfinite(c->alpha_0) || !(c->alpha_0 > 0.0)) return fail(h, SDDP_EINVAL, "%s%s", "alpha_0 must be finite and > 0", "");
+    if (!std::isfinite(c->alpha_converge_threshold)) return fail(h, SDDP_EINVAL, "%s%s", "alpha_converge_threshold must be finite", "");
+    if (!std::isfinite(c->mu0) || !(c->mu0 >= 0.0)) return fail(h, SDDP_EINVAL, "%s%s", "mu0 must be finite and >= 0", "");
+    if (!std::isfinite(c->mu_min) || !(c->mu_min > 0.0)) return fail(h, SDDP_EINVAL, "%s%s", "mu_min must be finite and > 0", "");
+    if (!std::isfinite(c->mu_max) || !(c->mu_max >= c->mu_min)) return fail(h, SDDP_EINVAL, "%s%s", "mu_max must be finite and >= mu_min", "");
+    if (!std::isfinite(c->beta) || !std::isfinite(c->cost_reduction_ths) || !std::isfinite(c->defect_ths))
+        return fail(h, SDDP_EINVAL, "%s%s", "beta, cost_reduction_ths and defect_ths must be finite", "");
+    if (!std::isfinite(c->dt)) return fail(h, SDDP_EINVAL, "%s%s", "dt must be finite", "");
     if (c->defect_contraction_rate > 1.0) return fail(h, SDDP_EINVAL, "%s%s", "defect_contraction_rate must be <= 1", "");
     if (!(c->friction_cone_weight >= 0.0) || !(c->friction_cone_mu >= 0.0) || !(c->friction_cone_sharpness >= 0.0))
         return fail(h, SDDP_EINVAL, "%s%s", "friction_cone_weight, _mu and _sharpness must be >= 0", "");
@@ -464,6 +486,7 @@ int sddp_destroy(SddpHandle* h) {
     if (h->st_in) cudaStreamDestroy(h->st_in);
     if (h->st_cmp) cudaStreamDestroy(h->st_cmp);
     if (h->st_out) cudaStreamDestroy(h->st_out);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
     delete h;
     return 0;
 }
@@ -493,6 +516,7 @@ int sddp_launch_count(const SddpHandle* h, long long* out) {
         else KERNEL<Lip, Smem<Lip>, MINB_DENSE><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);                         \
         (h)->launches++;                                                                                                    \
         CU(cudaGetLastError());                                                                                             \
+        CU(mark_last(h, stream));                                                                                           \
     } while (0)
 
 int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const double* x, const double* u, const double* p,
@@ -586,12 +610,13 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     }
     // The handle's workspace serves one solve at a time; this entry point runs on its own streams, so work the
     // caller queued earlier on other streams with the same handle must finish first.
-    CU(cudaDeviceSynchronize());
+    // (An event recorded after the last launch of every device entry point; nothing else on the device is waited for.)
+    if (h->ev_last_valid) CU(cudaEventSynchronize(h->ev_last));
     if (!h->st_in) {
         CU(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->st_cmp, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
-        h->host_chunk = 16384;
+        h->host_chunk = 0;
         const char* env = getenv("SDDP_HOST_CHUNK");
         if (env && atoi(env) > 0) h->host_chunk = atoi(env);
     }
@@ -606,7 +631,16 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     int32_t* d_it = (int32_t*)(d_c + Bz);
     int32_t* d_st = d_it + Bz;
     int32_t* d_ord = d_st + Bz;
-    const int chunk = h->host_chunk;
+    // Chunk size: the copies of one chunk overlap the solve of another, so a batch needs several chunks whatever its
+    // size (a fixed 16K left the 8192-problem shards of an 8-GPU run with one chunk: copy, solve, copy in series).
+    // Default: a quarter of the batch, at least two problems per CTA slot (so a chunk still fills the GPU and its tail
+    // of slow problems stays small) and at most 16384; SDDP_HOST_CHUNK overrides.
+    int chunk = h->host_chunk;
+    if (chunk <= 0) {
+        chunk = (B + 3) / 4;
+        if (chunk < 2 * h->slots) chunk = 2 * h->slots;
+        if (chunk > 16384) chunk = 16384;
+    }
     const int nchunk = (B + chunk - 1) / chunk;
     // Small batches (the reference's own use: one problem per call): one pinned staging buffer, one copy in, one copy
     // out, one stream, no events -- the latency of a single solve is mostly launch and copy overhead otherwise.

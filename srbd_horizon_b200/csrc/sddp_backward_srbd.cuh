@@ -30,9 +30,11 @@ struct alignas(16) SmemSrbd {
     double VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
     double Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
     double W[NU * LDW];        // B = [Qux | Qu | quy | .] -> Wn = Es B  (quy: lu + fu^T ys of the y recursion)
-    double Quu[NU * NU];       // Quu -> (strict upper) D Lt^T = frozen raw columns, (lower) Es
+    double Quu[NU * NU];       // Quu -> Es = D^-1/2 Lt^-1 (lower triangular, zeros above the diagonal)
     double Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
-    double Qu[NU], kk[NU], invp[NU], rs[NU];
+    double Qu[NU], kk[NU];
+    double ir[2 * NU];         // d1: (1 / pivot_j, 1 / sqrt(pivot_j)) pairs
+    double prow[2][NU];        // d1: the published column of the current pivot step (ping-pong)
     double nb[2][NodeBuf<Srbd>::SIZE];
     double escr[24];           // expand scratch: E(oref) and the orientation residuals
     double sacc[NWARP][8];
@@ -64,6 +66,16 @@ SDDP_DEV double fast_rcp(double p) {
     x = fma(x, e, x);
     e = fma(-p, x, 1.0);
     return fma(x, e, x);
+}
+
+// 1/sqrt(p) from the hardware seed (MUFU.RSQ64H) and two Newton steps; branch free (sqrt() has a slow path).
+SDDP_DEV double fast_rsqrt(double p) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+    double e = fma(-p * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-p * y, y, 1.0);
+    return fma(0.5 * y, e, y);
 }
 
 #ifndef SDDP_ROW128
@@ -167,6 +179,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
     cp_wait_all();
     __syncthreads();                           // node N-1 landed
+    PROF(19);
 
     const unsigned long long c1d = __ldg(c.ztab + ZT_C1OFF + tid);     // this thread's Quu entries (see c1)
     for (int k = N - 1; k >= 0; k--) {
@@ -263,60 +276,86 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         const double* o = xk + M::XO;
         const double* w = xk + M::XW;
         if (warp == 0) {
-            // ---- d1: Quu + mu I = Lt D Lt^T; lane t owns column t.  Row j of Lt^T (the multipliers of step j)
-            //          overwrites the strict upper triangle of S.Quu; D^-1 goes to S.invp.
+            // ---- d1: Quu + mu I = Lt D Lt^T; lane t owns column t.  Es = D^-1/2 Lt^-1 overwrites S.Quu row by row.
             if (has_gap) {   // gap terms of the model (the only use of cg after c1)
                 double g1 = 0, g2 = 0, yg = 0;
                 for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * cg[i]; g2 += cg[i] * S.sv[i]; yg += S.y[i] * cg[i]; }
                 g1 = rho_b * warp_sum(g1); g2 = rho_b * warp_sum(g2); yg = rho_b * warp_sum(yg);
                 if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
             } else if (lane == 0) { S.red[R_G1] = 0.0; S.red[R_G2] = 0.0; S.red[R_YG] = 0.0; }
-            // Lane t holds column t.  Step j: lane j publishes its (final) column raw, row j of the strict upper
-            // triangle of S.Quu, and 1/pivot; every other lane then applies  a[i] -= col_j[i] * (a[j] / pivot_j),  i > j.
-            // The element that becomes the next pivot (i = j+1) is updated first and its reciprocal started at
-            // once, so the rest of the update overlaps the reciprocal latency.
-            // Lane j skips step j and keeps taking part afterwards: its registers then carry -pivot_j times column j
-            // of E = Lt^-1 (E[:,j] starts as -col_j / pivot_j and obeys the same linear recurrence), so the inverse
-            // factor costs no extra arithmetic in lanes the factorisation no longer needs.
-            double a[NU];
+            // Lane t holds column t.  Step j: lane j publishes its (final) column raw and 1/pivot, 1/sqrt(pivot); every other
+            // lane then applies  a[i] -= col_j[i] * (a[j] / pivot_j),  i > j.  The element that becomes the next pivot
+            // (i = j+1) is updated first and its reciprocal started at once, so the rest of the update overlaps the
+            // reciprocal latency.  Lane j skips step j and keeps taking part afterwards: its registers then carry
+            // -pivot_j times column j of E = Lt^-1 (E[:,j] starts as -col_j / pivot_j and obeys the same linear recurrence),
+            // so the inverse factor costs no extra arithmetic in lanes the factorisation no longer needs.
+            // Rolled over the pivot steps (R per loop trip): the kernel is instruction-fetch bound (profiles/README.md), and
+            // the fully unrolled factorisation was 21 KB of straight-line code per node.  The column lives in a rotating
+            // register frame b[q] = a_t[jb + q] (shifted down by R at the end of a trip, zero filled), so every index is
+            // static; the published column goes to a ping-pong row in the same frame, and row j of Es = D^-1/2 Lt^-1 is
+            // stored at step j, when lane t < j holds its final E[j][t] = -a_t[j] / pivot_t (the multiplier of that step),
+            // which replaces the separate write-out pass.  Chunks of 8 entries that lie wholly in the zero tail of the
+            // frame (q >= NU - jb) are skipped with warp-uniform branches.
+            constexpr int R = 4;
+            static_assert(NU % R == 0 && NU % 8 == 0, "d1 frame");
+            double b[NU];
             const int t = lane < NU ? lane : NU - 1;
 #pragma unroll
-            for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
+            for (int i = 0; i < NU; i++) b[i] = S.Quu[i * NU + t];
             __syncwarp();
             bool bad = false;
-            double myinv = fast_rcp(a[0]);          // lane 0's pivot
-            double pinv = 0.0;                      // 1 / pivot of this lane's column
+            double myinv = fast_rcp(b[0]), myrs = fast_rsqrt(b[0]);      // lane 0's pivot
+            double npinv = 0.0;                                          // -1 / pivot of this lane's column
+#pragma unroll 1
+            for (int jb = 0; jb < NU; jb += R) {
+                const int live = NU - jb;                                // entries q < live of the frame are in use
 #pragma unroll
-            for (int j = 0; j < NU; j++) {
-                if (lane == j) {
-                    const double p = a[j];
-                    bad = !(p > 0.0) || !isfinite(p);
-                    pinv = myinv;
-                    S.invp[j] = myinv;
-                    store_row<NU>(S.Quu + j * NU, a, j + 1);
+                for (int s_ = 0; s_ < R; s_++) {
+                    const int j = jb + s_;
+                    double* pr = S.prow[s_ & 1];                         // (R is even: j & 1 == s_ & 1)
+                    if (lane == j) {
+                        const double p = b[s_];
+                        bad = !(p > 0.0) || !isfinite(p);
+                        npinv = -myinv;
+                        *reinterpret_cast<double2*>(S.ir + 2 * j) = make_double2(myinv, myrs);
+#pragma unroll
+                        for (int c8 = 0; c8 < NU; c8 += 8)
+                            if (c8 < live) {
+#pragma unroll
+                                for (int q = c8; q < c8 + 8; q += 2) {
+                                    if (q >= s_ + 1) *reinterpret_cast<double2*>(pr + q) = make_double2(b[q], b[q + 1]);
+                                    else if (q + 1 >= s_ + 1) pr[q + 1] = b[q + 1];
+                                }
+                            }
+                    }
+                    __syncwarp();
+                    const double2 ir = *reinterpret_cast<const double2*>(S.ir + 2 * j);
+                    const double m = b[s_];
+                    const double sj = (lane == j) ? 0.0 : ir.x * m;
+                    b[s_ + 1] -= pr[s_ + 1] * sj;
+                    myinv = fast_rcp(b[s_ + 1]);                         // meaningful on lane j + 1
+                    myrs = fast_rsqrt(b[s_ + 1]);
+#pragma unroll
+                    for (int c8 = 0; c8 < NU; c8 += 8)
+                        if (c8 < live) {
+                            double2 cc[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) if (c8 + 2 * q + 1 >= s_ + 2) cc[q] = *reinterpret_cast<const double2*>(pr + c8 + 2 * q);
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int i = c8 + 2 * q;
+                                if (i >= s_ + 2) b[i] -= cc[q].x * sj;
+                                if (i + 1 >= s_ + 2) b[i + 1] -= cc[q].y * sj;
+                            }
+                        }
+                    // row j of Es: (t < j) -E-multiplier / pivot_t * rs_j, (t == j) rs_j, (t > j) 0
+                    const double ev = (lane < j) ? npinv * m * ir.y : (lane == j ? ir.y : 0.0);
+                    if (lane < NU) S.Quu[j * NU + lane] = ev;
                 }
-                __syncwarp();
-                if (j + 1 < NU) {
-                    const double sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
-                    a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
-                    myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
-                    if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
-                }
+#pragma unroll
+                for (int q = 0; q < NU; q++) b[q] = (q + R < NU) ? b[q + R] : 0.0;
             }
             if (__any_sync(FULL, bad) && lane == 0) S.iflag[1] = 1;
-            if (lane < NU) S.rs[lane] = sqrt(pinv);
-            __syncwarp();
-            {   // Es = rs . E -> S.Quu, zeros above the diagonal (the raw columns are dead).  Branch free: selects and
-                // one predicated pair of stores per row pair (a divergent branch per entry costs ~10x more).
-                const double np = -pinv;
-#pragma unroll
-                for (int i = 0; i < NU; i += 2) {
-                    const double2 r = *reinterpret_cast<const double2*>(S.rs + i);
-                    const double v0 = (i > t) ? np * a[i] * r.x : (i == t ? r.x : 0.0);
-                    const double v1 = (i + 1 > t) ? np * a[i + 1] * r.y : (i + 1 == t ? r.y : 0.0);
-                    if (lane < NU) { S.Quu[i * NU + lane] = v0; S.Quu[(i + 1) * NU + lane] = v1; }
-                }
-            }
             PROF_T(14, 0);
             STAMP(4); STAMP(5); STAMP(6); STAMP(7);
         } else {
@@ -451,6 +490,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         }
         STAMP(11);
         __syncthreads();
+        PROF(12);
         // ---- f: [Vxx Vx y] = [sym(Qxx) Qx qxy] - Wn^T Wn: upper-triangular 8x8 tiles of the 40x40 product, K = 24 in
         //         six DMMA steps.  Results go to VT (T is dead), Vx, y (column 38 = Wn^T Es quy = -K^T quy),
         //         Vx[37] = -|w0|^2 and y[37] = quy . k.

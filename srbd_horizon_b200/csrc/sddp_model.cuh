@@ -33,11 +33,13 @@ __device__ long long g_prof_last;
 #define PROF(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long t_ = clock64(); g_prof[i] += t_ - g_prof_last; g_prof_last = t_; } } while (0)
 #define PROF_RESET do { if (threadIdx.x == 0 && blockIdx.x == 0) g_prof_last = clock64(); } while (0)
 #define PROF_T(i, thr) do { if (threadIdx.x == (thr) && blockIdx.x == 0) { g_prof[i] += clock64() - g_prof_last; } } while (0)
+#define PROF_INC(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_prof[i] += 1; } while (0)
 #else
 #define PROF_DECL
 #define PROF(i)
 #define PROF_RESET
 #define PROF_T(i, thr)
+#define PROF_INC(i)
 #endif
 
 

@@ -396,6 +396,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
     };
     __syncthreads();      // the buffers may still be in use by the caller's previous phase
     prefetch(0);
+    PROF(23);
     if (ncand == 1) {
         // One candidate (the usual first wave): its work is spread over the warps instead of leaving three idle.
         // Per node: warp 0 forms u = U + alpha k + K dx; then warp 0 integrates (accel, Euler step) while warp 1 sums
@@ -407,6 +408,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         for (int k = 0; k < N; k++) {
             cp_wait_all();
             __syncthreads();                  // node k landed; everyone is done with node k-1
+            PROF(24);
             if (k + 1 < N) prefetch(k + 1);
             else {
                 double* nbt = S.nb[(k + 1) & 1];
@@ -452,6 +454,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             }
             STAMP(13);
             __syncthreads();                  // u^_k visible
+            PROF(25);
             STAMP(14);
             const int kind = node_kind(k, N);
             if (w == 0) {
@@ -476,6 +479,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
                 Jw += M::cost_lane(c, kind, lane, xc, ub, nb + NBL::OP, S.sacc[0], 8);
             }
             STAMP(15);
+            PROF(26);
         }
         cp_wait_all();
         __syncthreads();
@@ -487,6 +491,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         __syncthreads();
         if (tid == 0) S.Jc[0] = S.red[R_W0] + S.red[R_W0 + 1] + S.red[R_W0 + 2] + S.red[R_W0 + 3];
         __syncthreads();
+        PROF(27);
         return;
     }
     for (int i = lane; i < NX; i += 32) xh[i] = x0[i];
@@ -586,8 +591,10 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     }
     double mu = c.mu0;
     int status = 1 /*MAX_ITERS*/, it = 0;
+    PROF(4);
+    PROF_INC(31);
     for (it = 0; it < c.max_iters; it++) {
-        PROF_RESET;
+        PROF_INC(30);
         compute_packs<M>(c, X, U, packs, tid);
         PROF(0);
         bool reg_fail = false;
@@ -627,7 +634,8 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
             __syncthreads();
             if (tid < NCAND) { S.alpha[tid] = al[tid]; S.rho[tid] = fixed ? c.rho_fixed : al[tid]; }
             __syncthreads();
-            PROF_RESET;
+            PROF(5);
+            PROF_INC(29);
             forward_wave<M, SM>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid);
             PROF(2);
             for (int j = 0; j < ncand; j++) {
@@ -662,6 +670,7 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     }
     __syncthreads();
     if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
+    PROF(6);
 }
 
 template <class M>
