@@ -24,8 +24,8 @@
  *     work is enqueued on it, nothing synchronises except the *_host calls;
  *   - every function returns 0 on success, a negative SDDP_E* code otherwise,
  *     never throws; sddp_last_error() gives the message for the calling handle;
- *   - a handle is bound to the device current at sddp_create, owns only its
- *     workspace, is not thread-safe; distinct handles are independent;
+ *   - a handle is bound to the device current at sddp_create (every later call must be made with that device
+ *     current, SDDP_EINVAL otherwise), owns only its workspace, is not thread-safe; distinct handles are independent;
  *   - per-problem numerical outcome is reported in status[b], not in the return code.
  *
  * Layouts (row-major, problem-major):
@@ -43,13 +43,13 @@
 extern "C" {
 #endif
 
-#define SDDP_ABI_VERSION 2
+#define SDDP_ABI_VERSION 3
 
 enum { SDDP_MODEL_SRBD = 0, SDDP_MODEL_LIP = 1 };
 enum { SDDP_INERTIA_LITERAL = 0, SDDP_INERTIA_ROTATED = 1 };   /* prb.py:99 as written / README.md:2 intent */
 enum { SDDP_HESSIAN_EXACT = 0, SDDP_HESSIAN_GN = 1 };
-enum { SDDP_NODE_FIRST = 0, SDDP_NODE_MID = 1, SDDP_NODE_TERM = 2 };
-enum { SDDP_CONVERGED = 0, SDDP_MAX_ITERS = 1, SDDP_LS_FAILED = 2, SDDP_REG_FAILED = 3, SDDP_NAN = 4 };
+enum { SDDP_NODE_FIRST = 0, SDDP_NODE_MID = 1, SDDP_NODE_TERM = 2, SDDP_NODE_TAIL = 3 };   /* TAIL: a MID node of the LIP-style tail (lip_tail_start) */
+enum { SDDP_NOT_SOLVED = -1, SDDP_CONVERGED = 0, SDDP_MAX_ITERS = 1, SDDP_LS_FAILED = 2, SDDP_REG_FAILED = 3, SDDP_NAN = 4 };
 enum { SDDP_HIST = 4 };   /* per iteration: cost, alpha (0 = no step), mu, max|defect| */
 enum { SDDP_EINVAL = -1, SDDP_ECUDA = -2, SDDP_ENOMEM = -3, SDDP_ECAPACITY = -4 };
 
@@ -60,8 +60,11 @@ typedef struct SddpConfig {
     int32_t hessian_mode;      /* SDDP_HESSIAN_* */
     int32_t multiple_shooting; /* 1: keep the x warm start, carry defects (README.md:5-6) */
     int32_t max_iters;         /* ddp.py:17-19 */
-    int32_t reserved0;
-    int32_t reserved1;
+    int32_t dense_backward;    /* SRBD only. 1: generic dense Riccati kernel instead of the structured one (A/B check; same results) */
+    int32_t lip_tail_start;    /* SRBD only. 0: off. k >= 1: nodes k..N-1 use the LIP-style model of the reference's model scheduler
+                                * (README.md:7, isrbd_example.py:344-353): no rotational dynamics (wdot = 0, hence no wdot term in
+                                * min_qddot) and the constraints lip_com_height (r_z - com_z) and lip_zero_angular_momentum (w),
+                                * penalised with constraint_weight like every equality constraint (ddp.py:191-196) */
     double dt;                 /* prb.py:110 */
     double mass;               /* prb.py:92 */
     double inertia[9];         /* prb.py:94-95, row-major */
@@ -96,6 +99,18 @@ typedef struct SddpConfig {
     double friction_cone_weight;
     double friction_cone_mu;          /* prb.py:174 friction_cone_coefficient, default 0.8 */
     double friction_cone_sharpness;   /* ddp.py:182 exp_parameter, default 6.0 */
+    /* Bounds as the barriers the adapter sketches for variable bounds (ddp.py:204-209): for a bounded component v,
+     *   L += weight * ( exp(bound_sharpness * (v - ub)) + exp(bound_sharpness * (lb - v)) )   on nodes 0..N-1.
+     * force_bound: box |f_ik| <= force_bound on every contact-force component (isrbd_example.py:200 max_contact_force,
+     * in units of force_scaling); unilateral_weight: f_iz >= 0 alone (the "unilaterality" of isrbd_example.py:198,
+     * lb = 0, no ub); cdot_bound: box |cdot_ik| <= cdot_bound on the contact-point velocities (isrbd_example.py:195).
+     * Every weight = 0 (default) reproduces the reference (bounds ignored by its DDP adapter).  SRBD only. */
+    double force_bound_weight;
+    double force_bound;
+    double unilateral_weight;
+    double cdot_bound_weight;
+    double cdot_bound;
+    double bound_sharpness;
 } SddpConfig;
 
 typedef struct SddpHandle SddpHandle;
@@ -105,8 +120,8 @@ size_t sddp_config_size(void);
 /* nx, nu, np of a model */
 int sddp_dims(int model, int *nx, int *nu, int *np);
 
-/* Bytes of device workspace a handle allocates (independent of the batch size:
- * scratch is per resident CTA, not per problem). */
+/* Upper bound of the bytes of device workspace a handle allocates (independent of the batch size: scratch is per
+ * resident CTA, not per problem; sized for the current device, or for a B200 when there is none).  0: cfg is refused. */
 size_t sddp_workspace_bytes(const SddpConfig *cfg);
 
 int sddp_create(const SddpConfig *cfg, SddpHandle **out);
@@ -161,8 +176,10 @@ int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *
  * solves of exactly n problems.  Problems that behave alike (same contact schedule, similar iteration counts)
  * should be neighbours: co-resident CTAs then run the same phases at the same time and share their instructions
  * in the SM's instruction cache (about 10 % on BASELINE configs[4]).  on_host = 0: `order` is a DEVICE array the
- * caller keeps alive, used by sddp_solve_batch; on_host = 1: HOST array, copied, used by sddp_solve_batch_host
- * (checked to be a permutation).  order = NULL clears.  The reference has no counterpart (one problem per process). */
+ * caller keeps alive, used by sddp_solve_batch; it is NOT checked: entries outside 0..n-1 are skipped and a problem
+ * that no entry names stays unsolved with status[b] = -1 (duplicates solve a problem twice).  on_host = 1: HOST array,
+ * copied, used by sddp_solve_batch_host (checked to be a permutation).  order = NULL clears.  The reference has no
+ * counterpart (one problem per process). */
 int sddp_set_dispatch_order(SddpHandle *h, const int32_t *order, int n, int on_host);
 
 /* ---- receding-horizon glue on the device (the caller side of the path: dsrbd_example.py:102-131,158-160, wpg.py:68-101) ----

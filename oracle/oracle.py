@@ -34,6 +34,7 @@ def lib():
         L = ctypes.CDLL(_LIB_PATH)
         cp = ctypes.POINTER(SddpConfig)
         L.orc_dynamics.argtypes = [cp, _dp, _dp, _dp]
+        L.orc_dynamics_kind.argtypes = [cp, ctypes.c_int, _dp, _dp, _dp]
         L.orc_cost.argtypes = [cp, ctypes.c_int, _dp, _dp, _dp]
         L.orc_cost.restype = ctypes.c_double
         L.orc_derivs.argtypes = [cp, ctypes.c_int] + [_dp] * 10
@@ -61,11 +62,12 @@ def _c(a, shape=None):
     return a
 
 
-def dynamics(cfg: SddpConfig, x, u):
+def dynamics(cfg: SddpConfig, x, u, kind: int = 1):
+    """x + dt ode(x, u) of a node of the given kind (3: LIP-style tail node)."""
     nx, nu, _ = DIMS[cfg.model]
     x, u = _c(x, (nx,)), _c(u, (nu,))
     xn = np.empty(nx)
-    lib().orc_dynamics(ctypes.byref(cfg), _p(x), _p(u), _p(xn))
+    lib().orc_dynamics_kind(ctypes.byref(cfg), int(kind), _p(x), _p(u), _p(xn))
     return xn
 
 

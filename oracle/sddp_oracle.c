@@ -48,6 +48,7 @@
  *   before the   converged when |dJ(alpha_0)| <= cost_reduction_ths * (1 + |J|) * 1e-3 and max|d| <= defect_ths
  *   line search  (stationary point: nothing left to gain)
  *   on failure   mu <- max(mu*mu_factor, mu_min); mu > mu_max -> status LS_FAILED
+ *   bad input    a non-finite initial gap (multiple shooting) -> status NAN before the first iteration
  */
 #include "sddp_oracle.h"
 #include <math.h>
@@ -200,7 +201,9 @@ typedef struct {
 } RB;
 enum { Z_R = 0, Z_O = 3, Z_C = 7, Z_W = 19, Z_F = 22 };
 
-static void srbd_rb(const OrcConfig *c, const double *x, const double *u, int order, RB *rb) {
+/* tail: a node of the LIP-style tail (include/sddp.h lip_tail_start; isrbd_example.py:344-353): no rotational dynamics,
+ * wdot = 0 identically, so its Jacobian and curvature vanish; rddot is unchanged. */
+static void srbd_rb(const OrcConfig *c, const double *x, const double *u, int order, int tail, RB *rb) {
     const double *r = x + SX_R, *o = x + SX_O, *w = x + SX_W;
     double J[9], Ja[4][9], Jab[4][4][9], M[9];
     inertia_all(c, o, J, Ja, Jab);
@@ -218,6 +221,12 @@ static void srbd_rb(const OrcConfig *c, const double *x, const double *u, int or
     mat3vec(M, h, rb->wd);
     double ms = c->mass / c->force_scaling;
     rb->rdd[0] = fsum[0] / ms; rb->rdd[1] = fsum[1] / ms; rb->rdd[2] = fsum[2] / ms - c->gravity;
+    if (tail) {
+        rb->wd[0] = rb->wd[1] = rb->wd[2] = 0.0;
+        if (order >= 1) memset(rb->Jac, 0, sizeof rb->Jac);
+        if (order >= 2) memset(rb->Hc, 0, sizeof rb->Hc);
+        return;
+    }
     if (order < 1) return;
 
     /* first derivatives: Jac[:,p] = M (dh/dp - J_p wd) */
@@ -297,9 +306,9 @@ static void srbd_rb(const OrcConfig *c, const double *x, const double *u, int or
 }
 
 /* ------------------------------------------------------------------ dynamics */
-static void srbd_ode(const OrcConfig *c, const double *x, const double *u, double *xd) {
+static void srbd_ode(const OrcConfig *c, int tail, const double *x, const double *u, double *xd) {
     RB rb;
-    srbd_rb(c, x, u, 0, &rb);
+    srbd_rb(c, x, u, 0, tail, &rb);
     const double *o = x + SX_O, *w = x + SX_W;
     for (int k = 0; k < 3; k++) xd[SX_R + k] = x[SX_RD + k];
     /* odot = quat_prod([w/2, 0], o)  (LOCAL_WORLD_ALIGNED, prb.py:107-108) */
@@ -318,12 +327,13 @@ static void lip_ode(const OrcConfig *c, const double *x, const double *u, double
     xd[LX_RD + 2] -= c->gravity;
     for (int k = 0; k < 12; k++) xd[LX_CD + k] = u[LU_CDD(0) + k];
 }
-void orc_dynamics(const OrcConfig *c, const double *x, const double *u, double *xn) {
+void orc_dynamics_kind(const OrcConfig *c, int kind, const double *x, const double *u, double *xn) {
     int nx, nu, np; orc_dims(c->model, &nx, &nu, &np);
     double xd[NXM];
-    if (c->model == 0) srbd_ode(c, x, u, xd); else lip_ode(c, x, u, xd);
+    if (c->model == 0) srbd_ode(c, kind == ORC_NODE_TAIL, x, u, xd); else lip_ode(c, x, u, xd);
     for (int i = 0; i < nx; i++) xn[i] = x[i] + c->dt * xd[i];
 }
+void orc_dynamics(const OrcConfig *c, const double *x, const double *u, double *xn) { orc_dynamics_kind(c, ORC_NODE_MID, x, u, xn); }
 
 /* ------------------------------------------------------------------ cost accumulator
  * every residual of prb.py except min_qddot's wdot rows is affine in z=[x;u]:
@@ -354,9 +364,19 @@ static void acc_single(Acc *a, double wgt, int idx, double res) { /* res = z[idx
     acc_affine(a, wgt, 1, &idx, &one, res);
 }
 
+/* exponential barrier on one component (ddp.py:204-209): cost += wgt * exp(kap * g),  g = sgn * z[idx] + const */
+static void acc_barrier(Acc *a, double wgt, double kap, int idx, double sgn, double g) {
+    double e = wgt * exp(kap * g);
+    a->cost += e;
+    if (!a->derivs) return;
+    int nx = a->nx;
+    if (idx < nx) { a->lx[idx] += kap * sgn * e; a->lxx[idx * nx + idx] += kap * kap * e; }
+    else { a->lu[idx - nx] += kap * sgn * e; a->luu[(idx - nx) * a->nu + (idx - nx)] += kap * kap * e; }
+}
+
 static void srbd_cost(const OrcConfig *c, int kind, const double *x, const double *u, const double *p, Acc *a) {
     const int nx = 37;
-    int track = (kind != ORC_NODE_FIRST), input = (kind != ORC_NODE_TERM);
+    int track = (kind != ORC_NODE_FIRST), input = (kind != ORC_NODE_TERM), tail = (kind == ORC_NODE_TAIL);
     if (track) {
         /* rz_tracking, prb.py:184 */
         acc_single(a, c->r_tracking_gain, SX_R + 2, x[SX_R + 2] - c->com[2]);
@@ -390,7 +410,7 @@ static void srbd_cost(const OrcConfig *c, int kind, const double *x, const doubl
         double fs = c->force_scaling;
         /* min_qddot = [rddot; wdot; cddot_i], prb.py:104-106,200 */
         RB rb;
-        srbd_rb(c, x, u, a->derivs ? (c->hessian_mode == 0 ? 2 : 1) : 0, &rb);
+        srbd_rb(c, x, u, a->derivs ? (c->hessian_mode == 0 ? 2 : 1) : 0, tail, &rb);
         double gq = c->min_qddot_gain, ms = c->mass / fs;
         for (int k = 0; k < 3; k++) {
             int idx[4]; double coef[4];
@@ -452,8 +472,29 @@ static void srbd_cost(const OrcConfig *c, int kind, const double *x, const doubl
                 }
             }
         }
+        /* Bounds as exponential barriers (extension, off by default; ddp.py:204-209 sketches them for variable bounds):
+         * force box (isrbd_example.py:200), unilaterality f_z >= 0 (isrbd_example.py:198), contact-point velocity box (:195). */
+        {
+            const double kb = c->bound_sharpness;
+            for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) {
+                if (c->force_bound_weight != 0.0) {
+                    acc_barrier(a, c->force_bound_weight, kb, nx + SU_F(i) + k, 1.0, u[SU_F(i) + k] - c->force_bound);
+                    acc_barrier(a, c->force_bound_weight, kb, nx + SU_F(i) + k, -1.0, -c->force_bound - u[SU_F(i) + k]);
+                }
+                if (c->cdot_bound_weight != 0.0) {
+                    acc_barrier(a, c->cdot_bound_weight, kb, SX_CD + 3 * i + k, 1.0, x[SX_CD + 3 * i + k] - c->cdot_bound);
+                    acc_barrier(a, c->cdot_bound_weight, kb, SX_CD + 3 * i + k, -1.0, -c->cdot_bound - x[SX_CD + 3 * i + k]);
+                }
+            }
+            if (c->unilateral_weight != 0.0)
+                for (int i = 0; i < 4; i++) acc_barrier(a, c->unilateral_weight, kb, nx + SU_F(i) + 2, -1.0, -u[SU_F(i) + 2]);
+        }
         /* equality constraints, weight 1e6 (ddp.py:181,191-196); prb.py:166-181 */
         double cw = c->constraint_weight;
+        if (tail) {     /* LIP-style tail: lip_zero_angular_momentum (w) and lip_com_height (r_z - com_z), isrbd_example.py:352-353 */
+            for (int k = 0; k < 3; k++) acc_single(a, cw, SX_W + k, x[SX_W + k]);
+            acc_single(a, cw, SX_R + 2, x[SX_R + 2] - c->com[2]);
+        }
         for (int leg = 0; leg < 2; leg++) for (int ax = 0; ax < 2; ax++) { /* relative_vel_left_1 / right_3 */
             int ia = SX_CD + 3 * (2 * leg) + ax, ib = SX_CD + 3 * (2 * leg + 1) + ax;
             int idx[2] = {ia, ib};
@@ -563,7 +604,7 @@ void orc_derivs(const OrcConfig *c, int kind, const double *x, const double *u, 
         return;
     }
     RB rb;
-    srbd_rb(c, x, u, 1, &rb);
+    srbd_rb(c, x, u, 1, kind == ORC_NODE_TAIL, &rb);
     const double *o = x + SX_O, *w = x + SX_W;
     for (int k = 0; k < 3; k++) fx[(SX_R + k) * nx + SX_RD + k] += dt;
     for (int k = 0; k < 12; k++) fx[(SX_C + k) * nx + SX_CD + k] += dt;
@@ -598,7 +639,12 @@ void orc_derivs(const OrcConfig *c, int kind, const double *x, const double *u, 
 }
 
 /* ------------------------------------------------------------------ DDP */
-static int node_kind(int k, int N) { return k == 0 ? ORC_NODE_FIRST : (k == N ? ORC_NODE_TERM : ORC_NODE_MID); }
+static int node_kind_c(const OrcConfig *c, int k) {
+    if (k == 0) return ORC_NODE_FIRST;
+    if (k == c->N) return ORC_NODE_TERM;
+    return (c->model == 0 && c->lip_tail_start > 0 && k >= c->lip_tail_start) ? ORC_NODE_TAIL : ORC_NODE_MID;
+}
+#define node_kind(k, N) node_kind_c(c, (k))
 
 double orc_total_cost(const OrcConfig *c, const double *X, const double *U, const double *params) {
     int nx, nu, np; orc_dims(c->model, &nx, &nu, &np);
@@ -773,7 +819,7 @@ double orc_forward(const OrcConfig *c, const double *x0, const double *X, const 
             uk[i] = U[k * nu + i] + alpha * kk[i] + t;
         }
         J += orc_cost(c, node_kind(k, N), xk, uk, params + k * np);
-        orc_dynamics(c, xk, uk, Xn + (k + 1) * nx);
+        orc_dynamics_kind(c, node_kind(k, N), xk, uk, Xn + (k + 1) * nx);
         for (int i = 0; i < nx; i++) Xn[(k + 1) * nx + i] -= (1.0 - rho) * defect[k * nx + i];
     }
     J += orc_cost(c, ORC_NODE_TERM, Xn + N * nx, 0, params + N * np);
@@ -796,10 +842,10 @@ int orc_solve(const OrcConfig *c, const double *x0, const double *params,
     memset(hist, 0, sizeof(double) * c->max_iters * ORC_HIST);
     memcpy(X, x0, sizeof(double) * nx);
     if (!c->multiple_shooting) {
-        for (int k = 0; k < N; k++) orc_dynamics(c, X + k * nx, U + k * nu, X + (k + 1) * nx);
+        for (int k = 0; k < N; k++) orc_dynamics_kind(c, node_kind(k, N), X + k * nx, U + k * nu, X + (k + 1) * nx);
     } else {
         for (int k = 0; k < N; k++) {
-            orc_dynamics(c, X + k * nx, U + k * nu, d + k * nx);
+            orc_dynamics_kind(c, node_kind(k, N), X + k * nx, U + k * nu, d + k * nx);
             for (int i = 0; i < nx; i++) d[k * nx + i] -= X[(k + 1) * nx + i];
         }
     }
@@ -807,7 +853,10 @@ int orc_solve(const OrcConfig *c, const double *x0, const double *params,
     double mu = c->mu0;
     int status = ORC_MAX_ITERS, it = 0;
     const int fixed_rho = (c->defect_contraction_rate > 0.0);
-    for (it = 0; it < c->max_iters; it++) {
+    int bad_start = 0;     /* a non-finite initial gap (NaN / inf in the warm start or x0): status NAN, no iteration */
+    for (int i = 0; i < N * nx; i++) if (!(fabs(d[i]) <= 1.79e308)) bad_start = 1;
+    if (bad_start) status = ORC_NAN;
+    for (it = 0; it < (bad_start ? 0 : c->max_iters); it++) {
         double dV[3];
         int reg_fail = 0;
         while (orc_backward(c, X, U, params, d, mu, K, kff, dV)) {

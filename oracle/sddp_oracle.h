@@ -34,8 +34,8 @@ typedef struct OrcConfig {
     int32_t hessian_mode;      /* 0 = exact Hessian of the scalar L (ddp.py:210-214), 1 = Gauss-Newton */
     int32_t multiple_shooting; /* 0 = single shooting, 1 = keep x warm start / defects */
     int32_t max_iters;         /* ddp.py:17-19 */
-    int32_t reserved0;
-    int32_t reserved1;
+    int32_t dense_backward;    /* kernel selection of the CUDA library; ignored here */
+    int32_t lip_tail_start;    /* 0 = off; nodes k..N-1 use the LIP-style model (include/sddp.h) */
     double dt;                 /* prb.py:110  T/ns */
     double mass;               /* kindyn.mass(), prb.py:92 (synthetic here) */
     double inertia[9];         /* CRBA block, prb.py:94-95 (synthetic), row-major */
@@ -65,12 +65,18 @@ typedef struct OrcConfig {
     double friction_cone_weight;         /* 0 = reference behaviour (cone dropped, prb.py:173-177); see include/sddp.h */
     double friction_cone_mu;             /* prb.py:174 */
     double friction_cone_sharpness;      /* ddp.py:182 exp_parameter */
+    double force_bound_weight;           /* bounds as exponential barriers, ddp.py:204-209; see include/sddp.h */
+    double force_bound;
+    double unilateral_weight;
+    double cdot_bound_weight;
+    double cdot_bound;
+    double bound_sharpness;
 } OrcConfig;
 
 enum { ORC_HIST = 4 };   /* per-iteration record: cost, alpha, mu, max|defect| */
 
 /* node kinds: which cost groups are active (prb.py node ranges) */
-enum { ORC_NODE_FIRST = 0, ORC_NODE_MID = 1, ORC_NODE_TERM = 2 };
+enum { ORC_NODE_FIRST = 0, ORC_NODE_MID = 1, ORC_NODE_TERM = 2, ORC_NODE_TAIL = 3 };   /* TAIL: MID node of the LIP-style tail */
 
 enum { ORC_OK = 0, ORC_MAX_ITERS = 1, ORC_LS_FAILED = 2, ORC_REG_FAILED = 3, ORC_NAN = 4 };
 
@@ -78,6 +84,8 @@ void orc_dims(int model, int *nx, int *nu, int *np);
 
 /* x+ = x + dt * ode(x,u)   (ddp.py:228-230, explicit Euler) */
 void orc_dynamics(const OrcConfig *c, const double *x, const double *u, double *xn);
+/* the same for a node of the given kind (ORC_NODE_TAIL: LIP-style tail, no rotational dynamics) */
+void orc_dynamics_kind(const OrcConfig *c, int kind, const double *x, const double *u, double *xn);
 
 /* L_k or L_N  (ddp.py:179-226) */
 double orc_cost(const OrcConfig *c, int kind, const double *x, const double *u, const double *p);

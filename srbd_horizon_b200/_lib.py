@@ -11,8 +11,6 @@ from .config import SddpConfig
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("SDDP_LIB", os.path.join(CSRC, "libsddp.so"))   # SDDP_LIB: A/B builds while tuning
-# second build of the same sources with the friction-cone barrier compiled in (csrc/Makefile); loaded on demand
-CONE_LIB_PATH = os.environ.get("SDDP_LIB_CONE", os.path.join(CSRC, "libsddp_cone.so"))
 
 _vp = ctypes.c_void_p
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -45,19 +43,19 @@ _libs = {}
 
 
 def build(force: bool = False) -> str:
-    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU): both libraries, in parallel."""
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("sddp.cu", "sddp_solver.cuh", "sddp_backward_srbd.cuh", "sddp_model.cuh", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "sddp.h"))
-    outs = [os.path.join(CSRC, "libsddp.so"), os.path.join(CSRC, "libsddp_cone.so")]
+    outs = [os.path.join(CSRC, "libsddp.so")]
     stale = any((not os.path.exists(o)) or any(os.path.getmtime(s) > os.path.getmtime(o) for s in srcs) for o in outs)
     if force or stale:
-        subprocess.check_call(["make", "-C", CSRC, "-B", "-j2", "all"])
+        subprocess.check_call(["make", "-C", CSRC, "-B", "all"])
     return LIB_PATH
 
 
-def lib(cone: bool = False) -> ctypes.CDLL:
-    """The product library, or (cone=True) the build with the friction-cone barrier."""
-    path = CONE_LIB_PATH if cone else LIB_PATH
+def lib() -> ctypes.CDLL:
+    """The product library (csrc/libsddp.so, or the A/B build named by SDDP_LIB)."""
+    path = LIB_PATH
     if path not in _libs:
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -66,7 +64,7 @@ def lib(cone: bool = False) -> ctypes.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.sddp_abi_version() != 2:
+        if L.sddp_abi_version() != 3:
             raise RuntimeError(f"{os.path.basename(path)} ABI version mismatch")
         if L.sddp_config_size() != ctypes.sizeof(SddpConfig):
             raise RuntimeError("SddpConfig layout mismatch between config.py and include/sddp.h")

@@ -50,8 +50,8 @@ class SddpConfig(ctypes.Structure):
         ("hessian_mode", ctypes.c_int32),
         ("multiple_shooting", ctypes.c_int32),
         ("max_iters", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
-        ("reserved1", ctypes.c_int32),
+        ("dense_backward", ctypes.c_int32),
+        ("lip_tail_start", ctypes.c_int32),
         ("dt", ctypes.c_double),
         ("mass", ctypes.c_double),
         ("inertia", ctypes.c_double * 9),
@@ -83,6 +83,12 @@ class SddpConfig(ctypes.Structure):
         ("friction_cone_weight", ctypes.c_double),
         ("friction_cone_mu", ctypes.c_double),
         ("friction_cone_sharpness", ctypes.c_double),
+        ("force_bound_weight", ctypes.c_double),
+        ("force_bound", ctypes.c_double),
+        ("unilateral_weight", ctypes.c_double),
+        ("cdot_bound_weight", ctypes.c_double),
+        ("cdot_bound", ctypes.c_double),
+        ("bound_sharpness", ctypes.c_double),
     ]
 
     def copy(self) -> "SddpConfig":
@@ -152,6 +158,15 @@ DEFAULT_OPTS: Dict[str, float] = {
     "friction_cone_weight": 0.0,
     "friction_cone_mu": 0.8,               # prb.py:174
     "friction_cone_sharpness": 6.0,        # ddp.py:182
+    # bounds as exponential barriers (ddp.py:204-209); every weight 0 = ignored as in the reference
+    "force_bound_weight": 0.0,
+    "force_bound": 1.0,                    # isrbd_example.py:200 max_contact_force, in units of force_scaling
+    "unilateral_weight": 0.0,              # f_z >= 0 alone (isrbd_example.py:198)
+    "cdot_bound_weight": 0.0,
+    "cdot_bound": 1.0,                     # contact-point velocity box (isrbd_example.py:195)
+    "bound_sharpness": 6.0,                # ddp.py:182
+    # model scheduler: first node of the LIP-style tail, 0 = full SRBD (README.md:7, isrbd_example.py:344-353)
+    "lip_tail_start": 0,
 }
 
 
@@ -172,7 +187,8 @@ def make_config(model: int, N: int, dt: float, opts: Dict | None = None,
     c.hessian_mode = int(o["hessian_mode"])
     c.multiple_shooting = int(o["multiple_shooting"])
     c.max_iters = int(o["max_iters"])
-    c.reserved0 = int(o["dense_backward"])
+    c.dense_backward = int(o["dense_backward"])
+    c.lip_tail_start = int(o["lip_tail_start"])
     c.dt = float(dt)
     c.mass = robot.mass
     c.inertia = (ctypes.c_double * 9)(*robot.inertia)
@@ -187,7 +203,8 @@ def make_config(model: int, N: int, dt: float, opts: Dict | None = None,
         setattr(c, name, float(getattr(gains, name)))
     for name in ("alpha_0", "alpha_converge_threshold", "line_search_decrease_factor", "beta",
                  "cost_reduction_ths", "mu0", "defect_contraction_rate", "mu_min", "mu_max",
-                 "mu_factor", "defect_ths", "friction_cone_weight", "friction_cone_mu", "friction_cone_sharpness"):
+                 "mu_factor", "defect_ths", "friction_cone_weight", "friction_cone_mu", "friction_cone_sharpness",
+                 "force_bound_weight", "force_bound", "unilateral_weight", "cdot_bound_weight", "cdot_bound", "bound_sharpness"):
         setattr(c, name, float(o[name]))
     if c.N < 1 or c.max_iters < 1:
         raise ValueError("N and max_iters must be >= 1")

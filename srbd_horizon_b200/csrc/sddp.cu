@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) 
         PROF(7);
         if (s_prob >= a.B) break;
         const int b = a.order ? a.order[s_prob] : s_prob;
+        if (b < 0 || b >= a.B) continue;      // not a permutation (caller error, include/sddp.h): skip, status stays -1
         solve_one<M, SM>(c, a, S, b, blockIdx.x, tid);
         __syncthreads();
     }
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(NT, MINB) backward_kernel(DevCfg c, int B, con
         const double* Xb = X + (size_t)b * (N + 1) * NX;
         const double* Ub = U + (size_t)b * N * NU;
         double* packs = ws_pack + (size_t)blockIdx.x * N * M::PACK;
-        compute_packs<M>(c, Xb, Ub, packs, tid);
+        SM::prep(c, S, Xb, Ub, P + (size_t)b * (N + 1) * NP, packs, tid);
         int r = SM::backward(c, S, Xb, Ub, P + (size_t)b * (N + 1) * NP, D + (size_t)b * N * NX, packs, mu,
                              K + (size_t)b * N * NU * NX, kff + (size_t)b * N * NU, &S.red[12], true, tid);
         if (tid == 0) { rc[b] = r; dV[3 * b] = S.red[12]; dV[3 * b + 1] = S.red[13]; dV[3 * b + 2] = S.red[14]; }
@@ -244,6 +245,15 @@ static cudaError_t mark_last(SddpHandle* h, cudaStream_t st) {
     return e;
 }
 
+// A handle is bound to the device that was current at sddp_create (workspace, streams); calling with another current
+// device would launch there against this device's memory.
+static int check_device(SddpHandle* h) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != h->device)
+        return fail(h, SDDP_EINVAL, "%s%s", "the current CUDA device is not the one this handle was created on (cudaSetDevice first)", "");
+    return 0;
+}
+
 static int check_config(const SddpConfig* c, SddpHandle* h) {
     if (!c) return fail(h, SDDP_EINVAL, "%s%s", "config is NULL", "");
     if (c->model != SDDP_MODEL_SRBD && c->model != SDDP_MODEL_LIP) return fail(h, SDDP_EINVAL, "%s%s", "unknown model", "");
@@ -266,10 +276,12 @@ static int check_config(const SddpConfig* c, SddpHandle* h) {
     if (c->defect_contraction_rate > 1.0) return fail(h, SDDP_EINVAL, "%s%s", "defect_contraction_rate must be <= 1", "");
     if (!(c->friction_cone_weight >= 0.0) || !(c->friction_cone_mu >= 0.0) || !(c->friction_cone_sharpness >= 0.0))
         return fail(h, SDDP_EINVAL, "%s%s", "friction_cone_weight, _mu and _sharpness must be >= 0", "");
-#ifdef SDDP_NO_CONE
-    if (c->friction_cone_weight != 0.0)
-        return fail(h, SDDP_EINVAL, "%s%s", "friction_cone_weight > 0 needs the build with inequality support (libsddp_cone.so)", "");
-#endif
+    if (!(c->force_bound_weight >= 0.0) || !(c->unilateral_weight >= 0.0) || !(c->cdot_bound_weight >= 0.0) || !(c->bound_sharpness >= 0.0) ||
+        !(c->force_bound >= 0.0) || !(c->cdot_bound >= 0.0) || !std::isfinite(c->force_bound) || !std::isfinite(c->cdot_bound) ||
+        !std::isfinite(c->bound_sharpness) || !std::isfinite(c->friction_cone_sharpness) || !std::isfinite(c->friction_cone_mu))
+        return fail(h, SDDP_EINVAL, "%s%s", "bound weights, bounds and sharpness must be finite and >= 0", "");
+    if (c->lip_tail_start < 0 || c->lip_tail_start > c->N) return fail(h, SDDP_EINVAL, "%s%s", "lip_tail_start must be in 0..N", "");
+    if (c->model != SDDP_MODEL_SRBD && c->lip_tail_start != 0) return fail(h, SDDP_EINVAL, "%s%s", "lip_tail_start is an SRBD option", "");
     return 0;
 }
 
@@ -290,7 +302,12 @@ static void make_devcfg(const SddpConfig& s, DevCfg& d) {
     d.alpha0 = s.alpha_0; d.alpha_min = s.alpha_converge_threshold; d.ls_factor = s.line_search_decrease_factor;
     d.beta = s.beta; d.cost_ths = s.cost_reduction_ths; d.mu0 = s.mu0; d.rho_fixed = s.defect_contraction_rate;
     d.mu_min = s.mu_min; d.mu_max = s.mu_max; d.mu_factor = s.mu_factor; d.defect_ths = s.defect_ths;
-    d.w_cone = s.model == SDDP_MODEL_SRBD ? s.friction_cone_weight : 0.0; d.cone_mu = s.friction_cone_mu; d.cone_k = s.friction_cone_sharpness;
+    const bool srbd = s.model == SDDP_MODEL_SRBD;
+    d.w_cone = srbd ? s.friction_cone_weight : 0.0; d.cone_mu = s.friction_cone_mu; d.cone_k = s.friction_cone_sharpness;
+    d.w_fb = srbd ? s.force_bound_weight : 0.0; d.fb = s.force_bound; d.w_uni = srbd ? s.unilateral_weight : 0.0;
+    d.w_cdb = srbd ? s.cdot_bound_weight : 0.0; d.cdb = s.cdot_bound; d.kb = s.bound_sharpness;
+    d.ineq = (d.w_cone != 0.0 || d.w_fb != 0.0 || d.w_uni != 0.0 || d.w_cdb != 0.0) ? 1 : 0;
+    d.lip_tail = srbd ? s.lip_tail_start : 0;
     d.ztab = nullptr;
 }
 
@@ -334,7 +351,15 @@ static bool build_ztab(std::vector<unsigned long long>& tab) {
             if (kind == 0) d |= ((unsigned long long)(da * Srbd::NX + db) << 38) | ((unsigned long long)(db * Srbd::NX + da) << 50);
             if (kind == 1) d |= ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 38) | ((unsigned long long)(ZT_QUX_OFF + da * ZT_LDUX + db) << 50);
             tab[e++] = d;
-            if (kind != 2 && hs != 0) { if (nc >= ZT_CROUNDS * ZT_LAZY_THREADS) return false; tab[ZT_COFF + nc++] = d; }   // curvature-only list
+            if (kind != 2 && hs != 0) {      // compact list of the structured backward pass (layout: Srbd::apply_rec)
+                if (nc >= ZT_CROUNDS * ZT_LAZY_THREADS) return false;
+                const unsigned long long d1 = kind == 0 ? da * Srbd::NX + db : ZT_QUX_OFF + da * ZT_LDUX + db;
+                const unsigned long long d2 = kind == 0 ? db * Srbd::NX + da : d1;
+                unsigned long long xi = 0;      // overlapping affine Hessian value (index + 1): (o, o) and the (w, w) diagonal
+                if (pi >= ZO && pi < ZC && qi >= ZO && qi < ZC) { const int a = pi - ZO, b = qi - ZO; xi = 1 + Srbd::AF_OO + (a * 4 - a * (a - 1) / 2) + (b - a); }
+                if (pi >= ZW && pi < ZF && qi == pi) xi = 1 + Srbd::AF_WW;
+                tab[ZT_COFF + nc++] = 1ull | ((unsigned long long)hs << 1) | ((unsigned long long)hoff << 3) | (d1 << 12) | (d2 << 24) | (xi << 36);
+            }
         }
     if (e != NZ * (NZ + 1) / 2) return false;
     // Quu work table (sddp_backward_srbd.cuh, phase c1).  Types: 1 (f_a, f_b) a >= b, 2 (cddot_a, f_b), 3 (cddot_a, cddot_b) a >= b.
@@ -349,6 +374,22 @@ static bool build_ztab(std::vector<unsigned long long>& tab) {
         if (!cc.empty() && t < 72) { d |= cc.back() << 16; cc.pop_back(); }
         tab[ZT_C1OFF + t] = d;
     }
+    {   // affine Hessian entries scattered by Srbd::apply_rec: dst (offset in Qxx) | index into the record's AF_* values << 12
+        const int NX = Srbd::NX, XC = Srbd::XC, XCD = Srbd::XCD, XRD = Srbd::XRD;
+        std::vector<unsigned long long> aff;
+        auto put = [&](int row, int col, int idx) { aff.push_back((unsigned long long)(row * NX + col) | ((unsigned long long)idx << 12)); };
+        for (int e2 = 0; e2 < 12; e2++) put(XCD + e2, XCD + e2, Srbd::AF_CD + e2);            // relative_vel + cdotxy_tracking diagonals (prb.py:166-181)
+        for (int leg = 0; leg < 2; leg++) for (int ax = 0; ax < 2; ax++) { const int ia = XCD + 6 * leg + ax, ib = ia + 3; put(ia, ib, Srbd::AF_NCW); put(ib, ia, Srbd::AF_NCW); }
+        for (int j = 0; j < 2; j++) for (int ax = 0; ax < 2; ax++) {                            // rel_pos (prb.py:192-199)
+            const int ia = XC + 3 * j + ax, ib = ia + 6;
+            put(ia, ia, Srbd::AF_RELP); put(ib, ib, Srbd::AF_RELP); put(ia, ib, Srbd::AF_RELN); put(ib, ia, Srbd::AF_RELN);
+        }
+        for (int i = 0; i < 4; i++) put(XC + 3 * i + 2, XC + 3 * i + 2, Srbd::AF_CW);           // cz_tracking (prb.py:180)
+        for (int i = 0; i < 3; i++) put(XRD + i, XRD + i, Srbd::AF_RDOT);                       // rdot_tracking (prb.py:190)
+        put(2, 2, Srbd::AF_RZ);                                                                 // rz_tracking (prb.py:184)
+        if ((int)aff.size() != ZT_NAFF) return false;
+        for (size_t i = 0; i < aff.size(); i++) tab[ZT_AOFF + i] = aff[i];
+    }
     for (auto v : cc) light.push_back(v);
     for (size_t i = 0; i < light.size(); i++) {                            // threads 78..127: three entries each
         const size_t th = 78 + i % 50, sl = 1 + i / 50;
@@ -358,13 +399,19 @@ static bool build_ztab(std::vector<unsigned long long>& tab) {
     return true;
 }
 
-// kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.reserved0 = 1), 2 = LIP dense
+// kernel variants: 0 = SRBD structured (default), 1 = SRBD dense (A/B check, SddpConfig.dense_backward = 1), 2 = LIP dense,
+// 3 / 4 = 0 / 1 with the inequality barriers compiled in (any of their weights > 0)
 #ifndef SDDP_MINB
 #define SDDP_MINB 4
 #endif
 constexpr int MINB_FAST = SDDP_MINB, MINB_DENSE = 1;
-static int variant_of(const SddpConfig& c) { return c.model == SDDP_MODEL_LIP ? 2 : (c.reserved0 == 1 ? 1 : 0); }
-static size_t smem_of_variant(int v) { return v == 0 ? sizeof(SmemSrbd) : (v == 1 ? sizeof(Smem<Srbd>) : sizeof(Smem<Lip>)); }
+static bool has_ineq(const SddpConfig& c) {
+    return c.friction_cone_weight != 0.0 || c.force_bound_weight != 0.0 || c.unilateral_weight != 0.0 || c.cdot_bound_weight != 0.0;
+}
+static int variant_of(const SddpConfig& c) { return c.model == SDDP_MODEL_LIP ? 2 : (c.dense_backward == 1 ? 1 : 0) + (has_ineq(c) ? 3 : 0); }
+static size_t smem_of_variant(int v) {
+    return v == 0 ? sizeof(SmemSrbd) : (v == 1 ? sizeof(Smem<Srbd>) : (v == 2 ? sizeof(Smem<Lip>) : (v == 3 ? sizeof(SmemSrbdI) : sizeof(Smem<SrbdI>))));
+}
 
 template <class M, class SM, int MINB>
 static cudaError_t set_smem_attr(int* occ) {
@@ -417,7 +464,12 @@ int sddp_dims(int model, int* nx, int* nu, int* np) {
 
 size_t sddp_workspace_bytes(const SddpConfig* cfg) {
     if (!cfg || check_config(cfg, nullptr)) return 0;
-    return ws_layout(*cfg, 148 * kMaxSlotsPerSM).total;   // upper bound for a B200 (148 SMs)
+    int dev = 0, sms = 148;      // a B200 has 148 SMs; the current device is asked when there is one
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    } else (void)cudaGetLastError();
+    return ws_layout(*cfg, sms * kMaxSlotsPerSM).total;   // upper bound: kMaxSlotsPerSM resident CTAs per SM
 }
 
 const char* sddp_last_error(const SddpHandle* h) { return h ? h->err : g_create_err; }
@@ -447,7 +499,9 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
     h->eval_smem_bytes = cfg->model == SDDP_MODEL_SRBD ? sizeof(Smem<Srbd>) : sizeof(Smem<Lip>);
     if (h->variant == 0) CUC((set_smem_attr<Srbd, SmemSrbd, MINB_FAST>(&occ)));
     else if (h->variant == 1) CUC((set_smem_attr<Srbd, Smem<Srbd>, MINB_DENSE>(&occ)));
-    else CUC((set_smem_attr<Lip, Smem<Lip>, MINB_DENSE>(&occ)));
+    else if (h->variant == 2) CUC((set_smem_attr<Lip, Smem<Lip>, MINB_DENSE>(&occ)));
+    else if (h->variant == 3) CUC((set_smem_attr<SrbdI, SmemSrbdI, MINB_FAST>(&occ)));
+    else CUC((set_smem_attr<SrbdI, Smem<SrbdI>, MINB_DENSE>(&occ)));
     if (occ < 1) { fail(nullptr, SDDP_ECUDA, "%s%s", "solve kernel does not fit on this device", ""); sddp_destroy(h); return SDDP_ECUDA; }
     if (occ > kMaxSlotsPerSM) occ = kMaxSlotsPerSM;
     h->slots = h->sms * occ;
@@ -513,7 +567,9 @@ int sddp_launch_count(const SddpHandle* h, long long* out) {
     do {                                                                                                                    \
         if ((h)->variant == 0) KERNEL<Srbd, SmemSrbd, MINB_FAST><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);        \
         else if ((h)->variant == 1) KERNEL<Srbd, Smem<Srbd>, MINB_DENSE><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__); \
-        else KERNEL<Lip, Smem<Lip>, MINB_DENSE><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);                         \
+        else if ((h)->variant == 2) KERNEL<Lip, Smem<Lip>, MINB_DENSE><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);   \
+        else if ((h)->variant == 3) KERNEL<SrbdI, SmemSrbdI, MINB_FAST><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);  \
+        else KERNEL<SrbdI, Smem<SrbdI>, MINB_DENSE><<<grid, NT, (h)->smem_bytes, stream>>>(__VA_ARGS__);                      \
         (h)->launches++;                                                                                                    \
         CU(cudaGetLastError());                                                                                             \
         CU(mark_last(h, stream));                                                                                           \
@@ -523,11 +579,13 @@ int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const doubl
                           double* f, double* fx, double* fu, double* l, double* lx, double* lu, double* lxx, double* lux,
                           double* luu, void* stream) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (M < 0 || (M > 0 && (!kind || !x || !u || !p))) return fail(h, SDDP_EINVAL, "%s%s", "eval_derivatives: bad arguments", "");
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = M < h->sms * 8 ? M : h->sms * 8;
-    if (h->cfg.model == SDDP_MODEL_SRBD) eval_kernel<Srbd><<<grid, NT, h->eval_smem_bytes, st>>>(h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
+    if (h->variant >= 3) eval_kernel<SrbdI><<<grid, NT, h->eval_smem_bytes, st>>>(h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
+    else if (h->cfg.model == SDDP_MODEL_SRBD) eval_kernel<Srbd><<<grid, NT, h->eval_smem_bytes, st>>>(h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
     else eval_kernel<Lip><<<grid, NT, h->eval_smem_bytes, st>>>(h->dc, M, kind, x, u, p, f, fx, fu, l, lx, lu, lxx, lux, luu);
     h->launches++;
     CU(cudaGetLastError());
@@ -537,11 +595,13 @@ int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const doubl
 int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* params, double* X, double* U, double* K,
                      double* kff, double* hist, int32_t* iters, int32_t* status, double* cost, void* stream) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!x0 || !params || !X || !U || !iters || !status || !cost)))
         return fail(h, SDDP_EINVAL, "%s%s", "solve_batch: x0, params, X, U, iters, status, cost are required", "");
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(h->counter, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(status, 0xff, sizeof(int32_t) * (size_t)B, st));      // -1 = not solved (only a bad dispatch order leaves it)
     SolveArgs a;
     a.B = B; a.x0 = x0; a.params = params; a.X = X; a.U = U; a.K = K; a.kff = kff; a.hist = hist;
     a.iters = iters; a.status = status; a.cost = cost;
@@ -557,6 +617,7 @@ int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* param
 int sddp_backward_pass(SddpHandle* h, int B, const double* X, const double* U, const double* params, const double* defect,
                        double mu, double* K, double* kff, double* dV, int32_t* rc, void* stream) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!X || !U || !params || !defect || !K || !kff || !dV || !rc)))
         return fail(h, SDDP_EINVAL, "%s%s", "backward_pass: all arrays are required", "");
     if (B == 0) return 0;
@@ -569,6 +630,7 @@ int sddp_forward_pass(SddpHandle* h, int B, int n_alpha, const double* alpha, co
                       const double* X, const double* U, const double* params, const double* defect, const double* K,
                       const double* kff, double* Jn, double* Xn, double* Un, void* stream) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (B < 0 || n_alpha < 1 || (B > 0 && (!alpha || !rho || !x0 || !X || !U || !params || !defect || !K || !kff || !Jn)))
         return fail(h, SDDP_EINVAL, "%s%s", "forward_pass: bad arguments", "");
     if (B == 0) return 0;
@@ -581,6 +643,7 @@ int sddp_forward_pass(SddpHandle* h, int B, int n_alpha, const double* alpha, co
 int sddp_defects(SddpHandle* h, int B, const double* X, const double* U, const double* params, double* defect, double* cost,
                  void* stream) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!X || !U || !params))) return fail(h, SDDP_EINVAL, "%s%s", "defects: bad arguments", "");
     if (B == 0) return 0;
     int grid = B < h->slots ? B : h->slots;
@@ -591,6 +654,7 @@ int sddp_defects(SddpHandle* h, int B, const double* X, const double* U, const d
 int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* params, const double* X0, const double* U0,
                           double* X, double* U, double* K, double* kff, double* hist, int32_t* iters, int32_t* status, double* cost) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!x0 || !params || !X0 || !U0 || !X || !U || !iters || !status || !cost)))
         return fail(h, SDDP_EINVAL, "%s%s", "solve_batch_host: x0, params, X0, U0, X, U, iters, status, cost are required", "");
     if (B == 0) return 0;
@@ -763,6 +827,7 @@ int sddp_set_gait_tables(SddpHandle* h, const double* l_cycle, const double* l_s
 int sddp_mpc_advance(SddpHandle* h, int B, double* params, const int32_t* action, int32_t* step_counter, const double* rdot_ref_cmd,
                      void* stream) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!params || !action || !step_counter || !rdot_ref_cmd))) return fail(h, SDDP_EINVAL, "%s%s", "mpc_advance: bad arguments", "");
     if (!h->gait) return fail(h, SDDP_EINVAL, "%s%s", "mpc_advance: call sddp_set_gait_tables first", "");
     if (B == 0) return 0;
@@ -780,6 +845,7 @@ int sddp_mpc_advance(SddpHandle* h, int B, double* params, const int32_t* action
 
 int sddp_plant_step(SddpHandle* h, int B, double* state, const double* u, long long u_stride, void* stream) {
     if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!state || !u))) return fail(h, SDDP_EINVAL, "%s%s", "plant_step: bad arguments", "");
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;

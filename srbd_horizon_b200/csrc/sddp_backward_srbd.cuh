@@ -24,18 +24,19 @@
 #include <cstddef>
 #include "sddp_solver.cuh"
 
-struct alignas(16) SmemSrbd {
+template <class MT>
+struct alignas(16) SmemSrbdT {
     static constexpr int NX = 37, NU = 24, NP = 19;
     static constexpr int LDW = 44;   // row pitch of W: 88 words = 24 mod 32, so the 4 x 8 DMMA fragment loads are conflict free
     double VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
     double Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
     double W[NU * LDW];        // B = [Qux | Qu | quy | .] -> Wn = Es B  (quy: lu + fu^T ys of the y recursion)
-    double Quu[NU * NU];       // Quu -> Es = D^-1/2 Lt^-1 (lower triangular, zeros above the diagonal)
+    double Quu[NU * NU];       // Quu -> Et = Lt^-1 (unit lower triangular, zeros above the diagonal); Es = diag(rs) Et
     double Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
     double Qu[NU], kk[NU];
-    double ir[2 * NU];         // d1: (1 / pivot_j, 1 / sqrt(pivot_j)) pairs
+    double invp[NU], rs[NU];   // d1: 1 / pivot_j; 1 / sqrt(pivot_j) (row scaling of Et, applied in h and g)
     double prow[2][NU];        // d1: the published column of the current pivot step (ping-pong)
-    double nb[2][NodeBuf<Srbd>::SIZE];
+    double nb[2][NodeBuf<MT>::SIZE];
     double escr[24];           // expand scratch: E(oref) and the orientation residuals
     double sacc[NWARP][8];
     double red[16];
@@ -43,11 +44,18 @@ struct alignas(16) SmemSrbd {
     int iflag[4];
     __device__ double* Kbuf(int b) { return Qxx + b * (NU * NX); }
     __device__ double* scr() { return VT; }
-    __device__ static int backward(const DevCfg& c, SmemSrbd& S, const double* X, const double* U, const double* P, const double* D,
+    __device__ static int backward(const DevCfg& c, SmemSrbdT& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
+    // rigid-body packs of nodes 0..N-1, one thread per node
+    __device__ static void prep(const DevCfg& c, SmemSrbdT&, const double* X, const double* U, const double*, double* packs, int tid) {
+        compute_packs<MT>(c, X, U, packs, tid);
+    }
 };
+using SmemSrbd = SmemSrbdT<Srbd>;
+using SmemSrbdI = SmemSrbdT<SrbdI>;
 static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 44, "forward K double buffer must fit in Qxx + W");
 static_assert(offsetof(SmemSrbd, W) - offsetof(SmemSrbd, Qxx) == ZT_QUX_OFF * sizeof(double) && SmemSrbd::LDW == ZT_LDUX, "descriptor table destinations (sddp.cu:build_ztab)");
+#define SDDP_INEQ_ON(c) (MT::HAS_INEQ && (c).ineq != 0)
 SDDP_DEV void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 struct Bar96 { __device__ void operator()() const { bar_named(2, 96); } };      // warps 1-3
 
@@ -68,28 +76,17 @@ SDDP_DEV double fast_rcp(double p) {
     return fma(x, e, x);
 }
 
-// 1/sqrt(p) from the hardware seed (MUFU.RSQ64H) and two Newton steps; branch free (sqrt() has a slow path).
-SDDP_DEV double fast_rsqrt(double p) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-    double e = fma(-p * y, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    e = fma(-p * y, y, 1.0);
-    return fma(0.5 * y, e, y);
-}
-
 #ifndef SDDP_ROW128
 #define SDDP_ROW128 1
 #endif
 // a[i] -= row[i] * s for lo <= i < n; `lo` is a compile-time constant after unrolling.  Every thread of a warp reads
 // the same addresses (broadcast).  Loads first, then the FMAs, in batches of 8 (keeps the loads in flight together
 // without holding a whole second column in registers).  SDDP_ROW128: 128-bit loads (`row` is 16-byte aligned).
-template <int n>
+template <int n, int I0 = 0, int I1 = n>
 SDDP_DEV void axpy_row(double* a, const double* row, int lo, double s) {
-    static_assert(n % 8 == 0, "row length");
-#if SDDP_ROW128
+    static_assert(n % 8 == 0 && I0 % 8 == 0 && I1 % 8 == 0, "row length");
 #pragma unroll
-    for (int i0 = 0; i0 < n; i0 += 8) {
+    for (int i0 = I0; i0 < I1; i0 += 8) {
         double2 c[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) if (i0 + 2 * q + 1 >= lo) c[q] = *reinterpret_cast<const double2*>(row + i0 + 2 * q);
@@ -100,16 +97,6 @@ SDDP_DEV void axpy_row(double* a, const double* row, int lo, double s) {
             if (i + 1 >= lo) a[i + 1] -= c[q].y * s;
         }
     }
-#else
-#pragma unroll
-    for (int i0 = lo; i0 < n; i0 += 8) {
-        double col[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) if (i0 + q < n) col[q] = row[i0 + q];
-#pragma unroll
-        for (int q = 0; q < 8; q++) if (i0 + q < n) a[i0 + q] -= col[q] * s;
-    }
-#endif
 }
 // row[i] = a[i] for lo <= i < n
 template <int n>
@@ -140,11 +127,12 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
     out[2] = -v[0] * ho[1] + v[1] * ho[0] + v[2] * ho[3] - v[3] * ho[2];
 }
 
-__device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X, const double* U, const double* P, const double* D,
-                                  const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid) {
-    using M = Srbd;
-    using NBL = NodeBuf<Srbd>;
-    constexpr int NZ = Srbd::NZ;
+template <class MT>
+__device__ int SmemSrbdT<MT>::backward(const DevCfg& c, SmemSrbdT<MT>& S, const double* X, const double* U, const double* P, const double* D,
+                                       const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid) {
+    using M = MT;
+    using NBL = NodeBuf<MT>;
+    constexpr int NZ = MT::NZ;
     const int N = c.N, lane = tid & 31, warp = tid >> 5;
     const bool fixed = c.rho_fixed > 0.0;
     const double rho_b = fixed ? c.rho_fixed : 1.0;
@@ -175,7 +163,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
     prefetch(N - 1);
     if (tid == 0) { S.red[R_TOT] = 0.0; S.red[R_ACC1] = 0.0; S.red[R_ACC2] = 0.0; S.iflag[1] = 0; S.Qx[NX] = 0.0; S.qxy[NX] = 0.0; }
     __syncthreads();
-    M::expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, S.escr);
+    M::template expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, S.escr);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
     cp_wait_all();
     __syncthreads();                           // node N-1 landed
@@ -183,7 +171,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
 
     const unsigned long long c1d = __ldg(c.ztab + ZT_C1OFF + tid);     // this thread's Quu entries (see c1)
     for (int k = N - 1; k >= 0; k--) {
-        const int kind = node_kind(k, N);
+        const int kind = node_kind(c, k);
         double* nb = S.nb[k & 1];
         const double* xk = nb + NBL::OX;
         const double* uk = nb + NBL::OU;
@@ -215,10 +203,10 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             // the remaining (cddot, f) / (cddot, cddot) entries (4 or 1 products): the assignment is a host-built
             // table (sddp.cu:build_ztab), four 16-bit descriptors per thread.
             const double dt2 = dt * dt, g2 = 2.0 * c.gq;
-            if (SDDP_CONE_ON(c)) {          // friction-cone barrier (extension, off by default): 3 x 3 Hessian per foot -> escr
+            if (SDDP_INEQ_ON(c)) {          // inequality barriers (extension, off by default): 3 x 3 Hessian per foot -> escr
                 if (tid < 4) {
-                    double val, cg[3];
-                    M::cone_terms_cold(c, uk + 6 * tid + 3, val, cg, S.escr + 6 * tid);
+                    double val, cg_[3];
+                    M::cone_terms_cold(c, uk + 6 * tid + 3, val, cg_, S.escr + 6 * tid);
                 }
                 __syncthreads();
             }
@@ -240,7 +228,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                     v += g2 * im * im;
                     if (fa == fb) { const double sw1 = 1.0 - pk[8 + 2 * (fa / 3)]; v += 2.0 * (c.w_minf + c.w_fsw * sw1 * sw1) + mu; }
                 }
-                if (SDDP_CONE_ON(c) && fa / 3 == fb / 3) v += S.escr[6 * (fa / 3) + M::cone_hidx(ka, kb)];      // friction-cone barrier
+                if (SDDP_INEQ_ON(c) && fa / 3 == fb / 3) v += S.escr[6 * (fa / 3) + M::cone_hidx(ka, kb)];      // inequality barriers of the foot
                 const int ua = 6 * (fa / 3) + 3 + ka, ub = 6 * (fb / 3) + 3 + kb;
                 S.Quu[ua * NU + ub] = v;
                 S.Quu[ub * NU + ua] = v;
@@ -289,72 +277,119 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             // reciprocal latency.  Lane j skips step j and keeps taking part afterwards: its registers then carry
             // -pivot_j times column j of E = Lt^-1 (E[:,j] starts as -col_j / pivot_j and obeys the same linear recurrence),
             // so the inverse factor costs no extra arithmetic in lanes the factorisation no longer needs.
+#ifndef SDDP_D1V
+#define SDDP_D1V 1
+#endif
+#ifndef SDDP_D1R
+#define SDDP_D1R 4
+#endif
+#ifndef SDDP_D1SKIP
+#define SDDP_D1SKIP 1
+#endif
+            bool bad = false;
+            const int t = lane < NU ? lane : NU - 1;
+#if SDDP_D1V == 0
+            // (experiment: the fully unrolled form of round 1)
+            double a[NU];
+#pragma unroll
+            for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
+            __syncwarp();
+            double myinv = fast_rcp(a[0]);          // lane 0's pivot
+            double npinv = 0.0;
+#pragma unroll
+            for (int j = 0; j < NU; j++) {
+                if (lane == j) {
+                    const double p = a[j];
+                    bad = !(p > 0.0) || !isfinite(p);
+                    npinv = -myinv;
+                    S.invp[j] = myinv;
+                    store_row<NU>(S.Quu + j * NU, a, j + 1);
+                }
+                __syncwarp();
+                if (j + 1 < NU) {
+                    const double sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
+                    a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
+                    myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
+                    if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NU; i += 2) {
+                const double v0 = (i > t) ? npinv * a[i] : (i == t ? 1.0 : 0.0);
+                const double v1 = (i + 1 > t) ? npinv * a[i + 1] : (i + 1 == t ? 1.0 : 0.0);
+                if (lane < NU) { S.Quu[i * NU + lane] = v0; S.Quu[(i + 1) * NU + lane] = v1; }
+            }
+#else
             // Rolled over the pivot steps (R per loop trip): the kernel is instruction-fetch bound (profiles/README.md), and
             // the fully unrolled factorisation was 21 KB of straight-line code per node.  The column lives in a rotating
             // register frame b[q] = a_t[jb + q] (shifted down by R at the end of a trip, zero filled), so every index is
-            // static; the published column goes to a ping-pong row in the same frame, and row j of Es = D^-1/2 Lt^-1 is
-            // stored at step j, when lane t < j holds its final E[j][t] = -a_t[j] / pivot_t (the multiplier of that step),
-            // which replaces the separate write-out pass.  Chunks of 8 entries that lie wholly in the zero tail of the
-            // frame (q >= NU - jb) are skipped with warp-uniform branches.
-            constexpr int R = 4;
-            static_assert(NU % R == 0 && NU % 8 == 0, "d1 frame");
+            // static; the column of the pivot goes to a ping-pong row in the same frame, and row j of Et = Lt^-1 is stored
+            // at step j, when lane t < j holds its final E[j][t] = -a_t[j] / pivot_t (the multiplier of that step), which
+            // replaces the separate write-out pass.  The row scaling D^-1/2 of Es = D^-1/2 Et is applied where Es is used
+            // (phases h and g).  The frame is always updated whole: its zero tail costs a few FMAs in the shadow of the
+            // pivot chain, and a step stays one basic block.
+            // (SDDP_D1V == 3, experiment: nobody publishes a column, every lane stores its own a_i[j] = col_j[i] by symmetry.
+            //  25 % fewer cycles per step, tools/microbench/ldlt.cu V10 / V16 -- but the elimination then loses the scaling
+            //  invariance of symmetric LDL^T: at the first SRBD node behind a LIP-style tail, cond(Quu) = 2e9, the gains
+            //  come out at 2e-8 instead of 1e-13.  Not used.)
+            constexpr int R = SDDP_D1R;
+            static_assert(NU % R == 0 && R % 2 == 0, "d1 frame");
             double b[NU];
-            const int t = lane < NU ? lane : NU - 1;
 #pragma unroll
             for (int i = 0; i < NU; i++) b[i] = S.Quu[i * NU + t];
             __syncwarp();
-            bool bad = false;
-            double myinv = fast_rcp(b[0]), myrs = fast_rsqrt(b[0]);      // lane 0's pivot
+            double myinv = fast_rcp(b[0]);                               // lane 0's pivot
             double npinv = 0.0;                                          // -1 / pivot of this lane's column
 #pragma unroll 1
             for (int jb = 0; jb < NU; jb += R) {
-                const int live = NU - jb;                                // entries q < live of the frame are in use
 #pragma unroll
                 for (int s_ = 0; s_ < R; s_++) {
                     const int j = jb + s_;
                     double* pr = S.prow[s_ & 1];                         // (R is even: j & 1 == s_ & 1)
-                    if (lane == j) {
-                        const double p = b[s_];
-                        bad = !(p > 0.0) || !isfinite(p);
-                        npinv = -myinv;
-                        *reinterpret_cast<double2*>(S.ir + 2 * j) = make_double2(myinv, myrs);
-#pragma unroll
-                        for (int c8 = 0; c8 < NU; c8 += 8)
-                            if (c8 < live) {
-#pragma unroll
-                                for (int q = c8; q < c8 + 8; q += 2) {
-                                    if (q >= s_ + 1) *reinterpret_cast<double2*>(pr + q) = make_double2(b[q], b[q + 1]);
-                                    else if (q + 1 >= s_ + 1) pr[q + 1] = b[q + 1];
-                                }
-                            }
-                    }
-                    __syncwarp();
-                    const double2 ir = *reinterpret_cast<const double2*>(S.ir + 2 * j);
                     const double m = b[s_];
-                    const double sj = (lane == j) ? 0.0 : ir.x * m;
+#if SDDP_D1V == 3
+                    if (lane >= jb && lane < NU) pr[lane - jb] = m;      // col_j[lane] (entries <= j are never read)
+                    if (lane == j) {
+                        bad = !(m > 0.0) || !isfinite(m);
+                        npinv = -myinv;
+                        S.invp[j] = myinv;
+                    }
+#else
+                    if (lane == j) {
+                        bad = !(m > 0.0) || !isfinite(m);
+                        npinv = -myinv;
+                        S.invp[j] = myinv;
+    #if SDDP_D1SKIP
+                        store_row<8>(pr, b, s_ + 1);
+                        if (jb < 16) store_row<8>(pr + 8, b + 8, s_ + 1 - 8);
+                        if (jb < 8) store_row<8>(pr + 16, b + 16, s_ + 1 - 16);
+#else
+                        store_row<NU>(pr, b, s_ + 1);
+#endif
+                    }
+#endif
+                    __syncwarp();
+                    const double sj = (lane == j) ? 0.0 : S.invp[j] * m;
                     b[s_ + 1] -= pr[s_ + 1] * sj;
                     myinv = fast_rcp(b[s_ + 1]);                         // meaningful on lane j + 1
-                    myrs = fast_rsqrt(b[s_ + 1]);
-#pragma unroll
-                    for (int c8 = 0; c8 < NU; c8 += 8)
-                        if (c8 < live) {
-                            double2 cc[4];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) if (c8 + 2 * q + 1 >= s_ + 2) cc[q] = *reinterpret_cast<const double2*>(pr + c8 + 2 * q);
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const int i = c8 + 2 * q;
-                                if (i >= s_ + 2) b[i] -= cc[q].x * sj;
-                                if (i + 1 >= s_ + 2) b[i + 1] -= cc[q].y * sj;
-                            }
-                        }
-                    // row j of Es: (t < j) -E-multiplier / pivot_t * rs_j, (t == j) rs_j, (t > j) 0
-                    const double ev = (lane < j) ? npinv * m * ir.y : (lane == j ? ir.y : 0.0);
+#if SDDP_D1SKIP
+                    // chunks of 8 entries wholly in the zero tail of the frame (q >= NU - jb) are skipped (warp-uniform)
+                    axpy_row<NU, 0, 8>(b, pr, s_ + 2, sj);
+                    if (jb < 16) axpy_row<NU, 8, 16>(b, pr, s_ + 2, sj);
+                    if (jb < 8) axpy_row<NU, 16, 24>(b, pr, s_ + 2, sj);
+#else
+                    axpy_row<NU>(b, pr, s_ + 2, sj);
+#endif
+                    // row j of Et: (t < j) -multiplier / pivot_t, (t == j) 1, (t > j) 0
+                    const double ev = (lane < j) ? npinv * m : (lane == j ? 1.0 : 0.0);
                     if (lane < NU) S.Quu[j * NU + lane] = ev;
                 }
 #pragma unroll
                 for (int q = 0; q < NU; q++) b[q] = (q + R < NU) ? b[q + R] : 0.0;
             }
+#endif
+            if (lane < NU) S.rs[lane] = sqrt(-npinv);
             if (__any_sync(FULL, bad) && lane == 0) S.iflag[1] = 1;
             PROF_T(14, 0);
             STAMP(4); STAMP(5); STAMP(6); STAMP(7);
@@ -389,7 +424,6 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 for (int q = 0; q < 3; q++)
                     row[M::XW + q] = vw[q] + tw[q] + dw0 * Jac[M::ZW + q] + dw1 * Jac[NZ + M::ZW + q] + dw2 * Jac[2 * NZ + M::ZW + q];
             }
-            else if (r_ >= 64 && r_ < 80 && kind != NODE_FIRST) M::prep_E(pk, S.escr, r_ - 64);
             PROF_T(15, 32);
             STAMP(4);
             bar_named(2, 96);
@@ -451,8 +485,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             PROF_T(16, 32);
             STAMP(5);
             bar_named(2, 96);
-            // ---- e: + lx, lu, lxx, lux of the node (two barrier-separated passes among warps 1-3)
-            M::expand<LDW, 1>(c, kind, xk, uk, pk, pack, S.Qx, S.W + NX, S.Qxx, S.W, nullptr, tid - 32, 96, Bar96(), S.escr, S.qxy, S.W + NX + 1);
+            // ---- e: + lx, lu, lxx, lux of the node (one pass, disjoint destinations, no barrier inside)
+            M::apply_rec(c, kind, xk, uk, pk, pack, S.Qxx, S.Qx, S.qxy, S.W + NX, S.W + NX + 1, tid - 32);
             PROF_T(17, 32);
             STAMP(6);
         }
@@ -462,8 +496,8 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         PROF(11);
         if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; cp_wait_all(); __syncthreads(); return k + 1; }
 
-        // ---- h: Wn = Es B (B = [Qux | Qu | quy], 24 x 40 in S.W; Es lower triangular in S.Quu, entries above the
-        //         diagonal are zero).  In place: a warp owns whole 8-column blocks
+        // ---- h: Wn = Es B = diag(rs) Et B (B = [Qux | Qu | quy], 24 x 40 in S.W; Et lower triangular in S.Quu, entries
+        //         above the diagonal are zero).  In place: a warp owns whole 8-column blocks
         //         (warp 0: blocks 0 and 4) and reads all of a block before it writes; the three row tiles of a block
         //         are independent DMMA chains of 2, 4 and 6 steps.
         {
@@ -484,8 +518,10 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 }
                 __syncwarp();
 #pragma unroll
-                for (int I = 0; I < 3; I++)
-                    *reinterpret_cast<double2*>(S.W + (8 * I + fr) * LDW + 8 * J + 2 * fc) = make_double2(h0[I], h1[I]);
+                for (int I = 0; I < 3; I++) {
+                    const double r = S.rs[8 * I + fr];
+                    *reinterpret_cast<double2*>(S.W + (8 * I + fr) * LDW + 8 * J + 2 * fc) = make_double2(r * h0[I], r * h1[I]);
+                }
             }
         }
         STAMP(11);
@@ -496,6 +532,55 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
         //         Vx[37] = -|w0|^2 and y[37] = quy . k.
         // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
         //         at k0 = 8 I.
+#ifndef SDDP_FG_ROLLED
+#define SDDP_FG_ROLLED 1
+#endif
+#if SDDP_FG_ROLLED
+        // Warp w takes tiles w, w+4, w+8, w+12 of each product, one after the other through the same code (a rolled loop:
+        // the kernel is bound by instruction fetch, not by the latency of the DMMA chains, and four interleaved copies of
+        // the chains and epilogues were 12 KB of straight-line code per warp); the f and the g chain of a slot run
+        // interleaved.
+        {
+            const int fr = lane >> 2, fc = lane & 3;       // fragment row / column of this lane
+#pragma unroll 1
+            for (int t = warp; t < 15; t += NWARP) {
+                int fI = 0, rem = t;
+                while (rem >= 5 - fI) { rem -= 5 - fI; fI++; }
+                const int fJ = fI + rem, gI = t / 5, gJ = t - 5 * gI;
+                double f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
+                const double* rf = S.W + fc * LDW + fr;
+                const double* qa = S.Quu + fc * NU + 8 * gI + fr;
+#pragma unroll
+                for (int k0 = 0; k0 < NU; k0 += 4) {
+                    dmma884(f0, f1, rf[k0 * LDW + 8 * fI], rf[k0 * LDW + 8 * fJ]);
+                    // Es^T Wn = Et^T (diag(rs) Wn); Et is lower triangular: row tile gI starts at k0 = 8 gI
+                    if (k0 >= 8 * gI) dmma884(g0, g1, qa[k0 * NU], S.rs[k0 + fc] * rf[k0 * LDW + 8 * gJ]);
+                }
+                const int gi = 8 * fI + fr;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    // Branch free (a divergent branch per case costs more than the work): columns 37 / 38 use the
+                    // vectors Qx -> Vx and qxy -> y as one more row / column of the matrices, whose spare entry 37 is
+                    // kept zero, so Vx[37] = -|w0|^2 and y[37] = quy . k; inactive lanes hit dummy addresses.
+                    const int gj = 8 * fJ + 2 * fc + e;
+                    const double acc = e ? f1 : f0;
+                    const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
+                    const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
+                    const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
+                    double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
+                    double* d2 = m ? S.VT + gj * NX + gi : d1;
+                    if (!ok) { s1 = s2 = S.Qx + NX; d1 = d2 = S.escr + 23; }
+                    const double v = 0.5 * (*s1 + *s2) - acc;
+                    *d1 = v;
+                    *d2 = v;
+                    const int cc = 8 * gJ + 2 * fc + e, i = 8 * gI + fr;
+                    const double kv = e ? -g1 : -g0;
+                    if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
+                    if (cc == NX) { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
+                }
+            }
+        }
+#else
         // Warp w takes tiles w, w+4, w+8, w+12 of each product and runs their accumulation chains interleaved (a
         // single chain of six dependent DMMAs is latency bound); slot 3 of warp 3 is a dummy.
         {
@@ -523,11 +608,12 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
             for (int k0 = 0; k0 < NU; k0 += 4) {
                 const int l = k0 + fc;
                 double av[4], bv[4];
+                const double rl = S.rs[l];                  // Es^T Wn = Et^T (diag(rs) Wn)
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int i = 8 * gI[q] + fr;
                     av[q] = S.Quu[l * NU + i];
-                    bv[q] = S.W[l * LDW + 8 * gJ[q] + fr];
+                    bv[q] = rl * S.W[l * LDW + 8 * gJ[q] + fr];
                 }
 #pragma unroll
                 for (int q = 0; q < 4; q++) if (k0 >= 8 * gI[q]) dmma884(gc0[q], gc1[q], av[q], bv[q]);
@@ -568,6 +654,7 @@ __device__ int SmemSrbd::backward(const DevCfg& c, SmemSrbd& S, const double* X,
                 }
             }
         }
+#endif
         STAMP(9);
         cp_wait_all();                         // the prefetch of node k-1 (issued in c1) is long done: this barrier also
         __syncthreads();                       // publishes it, so the next node starts without one of its own

@@ -53,19 +53,21 @@ __device__ long long g_stamp[16 * 4];
 #define STAMP(id)
 #endif
 
-// The friction-cone barrier (include/sddp.h) is off unless SddpConfig.friction_cone_weight > 0.  -DSDDP_NO_CONE compiles
-// it out (A/B builds); -DSDDP_CONE_INLINE inlines the five exp() at every call site instead of one out-of-line copy.
-#ifdef SDDP_NO_CONE
-#define SDDP_CONE_ON(c) false
-#else
-#define SDDP_CONE_ON(c) ((c).w_cone != 0.0)
-#endif
+// The inequality barriers (include/sddp.h: friction cone, force / velocity boxes, unilaterality) are off unless one of
+// their weights is > 0.  Their exp() code sits in a second instantiation of the SRBD model (SrbdT<true>) and of every
+// kernel that uses it: merely compiled into the default kernels it costs them 14 % (register pressure: ptxas then
+// serialises the shared-memory loads of the factorisation through one register quad), so the default instantiation
+// (SrbdT<false>) has none of it.  One library, the variant is picked from the configuration at sddp_create.
+#define SDDP_CONE_ON(c) (HAS_INEQ && (c).ineq != 0)
 
 struct DevCfg {
     int model, N, inertia_mode, hessian_mode, ms, max_iters;
     double dt, mscaled, inv_ms, Ib[9], com[3], foot[12], fs, g, eta2;
     double w_r, w_rdot, w_w, w_rel, w_fsw, gq, w_minf, w_zmp, cw;
     double w_cone, cone_mu, cone_k;   // friction-cone barrier (include/sddp.h); w_cone = 0: off
+    double w_fb, fb, w_uni, w_cdb, cdb, kb;   // force box, unilaterality, contact-point velocity box (include/sddp.h); weights 0: off
+    int ineq;                         // any inequality barrier on
+    int lip_tail;                     // first node of the LIP-style tail, 0 = off (include/sddp.h lip_tail_start)
     double drel[2][2];   // drel[pair][axis] = -(foot[pair][axis] - foot[pair+2][axis])   prb.py:153-154
     double alpha0, alpha_min, ls_factor, beta, cost_ths, mu0, rho_fixed, mu_min, mu_max, mu_factor, defect_ths;
     const unsigned long long* ztab;   // SRBD: descriptors of the 595 upper-triangular entries of the wdot Hessian block
@@ -74,7 +76,7 @@ struct DevCfg {
 // z-block descriptor bit layout (built on the host, sddp.cu:build_ztab)
 enum { ZT_ROUNDS = 5, ZT_THREADS = 128, ZT_NXX_NUX = 517, ZT_LAZY_THREADS = 96 };   // 595 entries: 253 xx + 264 ux first, then 78 uu
 // Quu work table of the structured backward pass: ztab[ZT_C1OFF + tid] = four 16-bit descriptors type | i1 << 2 | i2 << 6
-enum { ZT_C1OFF = 640, ZT_COFF = 768, ZT_CROUNDS = 2, ZT_TOTAL = 768 + 2 * 96 };   // ZT_COFF: the xx / ux entries that have a curvature term
+enum { ZT_C1OFF = 640, ZT_COFF = 768, ZT_CROUNDS = 2, ZT_AOFF = 768 + 2 * 96, ZT_NAFF = 44, ZT_TOTAL = 768 + 2 * 96 + 48 };   // ZT_AOFF: dst | value index << 12 of the affine Hessian entries (Srbd::apply_rec)   // ZT_COFF: the xx / ux entries that have a curvature term
 #define C1_TYPE(d) (int)((d) & 3)
 #define C1_I1(d) (int)(((d) >> 2) & 15)
 #define C1_I2(d) (int)(((d) >> 6) & 15)
@@ -90,7 +92,7 @@ enum { ZT_C1OFF = 640, ZT_COFF = 768, ZT_CROUNDS = 2, ZT_TOTAL = 768 + 2 * 96 };
 #define ZT_DST2(d) (int)(((d) >> 50) & 4095)
 enum { ZT_QUX_OFF = 37 * 37 + 1, ZT_LDUX = 44 };   // layout of SmemSrbd (static_assert there)
 
-enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2 };
+enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2, NODE_TAIL = 3 };   // TAIL: a MID node of the LIP-style tail (no rotational dynamics)
 
 #define SDDP_DEV __device__ __forceinline__
 #ifndef SDDP_NOINLINE
@@ -156,13 +158,17 @@ SDDP_DEV void quat_dR(const double* q, int a, double* D) {
 }
 
 // =====================================================================================  SRBD
-struct Srbd {
+template <bool INEQ>
+struct SrbdT {
+    static constexpr bool HAS_INEQ = INEQ;
     static constexpr int NX = 37, NU = 24, NP = 19, NACC = 6, PACK = 256, NZ = 34;
     // x: r[0:3] o[3:7] c_i[7+3i] rdot[19:22] w[22:25] cdot_i[25+3i];  u: cddot_i[6i] f_i[6i+3]
     // p: rdot_ref[0:3] w_ref[3:6] otg[6] (c_ref_i, sw_i)[7+2i, 8+2i] oref[15:19]
     enum { XR = 0, XO = 3, XC = 7, XRD = 19, XW = 22, XCD = 25 };
     enum { ZR = 0, ZO = 3, ZC = 7, ZW = 19, ZF = 22 };
     enum { PK_WD = 0, PK_RDD = 3, PK_NU = 6, PK_HWW = 9, PK_JAC = 18, PK_HO = 120 };
+    // indices of the affine Hessian values (aff_value) that the table at ZT_AOFF / the compact curvature descriptors name
+    enum { AF_CD = 0, AF_RELP = 12, AF_RELN = 13, AF_NCW = 14, AF_CW = 15, AF_RDOT = 16, AF_RZ = 17, AF_WW = 18, AF_OO = 19, AF_N = 29 };
 
     SDDP_DEV static void inertia(const DevCfg& c, const double* R, double* J) {
         if (c.inertia_mode == 0) {
@@ -230,7 +236,7 @@ struct Srbd {
         m3::mv(J, x + XW, Jw);
         m3::cross(x + XW, Jw, pre + 9);
     }
-    SDDP_DEV static void accel_post(const DevCfg& c, const double* x, const double* u, const double* pre, double* acc) {
+    SDDP_DEV static void accel_post(const DevCfg& c, const double* x, const double* u, const double* pre, double* acc, bool tail = false) {
         double tau[3] = {0, 0, 0}, fsum[3] = {0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -243,12 +249,13 @@ struct Srbd {
         }
         double h[3] = {tau[0] - pre[9], tau[1] - pre[10], tau[2] - pre[11]};
         m3::mv(pre, h, acc);
+        if (tail) { acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; }      // LIP-style tail: no rotational dynamics
         acc[3] = fsum[0] * c.inv_ms; acc[4] = fsum[1] * c.inv_ms; acc[5] = fsum[2] * c.inv_ms - c.g;
     }
-    SDDP_DEV static void accel(const DevCfg& c, const double* x, const double* u, double* acc) {
+    SDDP_DEV static void accel(const DevCfg& c, const double* x, const double* u, double* acc, bool tail = false) {
         double pre[NPRE];
         accel_pre(c, x, pre);
-        accel_post(c, x, u, pre, acc);
+        accel_post(c, x, u, pre, acc, tail);
     }
     // Branch free: lanes of a warp own different components, and a divergent branch per component kind costs more
     // than the work.  Every component but the quaternion rate is a copy from one of the arrays.
@@ -276,17 +283,41 @@ struct Srbd {
         return -m3::skew_ab(q, i, a);
     }
 
-    // Exponential barrier on the linearised friction cone of one foot (include/sddp.h, extension, off by default):
-    // value, gradient (3) and Hessian (xx, xy, xz, yy, yz, zz) with respect to the foot's force f.
+    // Inequality barriers of one foot (include/sddp.h, extensions, off by default): exponential barrier on the linearised
+    // friction cone, on the force box |f_k| <= fb and on f_z >= 0.  Value, gradient (3) and Hessian (xx, xy, xz, yy, yz, zz)
+    // with respect to the foot's force f.
     SDDP_DEV static void cone_terms(const DevCfg& c, const double* f, double& val, double* g, double* h) {
-        const double k = c.cone_k, m = c.cone_mu, kz = k * m * f[2];
-        const double e1 = c.w_cone * exp(k * f[0] - kz), e2 = c.w_cone * exp(-k * f[0] - kz);
-        const double e3 = c.w_cone * exp(k * f[1] - kz), e4 = c.w_cone * exp(-k * f[1] - kz), e5 = c.w_cone * exp(-k * f[2]);
-        const double s4 = (e1 + e2) + (e3 + e4);
-        val = s4 + e5;
-        g[0] = k * (e1 - e2); g[1] = k * (e3 - e4); g[2] = -k * (m * s4 + e5);
-        h[0] = k * k * (e1 + e2); h[1] = 0.0; h[2] = -k * k * m * (e1 - e2);
-        h[3] = k * k * (e3 + e4); h[4] = -k * k * m * (e3 - e4); h[5] = k * k * (m * m * s4 + e5);
+        val = 0.0;
+        g[0] = g[1] = g[2] = 0.0;
+        h[0] = h[1] = h[2] = h[3] = h[4] = h[5] = 0.0;
+        if (c.w_cone != 0.0) {
+            const double k = c.cone_k, m = c.cone_mu, kz = k * m * f[2];
+            const double e1 = c.w_cone * exp(k * f[0] - kz), e2 = c.w_cone * exp(-k * f[0] - kz);
+            const double e3 = c.w_cone * exp(k * f[1] - kz), e4 = c.w_cone * exp(-k * f[1] - kz), e5 = c.w_cone * exp(-k * f[2]);
+            const double s4 = (e1 + e2) + (e3 + e4);
+            val = s4 + e5;
+            g[0] = k * (e1 - e2); g[1] = k * (e3 - e4); g[2] = -k * (m * s4 + e5);
+            h[0] = k * k * (e1 + e2); h[2] = -k * k * m * (e1 - e2);
+            h[3] = k * k * (e3 + e4); h[4] = -k * k * m * (e3 - e4); h[5] = k * k * (m * m * s4 + e5);
+        }
+        if (c.w_fb != 0.0) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const double ep = c.w_fb * exp(c.kb * (f[a] - c.fb)), em = c.w_fb * exp(c.kb * (-c.fb - f[a]));
+                val += ep + em;
+                g[a] += c.kb * (ep - em);
+                h[a == 0 ? 0 : (a == 1 ? 3 : 5)] += c.kb * c.kb * (ep + em);
+            }
+        }
+        if (c.w_uni != 0.0) {
+            const double e = c.w_uni * exp(-c.kb * f[2]);
+            val += e; g[2] -= c.kb * e; h[5] += c.kb * c.kb * e;
+        }
+    }
+    // Barrier on the contact-point velocity box |v| <= cdb: value, first and second derivative.
+    __device__ __noinline__ static void cdot_box_cold(const DevCfg& c, double v, double& val, double& g, double& h) {
+        const double ep = c.w_cdb * exp(c.kb * (v - c.cdb)), em = c.w_cdb * exp(c.kb * (-c.cdb - v));
+        val = ep + em; g = c.kb * (ep - em); h = c.kb * c.kb * (ep + em);
     }
     // Out-of-line copy for the call sites inside hot loops (forward-pass cost, node expansion): with the barrier off they
     // cost one predicated call instead of five inlined exp().
@@ -318,6 +349,10 @@ struct Srbd {
                         const double r = x[i] - ref;
                         s += wg * r * r;
                     }
+                    if (kind == NODE_TAIL && (i == 2 || i >= XW)) {        // lip_com_height, lip_zero_angular_momentum (isrbd_example.py:352-353)
+                        const double r = (i == 2) ? x[2] - c.com[2] : x[i];
+                        s += c.cw * r * r;
+                    }
                 } else if (i >= XO && i < XC) {                            // otg * (quat_prod(o, oref) - [0,0,0,1])  (prb.py:185-189)
                     if (track) {
                         const double* q = p + 15;
@@ -334,6 +369,11 @@ struct Srbd {
                 } else if (i >= XC) {                                      // contact points and their velocities
                     const bool vel = i >= XCD;
                     const int e = i - (vel ? XCD : XC), foot = e / 3, ax = e - 3 * foot;
+                    if (SDDP_CONE_ON(c) && c.w_cdb != 0.0 && vel && input) {      // contact-point velocity box (extension)
+                        double val, g_, h_;
+                        cdot_box_cold(c, x[i], val, g_, h_);
+                        s += val;
+                    }
                     if (!vel && ax == 2) {                                 // cz_tracking (prb.py:180)
                         if (input) { const double r = x[i] - p[7 + 2 * foot]; s += c.cw * r * r; }
                     } else if (ax < 2) {
@@ -356,7 +396,7 @@ struct Srbd {
                 else { double a = 1.0 - p[8 + 2 * i]; s += (c.w_minf + c.w_fsw * a * a) * v * v; }
             }
             if ((parts & 4) && lane < 3) s += c.gq * (acc[lane] * acc[lane] + acc[3 + lane] * acc[3 + lane]);
-            if ((parts & 2) && SDDP_CONE_ON(c) && lane < 4) {      // friction-cone barrier of foot `lane`
+            if ((parts & 2) && SDDP_CONE_ON(c) && lane < 4) {      // inequality barriers of foot `lane`
                 double val, g[3], h[6];
                 cone_terms_cold(c, u + 6 * lane + 3, val, g, h);
                 s += val;
@@ -369,6 +409,13 @@ struct Srbd {
     // pk[PK_WD..] wd(3) rdd(3) nu(3) Hww(9) Jac[3][34] Ho[4][34]
     __device__ SDDP_NOINLINE static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk) {
         if (kind == NODE_TERM) return;
+        if (kind == NODE_TAIL) {      // LIP-style tail: wdot = 0 identically, so no Jacobian and no curvature; rddot as usual
+            for (int i = 0; i < PACK; i++) pk[i] = 0.0;
+            double fsum[3] = {0, 0, 0};
+            for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) fsum[k] += u[6 * i + 3 + k];
+            pk[PK_RDD + 0] = fsum[0] * c.inv_ms; pk[PK_RDD + 1] = fsum[1] * c.inv_ms; pk[PK_RDD + 2] = fsum[2] * c.inv_ms - c.g;
+            return;
+        }
         const double* r = x;
         const double* o = x + XO;
         const double* w = x + XW;
@@ -476,6 +523,119 @@ struct Srbd {
         }
     }
 
+    // ---- structured backward pass, phase e: Qxx, Qux, Qx, Qu (+ the y-recursion copies Qx2, Qu2) += lxx, lux, lx, lu ------
+    // One pass over disjoint destinations, no barrier and no shared scratch (the round-1 version needed two barrier-
+    // separated passes among warps 1-3): the 2 gq Jac^T Jac part already rides on the caller's fx^T / fu^T products, so
+    // what is left is (1) the 184 curvature entries of the wdot block through the compact descriptor list at ZT_COFF,
+    // each carrying the index of the affine Hessian value that lands on the same entry (orientation tracking on (o, o),
+    // w tracking on the (w, w) diagonal), (2) the 44 other affine Hessian entries through the table at ZT_AOFF, (3) the
+    // gradients lx (37) and lu (24), one per thread.  tid in [0, ZT_LAZY_THREADS); Qux = Qxx + ZT_QUX_OFF.
+    // Compact descriptors: valid | hs << 1 | hoff << 3 | dst1 << 12 | dst2 << 24 | (affine value index + 1) << 36.
+    SDDP_DEV static double aff_value(const DevCfg& c, int kind, const double* x, const double* p, int l) {
+        const bool track = kind != NODE_FIRST, tail = kind == NODE_TAIL;
+        if (l < 12) {      // (cd, cd) diagonal: relative_vel + cdotxy_tracking (prb.py:166-181) [+ velocity box]
+            const int foot = l / 3, ax = l - 3 * foot;
+            const double sw_ = p[8 + 2 * foot];
+            double v = ax < 2 ? 2.0 * c.cw * (1.0 + sw_ * sw_) : 0.0;
+            if (SDDP_CONE_ON(c) && c.w_cdb != 0.0) { double val, g_, h_; cdot_box_cold(c, x[XCD + l], val, g_, h_); v += h_; }
+            return v;
+        }
+        if (l >= AF_OO) {      // (a, b), a <= b in row-major order: orientation tracking 2 otg^2 (E^T E)_ab (prb.py:185-189)
+            const double* qr = p + 15;
+            int t = l - AF_OO, a = 0;
+            while (t >= 4 - a) { t -= 4 - a; a++; }
+            const int b = a + t;
+            double ee = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) ee += E_row(qr, i, a) * E_row(qr, i, b);
+            return track ? 2.0 * p[6] * p[6] * ee : 0.0;
+        }
+        const double tw = (l == AF_RELP) ? 2.0 * c.w_rel : (l == AF_RELN ? -2.0 * c.w_rel : (l == AF_RDOT ? 2.0 * c.w_rdot : (l == AF_RZ ? 2.0 * c.w_r : (l == AF_WW ? 2.0 * c.w_w : 0.0))));
+        double v = track ? tw : 0.0;
+        if (l == AF_NCW) v = -2.0 * c.cw;
+        if (l == AF_CW) v = 2.0 * c.cw;
+        if (tail && (l == AF_RZ || l == AF_WW)) v += 2.0 * c.cw;      // lip_com_height, lip_zero_angular_momentum
+        return v;
+    }
+    SDDP_DEV static void apply_rec(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double* pk,
+                                   double* Qxx, double* Qx, double* Qx2, double* Qu, double* Qu2, int tid) {
+        const bool track = kind != NODE_FIRST, tail = kind == NODE_TAIL;
+        const bool exact = c.hessian_mode == 0 && !tail;      // Gauss-Newton / LIP-style tail: no curvature, affine parts only
+        const double g2 = 2.0 * c.gq;
+#pragma unroll
+        for (int r = 0; r < ZT_CROUNDS; r++) {
+            const unsigned long long d = __ldg(c.ztab + ZT_COFF + r * ZT_LAZY_THREADS + tid);
+            if (!(d & 1ull)) continue;
+            const double v = exact ? g2 * pk[(int)(d >> 3) & 511] : 0.0;
+            double hv = ((d >> 1) & 3) == 1 ? v : -v;
+            const int xi = (int)(d >> 36) & 63;
+            if (xi) hv += aff_value(c, kind, x, p, xi - 1);
+            const int o1 = (int)(d >> 12) & 4095, o2 = (int)(d >> 24) & 4095;
+            Qxx[o1] += hv;
+            if (o2 != o1) Qxx[o2] += hv;
+        }
+        if (tid < ZT_NAFF) {
+            const unsigned d = (unsigned)__ldg(c.ztab + ZT_AOFF + tid);
+            Qxx[d & 0xfffu] += aff_value(c, kind, x, p, (int)(d >> 12));
+        }
+        const int e = tid - (ZT_LAZY_THREADS - NX - NU);      // the last 61 threads: lu, lx
+        if (e < 0) return;
+        auto jtw = [&](int z) {      // 2 gq Jac[:, z] . wdot
+            return g2 * (pk[PK_JAC + z] * pk[PK_WD] + pk[PK_JAC + NZ + z] * pk[PK_WD + 1] + pk[PK_JAC + 2 * NZ + z] * pk[PK_WD + 2]);
+        };
+        if (e < NU) {                                  // lu
+            const int i = e / 6, r_ = e - 6 * i;
+            double g;
+            if (r_ < 3) g = g2 * u[e];
+            else {
+                const double a = 1.0 - p[8 + 2 * i];
+                g = g2 * c.inv_ms * pk[PK_RDD + r_ - 3] + 2.0 * (c.w_minf + c.w_fsw * a * a) * u[e] + jtw(ZF + 3 * i + r_ - 3);
+                if (SDDP_CONE_ON(c)) { double val, cg[3], ch[6]; cone_terms_cold(c, u + 6 * i + 3, val, cg, ch); g += cg[r_ - 3]; }
+            }
+            const int j = e * ZT_LDUX;
+            Qu[j] += g; Qu2[j] += g;
+        } else {                                       // lx
+            const int i = e - NU;
+            double g = 0.0;
+            if (i < XRD) g = jtw(i); else if (i >= XW && i < XCD) g = jtw(ZW + i - XW);
+            if (tail && (i == 2 || (i >= XW && i < XCD))) g += 2.0 * c.cw * ((i == 2) ? x[2] - c.com[2] : x[i]);
+            if (i == 2) { if (track) g += 2.0 * c.w_r * (x[2] - c.com[2]); }
+            else if (i >= XO && i < XC) {
+                if (track) {
+                    const double* qr = p + 15;
+                    const double* o = x + XO;
+                    const int a = i - XO;
+                    double s_ = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const double res = E_row(qr, r, 0) * o[0] + E_row(qr, r, 1) * o[1] + E_row(qr, r, 2) * o[2] + E_row(qr, r, 3) * o[3] - (r == 3 ? 1.0 : 0.0);
+                        s_ += E_row(qr, r, a) * res;
+                    }
+                    g += 2.0 * p[6] * p[6] * s_;
+                }
+            } else if (i >= XC && i < XRD) {
+                const int foot = (i - XC) / 3, ax = (i - XC) % 3;
+                if (ax == 2) g += 2.0 * c.cw * (x[i] - p[7 + 2 * foot]);
+                else if (track) {
+                    const int j = foot & 1, ia = XC + 3 * j + ax, ib = ia + 6;
+                    const double res = -x[ia] + x[ib] - c.drel[j][ax];
+                    g += (foot < 2) ? -2.0 * c.w_rel * res : 2.0 * c.w_rel * res;
+                }
+            } else if (i >= XRD && i < XW) { if (track) g += 2.0 * c.w_rdot * (x[i] - p[i - XRD]); }
+            else if (i >= XW && i < XCD) { if (track) g += 2.0 * c.w_w * (x[i] - p[3 + i - XW]); }
+            else if (i >= XCD) {
+                const int foot = (i - XCD) / 3, ax = (i - XCD) % 3;
+                if (ax < 2) {
+                    const int ia = XCD + 3 * (foot & ~1) + ax, ib = ia + 3;
+                    const double res = x[ia] - x[ib], sw_ = p[8 + 2 * foot];
+                    g += 2.0 * c.cw * (((foot & 1) ? -res : res) + sw_ * sw_ * x[i]);
+                }
+                if (SDDP_CONE_ON(c) && c.w_cdb != 0.0) { double val, g_, h_; cdot_box_cold(c, x[i], val, g_, h_); g += g_; }
+            }
+            Qx[i] += g; Qx2[i] += g;
+        }
+    }
+
     SDDP_DEV static int zmap_x(int pi) { return pi < 19 ? pi : (pi < 22 ? XW + (pi - 19) : -1); }
     SDDP_DEV static int zmap_u(int pi) { return 6 * ((pi - 22) / 3) + 3 + (pi - 22) % 3; }
 
@@ -494,67 +654,52 @@ struct Srbd {
         return 0.0;
     }
 
-    // Q buffers <- lx, lu, lxx, lux, luu of this node.  Every thread of the block must call.
+    // Q buffers <- lx, lu, lxx, lux, luu of this node.  Every thread of the block must call.  (Stage-1 kernel, generic
+    // dense solve kernel and the terminal node of the structured one; the structured backward pass itself adds the node
+    // terms in its phase e: apply_rec.)
     // Fast path (128 threads + descriptor table): three barrier-separated passes, each with one or a few
     // entries per thread and short uniform branches:
     //   1. zero fill   2. wdot block 2 gq (Jac^T Jac + Hc) through the descriptor table   3. affine residuals
-    // MODE 1 (structured backward pass, ZT_LAZY_THREADS threads, tid 0..95): the caller has already written the
-    // fx / fu products into Qx, Qu (and their copies Qx2, Qu2), Qxx, Qux and owns Quu; this call ADDS lx, lu, lxx,
-    // lux to them (no zero fill, no luu), so that the expansion runs in the shadow of the factorisation.  Qu and Qu2
-    // are columns of the Qux buffer there (stride LDUX).  The caller runs prep_E() and a barrier first.
     SDDP_DEV static void prep_E(const double* p, double* scratch, int t) {   // t in [0, 16)
         scratch[t] = E_row(p + 15, t >> 2, t & 3);
     }
-    template <int LDUX = NX, int MODE = 0, class Sync>
+    template <int LDUX = NX, class Sync>
     __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double* pk,
                                   double* Qx, double* Qu, double* Qxx, double* Qux, double* Quu, int tid, int nthr, Sync sync,
-                                  double* scratch = nullptr, double* Qx2 = nullptr, double* Qu2 = nullptr) {
-        if (MODE == 0 && (c.ztab == nullptr || nthr != ZT_THREADS || scratch == nullptr)) {
+                                  double* scratch = nullptr) {
+        if (c.ztab == nullptr || nthr != ZT_THREADS || scratch == nullptr) {
             expand_generic<LDUX>(c, kind, x, u, p, pk, Qx, Qu, Qxx, Qux, Quu, tid, nthr, sync);
             return;
         }
-        constexpr int NTH = MODE ? ZT_LAZY_THREADS : ZT_THREADS, ROUNDS = MODE ? ZT_CROUNDS : ZT_ROUNDS, EB = NTH - 32;
-        const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
-        // MODE 1: the caller has already added the 2 gq Jac^T Jac part (it rides on its fx^T / fu^T products), so only the
-        // entries with a curvature term are left: the compact list at ZT_COFF, nothing at all for the Gauss-Newton Hessian
+        constexpr int NTH = ZT_THREADS, ROUNDS = ZT_ROUNDS, EB = NTH - 32;
+        const bool track = kind != NODE_FIRST, input = kind != NODE_TERM, tail = kind == NODE_TAIL;
         unsigned long long zd[ROUNDS];
-        if (input) {      // MODE 0: latency hidden by the zero fill
+        if (input) {      // latency hidden by the zero fill
 #pragma unroll
-            for (int r = 0; r < ROUNDS; r++) zd[r] = MODE ? __ldg(c.ztab + ZT_COFF + r * NTH + tid) : __ldg(c.ztab + r * NTH + tid);
+            for (int r = 0; r < ROUNDS; r++) zd[r] = __ldg(c.ztab + r * NTH + tid);
         }
         double* Es = scratch;          // E(oref) 4x4, then the four orientation residuals
-        if (MODE == 0) {
-            for (int e = tid; e < NX * NX; e += NTH) Qxx[e] = 0.0;
-            for (int e = tid; e < NU * LDUX; e += NTH) Qux[e] = 0.0;
-            for (int e = tid; e < NU * NU; e += NTH) Quu[e] = 0.0;
-            if (tid < NX) Qx[tid] = 0.0;
-            if (tid < NU) Qu[tid] = 0.0;
-            if (track && tid >= EB && tid < EB + 16) prep_E(p, Es, tid - EB);
-            sync();
-        }
+        for (int e = tid; e < NX * NX; e += NTH) Qxx[e] = 0.0;
+        for (int e = tid; e < NU * LDUX; e += NTH) Qux[e] = 0.0;
+        for (int e = tid; e < NU * NU; e += NTH) Quu[e] = 0.0;
+        if (tid < NX) Qx[tid] = 0.0;
+        if (tid < NU) Qu[tid] = 0.0;
+        if (track && tid >= EB && tid < EB + 16) prep_E(p, Es, tid - EB);
+        sync();
         PROF(20);
         if (track && tid >= EB && tid < EB + 4) {
             const int r = tid - EB;
             const double* o = x + XO;
             Es[16 + r] = Es[4 * r] * o[0] + Es[4 * r + 1] * o[1] + Es[4 * r + 2] * o[2] + Es[4 * r + 3] * o[3] - (r == 3 ? 1.0 : 0.0);
         }
-        if (input) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc), upper triangle mirrored
+        if (input) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc), upper triangle mirrored (all zero on the LIP-style tail)
             const double* Jac = pk + PK_JAC;
             const double g2 = 2.0 * c.gq;
-            const bool exact = c.hessian_mode == 0;
+            const bool exact = c.hessian_mode == 0 && !tail;
 #pragma unroll
             for (int r = 0; r < ROUNDS; r++) {
                 const unsigned long long d = zd[r];
                 if (!ZT_VALID(d)) continue;
-                if (MODE) {        // destinations as offsets from Qxx (Qux = Qxx + ZT_QUX_OFF, pitch ZT_LDUX): no branch on the kind
-                    if (exact) {
-                        const double v = pk[ZT_HOFF(d)], hv = (ZT_HSIGN(d) == 1) ? g2 * v : -g2 * v;
-                        const int o1 = ZT_DST1(d), o2 = ZT_DST2(d);
-                        Qxx[o1] += hv;
-                        if (o2 != o1) Qxx[o2] += hv;
-                    }
-                    continue;
-                }
                 const int pi = ZT_PI(d), qi = ZT_QI(d), da = ZT_DA(d), db = ZT_DB(d), hs = ZT_HSIGN(d);
                 double hh = Jac[pi] * Jac[qi] + Jac[NZ + pi] * Jac[NZ + qi] + Jac[2 * NZ + pi] * Jac[2 * NZ + qi];
                 if (exact && hs) { const double v = pk[ZT_HOFF(d)]; hh += (hs == 1) ? v : -v; }
@@ -568,18 +713,13 @@ struct Srbd {
                 const int pi = tid;
                 const double g = g2 * (Jac[pi] * pk[PK_WD] + Jac[NZ + pi] * pk[PK_WD + 1] + Jac[2 * NZ + pi] * pk[PK_WD + 2]);
                 const int xi = zmap_x(pi);
-                if (MODE) {
-                    if (xi >= 0) { Qx[xi] += g; Qx2[xi] += g; } else { const int ui = zmap_u(pi) * LDUX; Qu[ui] += g; Qu2[ui] += g; }
-                } else {
-                    if (xi >= 0) Qx[xi] = g; else Qu[zmap_u(pi)] = g;
-                }
+                if (xi >= 0) Qx[xi] = g; else Qu[zmap_u(pi)] = g;
             }
         }
         sync();
         PROF(21);
-        if (MODE) PROF_T(18, 32);
-        // ---- affine residuals, Hessian: one entry per thread (119 entries; MODE 1 skips the luu entries 0..47, 96..107)
-        const int t = MODE ? (tid < 48 ? tid + 48 : tid + 60) : tid;
+        // ---- affine residuals, Hessian: one entry per thread (119 entries)
+        const int t = tid;
         // (each case only computes the destination and the value; one read-modify-write at the end keeps the cases
         //  short enough to be predicated instead of branched over)
         int hdst = -1;
@@ -619,15 +759,15 @@ struct Srbd {
             if (input) { const int id = XC + 3 * (t - 108) + 2; hdst = id * NX + id; hval = 2.0 * c.cw; }
         } else if (t < 115) {                           // rdot_tracking   (prb.py:190)
             if (track) { const int id = XRD + t - 112; hdst = id * NX + id; hval = 2.0 * c.w_rdot; }
-        } else if (t < 118) {                           // w_tracking   (prb.py:191)
-            if (track) { const int id = XW + t - 115; hdst = id * NX + id; hval = 2.0 * c.w_w; }
-        } else if (t == 118) {                          // rz_tracking   (prb.py:184)
-            if (track) { hdst = 2 * NX + 2; hval = 2.0 * c.w_r; }
+        } else if (t < 118) {                           // w_tracking   (prb.py:191) + lip_zero_angular_momentum on the tail
+            if (track) { const int id = XW + t - 115; hdst = id * NX + id; hval = 2.0 * c.w_w + (tail ? 2.0 * c.cw : 0.0); }
+        } else if (t == 118) {                          // rz_tracking   (prb.py:184) + lip_com_height on the tail
+            if (track) { hdst = 2 * NX + 2; hval = 2.0 * c.w_r + (tail ? 2.0 * c.cw : 0.0); }
         }
         if (hdst >= 0) {
-            if (MODE == 0 && huu) Quu[hdst] += hval; else Qxx[hdst] += hval;
+            if (huu) Quu[hdst] += hval; else Qxx[hdst] += hval;
         }
-        // ---- affine residuals, gradient: thread tg < 24 owns lu[tg], thread 32 + i owns lx[i] (MODE 0)
+        // ---- affine residuals, gradient: thread tg < 24 owns lu[tg], thread 32 + i owns lx[i]
         const int tg = tid;
         if (tg < NU) {
             if (input) {
@@ -639,14 +779,13 @@ struct Srbd {
                     g = 2.0 * c.gq * c.inv_ms * pk[PK_RDD + r - 3] + 2.0 * (c.w_minf + c.w_fsw * a * a) * u[tg];
                     if (SDDP_CONE_ON(c)) { double val, cg[3], ch[6]; cone_terms_cold(c, u + 6 * i + 3, val, cg, ch); g += cg[r - 3]; }
                 }
-                if (MODE) { Qu[tg * LDUX] += g; Qu2[tg * LDUX] += g; }
-                else Qu[tg] += g;
+                Qu[tg] += g;
             }
-        } else if (MODE ? (tg >= 64 || tg < NU + 5) : (tg >= 32 && tg < 32 + NX)) {
-            // MODE 1: lx[0..31] on the third warp (the only one without Hessian entries above), lx[32..36] on threads 24..28
-            const int i = MODE ? (tg >= 64 ? tg - 64 : 32 + tg - NU) : tg - 32;
+        } else if (tg >= 32 && tg < 32 + NX) {
+            const int i = tg - 32;
             double g = 0.0;
-            if (i == 2) { if (track) g = 2.0 * c.w_r * (x[2] - c.com[2]); }
+            if (tail && (i == 2 || (i >= XW && i < XCD))) g = 2.0 * c.cw * ((i == 2) ? x[2] - c.com[2] : x[i]);
+            if (i == 2) { if (track) g += 2.0 * c.w_r * (x[2] - c.com[2]); }
             else if (i >= XO && i < XC) {
                 if (track) {
                     const int a = i - XO;
@@ -661,7 +800,7 @@ struct Srbd {
                     g = (foot < 2) ? -2.0 * c.w_rel * res : 2.0 * c.w_rel * res;
                 }
             } else if (i >= XRD && i < XW) { if (track) g = 2.0 * c.w_rdot * (x[i] - p[i - XRD]); }
-            else if (i >= XW && i < XCD) { if (track) g = 2.0 * c.w_w * (x[i] - p[3 + i - XW]); }
+            else if (i >= XW && i < XCD) { if (track) g += 2.0 * c.w_w * (x[i] - p[3 + i - XW]); }
             else if (i >= XCD) {
                 const int foot = (i - XCD) / 3, ax = (i - XCD) % 3;
                 if (ax < 2 && input) {
@@ -671,18 +810,22 @@ struct Srbd {
                 }
             }
             Qx[i] += g;
-            if (MODE) Qx2[i] += g;
         }
-        if (MODE == 0 && input && SDDP_CONE_ON(c)) {      // luu of the friction-cone barrier (MODE 1: the caller builds Quu itself)
+        if (input && SDDP_CONE_ON(c)) {      // inequality barriers: luu blocks per foot, contact-point velocity box on lx / lxx
             sync();
             if (tid < 36) {
                 const int i = tid / 9, ka = (tid % 9) / 3, kb = tid % 3;
                 double val, cg[3], ch[6];
                 cone_terms_cold(c, u + 6 * i + 3, val, cg, ch);
                 Quu[(6 * i + 3 + ka) * NU + 6 * i + 3 + kb] += ch[cone_hidx(ka, kb)];
+            } else if (tid < 48 && c.w_cdb != 0.0) {
+                const int id = XCD + tid - 36;
+                double val, g_, h_;
+                cdot_box_cold(c, x[id], val, g_, h_);
+                Qx[id] += g_; Qxx[id * NX + id] += h_;
             }
         }
-        if (MODE == 0) sync();      // MODE 1: the caller's block barrier at the end of the phase follows immediately
+        sync();
         PROF(22);
     }
 
@@ -696,11 +839,11 @@ struct Srbd {
         for (int e = tid; e < NX; e += nthr) Qx[e] = 0.0;
         for (int e = tid; e < NU; e += nthr) Qu[e] = 0.0;
         sync();
-        const bool track = kind != NODE_FIRST, input = kind != NODE_TERM;
-        if (input) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc)
+        const bool track = kind != NODE_FIRST, input = kind != NODE_TERM, tail = kind == NODE_TAIL;
+        if (input) {   // gq * ||wdot||^2 : 2 gq (Jac^T Jac + Hc)  (all zero on the LIP-style tail)
             const double* Jac = pk + PK_JAC;
             const double g2 = 2.0 * c.gq;
-            const bool exact = c.hessian_mode == 0;
+            const bool exact = c.hessian_mode == 0 && !tail;
             if (c.ztab != nullptr && nthr == ZT_THREADS) {
 #pragma unroll
                 for (int r = 0; r < ZT_ROUNDS; r++) {
@@ -792,7 +935,18 @@ struct Srbd {
             Qx[ia] += w2 * (res + sa * sa * x[ia]); Qx[ib] += w2 * (-res + sb * sb * x[ib]);
         }
         sync();
-        if (input && SDDP_CONE_ON(c)) {       // friction-cone barrier (extension): gradient and 3 x 3 Hessian per foot
+        if (tail && tid == 0) {                                       // lip_com_height, lip_zero_angular_momentum (isrbd_example.py:352-353)
+            Qxx[2 * NX + 2] += 2.0 * c.cw; Qx[2] += 2.0 * c.cw * (x[2] - c.com[2]);
+            for (int i = XW; i < XW + 3; i++) { Qxx[i * NX + i] += 2.0 * c.cw; Qx[i] += 2.0 * c.cw * x[i]; }
+        }
+        if (input && SDDP_CONE_ON(c) && c.w_cdb != 0.0 && tid >= 4 && tid < 16) {      // contact-point velocity box
+            const int id = XCD + tid - 4;
+            double val, g_, h_;
+            cdot_box_cold(c, x[id], val, g_, h_);
+            Qx[id] += g_; Qxx[id * NX + id] += h_;
+        }
+        if (tail || (input && SDDP_CONE_ON(c))) sync();
+        if (input && SDDP_CONE_ON(c)) {       // inequality barriers of the feet (extension): gradient and 3 x 3 Hessian per foot
             if (tid < 4) {
                 double val, cg[3], ch[6];
                 cone_terms_cold(c, u + 6 * tid + 3, val, cg, ch);
@@ -849,6 +1003,9 @@ struct Srbd {
         sync();
     }
 };
+using Srbd = SrbdT<false>;       // the reference's problem: inequalities dropped (prb.py:173-177, ddp.py:197-209)
+using SrbdI = SrbdT<true>;       // with the inequality barriers compiled in
+
 
 // =====================================================================================  LIP
 struct Lip {
@@ -857,9 +1014,9 @@ struct Lip {
     enum { XR = 0, XC = 3, XRD = 15, XCD = 18 };
 
     static constexpr int NPRE = 1;
-    SDDP_DEV static void accel(const DevCfg&, const double*, const double*, double*) {}
+    SDDP_DEV static void accel(const DevCfg&, const double*, const double*, double*, bool = false) {}
     SDDP_DEV static void accel_pre(const DevCfg&, const double*, double*) {}
-    SDDP_DEV static void accel_post(const DevCfg&, const double*, const double*, const double*, double*) {}
+    SDDP_DEV static void accel_post(const DevCfg&, const double*, const double*, const double*, double*, bool = false) {}
     SDDP_DEV static double xdot_i(const DevCfg& c, int i, const double* x, const double* u, const double*) {
         if (i < 15) return x[i + 15];
         if (i < 18) { int k = i - 15; return c.eta2 * (x[k] - u[k]) - (k == 2 ? c.g : 0.0); }   // prb.py:317-318

@@ -58,6 +58,7 @@ struct Smem {
     int iflag[4];
     __device__ static int backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
+    __device__ static void prep(const DevCfg& c, Smem<M>&, const double* X, const double* U, const double*, double* packs, int tid);
     __device__ double* Kbuf(int b) { return T + b * (NU * NX); }   // forward pass: K of node k in buffer k & 1
     __device__ double* scr() { return fx; }    // per-warp scratch
 };
@@ -65,7 +66,12 @@ enum { R_TOT = 0, R_ACC1 = 1, R_ACC2 = 2, R_G1 = 3, R_G2 = 4, R_YG = 5, R_W0 = 8
 
 struct SyncBlock { __device__ void operator()() const { __syncthreads(); } };
 
-SDDP_DEV int node_kind(int k, int N) { return k == 0 ? NODE_FIRST : (k == N ? NODE_TERM : NODE_MID); }
+// FIRST: node 0 (no trackers), TERM: node N (trackers only), TAIL: a node 1..N-1 of the LIP-style tail (SddpConfig.lip_tail_start), else MID
+SDDP_DEV int node_kind(const DevCfg& c, int k) {
+    if (k == 0) return NODE_FIRST;
+    if (k == c.N) return NODE_TERM;
+    return (c.lip_tail > 0 && k >= c.lip_tail) ? NODE_TAIL : NODE_MID;
+}
 
 SDDP_DEV double warp_sum(double s) {
 #pragma unroll
@@ -85,7 +91,7 @@ __device__ SDDP_NOINLINE double warp_node(const DevCfg& c, int kind, const doubl
                             double* xnext, const double* dk, double omr, double* sacc, int lane) {
     if (kind != NODE_TERM && M::NACC > 1) {
         double acc[M::NACC];
-        M::accel(c, xs, us, acc);
+        M::accel(c, xs, us, acc, kind == NODE_TAIL);
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < M::NACC; q++) sacc[q] = acc[q];
@@ -118,7 +124,7 @@ __device__ double defects_and_cost(const DevCfg& c, SM& S, const double* X, cons
     double* xn = ps + NP;
     double part = 0.0;
     for (int k = w; k <= N; k += NWARP) {
-        const int kind = node_kind(k, N);
+        const int kind = node_kind(c, k);
         for (int i = lane; i < NX; i += 32) xs[i] = X[(size_t)k * NX + i];
         if (k < N) for (int i = lane; i < NU; i += 32) us[i] = U[(size_t)k * NU + i];
         for (int i = lane; i < NP; i += 32) ps[i] = P[(size_t)k * NP + i];
@@ -153,7 +159,7 @@ __device__ void open_loop_rollout(const DevCfg& c, SM& S, double* X, const doubl
             __syncwarp();
             if (M::NACC > 1) {
                 double acc[M::NACC];
-                M::accel(c, xs, us, acc);
+                M::accel(c, xs, us, acc, node_kind(c, k) == NODE_TAIL);
                 if (lane == 0) {
 #pragma unroll
                     for (int q = 0; q < M::NACC; q++) S.sacc[0][q] = acc[q];
@@ -196,7 +202,7 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
     __syncthreads();
 
     for (int k = N - 1; k >= 0; k--) {
-        const int kind = node_kind(k, N);
+        const int kind = node_kind(c, k);
         for (int i = tid; i < NX; i += NT) {
             xk[i] = X[(size_t)k * NX + i];
             cg[i] = (D != nullptr) ? rho_b * D[(size_t)k * NX + i] : 0.0;
@@ -456,12 +462,12 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             __syncthreads();                  // u^_k visible
             PROF(25);
             STAMP(14);
-            const int kind = node_kind(k, N);
+            const int kind = node_kind(c, k);
             if (w == 0) {
                 double* xn_ = xb[(k + 1) & 1];
                 if (M::NACC > 1) {
                     double acc[M::NACC];
-                    M::accel_post(c, xc, ub, &S.sacc[0][0] + 16, acc);
+                    M::accel_post(c, xc, ub, &S.sacc[0][0] + 16, acc, kind == NODE_TAIL);
                     if (lane == 0) {
 #pragma unroll
                         for (int q = 0; q < M::NACC; q++) S.sacc[0][q] = acc[q];
@@ -517,7 +523,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             }
             for (int i = lane; i < NX; i += 32) Xo[(size_t)k * NX + i] = xh[i];
             __syncwarp();
-            J += warp_node<M>(c, node_kind(k, N), xh, uh, nb + NBL::OP, xn, nb + NBL::OD, omr, S.sacc[w], lane);
+            J += warp_node<M>(c, node_kind(c, k), xh, uh, nb + NBL::OP, xn, nb + NBL::OD, omr, S.sacc[w], lane);
             for (int i = lane; i < NX; i += 32) xh[i] = xn[i];
             __syncwarp();
         }
@@ -548,7 +554,7 @@ struct SolveArgs {
 template <class M>
 __device__ void compute_packs(const DevCfg& c, const double* X, const double* U, double* packs, int tid) {
     if (M::PACK > 1)
-        for (int k = tid; k < c.N; k += NT) M::pack(c, node_kind(k, c.N), X + (size_t)k * M::NX, U + (size_t)k * M::NU, packs + (size_t)k * M::PACK);
+        for (int k = tid; k < c.N; k += NT) M::pack(c, node_kind(c, k), X + (size_t)k * M::NX, U + (size_t)k * M::NU, packs + (size_t)k * M::PACK);
     __syncthreads();
 }
 
@@ -574,6 +580,7 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     if (hist) for (int i = tid; i < c.max_iters * 4; i += NT) hist[i] = 0.0;
     __syncthreads();
     double J, dmax = 0.0;
+    bool bad_start = false;      // a non-finite initial gap (NaN / inf in the warm start or x0)
     if (!c.ms) {
         open_loop_rollout<M, SM>(c, S, X, U, tid);
         for (int i = tid; i < N * NX; i += NT) d[i] = 0.0;
@@ -582,20 +589,21 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     } else {
         J = defects_and_cost<M, SM>(c, S, X, U, P, d, tid);
         double m = 0.0;
-        for (int i = tid; i < N * NX; i += NT) { double v = fabs(d[i]); if (v > m || v != v) m = v; }
+        bool nf = false;
+        for (int i = tid; i < N * NX; i += NT) { const double v = fabs(d[i]); nf |= !(v <= 1.79e308); if (v > m) m = v; }      // fmax would drop a NaN
         m = warp_max(m);
         if ((tid & 31) == 0) S.red[R_W0 + (tid >> 5)] = m;
-        __syncthreads();
+        bad_start = __syncthreads_or(nf) != 0;
         for (int i = 0; i < NWARP; i++) dmax = fmax(dmax, S.red[R_W0 + i]);
         __syncthreads();
     }
     double mu = c.mu0;
-    int status = 1 /*MAX_ITERS*/, it = 0;
+    int status = bad_start ? 4 /*NAN*/ : 1 /*MAX_ITERS*/, it = 0;
     PROF(4);
     PROF_INC(31);
-    for (it = 0; it < c.max_iters; it++) {
+    for (it = 0; it < (bad_start ? 0 : c.max_iters); it++) {
         PROF_INC(30);
-        compute_packs<M>(c, X, U, packs, tid);
+        SM::prep(c, S, X, U, P, packs, tid);
         PROF(0);
         bool reg_fail = false;
         while (SM::backward(c, S, X, U, P, d, packs, mu, Kg, kg, &S.red[12], dmax != 0.0, tid)) {
@@ -671,6 +679,11 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     __syncthreads();
     if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
     PROF(6);
+}
+
+template <class M>
+__device__ void Smem<M>::prep(const DevCfg& c, Smem<M>&, const double* X, const double* U, const double*, double* packs, int tid) {
+    compute_packs<M>(c, X, U, packs, tid);
 }
 
 template <class M>

@@ -51,7 +51,7 @@ class BatchedDDP:
     def __init__(self, cfg: SddpConfig, device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("srbd_horizon_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.L = _lib.lib(cone=cfg.friction_cone_weight != 0.0)      # inequality support is a separate build (csrc/Makefile)
+        self.L = _lib.lib()
         self.cfg = cfg.copy()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.nx, self.nu, self.np = DIMS[cfg.model]

@@ -19,26 +19,31 @@ def _header_functions():
     return sorted(set(re.findall(r"\b(sddp_[a-z0-9_]+)\s*\(", src)))
 
 
-@pytest.mark.parametrize("cone", [False, True])
-def test_library_exports_every_declared_symbol(cone):
-    """libsddp.so and libsddp_cone.so (the build with the friction-cone barrier) export the whole header."""
-    L = _lib.lib(cone=cone)
+def test_library_exports_every_declared_symbol():
+    """libsddp.so exports the whole header."""
+    L = _lib.lib()
     declared = _header_functions()
     assert len(declared) >= 15
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(_lib.SYMBOLS) == declared
-    assert L.sddp_abi_version() == 2 and L.sddp_config_size() == ctypes.sizeof(SddpConfig)
+    assert L.sddp_abi_version() == 3 and L.sddp_config_size() == ctypes.sizeof(SddpConfig)
 
 
-def test_inequality_option_needs_the_build_that_has_it():
-    """The product library is built without the barrier code (it costs the hot path 3 %); it must say so instead of
-    silently ignoring friction_cone_weight.  (No GPU needed: the config check comes first.)"""
-    cfg = make_config(MODEL_SRBD, 10, 0.05, {"friction_cone_weight": 1.0})
-    assert _lib.lib().sddp_workspace_bytes(ctypes.byref(cfg)) == 0
-    assert _lib.lib(cone=True).sddp_workspace_bytes(ctypes.byref(cfg)) > 0
-    cfg.friction_cone_mu = -1.0
-    assert _lib.lib(cone=True).sddp_workspace_bytes(ctypes.byref(cfg)) == 0
+def test_inequality_options_are_checked_without_a_gpu():
+    """One library serves the inequality extensions (friction cone, bounds) and the model scheduler; bad values are
+    rejected by the config check (no GPU needed: sddp_workspace_bytes returns 0 for a config it refuses)."""
+    L = _lib.lib()
+    cfg = make_config(MODEL_SRBD, 10, 0.05, {"friction_cone_weight": 1.0, "force_bound_weight": 1.0, "lip_tail_start": 4})
+    assert L.sddp_workspace_bytes(ctypes.byref(cfg)) > 0
+    for name, bad in (("friction_cone_mu", -1.0), ("force_bound_weight", -1.0), ("bound_sharpness", float("inf")), ("lip_tail_start", 11),
+                      ("mu_min", 0.0), ("mu_max", float("nan")), ("alpha_0", float("inf")), ("mu0", -1.0)):
+        c2 = cfg.copy()
+        setattr(c2, name, bad)
+        assert L.sddp_workspace_bytes(ctypes.byref(c2)) == 0, name
+    lip = make_config(MODEL_LIP, 10, 0.05)
+    lip.lip_tail_start = 3
+    assert L.sddp_workspace_bytes(ctypes.byref(lip)) == 0
 
 
 def test_config_layout_matches_header_and_oracle():

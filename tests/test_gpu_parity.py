@@ -19,6 +19,9 @@ from srbd_horizon_b200.problems import make_batch
 from tests.helpers import golden_cases, random_point, relerr
 
 EX_OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}   # dsrbd_example.py:55-58
+# inequality extensions (include/sddp.h): all of them on, tight enough to be active at the solution
+INEQ = dict(friction_cone_weight=5.0, friction_cone_mu=0.7, friction_cone_sharpness=8.0, force_bound_weight=2.0, force_bound=0.15,
+            unilateral_weight=3.0, cdot_bound_weight=4.0, cdot_bound=0.4, bound_sharpness=7.0)
 NAMES = ["fx", "fu", "lx", "lu", "lxx", "lux", "luu"]
 
 
@@ -151,6 +154,13 @@ def _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9, sol_tol=1e-9):
     (MODEL_SRBD, 20, {"dense_backward": 1, "mu0": 1e-3}),
     (MODEL_LIP, 20, {}),                                    # dlip_example.py configuration
     (MODEL_LIP, 20, {"multiple_shooting": 0}),
+    (MODEL_SRBD, 20, {"lip_tail_start": 10}),               # model scheduler: SRBD on nodes 0..9, LIP-style tail (isrbd_example.py:344-353)
+    (MODEL_SRBD, 50, {"lip_tail_start": 12}),
+    (MODEL_SRBD, 20, {"lip_tail_start": 1, "multiple_shooting": 0}),
+    (MODEL_SRBD, 20, {"lip_tail_start": 10, "dense_backward": 1}),
+    (MODEL_SRBD, 20, dict(INEQ)),                           # every inequality barrier on (friction cone, force box, unilaterality, velocity box)
+    (MODEL_SRBD, 20, dict(INEQ, dense_backward=1)),
+    (MODEL_SRBD, 30, dict(INEQ, lip_tail_start=15, defect_contraction_rate=0.5)),
 ])
 def test_solve_matches_oracle(model, N, opts):
     B = 24
@@ -158,6 +168,21 @@ def test_solve_matches_oracle(model, N, opts):
     r = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
     ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
     assert (ro["status"] == 0).mean() > 0.7
+    _compare_solve(cfg, b, r, ro, B)
+
+
+def test_config4_enumerated_schedules_match_oracle():
+    """BASELINE configs[4] proper: N = 50, two problems of every one of the 60 wpg gait schedules (action x phase),
+    dispatched grouped by schedule as bench.py does, against the oracle iteration by iteration."""
+    B, N = 120, 50
+    cfg = make_config(MODEL_SRBD, N, 0.05, EX_OPTS)
+    b = make_batch(MODEL_SRBD, N, B, enumerate_schedules=True)
+    assert len(set(zip(b["actions"].tolist(), b["s0"].tolist()))) == 60
+    s = BatchedDDP(cfg)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")
+    r = s.solve(t(b["x0"]), t(b["params"]), t(b["X0"]), t(b["U0"]), order="schedule")
+    ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
+    assert (ro["status"] == 0).all()
     _compare_solve(cfg, b, r, ro, B)
 
 
@@ -267,23 +292,27 @@ def test_lip_and_rough_warm_starts_match_oracle_random_configurations(seed):
         _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9 if model == MODEL_LIP else 1e-5, sol_tol=1e-9 if model == MODEL_LIP else 1e-6)
 
 
-@pytest.mark.parametrize("dense", [0, 1])
-def test_friction_cone_barrier_matches_oracle(dense):
-    """Inequality handling (off by default): stage-1 derivatives and whole solves with the friction-cone barrier, on
-    the structured and on the generic dense kernel."""
+@pytest.mark.parametrize("dense,extra", [(0, {}), (1, {}), (0, dict(INEQ, lip_tail_start=7)), (1, dict(INEQ, lip_tail_start=7))])
+def test_friction_cone_barrier_matches_oracle(dense, extra):
+    """Inequality handling and the LIP-style tail (both off by default): stage-1 derivatives of every node kind (3 = tail
+    node) and whole solves, on the structured and on the generic dense kernel."""
     opts = dict(EX_OPTS, friction_cone_weight=5.0, friction_cone_sharpness=8.0, friction_cone_mu=0.7, dense_backward=dense)
+    opts.update(extra)
     cfg = make_config(MODEL_SRBD, 20, 0.05, opts)
     s = BatchedDDP(cfg)
     rng = np.random.default_rng(9)
     M = 24
-    kind = np.array([0, 1, 2] * 8, dtype=np.int32)
+    kind = np.array(([0, 1, 2, 3] if extra else [0, 1, 2]) * (M // (4 if extra else 3)), dtype=np.int32)
     pts = [random_point(rng, MODEL_SRBD) for _ in range(M)]
     x, u, p = (np.stack([q[i] for q in pts]) for i in range(3))
+    x[:, 25:37] = rng.uniform(-0.5, 0.5, (M, 12))       # contact-point velocities near their box
     out = s.eval_derivatives(kind, x, u, p)
     for m in range(M):
         ref = O.derivs(cfg, int(kind[m]), x[m], u[m], p[m])
         ref["l"] = np.array(O.cost(cfg, int(kind[m]), x[m], u[m], p[m]))
-        for name in ("l", "lu", "luu", "lx", "lxx", "lux"):
+        if kind[m] != 2:
+            ref["f"] = O.dynamics(cfg, x[m], u[m], int(kind[m]))
+        for name in ("l", "lu", "luu", "lx", "lxx", "lux") + (("f", "fx", "fu") if kind[m] != 2 else ()):
             if kind[m] == 2 and name in ("lu", "luu", "lux"):
                 continue                                   # terminal node: no input terms
             a = cpu(out[name][m])

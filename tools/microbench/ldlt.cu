@@ -60,7 +60,20 @@ __device__ __forceinline__ void store_row(double* row, const double* a, int lo) 
     }
 }
 
-struct alignas(16) Sm { double Q0[NU * NU]; double Quu[NU * NU]; double invp[NU]; double rs[NU]; };
+struct alignas(16) Sm { double Q0[NU * NU]; double Quu[NU * NU]; double invp[NU]; double rs[NU]; double prow[2][NU]; };
+__device__ int g_zero;
+__device__ __forceinline__ double tie(double s, double v, int zero) { return __hiloint2double(__double2hiint(s) + (__double2hiint(v) & zero), __double2loint(s)); }
+template <int I0, int I1>
+__device__ __forceinline__ void axpy_part(double* a, const double* row, int lo, double s) {
+#pragma unroll
+    for (int i0 = I0; i0 < I1; i0 += 8) {
+        double2 c[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (i0 + 2 * q + 1 >= lo) c[q] = *reinterpret_cast<const double2*>(row + i0 + 2 * q);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int i = i0 + 2 * q; if (i >= lo) a[i] -= c[q].x * s; if (i + 1 >= lo) a[i + 1] -= c[q].y * s; }
+    }
+}
 
 __device__ long long g_split[3];
 template <int V>
@@ -111,6 +124,53 @@ __device__ __forceinline__ void ldlt(Sm& S, int lane) {
                 if (V != 7 && j + 2 < NU) axpy_row<true>(a, (V == 8 ? S.Q0 : S.Quu) + j * NU, j + 2, sj);
             }
         }
+    } else if (V >= 11 && V <= 17) {
+        // rolled over the pivot steps, rotating register frame, Et rows stored in the loop.
+        // 11: plain  12: first 16 tied to the seed, last 8 to the result  13: three ties  14: R = 8 plain  15: R = 2 plain  16: R = 4, unrolled loop (no roll)
+        constexpr int R = (V == 14) ? 8 : (V == 15 ? 2 : 4);
+        const int zero = g_zero;
+        double npinv = 0.0;
+#pragma unroll 1
+        for (int jb = 0; jb < NU; jb += R) {
+#pragma unroll
+            for (int s_ = 0; s_ < R; s_++) {
+                const int j = jb + s_;
+                double* pr = S.prow[s_ & 1];
+                const double m = a[s_];
+                if (V == 16 || V == 17) {      // symmetric publish: col_j[lane] = this lane's own a[j]
+                    if (lane >= jb && lane < NU) pr[lane - jb] = m;
+                    if (lane == j) { npinv = -myinv; pinv = myinv; S.invp[j] = myinv; }
+                } else if (lane == j) {
+                    npinv = -myinv; pinv = myinv;
+                    S.invp[j] = myinv;
+                    store_row<true>(pr, a, s_ + 1);
+                }
+                __syncwarp();
+                const double sj = (lane == j) ? 0.0 : S.invp[j] * m;
+                a[s_ + 1] -= pr[s_ + 1] * sj;
+                if (V == 11 || V >= 14) { myinv = fast_rcp(a[s_ + 1]); axpy_part<0, NU>(a, pr, s_ + 2, sj); if (V == 17) __syncwarp(); }
+                else {
+                    const double pn = a[s_ + 1];
+                    double x0;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(pn));
+                    if (V == 12) {
+                        axpy_part<0, 16>(a, pr, s_ + 2, tie(sj, x0, zero));
+                        double e_ = fma(-pn, x0, 1.0); x0 = fma(x0, e_, x0); e_ = fma(-pn, x0, 1.0); myinv = fma(x0, e_, x0);
+                        axpy_part<16, NU>(a, pr, s_ + 2, tie(sj, myinv, zero));
+                    } else {
+                        axpy_part<0, 8>(a, pr, s_ + 2, tie(sj, x0, zero));
+                        double e_ = fma(-pn, x0, 1.0); x0 = fma(x0, e_, x0);
+                        axpy_part<8, 16>(a, pr, s_ + 2, tie(sj, x0, zero));
+                        e_ = fma(-pn, x0, 1.0); myinv = fma(x0, e_, x0);
+                        axpy_part<16, NU>(a, pr, s_ + 2, tie(sj, myinv, zero));
+                    }
+                }
+                const double ev = (lane < j) ? npinv * m : (lane == j ? 1.0 : 0.0);
+                if (lane < NU) S.Quu[j * NU + lane] = ev;
+            }
+#pragma unroll
+            for (int q = 0; q < NU; q++) a[q] = (q + R < NU) ? a[q + R] : 0.0;
+        }
     } else if (V == 2) {
 #pragma unroll
         for (int j = 0; j < NU; j++) {
@@ -139,7 +199,9 @@ __device__ __forceinline__ void ldlt(Sm& S, int lane) {
     const long long c2 = clock64();
     if (lane < NU) S.rs[lane] = sqrt(pinv);
     __syncwarp();
-    if (V == 9) {          // the divergent-branch epilogue the solver had first (kept as a warning)
+    if (V >= 11) {         // rows of Et are in place; scale them here only so that the result can be compared
+        if (lane < NU) for (int i = 0; i < NU; i++) S.Quu[i * NU + lane] *= S.rs[i];
+    } else if (V == 9) {          // the divergent-branch epilogue the solver had first (kept as a warning)
         if (lane < NU) {
 #pragma unroll
             for (int i = 0; i < NU; i++) {
@@ -211,7 +273,7 @@ int main() {
     for (int i = 0; i < NU; i++) for (int j = 0; j < NU; j++) {
         double v = 0;
         for (int k = 0; k < NU; k++) v += G[i * NU + k] * G[j * NU + k];
-        Q[i * NU + j] = v + (i == j ? (i % 6 < 3 ? 2.0 : 2e4) : 0.0);
+        Q[i * NU + j] = v * ((i % 6 < 3) ? 1.0 : 30.0) * ((j % 6 < 3) ? 1.0 : 30.0) + (i == j ? (i % 6 < 3 ? 2.0 : 2e8) : 0.0);
     }
     // reference Es = L^-1 of the Cholesky factor (Es = D^-1/2 Lt^-1)
     for (int i = 0; i < NU * NU; i++) L[i] = 0;
@@ -246,5 +308,12 @@ int main() {
     run<8>("V8 = V0 column updates only (timing)", dQ, dout, dcyc, ref);
     run<9>("V9 = V0 with a branch per entry in the Es write", dQ, dout, dcyc, ref);
     run<10>("V10 every lane publishes its row-j entry", dQ, dout, dcyc, ref);
+    run<11>("V11 rolled R=4, rotating frame, Et rows in loop", dQ, dout, dcyc, ref);
+    run<12>("V12 = V11, update tied behind seed / result", dQ, dout, dcyc, ref);
+    run<13>("V13 = V11, update in thirds tied to the rcp stages", dQ, dout, dcyc, ref);
+    run<14>("V14 = V11 with R=8", dQ, dout, dcyc, ref);
+    run<15>("V15 = V11 with R=2", dQ, dout, dcyc, ref);
+    run<16>("V16 = V11 with the symmetric publish of V10", dQ, dout, dcyc, ref);
+    run<17>("V17 = V16 + a second warp sync per step", dQ, dout, dcyc, ref);
     return 0;
 }
