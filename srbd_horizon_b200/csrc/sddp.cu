@@ -497,6 +497,9 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
     h->variant = variant_of(h->cfg);
     h->smem_bytes = smem_of_variant(h->variant);
     h->eval_smem_bytes = cfg->model == SDDP_MODEL_SRBD ? sizeof(Smem<Srbd>) : sizeof(Smem<Lip>);
+    // the latency variants of the structured solve kernel (small batches)
+    if (h->variant == 0) CUC((cudaFuncSetAttribute(solve_kernel<Srbd, SmemSrbdL, MINB_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSrbdL))));
+    if (h->variant == 3) CUC((cudaFuncSetAttribute(solve_kernel<SrbdI, SmemSrbdIL, MINB_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSrbdIL))));
     if (h->variant == 0) CUC((set_smem_attr<Srbd, SmemSrbd, MINB_FAST>(&occ)));
     else if (h->variant == 1) CUC((set_smem_attr<Srbd, Smem<Srbd>, MINB_DENSE>(&occ)));
     else if (h->variant == 2) CUC((set_smem_attr<Lip, Smem<Lip>, MINB_DENSE>(&occ)));
@@ -610,6 +613,16 @@ int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* param
     a.order = (h->order_dev && h->order_n == B) ? h->order_dev : nullptr;
     a.sms = h->sms;
     int grid = B < h->slots ? B : h->slots;
+    // Batches that do not fill the GPU are latency bound: they take the latency variant of the structured kernel (unrolled
+    // factorisation, interleaved tensor-core chains); full batches are bound by instruction fetch and take the rolled one.
+    if (B < h->slots && (h->variant == 0 || h->variant == 3)) {
+        if (h->variant == 0) solve_kernel<Srbd, SmemSrbdL, MINB_FAST><<<grid, NT, h->smem_bytes, st>>>(h->dc, a);
+        else solve_kernel<SrbdI, SmemSrbdIL, MINB_FAST><<<grid, NT, h->smem_bytes, st>>>(h->dc, a);
+        h->launches++;
+        CU(cudaGetLastError());
+        CU(mark_last(h, st));
+        return 0;
+    }
     DISPATCH(h, solve_kernel, grid, st, h->dc, a);
     return 0;
 }

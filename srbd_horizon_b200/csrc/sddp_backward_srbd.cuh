@@ -24,7 +24,9 @@
 #include <cstddef>
 #include "sddp_solver.cuh"
 
-template <class MT>
+// LAT: the latency variant (batches smaller than the grid): unrolled factorisation and interleaved f/g tiles; otherwise the
+// throughput variant (rolled, a third of the code).  Same arithmetic up to the order of independent operations.
+template <class MT, bool LAT = false>
 struct alignas(16) SmemSrbdT {
     static constexpr int NX = 37, NU = 24, NP = 19;
     static constexpr int LDW = 44;   // row pitch of W: 88 words = 24 mod 32, so the 4 x 8 DMMA fragment loads are conflict free
@@ -53,6 +55,8 @@ struct alignas(16) SmemSrbdT {
 };
 using SmemSrbd = SmemSrbdT<Srbd>;
 using SmemSrbdI = SmemSrbdT<SrbdI>;
+using SmemSrbdL = SmemSrbdT<Srbd, true>;
+using SmemSrbdIL = SmemSrbdT<SrbdI, true>;
 static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 44, "forward K double buffer must fit in Qxx + W");
 static_assert(offsetof(SmemSrbd, W) - offsetof(SmemSrbd, Qxx) == ZT_QUX_OFF * sizeof(double) && SmemSrbd::LDW == ZT_LDUX, "descriptor table destinations (sddp.cu:build_ztab)");
 #define SDDP_INEQ_ON(c) (MT::HAS_INEQ && (c).ineq != 0)
@@ -127,8 +131,123 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
     out[2] = -v[0] * ho[1] + v[1] * ho[0] + v[2] * ho[3] - v[3] * ho[2];
 }
 
-template <class MT>
-__device__ int SmemSrbdT<MT>::backward(const DevCfg& c, SmemSrbdT<MT>& S, const double* X, const double* U, const double* P, const double* D,
+// d1 as a function of its own (SDDP_D1CALL): a call gives ptxas a fresh register budget for the 24-entry column frame;
+// inlined into the node loop, next to ~40 registers of long-lived solver state, the shared-memory loads of a pivot step
+// were serialised through one register quad (9.3 K cycles per factorisation against 6.5 K in tools/microbench/ldlt.cu).
+// Returns whether a pivot was not positive and finite.  LAT: the fully unrolled form (lowest latency, 21 KB of code).
+#ifndef SDDP_D1CALL
+#define SDDP_D1CALL 1
+#endif
+#ifndef SDDP_D1SKIP
+#define SDDP_D1SKIP 1
+#endif
+#if SDDP_D1CALL
+#define SDDP_D1ATTR __device__ __noinline__
+#else
+#define SDDP_D1ATTR __device__ __forceinline__
+#endif
+template <bool LAT, class SMT>
+SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
+    constexpr int NU = SMT::NU;
+    bool bad = false;
+    const int t = lane < NU ? lane : NU - 1;
+    double npinv = 0.0;                                          // -1 / pivot of this lane's column
+    if constexpr (LAT) {
+    // the fully unrolled form: lowest latency (small batches), 21 KB of straight-line code
+    double a[NU];
+#pragma unroll
+    for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
+    __syncwarp();
+    double myinv = fast_rcp(a[0]);          // lane 0's pivot
+#pragma unroll
+    for (int j = 0; j < NU; j++) {
+        if (lane == j) {
+            const double p = a[j];
+            bad = !(p > 0.0) || !isfinite(p);
+            npinv = -myinv;
+            S.invp[j] = myinv;
+            store_row<NU>(S.Quu + j * NU, a, j + 1);
+        }
+        __syncwarp();
+        if (j + 1 < NU) {
+            const double sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
+            a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
+            myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
+            if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NU; i += 2) {
+        const double v0 = (i > t) ? npinv * a[i] : (i == t ? 1.0 : 0.0);
+        const double v1 = (i + 1 > t) ? npinv * a[i + 1] : (i + 1 == t ? 1.0 : 0.0);
+        if (lane < NU) { S.Quu[i * NU + lane] = v0; S.Quu[(i + 1) * NU + lane] = v1; }
+    }
+    } else {
+    // Rolled over the pivot steps (R per loop trip): the kernel is instruction-fetch bound (profiles/README.md), and
+    // the fully unrolled factorisation was 21 KB of straight-line code per node.  The column lives in a rotating
+    // register frame b[q] = a_t[jb + q] (shifted down by R at the end of a trip, zero filled), so every index is
+    // static; the column of the pivot goes to a ping-pong row in the same frame, and row j of Et = Lt^-1 is stored
+    // at step j, when lane t < j holds its final E[j][t] = -a_t[j] / pivot_t (the multiplier of that step), which
+    // replaces the separate write-out pass.  The row scaling D^-1/2 of Es = D^-1/2 Et is applied where Es is used
+    // (phases h and g).  The frame is always updated whole: its zero tail costs a few FMAs in the shadow of the
+    // pivot chain, and a step stays one basic block.
+    // (Measured and rejected: nobody publishes a column, every lane stores its own a_i[j] = col_j[i] by symmetry.  25 % fewer
+    //  cycles per step, tools/microbench/ldlt.cu V10 / V16 -- but the elimination then loses the scaling invariance of
+    //  symmetric LDL^T: at the first SRBD node behind a LIP-style tail, cond(Quu) = 2e9, the gains come out at 2e-8
+    //  instead of 1e-13.)
+    constexpr int R = 4;
+    static_assert(NU % R == 0 && R % 2 == 0, "d1 frame");
+    double b[NU];
+#pragma unroll
+    for (int i = 0; i < NU; i++) b[i] = S.Quu[i * NU + t];
+    __syncwarp();
+    double myinv = fast_rcp(b[0]);                               // lane 0's pivot
+#pragma unroll 1
+    for (int jb = 0; jb < NU; jb += R) {
+#pragma unroll
+        for (int s_ = 0; s_ < R; s_++) {
+            const int j = jb + s_;
+            double* pr = S.prow[s_ & 1];                         // (R is even: j & 1 == s_ & 1)
+            const double m = b[s_];
+            if (lane == j) {
+                bad = !(m > 0.0) || !isfinite(m);
+                npinv = -myinv;
+                S.invp[j] = myinv;
+#if SDDP_D1SKIP
+                store_row<8>(pr, b, s_ + 1);
+                if (jb < 16) store_row<8>(pr + 8, b + 8, s_ + 1 - 8);
+                if (jb < 8) store_row<8>(pr + 16, b + 16, s_ + 1 - 16);
+#else
+                store_row<NU>(pr, b, s_ + 1);
+#endif
+            }
+            __syncwarp();
+            const double sj = (lane == j) ? 0.0 : S.invp[j] * m;
+            b[s_ + 1] -= pr[s_ + 1] * sj;
+            myinv = fast_rcp(b[s_ + 1]);                         // meaningful on lane j + 1
+#if SDDP_D1SKIP
+            // chunks of 8 entries wholly in the zero tail of the frame (q >= NU - jb) are skipped (warp-uniform)
+            axpy_row<NU, 0, 8>(b, pr, s_ + 2, sj);
+            if (jb < 16) axpy_row<NU, 8, 16>(b, pr, s_ + 2, sj);
+            if (jb < 8) axpy_row<NU, 16, 24>(b, pr, s_ + 2, sj);
+#else
+            axpy_row<NU>(b, pr, s_ + 2, sj);
+#endif
+            // row j of Et: (t < j) -multiplier / pivot_t, (t == j) 1, (t > j) 0
+            const double ev = (lane < j) ? npinv * m : (lane == j ? 1.0 : 0.0);
+            if (lane < NU) S.Quu[j * NU + lane] = ev;
+        }
+#pragma unroll
+        for (int q = 0; q < NU; q++) b[q] = (q + R < NU) ? b[q + R] : 0.0;
+    }
+    }
+    if (lane < NU) S.rs[lane] = sqrt(-npinv);
+    return bad;
+}
+
+template <class MT, bool LAT>
+__device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>& S, const double* X, const double* U, const double* P, const double* D,
                                        const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid) {
     using M = MT;
     using NBL = NodeBuf<MT>;
@@ -277,119 +396,7 @@ __device__ int SmemSrbdT<MT>::backward(const DevCfg& c, SmemSrbdT<MT>& S, const 
             // reciprocal latency.  Lane j skips step j and keeps taking part afterwards: its registers then carry
             // -pivot_j times column j of E = Lt^-1 (E[:,j] starts as -col_j / pivot_j and obeys the same linear recurrence),
             // so the inverse factor costs no extra arithmetic in lanes the factorisation no longer needs.
-#ifndef SDDP_D1V
-#define SDDP_D1V 1
-#endif
-#ifndef SDDP_D1R
-#define SDDP_D1R 4
-#endif
-#ifndef SDDP_D1SKIP
-#define SDDP_D1SKIP 1
-#endif
-            bool bad = false;
-            const int t = lane < NU ? lane : NU - 1;
-#if SDDP_D1V == 0
-            // (experiment: the fully unrolled form of round 1)
-            double a[NU];
-#pragma unroll
-            for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
-            __syncwarp();
-            double myinv = fast_rcp(a[0]);          // lane 0's pivot
-            double npinv = 0.0;
-#pragma unroll
-            for (int j = 0; j < NU; j++) {
-                if (lane == j) {
-                    const double p = a[j];
-                    bad = !(p > 0.0) || !isfinite(p);
-                    npinv = -myinv;
-                    S.invp[j] = myinv;
-                    store_row<NU>(S.Quu + j * NU, a, j + 1);
-                }
-                __syncwarp();
-                if (j + 1 < NU) {
-                    const double sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
-                    a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
-                    myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
-                    if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < NU; i += 2) {
-                const double v0 = (i > t) ? npinv * a[i] : (i == t ? 1.0 : 0.0);
-                const double v1 = (i + 1 > t) ? npinv * a[i + 1] : (i + 1 == t ? 1.0 : 0.0);
-                if (lane < NU) { S.Quu[i * NU + lane] = v0; S.Quu[(i + 1) * NU + lane] = v1; }
-            }
-#else
-            // Rolled over the pivot steps (R per loop trip): the kernel is instruction-fetch bound (profiles/README.md), and
-            // the fully unrolled factorisation was 21 KB of straight-line code per node.  The column lives in a rotating
-            // register frame b[q] = a_t[jb + q] (shifted down by R at the end of a trip, zero filled), so every index is
-            // static; the column of the pivot goes to a ping-pong row in the same frame, and row j of Et = Lt^-1 is stored
-            // at step j, when lane t < j holds its final E[j][t] = -a_t[j] / pivot_t (the multiplier of that step), which
-            // replaces the separate write-out pass.  The row scaling D^-1/2 of Es = D^-1/2 Et is applied where Es is used
-            // (phases h and g).  The frame is always updated whole: its zero tail costs a few FMAs in the shadow of the
-            // pivot chain, and a step stays one basic block.
-            // (SDDP_D1V == 3, experiment: nobody publishes a column, every lane stores its own a_i[j] = col_j[i] by symmetry.
-            //  25 % fewer cycles per step, tools/microbench/ldlt.cu V10 / V16 -- but the elimination then loses the scaling
-            //  invariance of symmetric LDL^T: at the first SRBD node behind a LIP-style tail, cond(Quu) = 2e9, the gains
-            //  come out at 2e-8 instead of 1e-13.  Not used.)
-            constexpr int R = SDDP_D1R;
-            static_assert(NU % R == 0 && R % 2 == 0, "d1 frame");
-            double b[NU];
-#pragma unroll
-            for (int i = 0; i < NU; i++) b[i] = S.Quu[i * NU + t];
-            __syncwarp();
-            double myinv = fast_rcp(b[0]);                               // lane 0's pivot
-            double npinv = 0.0;                                          // -1 / pivot of this lane's column
-#pragma unroll 1
-            for (int jb = 0; jb < NU; jb += R) {
-#pragma unroll
-                for (int s_ = 0; s_ < R; s_++) {
-                    const int j = jb + s_;
-                    double* pr = S.prow[s_ & 1];                         // (R is even: j & 1 == s_ & 1)
-                    const double m = b[s_];
-#if SDDP_D1V == 3
-                    if (lane >= jb && lane < NU) pr[lane - jb] = m;      // col_j[lane] (entries <= j are never read)
-                    if (lane == j) {
-                        bad = !(m > 0.0) || !isfinite(m);
-                        npinv = -myinv;
-                        S.invp[j] = myinv;
-                    }
-#else
-                    if (lane == j) {
-                        bad = !(m > 0.0) || !isfinite(m);
-                        npinv = -myinv;
-                        S.invp[j] = myinv;
-    #if SDDP_D1SKIP
-                        store_row<8>(pr, b, s_ + 1);
-                        if (jb < 16) store_row<8>(pr + 8, b + 8, s_ + 1 - 8);
-                        if (jb < 8) store_row<8>(pr + 16, b + 16, s_ + 1 - 16);
-#else
-                        store_row<NU>(pr, b, s_ + 1);
-#endif
-                    }
-#endif
-                    __syncwarp();
-                    const double sj = (lane == j) ? 0.0 : S.invp[j] * m;
-                    b[s_ + 1] -= pr[s_ + 1] * sj;
-                    myinv = fast_rcp(b[s_ + 1]);                         // meaningful on lane j + 1
-#if SDDP_D1SKIP
-                    // chunks of 8 entries wholly in the zero tail of the frame (q >= NU - jb) are skipped (warp-uniform)
-                    axpy_row<NU, 0, 8>(b, pr, s_ + 2, sj);
-                    if (jb < 16) axpy_row<NU, 8, 16>(b, pr, s_ + 2, sj);
-                    if (jb < 8) axpy_row<NU, 16, 24>(b, pr, s_ + 2, sj);
-#else
-                    axpy_row<NU>(b, pr, s_ + 2, sj);
-#endif
-                    // row j of Et: (t < j) -multiplier / pivot_t, (t == j) 1, (t > j) 0
-                    const double ev = (lane < j) ? npinv * m : (lane == j ? 1.0 : 0.0);
-                    if (lane < NU) S.Quu[j * NU + lane] = ev;
-                }
-#pragma unroll
-                for (int q = 0; q < NU; q++) b[q] = (q + R < NU) ? b[q + R] : 0.0;
-            }
-#endif
-            if (lane < NU) S.rs[lane] = sqrt(-npinv);
+            const bool bad = ldlt_warp<LAT>(S, lane);
             if (__any_sync(FULL, bad) && lane == 0) S.iflag[1] = 1;
             PROF_T(14, 0);
             STAMP(4); STAMP(5); STAMP(6); STAMP(7);
@@ -532,10 +539,7 @@ __device__ int SmemSrbdT<MT>::backward(const DevCfg& c, SmemSrbdT<MT>& S, const 
         //         Vx[37] = -|w0|^2 and y[37] = quy . k.
         // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
         //         at k0 = 8 I.
-#ifndef SDDP_FG_ROLLED
-#define SDDP_FG_ROLLED 1
-#endif
-#if SDDP_FG_ROLLED
+        if constexpr (!LAT) {
         // Warp w takes tiles w, w+4, w+8, w+12 of each product, one after the other through the same code (a rolled loop:
         // the kernel is bound by instruction fetch, not by the latency of the DMMA chains, and four interleaved copies of
         // the chains and epilogues were 12 KB of straight-line code per warp); the f and the g chain of a slot run
@@ -580,7 +584,7 @@ __device__ int SmemSrbdT<MT>::backward(const DevCfg& c, SmemSrbdT<MT>& S, const 
                 }
             }
         }
-#else
+        } else {
         // Warp w takes tiles w, w+4, w+8, w+12 of each product and runs their accumulation chains interleaved (a
         // single chain of six dependent DMMAs is latency bound); slot 3 of warp 3 is a dummy.
         {
@@ -654,7 +658,7 @@ __device__ int SmemSrbdT<MT>::backward(const DevCfg& c, SmemSrbdT<MT>& S, const 
                 }
             }
         }
-#endif
+        }
         STAMP(9);
         cp_wait_all();                         // the prefetch of node k-1 (issued in c1) is long done: this barrier also
         __syncthreads();                       // publishes it, so the next node starts without one of its own

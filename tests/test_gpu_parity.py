@@ -168,7 +168,10 @@ def test_solve_matches_oracle(model, N, opts):
     r = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
     ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
     assert (ro["status"] == 0).mean() > 0.7
-    _compare_solve(cfg, b, r, ro, B)
+    # At the first SRBD node behind a LIP-style tail the 1e6 penalties on w and r_z of the tail's value function make
+    # cond(Quu) = 2e9 (tools/dbg_bwd.py): gains agree to 1e-13 there, but one problem of this batch whose line search goes
+    # down to alpha = 1/16 carries 2.3e-9 into an intermediate cost (final X, U: 2e-11).  History tolerance 1e-8 for those.
+    _compare_solve(cfg, b, r, ro, B, hist_tol=1e-8 if opts.get("lip_tail_start") else 1e-9)
 
 
 def test_config4_enumerated_schedules_match_oracle():
@@ -183,7 +186,15 @@ def test_config4_enumerated_schedules_match_oracle():
     r = s.solve(t(b["x0"]), t(b["params"]), t(b["X0"]), t(b["U0"]), order="schedule")
     ro = O.solve_batch(cfg, b["x0"], b["params"], b["X0"], b["U0"], nthreads=8)
     assert (ro["status"] == 0).all()
-    _compare_solve(cfg, b, r, ro, B)
+    # Final trajectories, gains and every discrete decision agree at the usual 1e-9 for all 120 problems.  The per-
+    # iteration cost does too for all but the few problems that need 15+ iterations with line-search reductions (jump
+    # schedules started at rest): while their cost falls from 5e5 to 8e4 the iteration map amplifies rounding differences
+    # to 1.5e-8 in the intermediate costs before the iterates contract again (final cost: 1e-13).  Bound: 1e-7, and at
+    # most 5 % of the batch above 1e-9.
+    _compare_solve(cfg, b, r, ro, B, hist_tol=1e-7)
+    hist, iters = cpu(r.hist), cpu(r.iters)
+    e = np.array([relerr(hist[i, :iters[i], 0], ro["hist"][i, :iters[i], 0]) for i in range(B)])
+    assert (e > 1e-9).sum() <= B // 20, np.sort(e)[-8:]
 
 
 def test_solve_host_entry_point_and_ragged_batches():

@@ -92,7 +92,7 @@ if len(sys.argv) > 4:
                     return i
         raise SystemExit(f"marker not found: {f}: {marker}")
     B, Mo, So = "sddp_backward_srbd.cuh", "sddp_model.cuh", "sddp_solver.cuh"
-    marks = [("bwd load + top", ln(B, "__device__ int SmemSrbdT<MT>::backward(")), ("bwd c1 (Quu, gap)", ln(B, "// ---- c1:")),
+    marks = [("bwd load + top", ln(B, "__device__ int SmemSrbdT<MT, LAT>::backward(")), ("bwd c1 (Quu, gap)", ln(B, "// ---- c1:")),
              ("bwd d1 (warp-0 LDL^T, E)", ln(B, "// ---- d1:")), ("bwd c2 (T = V fx)", ln(B, "// ---- c2:")),
              ("bwd c3 (fx^T T, fu^T T)", ln(B, "// ---- c3:")), ("bwd e call", ln(B, "// ---- e:")),
              ("bwd h (Wn = Es B, DMMA)", ln(B, "// ---- h:")), ("bwd f,g (syrk + gains, DMMA)", ln(B, "// ---- f:")),
@@ -100,7 +100,7 @@ if len(sys.argv) > 4:
     spec = {name: [(B, lo, marks[i + 1][1] - 1)] for i, (name, lo) in enumerate(marks[:-1])}
     spec["bwd row helpers (axpy/store, in d1)"] = [(B, ln(B, "SDDP_DEV void axpy_row"), ln(B, "// out[b] = sum_a v[a] * (dt Aoo)") - 1)]
     spec["bwd dmma/rcp/contract helpers"] = [(B, ln(B, "SDDP_DEV void dmma884"), ln(B, "#ifndef SDDP_ROW128") - 1),
-                                             (B, ln(B, "// out[b] = sum_a v[a] * (dt Aoo)"), ln(B, "__device__ int SmemSrbdT<MT>::backward(") - 1)]
+                                             (B, ln(B, "// out[b] = sum_a v[a] * (dt Aoo)"), ln(B, "__device__ int SmemSrbdT<MT, LAT>::backward(") - 1)]
     srbd0, lip0 = ln(Mo, "struct SrbdT {"), ln(Mo, "struct Lip {")
     spec["model: accel/xdot/cost lanes"] = [(Mo, ln(Mo, "SDDP_DEV static void accel("), ln(Mo, "static void pack(") - 1)]
     spec["model: pack (thread per node)"] = [(Mo, ln(Mo, "static void pack("), ln(Mo, "SDDP_DEV static int zmap_x") - 1)]

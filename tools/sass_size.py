@@ -38,13 +38,13 @@ def mark(f, marker, nth=1):
     return None
 B, Mo, So = "sddp_backward_srbd.cuh", "sddp_model.cuh", "sddp_solver.cuh"
 try:
-    marks = [("bwd load + top", mark(B, "__device__ int SmemSrbdT<MT>::backward(")), ("bwd c1 (Quu, gap)", mark(B, "// ---- c1:")),
+    marks = [("bwd load + top", mark(B, "__device__ int SmemSrbdT<MT, LAT>::backward(")), ("bwd c1 (Quu, gap)", mark(B, "// ---- c1:")),
              ("bwd d1 (warp-0 LDL^T, E)", mark(B, "// ---- d1:")), ("bwd c2 (T = V fx)", mark(B, "// ---- c2:")),
              ("bwd c3 (fx^T T, fu^T T)", mark(B, "// ---- c3:")), ("bwd e call", mark(B, "// ---- e:")),
              ("bwd h (Wn = Es B, DMMA)", mark(B, "// ---- h:")), ("bwd f,g (syrk + gains, DMMA)", mark(B, "// ---- f:")),
              ("bwd mu path + model", mark(B, "if (mu != 0.0) {   // regularised step")), ("", 10 ** 9)]
     spec = {name: [(B, lo, marks[i + 1][1] - 1)] for i, (name, lo) in enumerate(marks[:-1])}
-    spec["bwd helpers (dmma, rcp, rows, contract)"] = [(B, 1, mark(B, "__device__ int SmemSrbdT<MT>::backward(") - 1)]
+    spec["bwd helpers (dmma, rcp, rows, contract)"] = [(B, 1, mark(B, "__device__ int SmemSrbdT<MT, LAT>::backward(") - 1)]
     spec["model: accel/xdot/cost lanes"] = [(Mo, mark(Mo, "SDDP_DEV static void accel_pre("), mark(Mo, "static void pack(") - 1)]
     spec["model: pack"] = [(Mo, mark(Mo, "static void pack("), mark(Mo, "SDDP_DEV static int zmap_x") - 1)]
     spec["model: expand (lx, lxx, lux terms)"] = [(Mo, mark(Mo, "SDDP_DEV static int zmap_x"), mark(Mo, "struct Lip {") - 1)]
