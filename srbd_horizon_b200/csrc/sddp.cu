@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int*
         for (int i = tid; i < NU; i += NT) uk[i] = u[(size_t)m * NU + i];
         for (int i = tid; i < NP; i += NT) pk[i] = p[(size_t)m * NP + i];
         __syncthreads();
-        if (tid == 0 && kd != NODE_TERM) M::pack(c, kd, xk, uk, pack);
+        if (tid == 0 && kd != NODE_TERM) M::pack(c, kd, xk, uk, pack, S.Vxx, 1);
         __syncthreads();
         M::expand(c, kd, xk, uk, pk, pack, S.Qx, S.Qu, S.Qxx, S.Qux, S.Quu, tid, NT, sync);
         if (kd != NODE_TERM) M::expand_f(c, xk, uk, pack, S.fx, S.fu, tid, NT, sync);

@@ -49,8 +49,10 @@ struct alignas(16) SmemSrbdT {
     __device__ static int backward(const DevCfg& c, SmemSrbdT& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
     // rigid-body packs of nodes 0..N-1, one thread per node
-    __device__ static void prep(const DevCfg& c, SmemSrbdT&, const double* X, const double* U, const double*, double* packs, int tid) {
-        compute_packs<MT>(c, X, U, packs, tid);
+    __device__ static void prep(const DevCfg& c, SmemSrbdT& S, const double* X, const double* U, const double*, double* packs, int tid) {
+        // scratch: VT, Qxx, W, Quu and the first vectors (all dead between the forward and the backward pass)
+        static_assert(offsetof(SmemSrbdT, Qu) >= PACK_SCRATCH * NT * sizeof(double), "pack scratch");
+        compute_packs<MT>(c, X, U, packs, S.VT, tid);
     }
 };
 using SmemSrbd = SmemSrbdT<Srbd>;
@@ -664,28 +666,46 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         __syncthreads();                       // publishes it, so the next node starts without one of its own
         STAMP(10);
         PROF(13);
-        if (mu != 0.0) {   // regularised step (rare): Vxx -= mu K^T K, Vx -= mu K^T k, gains re-read from global
+        if (mu != 0.0) {
+            // Regularised step (every backward pass after a failed factorisation or line search: 17 % of the node-iterations
+            // of BASELINE configs[4]): [Vxx Vx] -= mu [K k]^T [K k].  Qxx is dead after the barrier above, so [K | k] of this
+            // node (the gains this CTA just wrote; L2 hits) is staged there at the pitch of W and the product runs as the
+            // same upper-triangular tile syrk as phase f on the FP64 tensor cores; entry (37, 37) is |k|^2.
+            double* Ks = S.Qxx;
+            const double* Kn = Kg + (size_t)k * NU * NX;
+            for (int e = tid; e < NU * LDW; e += NT) {
+                const int l = e / LDW, cc = e - l * LDW;
+                Ks[e] = cc < NX ? Kn[l * NX + cc] : (cc == NX ? S.kk[l] : 0.0);
+            }
             __syncthreads();
-            for (int e = tid; e < NX * NX + NX; e += NT) {
-                const int i = e / NX, j = e % NX;
-                if (i < NX && j < i) continue;
-                double t = 0.0;
-                if (i < NX) {
-                    for (int l = 0; l < NU; l++) t += Kg[((size_t)k * NU + l) * NX + i] * Kg[((size_t)k * NU + l) * NX + j];
-                    const double v = S.VT[i * NX + j] - mu * t;
-                    S.VT[i * NX + j] = v;
-                    S.VT[j * NX + i] = v;
-                } else {
-                    for (int l = 0; l < NU; l++) t += Kg[((size_t)k * NU + l) * NX + j] * S.kk[l];
-                    S.Vx[j] -= mu * t;
+            const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll 1
+            for (int t = warp; t < 15; t += NWARP) {
+                int fI = 0, rem = t;
+                while (rem >= 5 - fI) { rem -= 5 - fI; fI++; }
+                const int fJ = fI + rem;
+                double f0 = 0.0, f1 = 0.0;
+                const double* rf = Ks + fc * LDW + fr;
+#pragma unroll
+                for (int k0 = 0; k0 < NU; k0 += 4) dmma884(f0, f1, rf[k0 * LDW + 8 * fI], rf[k0 * LDW + 8 * fJ]);
+                const int gi = 8 * fI + fr;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int gj = 8 * fJ + 2 * fc + e;
+                    const double acc = e ? f1 : f0;
+                    if (gj >= gi && gj < NX) {              // (gi <= gj < NX)
+                        const double v = S.VT[gi * NX + gj] - mu * acc;
+                        S.VT[gi * NX + gj] = v;
+                        S.VT[gj * NX + gi] = v;
+                    } else if (gj == NX && gi < NX) S.Vx[gi] -= mu * acc;
+                    else if (gj == NX && gi == NX) S.red[6] = acc;      // |k|^2
                 }
             }
             __syncthreads();                   // the next node reads Vxx, Vx right away
         }
         if (tid == 0) {   // model accumulators
             const double sw = -S.Vx[NX];        // |w0|^2 (see f)
-            double sk = 0.0;
-            if (mu != 0.0) for (int i = 0; i < NU; i++) sk += S.kk[i] * S.kk[i];
+            const double sk = (mu != 0.0) ? S.red[6] : 0.0;
             const double sq = S.y[NX];          // quy . k
             const double kQk = sw - mu * sk;
             S.red[R_TOT] += S.red[R_G1] + 0.5 * S.red[R_G2] + (-sw) + 0.5 * kQk;

@@ -407,7 +407,22 @@ struct SrbdT {
 
     // ---- single-thread rigid-body pack (see file header) ------------------------------------
     // pk[PK_WD..] wd(3) rdd(3) nu(3) Hww(9) Jac[3][34] Ho[4][34]
-    __device__ SDDP_NOINLINE static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk) {
+    // One thread per node.  Every per-thread array is indexed statically (registers): the four inertia derivatives
+    // Ja = dJ/dq_a, the only intermediate too large for that, live in the shared-memory scratch sc[(9 a + i) * ss]
+    // (ss = number of threads that share the scratch; the solve kernel's shared memory is idle between the forward and
+    // the backward pass).  The round-1 version kept Ra[4][9], Ja[4][9] in local memory: 1.1 K local loads per pack, with
+    // 200 packs in flight per SM they thrashed L1 (54 % hits) and the pack phase took 6 % of the solve.
+    // With v x e_b = (0, v2, -v1), (-v2, 0, v0), (v1, -v0, 0): the three columns M (v x e_b) of a lever arm or force.
+    SDDP_DEV static void put3(double* Jac, const double* M, int z0, double v0, double v1, double v2) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double m0 = M[3 * k], m1 = M[3 * k + 1], m2 = M[3 * k + 2];
+            Jac[k * NZ + z0] = m1 * v2 - m2 * v1;
+            Jac[k * NZ + z0 + 1] = m2 * v0 - m0 * v2;
+            Jac[k * NZ + z0 + 2] = m0 * v1 - m1 * v0;
+        }
+    }
+    __device__ SDDP_NOINLINE static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk, double* sc, int ss) {
         if (kind == NODE_TERM) return;
         if (kind == NODE_TAIL) {      // LIP-style tail: wdot = 0 identically, so no Jacobian and no curvature; rddot as usual
             for (int i = 0; i < PACK; i++) pk[i] = 0.0;
@@ -416,109 +431,134 @@ struct SrbdT {
             pk[PK_RDD + 0] = fsum[0] * c.inv_ms; pk[PK_RDD + 1] = fsum[1] * c.inv_ms; pk[PK_RDD + 2] = fsum[2] * c.inv_ms - c.g;
             return;
         }
-        const double* r = x;
-        const double* o = x + XO;
-        const double* w = x + XW;
-        double R[9], Ra[4][9], J[9], Ja[4][9], M[9];
+        const double o[4] = {x[XO], x[XO + 1], x[XO + 2], x[XO + 3]};
+        const double r[3] = {x[0], x[1], x[2]}, w[3] = {x[XW], x[XW + 1], x[XW + 2]};
+        double R[9], J[9], M[9];
         quat_R(o, R);
         inertia(c, R, J);
         m3::inv(J, M);
-        for (int a = 0; a < 4; a++) { quat_dR(o, a, Ra[a]); inertia_d(c, R, Ra[a], Ja[a]); }
-        double tau[3] = {0, 0, 0}, fsum[3] = {0, 0, 0};
+        double* Jac = pk + PK_JAC;   // [3][34]: Jac[:,p] = M (dh/dp - J_p wd), h = tau - w x J w
+        // d tau / d r_b = F x e_b;  d tau / d c_ib = -f_i x e_b;  d tau / d f_ib = (c_i - r) x e_b
+        double tau[3] = {0, 0, 0}, F[3] = {0, 0, 0};
+#pragma unroll
         for (int i = 0; i < 4; i++) {
             const double* ci = x + XC + 3 * i;
             const double* fi = u + 6 * i + 3;
-            double d[3] = {ci[0] - r[0], ci[1] - r[1], ci[2] - r[2]}, t[3];
-            m3::cross(d, fi, t);
-            for (int k = 0; k < 3; k++) { tau[k] += t[k]; fsum[k] += fi[k]; }
+            const double f[3] = {fi[0], fi[1], fi[2]}, d[3] = {ci[0] - r[0], ci[1] - r[1], ci[2] - r[2]};
+            double t[3];
+            m3::cross(d, f, t);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { tau[k] += t[k]; F[k] += f[k]; }
+            put3(Jac, M, ZC + 3 * i, -f[0], -f[1], -f[2]);
+            put3(Jac, M, ZF + 3 * i, d[0], d[1], d[2]);
         }
-        double Jw[3], wJw[3], h[3], wd[3];
+        put3(Jac, M, ZR, F[0], F[1], F[2]);
+        double Jw[3], wJw[3], wd[3];
         m3::mv(J, w, Jw);
         m3::cross(w, Jw, wJw);
-        for (int k = 0; k < 3; k++) h[k] = tau[k] - wJw[k];
+        const double h[3] = {tau[0] - wJw[0], tau[1] - wJw[1], tau[2] - wJw[2]};
         m3::mv(M, h, wd);
+#pragma unroll
         for (int k = 0; k < 3; k++) pk[PK_WD + k] = wd[k];
-        pk[PK_RDD + 0] = fsum[0] * c.inv_ms; pk[PK_RDD + 1] = fsum[1] * c.inv_ms; pk[PK_RDD + 2] = fsum[2] * c.inv_ms - c.g;
-
-        // Jacobian columns: Jac[:,p] = M (dh/dp - J_p wd)
-        double* Jac = pk + PK_JAC;   // [3][34]
-        auto put_col = [&](int pcol, const double* col) {
-            double out[3];
-            m3::mv(M, col, out);
-            Jac[pcol] = out[0]; Jac[NZ + pcol] = out[1]; Jac[2 * NZ + pcol] = out[2];
-        };
-        for (int b = 0; b < 3; b++) {
-            // d tau / d r_b = sum_i skew(f_i)[:,b];  d tau / d c_ib = -skew(f_i)[:,b];  d tau / d f_ib = skew(c_i - r)[:,b]
-            double colr[3] = {0, 0, 0};
-            for (int i = 0; i < 4; i++) {
-                const double* ci = x + XC + 3 * i;
-                const double* fi = u + 6 * i + 3;
-                double d[3] = {ci[0] - r[0], ci[1] - r[1], ci[2] - r[2]};
-                double cf[3] = {m3::skew_ab(fi, 0, b), m3::skew_ab(fi, 1, b), m3::skew_ab(fi, 2, b)};
-                double cc[3] = {-cf[0], -cf[1], -cf[2]};
-                double cd[3] = {m3::skew_ab(d, 0, b), m3::skew_ab(d, 1, b), m3::skew_ab(d, 2, b)};
-                for (int k = 0; k < 3; k++) colr[k] += cf[k];
-                put_col(ZC + 3 * i + b, cc);
-                put_col(ZF + 3 * i + b, cd);
+        pk[PK_RDD + 0] = F[0] * c.inv_ms; pk[PK_RDD + 1] = F[1] * c.inv_ms; pk[PK_RDD + 2] = F[2] * c.inv_ms - c.g;
+        {   // d(-w x Jw)/dw_b = Jw x e_b - w x J[:,b]
+            double cw[9];      // cw[3 k + b]
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const double Jcol[3] = {J[b], J[3 + b], J[6 + b]};
+                double t[3];
+                m3::cross(w, Jcol, t);
+#pragma unroll
+                for (int k = 0; k < 3; k++) cw[3 * k + b] = -t[k];
             }
-            put_col(ZR + b, colr);
-            // d(-w x Jw)/dw_b = skew(Jw)[:,b] - (skew(w) J)[:,b]
-            double Jcol[3] = {J[b], J[3 + b], J[6 + b]}, t[3];
-            m3::cross(w, Jcol, t);
-            double cw_[3] = {m3::skew_ab(Jw, 0, b) - t[0], m3::skew_ab(Jw, 1, b) - t[1], m3::skew_ab(Jw, 2, b) - t[2]};
-            put_col(ZW + b, cw_);
+            cw[3 * 1 + 0] += Jw[2]; cw[3 * 2 + 0] -= Jw[1];
+            cw[3 * 0 + 1] -= Jw[2]; cw[3 * 2 + 1] += Jw[0];
+            cw[3 * 0 + 2] += Jw[1]; cw[3 * 1 + 2] -= Jw[0];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const double col[3] = {cw[b], cw[3 + b], cw[6 + b]};
+                double out[3];
+                m3::mv(M, col, out);
+                Jac[ZW + b] = out[0]; Jac[NZ + ZW + b] = out[1]; Jac[2 * NZ + ZW + b] = out[2];
+            }
         }
-        for (int a = 0; a < 4; a++) {
-            double Jaw[3], t[3], Jawd[3];
-            m3::mv(Ja[a], w, Jaw); m3::cross(w, Jaw, t); m3::mv(Ja[a], wd, Jawd);
-            double co[3] = {-t[0] - Jawd[0], -t[1] - Jawd[1], -t[2] - Jawd[2]};
-            put_col(ZO + a, co);
+        const bool exact = c.hessian_mode == 0;
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {      // d/do_a: -w x (J_a w) - J_a wd
+            double Ra[9], Ja[9], Jaw[3], t[3], Jawd[3], out[3];
+            quat_dR(o, a, Ra);
+            inertia_d(c, R, Ra, Ja);
+            m3::mv(Ja, w, Jaw); m3::cross(w, Jaw, t); m3::mv(Ja, wd, Jawd);
+            const double co[3] = {-t[0] - Jawd[0], -t[1] - Jawd[1], -t[2] - Jawd[2]};
+            m3::mv(M, co, out);
+            Jac[ZO + a] = out[0]; Jac[NZ + ZO + a] = out[1]; Jac[2 * NZ + ZO + a] = out[2];
+            if (exact) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) sc[(9 * a + i) * ss] = Ja[i];
+            }
         }
-        if (c.hessian_mode != 0) return;
+        if (!exact) return;
 
         // curvature of lambda^T wdot at lambda = wd:  nu = M wd
         //   phi_pq = nu^T ( h_pq - J_p wd_q - J_q wd_p - J_pq wd )
-        double nu[3];
+        double nu[3], wxn[3], nxw[3];
         m3::mv(M, wd, nu);
+#pragma unroll
         for (int k = 0; k < 3; k++) pk[PK_NU + k] = nu[k];
-        double wxn[3];
         m3::cross(w, nu, wxn);       // w^T skew(nu) A w = (w x nu) . (A w)
-        {   // (w,w): skew(nu) J - J skew(nu)
-            for (int a = 0; a < 3; a++)
-                for (int b = 0; b < 3; b++) {
-                    double s1 = 0, s2 = 0;
-                    for (int k = 0; k < 3; k++) { s1 += m3::skew_ab(nu, a, k) * J[3 * k + b]; s2 += J[3 * a + k] * m3::skew_ab(nu, k, b); }
-                    pk[PK_HWW + 3 * a + b] = s1 - s2;
-                }
-        }
+        m3::cross(nu, w, nxw);
+        // (w,w): skew(nu) J - J skew(nu)
+        pk[PK_HWW + 0] = (-nu[2] * J[3] + nu[1] * J[6]) - (J[1] * nu[2] - J[2] * nu[1]);
+        pk[PK_HWW + 1] = (-nu[2] * J[4] + nu[1] * J[7]) - (-J[0] * nu[2] + J[2] * nu[0]);
+        pk[PK_HWW + 2] = (-nu[2] * J[5] + nu[1] * J[8]) - (J[0] * nu[1] - J[1] * nu[0]);
+        pk[PK_HWW + 3] = (nu[2] * J[0] - nu[0] * J[6]) - (J[4] * nu[2] - J[5] * nu[1]);
+        pk[PK_HWW + 4] = (nu[2] * J[1] - nu[0] * J[7]) - (-J[3] * nu[2] + J[5] * nu[0]);
+        pk[PK_HWW + 5] = (nu[2] * J[2] - nu[0] * J[8]) - (J[3] * nu[1] - J[4] * nu[0]);
+        pk[PK_HWW + 6] = (-nu[1] * J[0] + nu[0] * J[3]) - (J[7] * nu[2] - J[8] * nu[1]);
+        pk[PK_HWW + 7] = (-nu[1] * J[1] + nu[0] * J[4]) - (-J[6] * nu[2] + J[8] * nu[0]);
+        pk[PK_HWW + 8] = (-nu[1] * J[2] + nu[0] * J[5]) - (J[6] * nu[1] - J[7] * nu[0]);
         double* Ho = pk + PK_HO;   // [4][34]
-        for (int a = 0; a < 4; a++) {
-            double Jan[3];
-            m3::mv(Ja[a], nu, Jan);
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {      // first pass: Ho[a][q] = -(J_a nu) . Jac[:,q]
+            double Ja[9], Jan[3];
+#pragma unroll
+            for (int i = 0; i < 9; i++) Ja[i] = sc[(9 * a + i) * ss];
+            m3::mv(Ja, nu, Jan);
+#pragma unroll 2
             for (int q = 0; q < NZ; q++) Ho[a * NZ + q] = -(Jan[0] * Jac[q] + Jan[1] * Jac[NZ + q] + Jan[2] * Jac[2 * NZ + q]);
         }
-        for (int a = 0; a < 4; a++) {
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {      // second pass: the terms of the (o, w) and (o, o) blocks
+            double Ja[9], Ra[9], Jaw[3], t1[3], t2[3];
+#pragma unroll
+            for (int i = 0; i < 9; i++) Ja[i] = sc[(9 * a + i) * ss];
             // (o_a, w): (skew(nu) J_a - J_a skew(nu)) w = nu x (J_a w) - J_a (nu x w)
-            double Jaw[3], t1[3], nxw[3], t2[3];
-            m3::mv(Ja[a], w, Jaw); m3::cross(nu, Jaw, t1);
-            m3::cross(nu, w, nxw); m3::mv(Ja[a], nxw, t2);
+            m3::mv(Ja, w, Jaw); m3::cross(nu, Jaw, t1); m3::mv(Ja, nxw, t2);
+#pragma unroll
             for (int k = 0; k < 3; k++) Ho[a * NZ + ZW + k] += t1[k] - t2[k];
             // symmetric counterpart of the -(J_b nu).Jac[:,o_a] term inside the (o,o) block
+            const double ca[3] = {Jac[ZO + a], Jac[NZ + ZO + a], Jac[2 * NZ + ZO + a]};
+            quat_dR(o, a, Ra);
+#pragma unroll 1
             for (int b = 0; b < 4; b++) {
-                double Jbn[3];
-                m3::mv(Ja[b], nu, Jbn);
-                Ho[a * NZ + ZO + b] -= Jbn[0] * Jac[ZO + a] + Jbn[1] * Jac[NZ + ZO + a] + Jbn[2] * Jac[2 * NZ + ZO + a];
-            }
-            for (int b = a; b < 4; b++) {
-                double eb[4] = {0, 0, 0, 0};
-                eb[b] = 1.0;
-                double Rab[9], Jab[9], t3[3], t4[3];
-                quat_dR(eb, a, Rab);
-                inertia_dd(c, R, Ra[a], Ra[b], Rab, Jab);
-                m3::mv(Jab, w, t3); m3::mv(Jab, wd, t4);
-                double v = m3::dot(wxn, t3) - m3::dot(nu, t4);
-                Ho[a * NZ + ZO + b] += v;
-                if (b != a) Ho[b * NZ + ZO + a] += v;
+                double Jb[9], Jbn[3];
+#pragma unroll
+                for (int i = 0; i < 9; i++) Jb[i] = sc[(9 * b + i) * ss];
+                m3::mv(Jb, nu, Jbn);
+                double acc = -(Jbn[0] * ca[0] + Jbn[1] * ca[1] + Jbn[2] * ca[2]);
+                if (b >= a) {      // J_ab term, symmetric: also lands on Ho[b][o_a]
+                    double eb[4], Rb[9], Rab[9], Jab[9], t3[3], t4[3];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) eb[i] = (i == b) ? 1.0 : 0.0;
+                    quat_dR(o, b, Rb);
+                    quat_dR(eb, a, Rab);
+                    inertia_dd(c, R, Ra, Rb, Rab, Jab);
+                    m3::mv(Jab, w, t3); m3::mv(Jab, wd, t4);
+                    const double v = m3::dot(wxn, t3) - m3::dot(nu, t4);
+                    acc += v;
+                    if (b != a) Ho[b * NZ + ZO + a] += v;
+                }
+                Ho[a * NZ + ZO + b] += acc;
             }
         }
     }
@@ -1056,7 +1096,7 @@ struct Lip {
         }
         return s;
     }
-    __device__ static void pack(const DevCfg&, int, const double*, const double*, double*) {}
+    __device__ static void pack(const DevCfg&, int, const double*, const double*, double*, double*, int) {}
 
     template <int LDUX = NX, class Sync>
     __device__ static void expand(const DevCfg& c, int kind, const double* x, const double* u, const double* p, const double*,

@@ -551,10 +551,13 @@ struct SolveArgs {
     int sms;
 };
 
+// `scratch`: PACK_SCRATCH * NT doubles of shared memory nobody else uses during the call (one column per thread)
+constexpr int PACK_SCRATCH = 36;
 template <class M>
-__device__ void compute_packs(const DevCfg& c, const double* X, const double* U, double* packs, int tid) {
+__device__ void compute_packs(const DevCfg& c, const double* X, const double* U, double* packs, double* scratch, int tid) {
     if (M::PACK > 1)
-        for (int k = tid; k < c.N; k += NT) M::pack(c, node_kind(c, k), X + (size_t)k * M::NX, U + (size_t)k * M::NU, packs + (size_t)k * M::PACK);
+        for (int k = tid; k < c.N; k += NT)
+            M::pack(c, node_kind(c, k), X + (size_t)k * M::NX, U + (size_t)k * M::NU, packs + (size_t)k * M::PACK, scratch + tid, NT);
     __syncthreads();
 }
 
@@ -682,8 +685,9 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
 }
 
 template <class M>
-__device__ void Smem<M>::prep(const DevCfg& c, Smem<M>&, const double* X, const double* U, const double*, double* packs, int tid) {
-    compute_packs<M>(c, X, U, packs, tid);
+__device__ void Smem<M>::prep(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double*, double* packs, int tid) {
+    static_assert(M::PACK == 1 || sizeof(Smem<M>) >= PACK_SCRATCH * NT * sizeof(double), "pack scratch");
+    compute_packs<M>(c, X, U, packs, S.Vxx, tid);      // the matrices are dead between the forward and the backward pass
 }
 
 template <class M>

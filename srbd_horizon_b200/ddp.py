@@ -77,7 +77,7 @@ class BatchedDDP:
             if not hasattr(self.cfg, k):
                 raise KeyError(k)
             setattr(self.cfg, k, v)
-        _lib.check(self.L.sddp_set_config(self.h, ctypes.byref(self.cfg)), self.h)
+        _lib.check(self.L.sddp_set_config(self.h, ctypes.byref(self.cfg)), self.h, self.L)
 
     # -- helpers ------------------------------------------------------------------------------
     def _t(self, a, shape, name):
@@ -153,10 +153,10 @@ class BatchedDDP:
                 raise ValueError("order must have one entry per problem")
         with torch.cuda.device(dev):
             if order is not None:
-                _lib.check(self.L.sddp_set_dispatch_order(self.h, _ptr(order), B, 0), self.h)
+                _lib.check(self.L.sddp_set_dispatch_order(self.h, _ptr(order), B, 0), self.h, self.L)
             try:
                 _lib.check(self.L.sddp_solve_batch(self.h, B, _ptr(x0), _ptr(params), _ptr(X), _ptr(U), _ptr(K), _ptr(k),
-                                                   _ptr(hist), _ptr(iters), _ptr(status), _ptr(cost), self._stream()), self.h)
+                                                   _ptr(hist), _ptr(iters), _ptr(status), _ptr(cost), self._stream()), self.h, self.L)
             finally:
                 if order is not None:
                     self.L.sddp_set_dispatch_order(self.h, None, 0, 0)
@@ -196,11 +196,11 @@ class BatchedDDP:
                 raise ValueError("order must have one entry per problem")
         with torch.cuda.device(self.device):
             if order is not None:
-                _lib.check(self.L.sddp_set_dispatch_order(self.h, _np_ptr(order), B, 1), self.h)
+                _lib.check(self.L.sddp_set_dispatch_order(self.h, _np_ptr(order), B, 1), self.h, self.L)
             try:
                 _lib.check(self.L.sddp_solve_batch_host(self.h, B, _np_ptr(x0), _np_ptr(params), _np_ptr(X0), _np_ptr(U0), _np_ptr(X),
                                                         _np_ptr(U), _np_ptr(K), _np_ptr(k), _np_ptr(hist), _np_ptr(iters), _np_ptr(status),
-                                                        _np_ptr(cost)), self.h)
+                                                        _np_ptr(cost)), self.h, self.L)
             finally:
                 if order is not None:
                     self.L.sddp_set_dispatch_order(self.h, None, 0, 1)
@@ -219,7 +219,7 @@ class BatchedDDP:
                    lux=z(M, nu, nx), luu=z(M, nu, nu))
         with torch.cuda.device(dev):
             _lib.check(self.L.sddp_eval_derivatives(self.h, M, _ptr(kind), _ptr(x), _ptr(u), _ptr(p), *[_ptr(out[n]) for n in
-                       ("f", "fx", "fu", "l", "lx", "lu", "lxx", "lux", "luu")], self._stream()), self.h)
+                       ("f", "fx", "fu", "l", "lx", "lu", "lxx", "lux", "luu")], self._stream()), self.h, self.L)
         return out
 
     def backward_pass(self, X, U, params, defect, mu: float):
@@ -232,7 +232,7 @@ class BatchedDDP:
         dV = torch.empty((B, 3), dtype=torch.float64, device=dev); rc = torch.empty(B, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(self.L.sddp_backward_pass(self.h, B, _ptr(X), _ptr(U), _ptr(params), _ptr(defect), float(mu), _ptr(K),
-                                                 _ptr(k), _ptr(dV), _ptr(rc), self._stream()), self.h)
+                                                 _ptr(k), _ptr(dV), _ptr(rc), self._stream()), self.h, self.L)
         return rc, K, k, dV
 
     def forward_pass(self, alpha, rho, x0, X, U, params, defect, K, k, trajectories: bool = True):
@@ -250,7 +250,7 @@ class BatchedDDP:
         Un = torch.empty((B, na, N, nu), dtype=torch.float64, device=dev) if trajectories else None
         with torch.cuda.device(dev):
             _lib.check(self.L.sddp_forward_pass(self.h, B, na, _ptr(alpha), _ptr(rho), _ptr(x0), _ptr(X), _ptr(U), _ptr(params),
-                                                _ptr(defect), _ptr(K), _ptr(k), _ptr(Jn), _ptr(Xn), _ptr(Un), self._stream()), self.h)
+                                                _ptr(defect), _ptr(K), _ptr(k), _ptr(Jn), _ptr(Xn), _ptr(Un), self._stream()), self.h, self.L)
         return Jn, Xn, Un
 
     def defects(self, X, U, params):
@@ -260,7 +260,7 @@ class BatchedDDP:
         D = torch.empty((B, N, nx), dtype=torch.float64, device=self.device)
         cost = torch.empty(B, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.L.sddp_defects(self.h, B, _ptr(X), _ptr(U), _ptr(params), _ptr(D), _ptr(cost), self._stream()), self.h)
+            _lib.check(self.L.sddp_defects(self.h, B, _ptr(X), _ptr(U), _ptr(params), _ptr(D), _ptr(cost), self._stream()), self.h, self.L)
         return D, cost
 
 

@@ -71,7 +71,7 @@ class BatchedMPC:
         self.step_counter = torch.zeros(B, dtype=torch.int32, device=dev)
         c_init_z = float(solver.cfg.foot[2])
         tabs = [np.ascontiguousarray(a, dtype=np.float64) for a in gait_tables(c_init_z)]
-        _lib.check(solver.L.sddp_set_gait_tables(solver.h, *[a.ctypes.data_as(ctypes.c_void_p) for a in tabs]), solver.h)
+        _lib.check(solver.L.sddp_set_gait_tables(solver.h, *[a.ctypes.data_as(ctypes.c_void_p) for a in tabs]), solver.h, solver.L)
         self.last = None
 
     def _p(self, t):
@@ -85,13 +85,13 @@ class BatchedMPC:
         assert a.shape == (self.B,) and cmd.shape == (self.B, 3)
         with torch.cuda.device(s.device):
             self._lib.check(s.L.sddp_mpc_advance(s.h, self.B, self._p(self.params), self._p(a), self._p(self.step_counter),
-                                                 self._p(cmd), s._stream()), s.h)
+                                                 self._p(cmd), s._stream()), s.h, s.L)
 
     def plant_step(self):
         torch = self._torch
         s = self.solver
         with torch.cuda.device(s.device):
-            self._lib.check(s.L.sddp_plant_step(s.h, self.B, self._p(self.state), self._p(self.U), s.N * s.nu, s._stream()), s.h)
+            self._lib.check(s.L.sddp_plant_step(s.h, self.B, self._p(self.state), self._p(self.U), s.N * s.nu, s._stream()), s.h, s.L)
 
     def tick(self, actions, rdot_ref_cmd, gains: bool = False):
         """One closed-loop tick for all B robots; returns the BatchResult of the solve (X, U alias the warm start)."""

@@ -123,7 +123,8 @@ def test_backward_reports_cholesky_failure():
     assert int(cpu(rc)[0]) == rc_o == 10
 
 
-def _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9, sol_tol=1e-9):
+def _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9, sol_tol=1e-9, k_tol=None):
+    k_tol = sol_tol if k_tol is None else k_tol
     iters, status = cpu(r.iters), cpu(r.status)
     hist, X, U, K, k, cost = cpu(r.hist), cpu(r.X), cpu(r.U), cpu(r.K), cpu(r.k), cpu(r.cost)
     np.testing.assert_array_equal(status, ro["status"])
@@ -137,7 +138,7 @@ def _compare_solve(cfg, b, r, ro, B, hist_tol=1e-9, sol_tol=1e-9):
         assert relerr(X[i], ro["X"][i]) < sol_tol and relerr(U[i], ro["U"][i]) < sol_tol, i
         if status[i] != 3:   # REG_FAILED leaves the gains of an aborted backward pass: undefined
             assert relerr(K[i], ro["K"][i]) < 10 * sol_tol, i
-            assert np.max(np.abs(k[i] - ro["k"][i])) < sol_tol * max(1.0, np.max(np.abs(ro["U"][i]))), i
+            assert np.max(np.abs(k[i] - ro["k"][i])) < k_tol * max(1.0, np.max(np.abs(ro["U"][i]))), i
         assert cost[i] == pytest.approx(ro["cost"][i], rel=max(1e-9, 1e-3 * sol_tol))
 
 
@@ -190,11 +191,15 @@ def test_config4_enumerated_schedules_match_oracle():
     # iteration cost does too for all but the few problems that need 15+ iterations with line-search reductions (jump
     # schedules started at rest): while their cost falls from 5e5 to 8e4 the iteration map amplifies rounding differences
     # to 1.5e-8 in the intermediate costs before the iterates contract again (final cost: 1e-13).  Bound: 1e-7, and at
-    # most 5 % of the batch above 1e-9.
-    _compare_solve(cfg, b, r, ro, B, hist_tol=1e-7)
-    hist, iters = cpu(r.hist), cpu(r.iters)
+    # most 5 % of the batch above 1e-9.  The feed-forward term k of the last backward pass (it does not vanish: the solve
+    # stops on the cost-reduction test) carries the same amplification, 3.4e-8 absolute on problem 73 (13 iterations)
+    # for the structured kernel and 1.4e-8 for the generic dense one (tools/dbg_config4.py): same bound, same 5 % cap.
+    _compare_solve(cfg, b, r, ro, B, hist_tol=1e-7, k_tol=1e-7)
+    hist, iters, k = cpu(r.hist), cpu(r.iters), cpu(r.k)
     e = np.array([relerr(hist[i, :iters[i], 0], ro["hist"][i, :iters[i], 0]) for i in range(B)])
     assert (e > 1e-9).sum() <= B // 20, np.sort(e)[-8:]
+    ek = np.array([np.max(np.abs(k[i] - ro["k"][i])) / max(1.0, np.max(np.abs(ro["U"][i]))) for i in range(B)])
+    assert (ek > 1e-9).sum() <= B // 20, np.sort(ek)[-8:]
 
 
 def test_solve_host_entry_point_and_ragged_batches():
