@@ -355,6 +355,7 @@ def main():
     gX, gU, gc = r.X[:cpu_n].cpu().numpy(), r.U[:cpu_n].cpu().numpy(), r.cost[:cpu_n].cpu().numpy()
     per = np.array([max(rel(gX[i], ro["X"][i]), rel(gU[i], ro["U"][i])) for i in range(cpu_n)])
     parity = {"problems": cpu_n, "parity_max_rel_err": float(per.max()), "parity_median_rel_err": float(np.median(per)),
+              "frac_above_1e-9": float((per > 1e-9).mean()),
               "cost_max_rel_err": float(np.max(np.abs(gc - ro["cost"]) / np.abs(ro["cost"]))),
               "iters_equal": bool((r.iters[:cpu_n].cpu().numpy() == ro["iters"]).all()), "status_equal": bool((r.status[:cpu_n].cpu().numpy() == ro["status"]).all()),
               "host_path_equals_device_path": bool(np.array_equal(rh["X"], r.X.cpu().numpy()) and np.array_equal(rh["U"], r.U.cpu().numpy())),
@@ -398,25 +399,23 @@ def closed_loop(kind, dev, ticks, skip, with_cpu=True):
         pr = P.LIPProblem(); pr.createLIPProblem(ns, 1.0)
     gpu_ms, cpu_ms, iters = [], [], []
     solver = DDPSolver(pr.prb, dict(EX_OPTS), device=dev) if dev is not None else None
-    cfgm = solver.cfg if solver else make_config(MODEL_SRBD if kind == "srbd" else 1, ns, 0.05, EX_OPTS)
-    if kind == "srbd":
-        gen = wpg.steps_phase(pr.f, pr.c, pr.cdot, float(pr.initial_foot_position[0][2]), pr.c_ref, pr.w_ref,
-                              pr.orientation_tracking_gain, pr.cdot_switch, ns, number_of_legs=2, contact_model=2)
-    else:
-        gen = wpg.steps_phase(None, pr.c, pr.cdot, float(pr.initial_foot_position[0][2]), pr.c_ref, None, None, pr.cdot_switch, ns,
-                              number_of_legs=2, contact_model=2)
+    cfgm = solver.cfg if solver else make_config(pr.prb.model, ns, pr.prb.getDt(), EX_OPTS, pr.prb.robot, pr.prb.gains)
+    aux = pr
+    if kind != "srbd":      # dlip_example.py:33-36,85 hands the SRBD problem's w_ref / gain parameters to the gait scheduler
+        aux = P.SRBDProblem(); aux.createSRBDProblem(ns, 1.0)
+    gen = wpg.steps_phase(getattr(pr, "f", None), pr.c, pr.cdot, float(pr.initial_foot_position[0][2]), pr.c_ref, aux.w_ref,
+                          aux.orientation_tracking_gain, pr.cdot_switch, ns, number_of_legs=2, contact_model=2)
     state = pr.getInitialState()
     ustat = pr.getStaticInput()
     if solver:
         solver.set_u_warmstart(np.tile(ustat[:, None], (1, ns)))
     Xc = np.tile(state, (ns + 1, 1)); Uc = np.tile(ustat, (ns, 1))
-    from srbd_horizon_b200.ddp import flat_parameters_of
     for tick in range(ticks):
         if solver:
             solver.setInitialState(state)
         mpc_tick_references(pr, [0.5, 0.0, 0.0] if tick >= 10 else [0.0, 0.0, 0.0])
         gen.set("step" if tick >= 10 else "standing")
-        params = solver.get_params_value() if solver else flat_parameters_of(pr.prb)
+        params = pr.prb.flat_parameters()
         if solver:
             t0 = time.perf_counter()
             solver.solve()
@@ -427,8 +426,12 @@ def closed_loop(kind, dev, ticks, skip, with_cpu=True):
             cpu_ms.append(1e3 * (time.perf_counter() - t0))
             Xc, Uc = ro["X"][0], ro["U"][0]
             iters.append(int(ro["iters"][0]))
-        u0 = solver.getSolutionDict()["u_opt"][:, 0] if solver else Uc[0]
-        state = plant_step(solver.ddp_solver, state, u0) if solver else O.plant_step(cfgm, state, u0)
+        if solver:
+            state = plant_step(solver.ddp_solver, state, solver.getSolutionDict()["u_opt"][:, 0])
+        else:      # CPU arm alone: the oracle's Euler step, SRBD quaternion renormalised (dsrbd_example.py:158-160)
+            state = O.dynamics(cfgm, state, Uc[0], 0)
+            if kind == "srbd":
+                state[3:7] /= np.linalg.norm(state[3:7])
     return gpu_ms[skip:], cpu_ms[skip:], iters[skip:]
 
 

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SDDP_ABI_VERSION 3
+#define SDDP_ABI_VERSION 4
 
 enum { SDDP_MODEL_SRBD = 0, SDDP_MODEL_LIP = 1 };
 enum { SDDP_INERTIA_LITERAL = 0, SDDP_INERTIA_ROTATED = 1 };   /* prb.py:99 as written / README.md:2 intent */
@@ -181,6 +181,30 @@ int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *
  * copied, used by sddp_solve_batch_host (checked to be a permutation).  order = NULL clears.  The reference has no
  * counterpart (one problem per process). */
 int sddp_set_dispatch_order(SddpHandle *h, const int32_t *order, int n, int on_host);
+
+/* ---- result records and the multi-GPU gather (SURVEY.md 2.1 K5 "result pack", 8e) ----
+ * A result record is one contiguous fp64 block per problem:  X[(N+1) nx] | U[N nu] | cost | iters | status
+ * (sddp_record_doubles(h) doubles; iters and status as doubles).  A slab is an array of records, one per problem of the
+ * WHOLE batch (all GPUs).  After sddp_set_result_peers(h, n, slabs, first) every sddp_solve_batch of this handle stores
+ * the record of its problem b, the moment that problem is finished, into slabs[p] + (first + b) * record for every
+ * p < n -- from inside the solve kernel, by the CTA that solved it.  With the slabs of all GPUs of the box in the list
+ * (peer memory: cudaDeviceEnablePeerAccess in one process, or the IPC helpers below across processes) this IS the
+ * all-gather of the results: it rides over NVLink / NVSwitch while the rest of the batch is still being solved, and no
+ * collective follows the kernel.  The caller only has to order "all kernels finished" before anyone reads a slab
+ * (any barrier: a 4-byte all-reduce, MPI_Barrier, cudaStreamWaitEvent on IPC events).  With n = 1 and the own slab it
+ * is the packed send buffer for ONE ncclAllGather / MPI_Allgather instead of five.  n = 0 (default) switches it off.
+ * The reference has no counterpart (one problem per process, results returned by pyddp in host memory). */
+enum { SDDP_RECORD_TAIL = 3, SDDP_IPC_HANDLE_BYTES = 64, SDDP_MAX_RESULT_PEERS = 8 };
+long long sddp_record_doubles(const SddpHandle *h);
+/* (Re)allocates the handle-owned slab of n_records records with plain cudaMalloc (exportable with sddp_ipc_export);
+ * n_records = 0 frees it.  Freed by sddp_destroy. */
+int sddp_slab_alloc(SddpHandle *h, long long n_records, double **out);
+/* Thin wrappers of cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) / cudaIpcCloseMemHandle so that a
+ * host language without CUDA bindings can exchange the 64 handle bytes over any channel it has. */
+int sddp_ipc_export(const void *dev_ptr, unsigned char handle[SDDP_IPC_HANDLE_BYTES]);
+int sddp_ipc_open(const unsigned char handle[SDDP_IPC_HANDLE_BYTES], void **dev_ptr);
+int sddp_ipc_close(void *dev_ptr);
+int sddp_set_result_peers(SddpHandle *h, int n_peers, double *const *slabs, long long first_record);
 
 /* ---- receding-horizon glue on the device (the caller side of the path: dsrbd_example.py:102-131,158-160, wpg.py:68-101) ----
  * gait tables of wpg.steps_phase (wpg.py:19-64): four arrays of 21 entries, l_cycle, l_switch, r_cycle, r_switch (host pointers) */

@@ -37,6 +37,12 @@ SYMBOLS = {
     "sddp_fp64_peak_tflops": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), _vp]),
     "sddp_set_dispatch_order": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
     "sddp_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
+    "sddp_record_doubles": (ctypes.c_longlong, [_vp]),
+    "sddp_slab_alloc": (ctypes.c_int, [_vp, ctypes.c_longlong, ctypes.POINTER(_vp)]),
+    "sddp_ipc_export": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "sddp_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "sddp_ipc_close": (ctypes.c_int, [_vp]),
+    "sddp_set_result_peers": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.c_longlong]),
 }
 
 _libs = {}
@@ -64,7 +70,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.sddp_abi_version() != 3:
+        if L.sddp_abi_version() != 4:
             raise RuntimeError(f"{os.path.basename(path)} ABI version mismatch")
         if L.sddp_config_size() != ctypes.sizeof(SddpConfig):
             raise RuntimeError("SddpConfig layout mismatch between config.py and include/sddp.h")

@@ -219,6 +219,8 @@ struct SddpHandle {
     cudaEvent_t ev_last; bool ev_last_valid;   // recorded after the last launch that uses the workspace
     int host_chunk;
     long long launches;
+    double* slab; long long slab_records;       // handle-owned result slab (sddp_slab_alloc)
+    int n_peers; double* peers[SDDP_MAX_PEERS]; long long first_record;      // sddp_set_result_peers
     const int32_t* order_dev; int order_n;      // caller-owned device permutation for sddp_solve_batch
     std::vector<int32_t> order_host;            // copy of the host permutation for sddp_solve_batch_host
     char err[512];
@@ -536,6 +538,7 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
 int sddp_destroy(SddpHandle* h) {
     if (!h) return 0;
     if (h->ws_d) cudaFree(h->ws_d);
+    if (h->slab) cudaFree(h->slab);
     if (h->ztab) cudaFree(h->ztab);
     if (h->gait) cudaFree(h->gait);
     if (h->stage) cudaFree(h->stage);
@@ -612,6 +615,13 @@ int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* param
     a.counter = h->counter;
     a.order = (h->order_dev && h->order_n == B) ? h->order_dev : nullptr;
     a.sms = h->sms;
+    a.n_peers = h->n_peers; a.first = h->first_record;
+    {
+        int nx, nu, np, pack;
+        model_dims(h->cfg.model, nx, nu, np, pack);
+        a.rec = (h->cfg.N + 1) * nx + h->cfg.N * nu + SDDP_RECORD_TAIL;
+    }
+    for (int p = 0; p < SDDP_MAX_PEERS; p++) a.peers[p] = p < h->n_peers ? h->peers[p] : nullptr;
     int grid = B < h->slots ? B : h->slots;
     // Batches that do not fill the GPU are latency bound: they take the latency variant of the structured kernel (unrolled
     // factorisation, interleaved tensor-core chains); full batches are bound by instruction fetch and take the rolled one.
@@ -737,7 +747,10 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         memcpy(hi + Bz * (s_x0 + s_p), X0, Bz * s_X * 8);
         memcpy(hi + Bz * (s_x0 + s_p + s_X), U0, Bz * s_U * 8);
         CU(cudaMemcpyAsync(d_x0, hi, in_bytes, cudaMemcpyHostToDevice, h->st_cmp));
+        const int keep_peers = h->n_peers;
+        h->n_peers = 0;
         int rc1 = sddp_solve_batch(h, B, d_x0, d_p, d_X, d_U, K ? d_K : nullptr, kff ? d_k : nullptr, hist ? d_h : nullptr, d_it, d_st, d_c, h->st_cmp);
+        h->n_peers = keep_peers;
         if (rc1) return rc1;
         char* ho = (char*)h->hstage + in_bytes;
         CU(cudaMemcpyAsync(ho, d_X, out_bytes, cudaMemcpyDeviceToHost, h->st_cmp));
@@ -766,7 +779,8 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         for (size_t i = 0; i < Bz; i++) { const int g = h->order_host[i], c = g / chunk; ordl[fill[c]++] = g - c * chunk; }
     }
     const int32_t* saved_order = h->order_dev;
-    const int saved_n = h->order_n;
+    const int saved_n = h->order_n, saved_peers = h->n_peers;
+    h->n_peers = 0;      // result records are a feature of the device entry point (chunk-local problem indices here)
     std::vector<cudaEvent_t> ev_in(nchunk), ev_cmp(nchunk);
     int rc = 0;
     for (int c = 0; c < nchunk; c++) {
@@ -803,12 +817,74 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         cp(status + o, d_st + o, n * 4, cudaMemcpyDeviceToHost, h->st_out);
         if (e != cudaSuccess) rc = fail(h, SDDP_ECUDA, "solve_batch_host (copy out): %s%s", cudaGetErrorString(e), "");
     }
-    h->order_dev = saved_order; h->order_n = saved_n;
+    h->order_dev = saved_order; h->order_n = saved_n; h->n_peers = saved_peers;
     cudaError_t e1 = cudaStreamSynchronize(h->st_in), e2 = cudaStreamSynchronize(h->st_cmp), e3 = cudaStreamSynchronize(h->st_out);
     for (int c = 0; c < nchunk; c++) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_cmp[c]); }
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(h, SDDP_ECUDA, "solve_batch_host (sync): %s%s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)), "");
+    return 0;
+}
+
+// ---- result records and the multi-GPU gather
+static_assert(SDDP_MAX_PEERS == SDDP_MAX_RESULT_PEERS, "include/sddp.h");
+long long sddp_record_doubles(const SddpHandle* h) {
+    if (!h) return 0;
+    int nx, nu, np, pack;
+    model_dims(h->cfg.model, nx, nu, np, pack);
+    return (long long)(h->cfg.N + 1) * nx + (long long)h->cfg.N * nu + SDDP_RECORD_TAIL;
+}
+
+int sddp_slab_alloc(SddpHandle* h, long long n_records, double** out) {
+    if (!h || !out || n_records < 0) return h ? fail(h, SDDP_EINVAL, "%s%s", "slab_alloc: bad arguments", "") : SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
+    for (int p = 0; p < h->n_peers; p++)
+        if (h->peers[p] == h->slab) return fail(h, SDDP_EINVAL, "%s%s", "slab_alloc: the current slab is still a result peer (sddp_set_result_peers(h, 0, NULL, 0) first)", "");
+    if (h->slab) { cudaFree(h->slab); h->slab = nullptr; h->slab_records = 0; }
+    *out = nullptr;
+    if (n_records == 0) return 0;
+    // plain cudaMalloc: the allocation base is what cudaIpcGetMemHandle exports
+    cudaError_t e = cudaMalloc((void**)&h->slab, (size_t)n_records * (size_t)sddp_record_doubles(h) * sizeof(double));
+    if (e != cudaSuccess) { h->slab = nullptr; return fail(h, SDDP_ENOMEM, "cudaMalloc(result slab): %s%s", cudaGetErrorString(e), ""); }
+    h->slab_records = n_records;
+    *out = h->slab;
+    return 0;
+}
+
+int sddp_ipc_export(const void* dev_ptr, unsigned char handle[SDDP_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == SDDP_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    if (!dev_ptr || !handle) return SDDP_EINVAL;
+    cudaIpcMemHandle_t m;
+    cudaError_t e = cudaIpcGetMemHandle(&m, const_cast<void*>(dev_ptr));
+    if (e != cudaSuccess) return fail(nullptr, SDDP_ECUDA, "cudaIpcGetMemHandle: %s%s", cudaGetErrorString(e), "");
+    memcpy(handle, &m, sizeof(m));
+    return 0;
+}
+
+int sddp_ipc_open(const unsigned char handle[SDDP_IPC_HANDLE_BYTES], void** dev_ptr) {
+    if (!handle || !dev_ptr) return SDDP_EINVAL;
+    cudaIpcMemHandle_t m;
+    memcpy(&m, handle, sizeof(m));
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, m, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { *dev_ptr = nullptr; return fail(nullptr, SDDP_ECUDA, "cudaIpcOpenMemHandle: %s%s", cudaGetErrorString(e), ""); }
+    return 0;
+}
+
+int sddp_ipc_close(void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    return e == cudaSuccess ? 0 : fail(nullptr, SDDP_ECUDA, "cudaIpcCloseMemHandle: %s%s", cudaGetErrorString(e), "");
+}
+
+int sddp_set_result_peers(SddpHandle* h, int n_peers, double* const* slabs, long long first_record) {
+    if (!h) return SDDP_EINVAL;
+    if (n_peers < 0 || n_peers > SDDP_MAX_PEERS || (n_peers > 0 && !slabs) || first_record < 0)
+        return fail(h, SDDP_EINVAL, "%s%s", "set_result_peers: 0..8 slabs, first_record >= 0", "");
+    for (int p = 0; p < n_peers; p++)
+        if (!slabs[p]) return fail(h, SDDP_EINVAL, "%s%s", "set_result_peers: NULL slab", "");
+    h->n_peers = n_peers;
+    h->first_record = first_record;
+    for (int p = 0; p < SDDP_MAX_PEERS; p++) h->peers[p] = p < n_peers ? slabs[p] : nullptr;
     return 0;
 }
 

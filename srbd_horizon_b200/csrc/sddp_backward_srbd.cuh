@@ -140,6 +140,9 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
 #ifndef SDDP_D1CALL
 #define SDDP_D1CALL 1
 #endif
+#ifndef SDDP_ROTATE
+#define SDDP_ROTATE 0      // 148: rotate the warp roles of the d phase by blockIdx / 148 (A/B experiment, profiles/README.md)
+#endif
 #ifndef SDDP_D1SKIP
 #define SDDP_D1SKIP 1
 #endif
@@ -384,7 +387,13 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 
         const double* o = xk + M::XO;
         const double* w = xk + M::XW;
-        if (warp == 0) {
+#if SDDP_ROTATE
+        // Role rotation (experiment): the factorisation warp of co-resident CTAs sits on different SM sub-partitions
+        const int vwarp = (warp + 4 - ((blockIdx.x / SDDP_ROTATE) & 3)) & 3, vt = vwarp * 32 + lane - 32;
+#else
+        const int vwarp = warp, vt = tid - 32;
+#endif
+        if (vwarp == 0) {
             // ---- d1: Quu + mu I = Lt D Lt^T; lane t owns column t.  Es = D^-1/2 Lt^-1 overwrites S.Quu row by row.
             if (has_gap) {   // gap terms of the model (the only use of cg after c1)
                 double g1 = 0, g2 = 0, yg = 0;
@@ -404,7 +413,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             STAMP(4); STAMP(5); STAMP(6); STAMP(7);
         } else {
             // ---- c2: T = Vxx' fx = V + dt V A, in place, one thread per row (warps 1-2)
-            const int r_ = tid - 32;
+            const int r_ = vt;
             if (r_ < NX) {
                 double* row = S.VT + r_ * NX;
                 double vr[3], vo[4], vw[3];
@@ -438,7 +447,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             bar_named(2, 96);
             // ---- c3: columns of fx^T (.) and fu^T (.) applied to T (j < 37), v+ (j = 37) and ys (j = 38); warps 1-3.
             //          Plain stores: lxx, lux, lx, lu are added afterwards (expand MODE 1)
-            for (int task = tid - 32; task < 39 * 3; task += 96) {
+            for (int task = vt; task < 39 * 3; task += 96) {
                 const int j = task % 39, g = task / 39;
                 const double* col = (j < NX) ? S.VT + j : (j == NX ? S.vp : S.ys);
                 const int cs = (j < NX) ? NX : 1;      // stride between rows of this "column"
@@ -495,11 +504,11 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             STAMP(5);
             bar_named(2, 96);
             // ---- e: + lx, lu, lxx, lux of the node (one pass, disjoint destinations, no barrier inside)
-            M::apply_rec(c, kind, xk, uk, pk, pack, S.Qxx, S.Qx, S.qxy, S.W + NX, S.W + NX + 1, tid - 32);
+            M::apply_rec(c, kind, xk, uk, pk, pack, S.Qxx, S.Qx, S.qxy, S.W + NX, S.W + NX + 1, vt);
             PROF_T(17, 32);
             STAMP(6);
         }
-        if (warp != 0) STAMP(7);
+        if (vwarp != 0) STAMP(7);
         __syncthreads();
         STAMP(8);
         PROF(11);

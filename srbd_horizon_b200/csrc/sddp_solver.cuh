@@ -20,6 +20,9 @@
 #ifndef SDDP_FIRST_WAVE_SINGLE
 #define SDDP_FIRST_WAVE_SINGLE 1
 #endif
+#ifndef SDDP_MAX_PEERS
+#define SDDP_MAX_PEERS 8     // GPUs of one NVLink box
+#endif
 constexpr int NT = 128;      // threads per CTA
 constexpr int NWARP = NT / 32;
 constexpr int NCAND = NWARP; // line-search candidates evaluated per wave
@@ -549,6 +552,11 @@ struct SolveArgs {
     int* counter;
     const int* order;     // dispatch order (permutation of 0..B-1) or nullptr
     int sms;
+    // result records (include/sddp.h, sddp_set_result_peers): X | U | cost | iters | status of problem b goes to
+    // peers[p] + (first + b) * rec for every p < n_peers -- own slab and, over NVLink, the slabs of the other GPUs
+    int n_peers, rec;
+    long long first;
+    double* peers[SDDP_MAX_PEERS];
 };
 
 // `scratch`: PACK_SCRATCH * NT doubles of shared memory nobody else uses during the call (one column per thread)
@@ -681,6 +689,20 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     }
     __syncthreads();
     if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
+    if (a.n_peers > 0) {
+        // Gather without a collective: this problem's record is stored straight into every GPU's whole-batch slab (peer
+        // memory over NVLink / NVSwitch) while the other CTAs keep solving, so the transfer rides under the batch.
+        const size_t off = (size_t)(a.first + b) * a.rec;
+        for (size_t i = tid; i < xsz + usz + 3; i += NT) {
+            double v;
+            if (i < xsz) v = X[i];
+            else if (i < xsz + usz) v = U[i - xsz];
+            else v = (i == xsz + usz) ? J : (i == xsz + usz + 1 ? (double)it : (double)status);
+#pragma unroll
+            for (int p = 0; p < SDDP_MAX_PEERS; p++)
+                if (p < a.n_peers) a.peers[p][off + i] = v;
+        }
+    }
     PROF(6);
 }
 

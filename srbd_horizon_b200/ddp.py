@@ -124,9 +124,11 @@ class BatchedDDP:
         o1 = torch.argsort(effort, descending=True, stable=True)
         return o1[torch.argsort(group[o1], stable=True)].to(torch.int32)
 
-    def solve(self, x0, params, X0, U0, gains: bool = True, history: bool = True, inplace: bool = False, order=None) -> BatchResult:
+    def solve(self, x0, params, X0, U0, gains: bool = True, history: bool = True, inplace: bool = False, order=None, gather=None) -> BatchResult:
         """x0[B,nx], params[B,N+1,np], warm starts X0[B,N+1,nx], U0[B,N,nu] (device tensors).
-        order: None (natural dispatch order), "schedule" (`dispatch_order(params)`) or an int32 device permutation."""
+        order: None (natural dispatch order), "schedule" (`dispatch_order(params)`) or an int32 device permutation.
+        gather: a `parallel.ResultGather` of this solver: the kernel also stores every problem's result record into the
+        whole-batch slabs it names (multi-GPU gather); `gather.finish()` afterwards returns the whole-batch views."""
         x0 = torch.as_tensor(x0, dtype=torch.float64, device=self.device).contiguous()
         B = x0.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
@@ -152,6 +154,10 @@ class BatchedDDP:
             if order.shape != (B,):
                 raise ValueError("order must have one entry per problem")
         with torch.cuda.device(dev):
+            if gather is not None:
+                if gather.solver is not self:
+                    raise ValueError("gather belongs to another solver")
+                gather.arm(B)
             if order is not None:
                 _lib.check(self.L.sddp_set_dispatch_order(self.h, _ptr(order), B, 0), self.h, self.L)
             try:
@@ -160,6 +166,8 @@ class BatchedDDP:
             finally:
                 if order is not None:
                     self.L.sddp_set_dispatch_order(self.h, None, 0, 0)
+                if gather is not None:
+                    gather.disarm()
         r = BatchResult(X, U, K, k, hist, iters, status, cost)
         r._keepalive = order      # the kernel reads the permutation asynchronously
         return r

@@ -69,3 +69,19 @@ def test_gather_results_gloo_world2(B):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_record_layout_and_slab_views():
+    """The packed result record (include/sddp.h: X | U | cost | iters | status) and its whole-batch views."""
+    from srbd_horizon_b200.parallel import record_layout, slab_views
+    N, nx, nu, B = 5, 37, 24, 4
+    lay = record_layout(N, nx, nu)
+    assert lay["size"][1] == (N + 1) * nx + N * nu + 3 and lay["U"][0] == (N + 1) * nx and lay["status"][0] == lay["size"][1] - 1
+    slab = torch.arange(B * lay["size"][1], dtype=torch.float64).reshape(B, -1).clone()
+    slab[:, lay["iters"][0]] = torch.tensor([3, 4, 5, 6], dtype=torch.float64)
+    slab[:, lay["status"][0]] = torch.tensor([0, 1, 0, 2], dtype=torch.float64)
+    v = slab_views(slab, N, nx, nu)
+    assert v["X"].shape == (B, N + 1, nx) and v["U"].shape == (B, N, nu) and v["cost"].shape == (B,)
+    assert v["X"].data_ptr() == slab.data_ptr()                       # views, not copies
+    assert v["U"][2, 1, 3] == slab[2, lay["U"][0] + nu + 3] and v["X"][1, 2, 5] == slab[1, 2 * nx + 5]
+    assert v["iters"].tolist() == [3, 4, 5, 6] and v["status"].tolist() == [0, 1, 0, 2] and v["iters"].dtype == torch.int32
