@@ -140,6 +140,13 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
 #ifndef SDDP_D1CALL
 #define SDDP_D1CALL 1
 #endif
+#ifndef SDDP_C3_UNROLL
+#define SDDP_C3_UNROLL 3
+#define SDDP_C3F_UNROLL 1
+#endif
+#ifndef SDDP_C2_UNROLL
+#define SDDP_C2_UNROLL 19
+#endif
 #ifndef SDDP_ROTATE
 #define SDDP_ROTATE 0      // 148: rotate the warp roles of the d phase by blockIdx / 148 (A/B experiment, profiles/README.md)
 #endif
@@ -428,14 +435,15 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 contract_Aow(vo, ho, tw);     // (V dt Aow): w columns
                 const double dw0 = dt * vw[0], dw1 = dt * vw[1], dw2 = dt * vw[2];
                 // cd and rd columns first (they read the c and r entries before those are overwritten)
-#pragma unroll
+                constexpr int C2U = LAT ? 19 : SDDP_C2_UNROLL;
+#pragma unroll C2U
                 for (int q = 0; q < 12; q++) row[M::XCD + q] += dt * row[M::XC + q];
 #pragma unroll
                 for (int q = 0; q < 3; q++) row[M::XRD + q] += dt * vr[q];
-#pragma unroll
+#pragma unroll C2U
                 for (int z = 0; z < 19; z++) {        // r, o, c columns: + dt vw . dwdot/dz
                     double v = row[z] + dw0 * Jac[z] + dw1 * Jac[NZ + z] + dw2 * Jac[2 * NZ + z];
-                    if (z >= 3 && z < 7) v += to[z - 3];
+                    if (z >= 3 && z < 7) v += (z == 3 ? to[0] : (z == 4 ? to[1] : (z == 5 ? to[2] : to[3])));
                     row[z] = v;
                 }
 #pragma unroll
@@ -446,6 +454,8 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             STAMP(4);
             bar_named(2, 96);
             // ---- c3: columns of fx^T (.) and fu^T (.) applied to T (j < 37), v+ (j = 37) and ys (j = 38); warps 1-3.
+            //          (throughput variant: the 12-row loops are only partly unrolled, the kernel is bound by instruction fetch)
+            constexpr int C3U = LAT ? 12 : SDDP_C3_UNROLL, C3F = LAT ? 4 : SDDP_C3F_UNROLL;
             //          Plain stores: lxx, lux, lx, lu are added afterwards (expand MODE 1)
             for (int task = vt; task < 39 * 3; task += 96) {
                 const int j = task % 39, g = task / 39;
@@ -480,7 +490,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                     for (int q = 0; q < 3; q++)
                         oxx[(M::XW + q) * os] = col[(M::XW + q) * cs] + aw[q] + (Jac[M::ZW + q] * tw0 + Jac[NZ + M::ZW + q] * tw1 + Jac[2 * NZ + M::ZW + q] * tw2);
                 } else if (g == 1) {   // rows c, cd
-#pragma unroll
+#pragma unroll C3U
                     for (int q = 0; q < 12; q++) {
                         double tc = col[(M::XC + q) * cs];
                         oxx[(M::XC + q) * os] = tc + (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
@@ -490,7 +500,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                     double* oux = S.W + j;           // columns NX, NX+1 of W: Qu = lu + fu^T v+ and quy = lu + fu^T ys
                     const int us = LDW;
                     const double trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
-#pragma unroll
+#pragma unroll C3F
                     for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int q = 0; q < 3; q++) {

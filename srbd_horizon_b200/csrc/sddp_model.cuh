@@ -95,6 +95,9 @@ enum { ZT_QUX_OFF = 37 * 37 + 1, ZT_LDUX = 44 };   // layout of SmemSrbd (static
 enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2, NODE_TAIL = 3 };   // TAIL: a MID node of the LIP-style tail (no rotational dynamics)
 
 #define SDDP_DEV __device__ __forceinline__
+#ifndef SDDP_E_UNROLL
+#define SDDP_E_UNROLL 2
+#endif
 #ifndef SDDP_NOINLINE
 #define SDDP_NOINLINE
 #endif
@@ -602,7 +605,8 @@ struct SrbdT {
         const bool track = kind != NODE_FIRST, tail = kind == NODE_TAIL;
         const bool exact = c.hessian_mode == 0 && !tail;      // Gauss-Newton / LIP-style tail: no curvature, affine parts only
         const double g2 = 2.0 * c.gq;
-#pragma unroll
+        constexpr int EU = SDDP_E_UNROLL;
+#pragma unroll EU
         for (int r = 0; r < ZT_CROUNDS; r++) {
             const unsigned long long d = __ldg(c.ztab + ZT_COFF + r * ZT_LAZY_THREADS + tid);
             if (!(d & 1ull)) continue;
