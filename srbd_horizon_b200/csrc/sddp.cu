@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(DevCfg c, int B, int 
             __syncthreads();
             if (tid < ncand) { S.alpha[tid] = alpha[base + tid]; S.rho[tid] = rho[base + tid]; }
             __syncthreads();
-            double* xo = Xn ? Xn + ((size_t)b * n_alpha + base) * xsz : ws_xn + (size_t)blockIdx.x * NCAND * xsz;
-            double* uo = Un ? Un + ((size_t)b * n_alpha + base) * usz : ws_un + (size_t)blockIdx.x * NCAND * usz;
+            double* xo = Xn ? Xn + ((size_t)b * n_alpha + base) * xsz : ws_xn + (size_t)blockIdx.x * NSLOT * xsz;
+            double* uo = Un ? Un + ((size_t)b * n_alpha + base) * usz : ws_un + (size_t)blockIdx.x * NSLOT * usz;
             forward_wave<M, SM>(c, S, x0 + (size_t)b * NX, X + (size_t)b * xsz, U + (size_t)b * usz, P + (size_t)b * (N + 1) * NP,
                             D + (size_t)b * N * NX, K + (size_t)b * N * NU * NX, kff + (size_t)b * usz, ncand, xo, xsz, uo, usz, tid);
             if (tid < ncand) Jn[(size_t)b * n_alpha + base + tid] = S.Jc[tid];
@@ -440,8 +440,8 @@ static WsLayout ws_layout(const SddpConfig& c, int slots) {
     size_t N = (size_t)c.N;
     w.d = (size_t)slots * N * nx;
     w.pack = (size_t)slots * N * pack;
-    w.xn = (size_t)slots * NCAND * (N + 1) * nx;
-    w.un = (size_t)slots * NCAND * N * nu;
+    w.xn = (size_t)slots * NSLOT * (N + 1) * nx;
+    w.un = (size_t)slots * NSLOT * N * nu;
     w.K = (size_t)slots * N * nu * nx;
     w.k = (size_t)slots * N * nu;
     w.total = (w.d + w.pack + w.xn + w.un + w.K + w.k) * sizeof(double) + 256;

@@ -584,14 +584,12 @@ struct SrbdT {
             return v;
         }
         if (l >= AF_OO) {      // (a, b), a <= b in row-major order: orientation tracking 2 otg^2 (E^T E)_ab (prb.py:185-189)
+            // E(q) is the matrix of a quaternion product, so E^T E = |q|^2 I for any q: the diagonal entries sit at
+            // l - AF_OO = 0, 4, 7, 9 of the row-major upper triangle
             const double* qr = p + 15;
-            int t = l - AF_OO, a = 0;
-            while (t >= 4 - a) { t -= 4 - a; a++; }
-            const int b = a + t;
-            double ee = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) ee += E_row(qr, i, a) * E_row(qr, i, b);
-            return track ? 2.0 * p[6] * p[6] * ee : 0.0;
+            const int t = l - AF_OO;
+            const bool diag = t == 0 || t == 4 || t == 7 || t == 9;
+            return (track && diag) ? 2.0 * p[6] * p[6] * (qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3]) : 0.0;
         }
         const double tw = (l == AF_RELP) ? 2.0 * c.w_rel : (l == AF_RELN ? -2.0 * c.w_rel : (l == AF_RDOT ? 2.0 * c.w_rdot : (l == AF_RZ ? 2.0 * c.w_r : (l == AF_WW ? 2.0 * c.w_w : 0.0))));
         double v = track ? tw : 0.0;
@@ -645,17 +643,11 @@ struct SrbdT {
             if (tail && (i == 2 || (i >= XW && i < XCD))) g += 2.0 * c.cw * ((i == 2) ? x[2] - c.com[2] : x[i]);
             if (i == 2) { if (track) g += 2.0 * c.w_r * (x[2] - c.com[2]); }
             else if (i >= XO && i < XC) {
-                if (track) {
+                if (track) {      // E^T (E o - e_4) = |q|^2 o - E[3][:],  E[3][:] = (-q0, -q1, -q2, q3)
                     const double* qr = p + 15;
-                    const double* o = x + XO;
                     const int a = i - XO;
-                    double s_ = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const double res = E_row(qr, r, 0) * o[0] + E_row(qr, r, 1) * o[1] + E_row(qr, r, 2) * o[2] + E_row(qr, r, 3) * o[3] - (r == 3 ? 1.0 : 0.0);
-                        s_ += E_row(qr, r, a) * res;
-                    }
-                    g += 2.0 * p[6] * p[6] * s_;
+                    const double qq = qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3];
+                    g += 2.0 * p[6] * p[6] * (qq * x[i] - (a == 3 ? qr[3] : -qr[a]));
                 }
             } else if (i >= XC && i < XRD) {
                 const int foot = (i - XC) / 3, ax = (i - XC) % 3;

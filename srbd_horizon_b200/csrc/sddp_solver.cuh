@@ -26,6 +26,7 @@
 constexpr int NT = 128;      // threads per CTA
 constexpr int NWARP = NT / 32;
 constexpr int NCAND = NWARP; // line-search candidates evaluated per wave
+constexpr int NSLOT = NCAND + 1;   // trial trajectories per CTA: one of them holds the current trajectory after the first accepted step
 constexpr unsigned FULL = 0xffffffffu;
 
 // per-node input buffer: x | u | p | d | (pack in the backward pass, k in the forward pass)
@@ -379,15 +380,16 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
 template <class M, class SM>
 __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const double* X, const double* U, const double* P,
                              const double* D, const double* Kg, const double* kg, int ncand, double* Xn, size_t xn_stride,
-                             double* Un, size_t un_stride, int tid) {
+                             double* Un, size_t un_stride, int tid, int skip = 1 << 30) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     using NBL = NodeBuf<M>;
     const int N = c.N, lane = tid & 31, w = tid >> 5;
     double* xh = S.scr() + w * (2 * NX + NU);
     double* uh = xh + NX;
     double* xn = uh + NU;
-    double* Xo = Xn + (size_t)w * xn_stride;
-    double* Uo = Un + (size_t)w * un_stride;
+    // candidate w writes trial slot w, stepping over slot `skip` (it holds the current trajectory, see solve_one)
+    double* Xo = Xn + (size_t)(w + (w >= skip ? 1 : 0)) * xn_stride;
+    double* Uo = Un + (size_t)(w + (w >= skip ? 1 : 0)) * un_stride;
     const bool active = w < ncand;
     const double alpha = active ? S.alpha[w] : 0.0, omr = active ? 1.0 - S.rho[w] : 0.0;
     double J = 0.0;
@@ -407,6 +409,8 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
     prefetch(0);
     PROF(23);
     if (ncand == 1) {
+        Xn += (size_t)(skip == 0 ? 1 : 0) * xn_stride;      // candidate 0's trial slot
+        Un += (size_t)(skip == 0 ? 1 : 0) * un_stride;
         // One candidate (the usual first wave): its work is spread over the warps instead of leaving three idle.
         // Per node: warp 0 forms u = U + alpha k + K dx; then warp 0 integrates (accel, Euler step) while warp 1 sums
         // the state-indexed cost terms and warp 2 the input-indexed ones.  Two block barriers per node.
@@ -583,8 +587,13 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     double* hist = a.hist ? a.hist + (size_t)b * c.max_iters * 4 : nullptr;
     double* d = a.ws_d + (size_t)slot * N * NX;
     double* packs = a.ws_pack + (size_t)slot * N * M::PACK;
-    double* Xn = a.ws_xn + (size_t)slot * NCAND * xsz;
-    double* Un = a.ws_un + (size_t)slot * NCAND * usz;
+    // NSLOT trial slots per CTA: the accepted candidate's slot BECOMES the current trajectory (no copy per iteration),
+    // the next waves use the other slots; the caller's X, U are written once, at the end.
+    double* Xn = a.ws_xn + (size_t)slot * NSLOT * xsz;
+    double* Un = a.ws_un + (size_t)slot * NSLOT * usz;
+    double* const Xuser = X;
+    double* const Uuser = U;
+    int cur = 1 << 30;      // trial slot that holds the current trajectory (none: it is still in the caller's buffers)
     const bool fixed = c.rho_fixed > 0.0;
 
     for (int i = tid; i < NX; i += NT) X[i] = x0[i];
@@ -655,7 +664,7 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
             __syncthreads();
             PROF(5);
             PROF_INC(29);
-            forward_wave<M, SM>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid);
+            forward_wave<M, SM>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid, cur);
             PROF(2);
             for (int j = 0; j < ncand; j++) {
                 double am = al[j], dJm = C0 + am * D1 + am * am * D2, Jj = S.Jc[j];
@@ -666,10 +675,9 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
             }
         }
         if (accepted) {
-            const double* Xs = Xn + (size_t)sel * xsz;
-            const double* Us = Un + (size_t)sel * usz;
-            for (size_t i = tid; i < xsz; i += NT) X[i] = Xs[i];
-            for (size_t i = tid; i < usz; i += NT) U[i] = Us[i];
+            cur = sel + (sel >= cur ? 1 : 0);
+            X = Xn + (size_t)cur * xsz;
+            U = Un + (size_t)cur * usz;
             const double omr = 1.0 - rho_acc;
             for (int i = tid; i < N * NX; i += NT) d[i] *= omr;
             dmax *= omr;
@@ -689,6 +697,10 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     }
     __syncthreads();
     if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
+    if (X != Xuser) {
+        for (size_t i = tid; i < xsz; i += NT) Xuser[i] = X[i];
+        for (size_t i = tid; i < usz; i += NT) Uuser[i] = U[i];
+    }
     if (a.n_peers > 0) {
         // Gather without a collective: this problem's record is stored straight into every GPU's whole-batch slab (peer
         // memory over NVLink / NVSwitch) while the other CTAs keep solving, so the transfer rides under the batch.
