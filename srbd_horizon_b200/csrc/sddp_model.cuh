@@ -410,30 +410,36 @@ struct SrbdT {
 
     // ---- single-thread rigid-body pack (see file header) ------------------------------------
     // pk[PK_WD..] wd(3) rdd(3) nu(3) Hww(9) Jac[3][34] Ho[4][34]
-    // One thread per node.  Every per-thread array is indexed statically (registers): the four inertia derivatives
-    // Ja = dJ/dq_a, the only intermediate too large for that, live in the shared-memory scratch sc[(9 a + i) * ss]
-    // (ss = number of threads that share the scratch; the solve kernel's shared memory is idle between the forward and
-    // the backward pass).  The round-1 version kept Ra[4][9], Ja[4][9] in local memory: 1.1 K local loads per pack, with
-    // 200 packs in flight per SM they thrashed L1 (54 % hits) and the pack phase took 6 % of the solve.
+    // One thread per node, and nothing is read back from memory: every per-thread array is indexed statically
+    // (registers), each Jacobian column is turned into its four curvature entries Ho[a][q] = -(J_a nu) . Jac[:,q] the
+    // moment it exists, and the only values that cross a rolled loop -- the ten second-derivative terms of the (o, o)
+    // block -- go through the shared-memory scratch sc[e * ss] (ss = threads sharing it; the solve kernel's shared
+    // memory is idle between the forward and the backward pass).  (Round 1 kept Ra[4][9], Ja[4][9] in local memory,
+    // 1.1 K local loads per pack thrashing L1 with 200 packs in flight per SM, and re-read the Jacobian from global
+    // memory for the Ho rows: the pack phase was 6-9 % of the solve.)
     // With v x e_b = (0, v2, -v1), (-v2, 0, v0), (v1, -v0, 0): the three columns M (v x e_b) of a lever arm or force.
-    SDDP_DEV static void put3(double* Jac, const double* M, int z0, double v0, double v1, double v2) {
+    template <bool HO>
+    SDDP_DEV static void put3(double* Jac, const double* M, const double (*Jan)[3], int z0, double v0, double v1, double v2) {
+        double col[3][3];      // col[k][b]
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const double m0 = M[3 * k], m1 = M[3 * k + 1], m2 = M[3 * k + 2];
-            Jac[k * NZ + z0] = m1 * v2 - m2 * v1;
-            Jac[k * NZ + z0 + 1] = m2 * v0 - m0 * v2;
-            Jac[k * NZ + z0 + 2] = m0 * v1 - m1 * v0;
+            col[k][0] = m1 * v2 - m2 * v1;
+            col[k][1] = m2 * v0 - m0 * v2;
+            col[k][2] = m0 * v1 - m1 * v0;
+#pragma unroll
+            for (int b = 0; b < 3; b++) Jac[k * NZ + z0 + b] = col[k][b];
+        }
+        if (HO) {
+            double* Ho = Jac + (PK_HO - PK_JAC);
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) Ho[a * NZ + z0 + b] = -(Jan[a][0] * col[0][b] + Jan[a][1] * col[1][b] + Jan[a][2] * col[2][b]);
         }
     }
-    __device__ SDDP_NOINLINE static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk, double* sc, int ss) {
-        if (kind == NODE_TERM) return;
-        if (kind == NODE_TAIL) {      // LIP-style tail: wdot = 0 identically, so no Jacobian and no curvature; rddot as usual
-            for (int i = 0; i < PACK; i++) pk[i] = 0.0;
-            double fsum[3] = {0, 0, 0};
-            for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) fsum[k] += u[6 * i + 3 + k];
-            pk[PK_RDD + 0] = fsum[0] * c.inv_ms; pk[PK_RDD + 1] = fsum[1] * c.inv_ms; pk[PK_RDD + 2] = fsum[2] * c.inv_ms - c.g;
-            return;
-        }
+    template <bool EXACT>
+    SDDP_DEV static void pack_impl(const DevCfg& c, const double* x, const double* u, double* pk, double* sc, int ss) {
         const double o[4] = {x[XO], x[XO + 1], x[XO + 2], x[XO + 3]};
         const double r[3] = {x[0], x[1], x[2]}, w[3] = {x[XW], x[XW + 1], x[XW + 2]};
         double R[9], J[9], M[9];
@@ -441,7 +447,7 @@ struct SrbdT {
         inertia(c, R, J);
         m3::inv(J, M);
         double* Jac = pk + PK_JAC;   // [3][34]: Jac[:,p] = M (dh/dp - J_p wd), h = tau - w x J w
-        // d tau / d r_b = F x e_b;  d tau / d c_ib = -f_i x e_b;  d tau / d f_ib = (c_i - r) x e_b
+        double* Ho = pk + PK_HO;     // [4][34]
         double tau[3] = {0, 0, 0}, F[3] = {0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -452,10 +458,7 @@ struct SrbdT {
             m3::cross(d, f, t);
 #pragma unroll
             for (int k = 0; k < 3; k++) { tau[k] += t[k]; F[k] += f[k]; }
-            put3(Jac, M, ZC + 3 * i, -f[0], -f[1], -f[2]);
-            put3(Jac, M, ZF + 3 * i, d[0], d[1], d[2]);
         }
-        put3(Jac, M, ZR, F[0], F[1], F[2]);
         double Jw[3], wJw[3], wd[3];
         m3::mv(J, w, Jw);
         m3::cross(w, Jw, wJw);
@@ -464,7 +467,37 @@ struct SrbdT {
 #pragma unroll
         for (int k = 0; k < 3; k++) pk[PK_WD + k] = wd[k];
         pk[PK_RDD + 0] = F[0] * c.inv_ms; pk[PK_RDD + 1] = F[1] * c.inv_ms; pk[PK_RDD + 2] = F[2] * c.inv_ms - c.g;
-        {   // d(-w x Jw)/dw_b = Jw x e_b - w x J[:,b]
+        // curvature of lambda^T wdot at lambda = wd:  nu = M wd,  phi_pq = nu^T ( h_pq - J_p wd_q - J_q wd_p - J_pq wd )
+        double nu[3], wxn[3], nxw[3];
+        m3::mv(M, wd, nu);
+        m3::cross(w, nu, wxn);       // w^T skew(nu) A w = (w x nu) . (A w)
+        m3::cross(nu, w, nxw);
+        if (EXACT) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) pk[PK_NU + k] = nu[k];
+            // second derivatives of the inertia inside the (o, o) block: v_ab = (w x nu) . (J_ab w) - nu . (J_ab wd), a <= b
+            // (rolled: ten pairs through one copy of inertia_dd; results cross to the unrolled code below through sc)
+            int e = 0;
+#pragma unroll 1
+            for (int a = 0; a < 4; a++) {
+                double Ra[9];
+                quat_dR(o, a, Ra);
+#pragma unroll 1
+                for (int b = a; b < 4; b++, e++) {
+                    double eb[4], Rb[9], Rab[9], Jab[9], t3[3], t4[3];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) eb[i] = (i == b) ? 1.0 : 0.0;
+                    quat_dR(o, b, Rb);
+                    quat_dR(eb, a, Rab);
+                    inertia_dd(c, R, Ra, Rb, Rab, Jab);
+                    m3::mv(Jab, w, t3); m3::mv(Jab, wd, t4);
+                    sc[e * ss] = m3::dot(wxn, t3) - m3::dot(nu, t4);
+                }
+            }
+        }
+        // d(-w x Jw)/dw_b = Jw x e_b - w x J[:,b]
+        double colW[3][3];      // colW[k][b] = Jac[k][ZW + b]
+        {
             double cw[9];      // cw[3 k + b]
 #pragma unroll
             for (int b = 0; b < 3; b++) {
@@ -482,88 +515,74 @@ struct SrbdT {
                 const double col[3] = {cw[b], cw[3 + b], cw[6 + b]};
                 double out[3];
                 m3::mv(M, col, out);
-                Jac[ZW + b] = out[0]; Jac[NZ + ZW + b] = out[1]; Jac[2 * NZ + ZW + b] = out[2];
+#pragma unroll
+                for (int k = 0; k < 3; k++) { colW[k][b] = out[k]; Jac[k * NZ + ZW + b] = out[k]; }
             }
         }
-        const bool exact = c.hessian_mode == 0;
-#pragma unroll 1
-        for (int a = 0; a < 4; a++) {      // d/do_a: -w x (J_a w) - J_a wd
-            double Ra[9], Ja[9], Jaw[3], t[3], Jawd[3], out[3];
+        // d/do_a: column M (-w x (J_a w) - J_a wd); J_a nu; the (o_a, w) curvature nu x (J_a w) - J_a (nu x w)
+        double Jan[4][3], colO[4][3];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            double Ra[9], Ja[9], Jaw[3], t[3], Jawd[3];
             quat_dR(o, a, Ra);
             inertia_d(c, R, Ra, Ja);
             m3::mv(Ja, w, Jaw); m3::cross(w, Jaw, t); m3::mv(Ja, wd, Jawd);
             const double co[3] = {-t[0] - Jawd[0], -t[1] - Jawd[1], -t[2] - Jawd[2]};
-            m3::mv(M, co, out);
-            Jac[ZO + a] = out[0]; Jac[NZ + ZO + a] = out[1]; Jac[2 * NZ + ZO + a] = out[2];
-            if (exact) {
+            m3::mv(M, co, colO[a]);
 #pragma unroll
-                for (int i = 0; i < 9; i++) sc[(9 * a + i) * ss] = Ja[i];
+            for (int k = 0; k < 3; k++) Jac[k * NZ + ZO + a] = colO[a][k];
+            if (EXACT) {
+                double t1[3], t2[3];
+                m3::mv(Ja, nu, Jan[a]);
+                m3::cross(nu, Jaw, t1); m3::mv(Ja, nxw, t2);
+#pragma unroll
+                for (int b = 0; b < 3; b++)
+                    Ho[a * NZ + ZW + b] = -(Jan[a][0] * colW[0][b] + Jan[a][1] * colW[1][b] + Jan[a][2] * colW[2][b]) + (t1[b] - t2[b]);
             }
         }
-        if (!exact) return;
-
-        // curvature of lambda^T wdot at lambda = wd:  nu = M wd
-        //   phi_pq = nu^T ( h_pq - J_p wd_q - J_q wd_p - J_pq wd )
-        double nu[3], wxn[3], nxw[3];
-        m3::mv(M, wd, nu);
+        if (EXACT) {      // (o_a, o_b) = -(J_a nu) . Jac[:,o_b] - (J_b nu) . Jac[:,o_a] + v_ab
 #pragma unroll
-        for (int k = 0; k < 3; k++) pk[PK_NU + k] = nu[k];
-        m3::cross(w, nu, wxn);       // w^T skew(nu) A w = (w x nu) . (A w)
-        m3::cross(nu, w, nxw);
-        // (w,w): skew(nu) J - J skew(nu)
-        pk[PK_HWW + 0] = (-nu[2] * J[3] + nu[1] * J[6]) - (J[1] * nu[2] - J[2] * nu[1]);
-        pk[PK_HWW + 1] = (-nu[2] * J[4] + nu[1] * J[7]) - (-J[0] * nu[2] + J[2] * nu[0]);
-        pk[PK_HWW + 2] = (-nu[2] * J[5] + nu[1] * J[8]) - (J[0] * nu[1] - J[1] * nu[0]);
-        pk[PK_HWW + 3] = (nu[2] * J[0] - nu[0] * J[6]) - (J[4] * nu[2] - J[5] * nu[1]);
-        pk[PK_HWW + 4] = (nu[2] * J[1] - nu[0] * J[7]) - (-J[3] * nu[2] + J[5] * nu[0]);
-        pk[PK_HWW + 5] = (nu[2] * J[2] - nu[0] * J[8]) - (J[3] * nu[1] - J[4] * nu[0]);
-        pk[PK_HWW + 6] = (-nu[1] * J[0] + nu[0] * J[3]) - (J[7] * nu[2] - J[8] * nu[1]);
-        pk[PK_HWW + 7] = (-nu[1] * J[1] + nu[0] * J[4]) - (-J[6] * nu[2] + J[8] * nu[0]);
-        pk[PK_HWW + 8] = (-nu[1] * J[2] + nu[0] * J[5]) - (J[6] * nu[1] - J[7] * nu[0]);
-        double* Ho = pk + PK_HO;   // [4][34]
-#pragma unroll 1
-        for (int a = 0; a < 4; a++) {      // first pass: Ho[a][q] = -(J_a nu) . Jac[:,q]
-            double Ja[9], Jan[3];
+            for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int i = 0; i < 9; i++) Ja[i] = sc[(9 * a + i) * ss];
-            m3::mv(Ja, nu, Jan);
-#pragma unroll 2
-            for (int q = 0; q < NZ; q++) Ho[a * NZ + q] = -(Jan[0] * Jac[q] + Jan[1] * Jac[NZ + q] + Jan[2] * Jac[2 * NZ + q]);
-        }
-#pragma unroll 1
-        for (int a = 0; a < 4; a++) {      // second pass: the terms of the (o, w) and (o, o) blocks
-            double Ja[9], Ra[9], Jaw[3], t1[3], t2[3];
-#pragma unroll
-            for (int i = 0; i < 9; i++) Ja[i] = sc[(9 * a + i) * ss];
-            // (o_a, w): (skew(nu) J_a - J_a skew(nu)) w = nu x (J_a w) - J_a (nu x w)
-            m3::mv(Ja, w, Jaw); m3::cross(nu, Jaw, t1); m3::mv(Ja, nxw, t2);
-#pragma unroll
-            for (int k = 0; k < 3; k++) Ho[a * NZ + ZW + k] += t1[k] - t2[k];
-            // symmetric counterpart of the -(J_b nu).Jac[:,o_a] term inside the (o,o) block
-            const double ca[3] = {Jac[ZO + a], Jac[NZ + ZO + a], Jac[2 * NZ + ZO + a]};
-            quat_dR(o, a, Ra);
-#pragma unroll 1
-            for (int b = 0; b < 4; b++) {
-                double Jb[9], Jbn[3];
-#pragma unroll
-                for (int i = 0; i < 9; i++) Jb[i] = sc[(9 * b + i) * ss];
-                m3::mv(Jb, nu, Jbn);
-                double acc = -(Jbn[0] * ca[0] + Jbn[1] * ca[1] + Jbn[2] * ca[2]);
-                if (b >= a) {      // J_ab term, symmetric: also lands on Ho[b][o_a]
-                    double eb[4], Rb[9], Rab[9], Jab[9], t3[3], t4[3];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) eb[i] = (i == b) ? 1.0 : 0.0;
-                    quat_dR(o, b, Rb);
-                    quat_dR(eb, a, Rab);
-                    inertia_dd(c, R, Ra, Rb, Rab, Jab);
-                    m3::mv(Jab, w, t3); m3::mv(Jab, wd, t4);
-                    const double v = m3::dot(wxn, t3) - m3::dot(nu, t4);
-                    acc += v;
-                    if (b != a) Ho[b * NZ + ZO + a] += v;
+                for (int b = a; b < 4; b++) {
+                    const int e = 4 * a - a * (a - 1) / 2 + (b - a);      // index of (a, b) in the rolled pair loop above
+                    const double v = sc[e * ss] - (Jan[a][0] * colO[b][0] + Jan[a][1] * colO[b][1] + Jan[a][2] * colO[b][2])
+                                               - (Jan[b][0] * colO[a][0] + Jan[b][1] * colO[a][1] + Jan[b][2] * colO[a][2]);
+                    Ho[a * NZ + ZO + b] = v;
+                    if (b != a) Ho[b * NZ + ZO + a] = v;
                 }
-                Ho[a * NZ + ZO + b] += acc;
-            }
+            // (w,w): skew(nu) J - J skew(nu)
+            pk[PK_HWW + 0] = (-nu[2] * J[3] + nu[1] * J[6]) - (J[1] * nu[2] - J[2] * nu[1]);
+            pk[PK_HWW + 1] = (-nu[2] * J[4] + nu[1] * J[7]) - (-J[0] * nu[2] + J[2] * nu[0]);
+            pk[PK_HWW + 2] = (-nu[2] * J[5] + nu[1] * J[8]) - (J[0] * nu[1] - J[1] * nu[0]);
+            pk[PK_HWW + 3] = (nu[2] * J[0] - nu[0] * J[6]) - (J[4] * nu[2] - J[5] * nu[1]);
+            pk[PK_HWW + 4] = (nu[2] * J[1] - nu[0] * J[7]) - (-J[3] * nu[2] + J[5] * nu[0]);
+            pk[PK_HWW + 5] = (nu[2] * J[2] - nu[0] * J[8]) - (J[3] * nu[1] - J[4] * nu[0]);
+            pk[PK_HWW + 6] = (-nu[1] * J[0] + nu[0] * J[3]) - (J[7] * nu[2] - J[8] * nu[1]);
+            pk[PK_HWW + 7] = (-nu[1] * J[1] + nu[0] * J[4]) - (-J[6] * nu[2] + J[8] * nu[0]);
+            pk[PK_HWW + 8] = (-nu[1] * J[2] + nu[0] * J[5]) - (J[6] * nu[1] - J[7] * nu[0]);
         }
+        // d tau / d r_b = F x e_b;  d tau / d c_ib = -f_i x e_b;  d tau / d f_ib = (c_i - r) x e_b
+        put3<EXACT>(Jac, M, Jan, ZR, F[0], F[1], F[2]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double* ci = x + XC + 3 * i;
+            const double* fi = u + 6 * i + 3;
+            put3<EXACT>(Jac, M, Jan, ZC + 3 * i, -fi[0], -fi[1], -fi[2]);
+            put3<EXACT>(Jac, M, Jan, ZF + 3 * i, ci[0] - r[0], ci[1] - r[1], ci[2] - r[2]);
+        }
+    }
+    __device__ SDDP_NOINLINE static void pack(const DevCfg& c, int kind, const double* x, const double* u, double* pk, double* sc, int ss) {
+        if (kind == NODE_TERM) return;
+        if (kind == NODE_TAIL) {      // LIP-style tail: wdot = 0 identically, so no Jacobian and no curvature; rddot as usual
+            for (int i = 0; i < PACK; i++) pk[i] = 0.0;
+            double fsum[3] = {0, 0, 0};
+            for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) fsum[k] += u[6 * i + 3 + k];
+            pk[PK_RDD + 0] = fsum[0] * c.inv_ms; pk[PK_RDD + 1] = fsum[1] * c.inv_ms; pk[PK_RDD + 2] = fsum[2] * c.inv_ms - c.g;
+            return;
+        }
+        if (c.hessian_mode == 0) pack_impl<true>(c, x, u, pk, sc, ss);
+        else pack_impl<false>(c, x, u, pk, sc, ss);
     }
 
     // ---- structured backward pass, phase e: Qxx, Qux, Qx, Qu (+ the y-recursion copies Qx2, Qu2) += lxx, lux, lx, lu ------

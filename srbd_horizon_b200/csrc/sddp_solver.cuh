@@ -564,7 +564,7 @@ struct SolveArgs {
 };
 
 // `scratch`: PACK_SCRATCH * NT doubles of shared memory nobody else uses during the call (one column per thread)
-constexpr int PACK_SCRATCH = 36;
+constexpr int PACK_SCRATCH = 10;
 template <class M>
 __device__ void compute_packs(const DevCfg& c, const double* X, const double* U, double* packs, double* scratch, int tid) {
     if (M::PACK > 1)
