@@ -43,6 +43,7 @@ struct alignas(16) SmemSrbdT {
     double sacc[NWARP][8];
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
+    const double* gp[8];       // base pointers of the per-node prefetches (registers are scarce in the node loops)
     int iflag[4];
     __device__ double* Kbuf(int b) { return Qxx + b * (NU * NX); }
     __device__ double* scr() { return VT; }
@@ -270,21 +271,27 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
     const double dt = c.dt;
     SyncBlock sync;
 
-    auto prefetch = [&](int k) {       // node k -> buffer k & 1
+    auto prefetch = [&](int k) {       // node k -> buffer k & 1 (base pointers from shared memory: see forward_wave)
         double* nb = S.nb[k & 1];
+        const double* Xs = S.gp[2] + (size_t)k * NX;
+        const double* Ds = S.gp[3] + (size_t)k * NX;
         for (int i = tid; i < NX; i += NT) {
-            cp_async8(nb + NBL::OX + i, X + (size_t)k * NX + i);
-            if (has_gap) cp_async8(nb + NBL::OD + i, D + (size_t)k * NX + i);
+            cp_async8(nb + NBL::OX + i, Xs + i);
+            if (has_gap) cp_async8(nb + NBL::OD + i, Ds + i);
         }
-        for (int i = tid; i < NU; i += NT) cp_async8(nb + NBL::OU + i, U + (size_t)k * NU + i);
-        for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, P + (size_t)k * NP + i);
-        const double* ps = packs + (size_t)k * M::PACK;
+        const double* Us = S.gp[4] + (size_t)k * NU;
+        for (int i = tid; i < NU; i += NT) cp_async8(nb + NBL::OU + i, Us + i);
+        const double* Ps = S.gp[5] + (size_t)k * NP;
+        for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, Ps + i);
+        const double* ps = S.gp[6] + (size_t)k * M::PACK;
         if (((((size_t)ps) | ((size_t)(nb + NBL::OK))) & 15) == 0) { for (int i = 2 * tid; i < M::PACK; i += 2 * NT) cp_async16(nb + NBL::OK + i, ps + i); }
         else { for (int i = tid; i < M::PACK; i += NT) cp_async8(nb + NBL::OK + i, ps + i); }
         cp_commit();
     };
 
     // terminal node: Vx = l_Nx, Vxx = l_Nxx (ddp.py:216-226: costs only)
+    __syncthreads();
+    if (tid == 0) { S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P; S.gp[6] = packs; }
     __syncthreads();
     {
         double* nb = S.nb[N & 1];
@@ -569,9 +576,9 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             const int fr = lane >> 2, fc = lane & 3;       // fragment row / column of this lane
 #pragma unroll 1
             for (int t = warp; t < 15; t += NWARP) {
-                int fI = 0, rem = t;
-                while (rem >= 5 - fI) { rem -= 5 - fI; fI++; }
-                const int fJ = fI + rem, gI = t / 5, gJ = t - 5 * gI;
+                // tile t of the upper triangle of the 5 x 5 grid, row-major: (fI, fJ) from two packed tables (4 bits each)
+                const int fI = (int)((0x433222111100000ull >> (4 * t)) & 15), fJ = (int)((0x443432432143210ull >> (4 * t)) & 15);
+                const int gI = t / 5, gJ = t - 5 * gI;
                 double f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
                 const double* rf = S.W + fc * LDW + fr;
                 const double* qa = S.Quu + fc * NU + 8 * gI + fr;
@@ -582,22 +589,38 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                     if (k0 >= 8 * gI) dmma884(g0, g1, qa[k0 * NU], S.rs[k0 + fc] * rf[k0 * LDW + 8 * gJ]);
                 }
                 const int gi = 8 * fI + fr;
+                if (fJ < 4) {
+                    // interior tile (rows and columns < 32): every entry is a matrix entry (on a diagonal tile the upper half)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int gj = 8 * fJ + 2 * fc + e;
+                        if (gj >= gi) {
+                            const double v = 0.5 * (S.Qxx[gi * NX + gj] + S.Qxx[gj * NX + gi]) - (e ? f1 : f0);
+                            S.VT[gi * NX + gj] = v;
+                            S.VT[gj * NX + gi] = v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        // Branch free (a divergent branch per case costs more than the work): columns 37 / 38 use the
+                        // vectors Qx -> Vx and qxy -> y as one more row / column of the matrices, whose spare entry 37 is
+                        // kept zero, so Vx[37] = -|w0|^2 and y[37] = quy . k; inactive lanes hit dummy addresses.
+                        const int gj = 8 * fJ + 2 * fc + e;
+                        const double acc = e ? f1 : f0;
+                        const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
+                        const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
+                        const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
+                        double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
+                        double* d2 = m ? S.VT + gj * NX + gi : d1;
+                        if (!ok) { s1 = s2 = S.Qx + NX; d1 = d2 = S.escr + 23; }
+                        const double v = 0.5 * (*s1 + *s2) - acc;
+                        *d1 = v;
+                        *d2 = v;
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    // Branch free (a divergent branch per case costs more than the work): columns 37 / 38 use the
-                    // vectors Qx -> Vx and qxy -> y as one more row / column of the matrices, whose spare entry 37 is
-                    // kept zero, so Vx[37] = -|w0|^2 and y[37] = quy . k; inactive lanes hit dummy addresses.
-                    const int gj = 8 * fJ + 2 * fc + e;
-                    const double acc = e ? f1 : f0;
-                    const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
-                    const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
-                    const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
-                    double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
-                    double* d2 = m ? S.VT + gj * NX + gi : d1;
-                    if (!ok) { s1 = s2 = S.Qx + NX; d1 = d2 = S.escr + 23; }
-                    const double v = 0.5 * (*s1 + *s2) - acc;
-                    *d1 = v;
-                    *d2 = v;
                     const int cc = 8 * gJ + 2 * fc + e, i = 8 * gI + fr;
                     const double kv = e ? -g1 : -g0;
                     if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
@@ -700,9 +723,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             const int fr = lane >> 2, fc = lane & 3;
 #pragma unroll 1
             for (int t = warp; t < 15; t += NWARP) {
-                int fI = 0, rem = t;
-                while (rem >= 5 - fI) { rem -= 5 - fI; fI++; }
-                const int fJ = fI + rem;
+                const int fI = (int)((0x433222111100000ull >> (4 * t)) & 15), fJ = (int)((0x443432432143210ull >> (4 * t)) & 15);
                 double f0 = 0.0, f1 = 0.0;
                 const double* rf = Ks + fc * LDW + fr;
 #pragma unroll

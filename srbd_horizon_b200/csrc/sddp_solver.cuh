@@ -59,6 +59,7 @@ struct Smem {
     double sacc[NWARP][8];
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
+    const double* gp[8];                 // base pointers of the per-node prefetches (see forward_wave)
     int iflag[4];
     __device__ static int backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
@@ -394,18 +395,27 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
     const double alpha = active ? S.alpha[w] : 0.0, omr = active ? 1.0 - S.rho[w] : 0.0;
     double J = 0.0;
     // node k's inputs (K_k, k_k, X_k, U_k, d_k, p_k) are fetched with cp.async while node k-1 is computed
+    // The six base pointers live in shared memory during the rollout: held in registers across the node loop they were
+    // spilled (the kernel sits at its 128-register cap) and re-read from local memory at every node, a quarter of them L1 misses.
     auto prefetch = [&](int k) {
         double* nb = S.nb[k & 1];
         double* Kb = S.Kbuf(k & 1);
-        const double* Ks = Kg + (size_t)k * NU * NX;
+        const double* Ks = S.gp[0] + (size_t)k * NU * NX;
         if ((NU * NX) % 2 == 0 && ((((size_t)Kb) | ((size_t)Ks)) & 15) == 0) { for (int e = 2 * tid; e < NU * NX; e += 2 * NT) cp_async16(Kb + e, Ks + e); }
         else { for (int e = tid; e < NU * NX; e += NT) cp_async8(Kb + e, Ks + e); }
-        for (int i = tid; i < NX; i += NT) { cp_async8(nb + NBL::OX + i, X + (size_t)k * NX + i); cp_async8(nb + NBL::OD + i, D + (size_t)k * NX + i); }
-        for (int i = tid; i < NU; i += NT) { cp_async8(nb + NBL::OU + i, U + (size_t)k * NU + i); cp_async8(nb + NBL::OK + i, kg + (size_t)k * NU + i); }
-        for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, P + (size_t)k * NP + i);
+        const double* Xs = S.gp[2] + (size_t)k * NX;
+        const double* Ds = S.gp[3] + (size_t)k * NX;
+        for (int i = tid; i < NX; i += NT) { cp_async8(nb + NBL::OX + i, Xs + i); cp_async8(nb + NBL::OD + i, Ds + i); }
+        const double* Us = S.gp[4] + (size_t)k * NU;
+        const double* ks = S.gp[1] + (size_t)k * NU;
+        for (int i = tid; i < NU; i += NT) { cp_async8(nb + NBL::OU + i, Us + i); cp_async8(nb + NBL::OK + i, ks + i); }
+        const double* Ps = S.gp[5] + (size_t)k * NP;
+        for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, Ps + i);
         cp_commit();
     };
     __syncthreads();      // the buffers may still be in use by the caller's previous phase
+    if (tid == 0) { S.gp[0] = Kg; S.gp[1] = kg; S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P; }
+    __syncthreads();
     prefetch(0);
     PROF(23);
     if (ncand == 1) {
@@ -425,7 +435,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             if (k + 1 < N) prefetch(k + 1);
             else {
                 double* nbt = S.nb[(k + 1) & 1];
-                for (int i = tid; i < NP; i += NT) cp_async8(nbt + NBL::OP + i, P + (size_t)N * NP + i);
+                for (int i = tid; i < NP; i += NT) cp_async8(nbt + NBL::OP + i, S.gp[5] + (size_t)N * NP + i);
                 cp_commit();
             }
             STAMP(12);
@@ -514,7 +524,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         if (k + 1 < N) prefetch(k + 1);
         else {                            // terminal parameters go to the free buffer
             double* nb = S.nb[(k + 1) & 1];
-            for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, P + (size_t)N * NP + i);
+            for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, S.gp[5] + (size_t)N * NP + i);
             cp_commit();
         }
         if (active) {

@@ -96,7 +96,7 @@ if len(sys.argv) > 4:
              ("bwd d1 (warp-0 LDL^T, E)", ln(B, "// ---- d1:")), ("bwd c2 (T = V fx)", ln(B, "// ---- c2:")),
              ("bwd c3 (fx^T T, fu^T T)", ln(B, "// ---- c3:")), ("bwd e call", ln(B, "// ---- e:")),
              ("bwd h (Wn = Es B, DMMA)", ln(B, "// ---- h:")), ("bwd f,g (syrk + gains, DMMA)", ln(B, "// ---- f:")),
-             ("bwd mu path + model", ln(B, "if (mu != 0.0) {   // regularised step")), ("", 10 ** 9)]
+             ("bwd mu path + model", ln(B, "if (mu != 0.0) {")), ("", 10 ** 9)]
     spec = {name: [(B, lo, marks[i + 1][1] - 1)] for i, (name, lo) in enumerate(marks[:-1])}
     spec["bwd row helpers (axpy/store, in d1)"] = [(B, ln(B, "SDDP_DEV void axpy_row"), ln(B, "// out[b] = sum_a v[a] * (dt Aoo)") - 1)]
     spec["bwd dmma/rcp/contract helpers"] = [(B, ln(B, "SDDP_DEV void dmma884"), ln(B, "#ifndef SDDP_ROW128") - 1),
