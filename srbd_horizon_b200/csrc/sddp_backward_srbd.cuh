@@ -291,7 +291,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 
     // terminal node: Vx = l_Nx, Vxx = l_Nxx (ddp.py:216-226: costs only)
     __syncthreads();
-    if (tid == 0) { S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P; S.gp[6] = packs; }
+    if (tid == 0) { S.gp[0] = Kg; S.gp[1] = kg; S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P; S.gp[6] = packs; }
     __syncthreads();
     {
         double* nb = S.nb[N & 1];
@@ -623,8 +623,8 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 for (int e = 0; e < 2; e++) {
                     const int cc = 8 * gJ + 2 * fc + e, i = 8 * gI + fr;
                     const double kv = e ? -g1 : -g0;
-                    if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
-                    if (cc == NX) { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
+                    if (cc < NX) const_cast<double*>(S.gp[0])[((size_t)k * NU + i) * NX + cc] = kv;
+                    if (cc == NX) { S.kk[i] = kv; const_cast<double*>(S.gp[1])[(size_t)k * NU + i] = kv; }
                 }
             }
         }
@@ -714,7 +714,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             // node (the gains this CTA just wrote; L2 hits) is staged there at the pitch of W and the product runs as the
             // same upper-triangular tile syrk as phase f on the FP64 tensor cores; entry (37, 37) is |k|^2.
             double* Ks = S.Qxx;
-            const double* Kn = Kg + (size_t)k * NU * NX;
+            const double* Kn = S.gp[0] + (size_t)k * NU * NX;
             for (int e = tid; e < NU * LDW; e += NT) {
                 const int l = e / LDW, cc = e - l * LDW;
                 Ks[e] = cc < NX ? Kn[l * NX + cc] : (cc == NX ? S.kk[l] : 0.0);

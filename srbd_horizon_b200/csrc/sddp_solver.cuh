@@ -424,9 +424,10 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         // One candidate (the usual first wave): its work is spread over the warps instead of leaving three idle.
         // Per node: warp 0 forms u = U + alpha k + K dx; then warp 0 integrates (accel, Euler step) while warp 1 sums
         // the state-indexed cost terms and warp 2 the input-indexed ones.  Two block barriers per node.
-        double* xb[2] = {S.scr(), S.scr() + NX};       // x^_k ping-pong
+        double* const xb0 = S.scr();                   // x^_k ping-pong: node k in xb0 + (k & 1) * NX (no pointer array: it would live in local memory)
         double* ub = S.scr() + 2 * NX;
-        for (int i = tid; i < NX; i += NT) xb[0][i] = x0[i];
+        for (int i = tid; i < NX; i += NT) xb0[i] = x0[i];
+        if (tid == 0) { S.gp[6] = Xn; S.gp[7] = Un; }   // trial trajectory of this candidate (published by the barrier below)
         double Jw = 0.0;
         for (int k = 0; k < N; k++) {
             cp_wait_all();
@@ -440,7 +441,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             }
             STAMP(12);
             const double* nb = S.nb[k & 1];
-            const double* xc = xb[k & 1];
+            const double* xc = xb0 + (k & 1) * NX;
             constexpr int MV = (4 * NU + 31) & ~31;       // whole warps take part in the shuffles
             static_assert(MV <= NT - 32, "the last warp copies x^");
             static_assert(M::NPRE <= 2 * 8, "accel_pre result lives in rows 2-3 of sacc");
@@ -462,10 +463,10 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
                 if (j < NU && part == 0) {
                     const double v = nb[NBL::OU + j] + S.alpha[0] * nb[NBL::OK + j] + t;      // (`alpha` is per warp = per candidate)
                     ub[j] = v;
-                    Un[(size_t)k * NU + j] = v;
+                    const_cast<double*>(S.gp[7])[(size_t)k * NU + j] = v;
                 }
             } else if (w == NWARP - 1) {       // meanwhile: copy x^ out, and the state-only part of the accelerations
-                for (int i = lane; i < NX; i += 32) Xn[(size_t)k * NX + i] = xc[i];
+                for (int i = lane; i < NX; i += 32) const_cast<double*>(S.gp[6])[(size_t)k * NX + i] = xc[i];
                 if (M::NACC > 1) {
                     double pre[M::NPRE];
                     M::accel_pre(c, xc, pre);
@@ -481,7 +482,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             STAMP(14);
             const int kind = node_kind(c, k);
             if (w == 0) {
-                double* xn_ = xb[(k + 1) & 1];
+                double* xn_ = xb0 + ((k + 1) & 1) * NX;
                 if (M::NACC > 1) {
                     double acc[M::NACC];
                     M::accel_post(c, xc, ub, &S.sacc[0][0] + 16, acc, kind == NODE_TAIL);
@@ -506,8 +507,8 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         }
         cp_wait_all();
         __syncthreads();
-        const double* xT = xb[N & 1];
-        if (w == 0) for (int i = lane; i < NX; i += 32) Xn[(size_t)N * NX + i] = xT[i];
+        const double* xT = xb0 + (N & 1) * NX;
+        if (w == 0) for (int i = lane; i < NX; i += 32) const_cast<double*>(S.gp[6])[(size_t)N * NX + i] = xT[i];
         if (w == 1) Jw += M::cost_lane(c, NODE_TERM, lane, xT, nullptr, S.nb[N & 1] + NBL::OP, S.sacc[0], 1);
         Jw = warp_sum(Jw);
         if (lane == 0) S.red[R_W0 + w] = Jw;
