@@ -598,19 +598,11 @@ int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const doubl
     return 0;
 }
 
-int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* params, double* X, double* U, double* K,
-                     double* kff, double* hist, int32_t* iters, int32_t* status, double* cost, void* stream) {
-    if (!h) return SDDP_EINVAL;
-    if (int rcd = check_device(h)) return rcd;
-    if (B < 0 || (B > 0 && (!x0 || !params || !X || !U || !iters || !status || !cost)))
-        return fail(h, SDDP_EINVAL, "%s%s", "solve_batch: x0, params, X, U, iters, status, cost are required", "");
-    if (B == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
+// Launch of the solve kernel for the arrays named in `a` (device pointers; a.h_* optional mapped host pointers).
+static int launch_solve(SddpHandle* h, int B, SolveArgs& a, cudaStream_t st) {
     CU(cudaMemsetAsync(h->counter, 0, sizeof(int), st));
-    CU(cudaMemsetAsync(status, 0xff, sizeof(int32_t) * (size_t)B, st));      // -1 = not solved (only a bad dispatch order leaves it)
-    SolveArgs a;
-    a.B = B; a.x0 = x0; a.params = params; a.X = X; a.U = U; a.K = K; a.kff = kff; a.hist = hist;
-    a.iters = iters; a.status = status; a.cost = cost;
+    CU(cudaMemsetAsync(a.status, 0xff, sizeof(int32_t) * (size_t)B, st));      // -1 = not solved (only a bad dispatch order leaves it)
+    a.B = B;
     a.ws_d = h->ws_d; a.ws_pack = h->ws_pack; a.ws_xn = h->ws_xn; a.ws_un = h->ws_un; a.ws_K = h->ws_K; a.ws_k = h->ws_k;
     a.counter = h->counter;
     a.order = (h->order_dev && h->order_n == B) ? h->order_dev : nullptr;
@@ -635,6 +627,20 @@ int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* param
     }
     DISPATCH(h, solve_kernel, grid, st, h->dc, a);
     return 0;
+}
+
+int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* params, double* X, double* U, double* K,
+                     double* kff, double* hist, int32_t* iters, int32_t* status, double* cost, void* stream) {
+    if (!h) return SDDP_EINVAL;
+    if (int rcd = check_device(h)) return rcd;
+    if (B < 0 || (B > 0 && (!x0 || !params || !X || !U || !iters || !status || !cost)))
+        return fail(h, SDDP_EINVAL, "%s%s", "solve_batch: x0, params, X, U, iters, status, cost are required", "");
+    if (B == 0) return 0;
+    SolveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x0 = x0; a.params = params; a.X = X; a.U = U; a.K = K; a.kff = kff; a.hist = hist;
+    a.iters = iters; a.status = status; a.cost = cost;
+    return launch_solve(h, B, a, (cudaStream_t)stream);
 }
 
 int sddp_backward_pass(SddpHandle* h, int B, const double* X, const double* U, const double* params, const double* defect,
@@ -718,6 +724,44 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     int32_t* d_it = (int32_t*)(d_c + Bz);
     int32_t* d_st = d_it + Bz;
     int32_t* d_ord = d_st + Bz;
+    // Host-direct path: when every buffer of the caller is mapped pinned host memory (cudaHostAlloc / cudaHostRegister:
+    // torch pin_memory() is) and K is not asked for, ONE launch solves the whole batch: the CTA that takes a problem pulls
+    // its inputs over PCIe and stores its results straight into the caller's arrays (sddp_solver.cuh, solve_one), so every
+    // transfer rides under the solves of the other CTAs and there are no chunk boundaries with their tails of slow
+    // problems.  (K is 7.1 KB per node: 355 KB per problem would make the stores PCIe bound; it takes the staged path.)
+    {
+        static int direct_env = -1;
+        if (direct_env < 0) { const char* e = getenv("SDDP_HOST_DIRECT"); direct_env = (e && e[0] == '0') ? 0 : 1; }
+        auto mapped = [](const void* p, void** dp) -> bool {
+            *dp = nullptr;
+            if (!p) return true;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+            if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+            *dp = at.devicePointer;
+            return true;
+        };
+        void *m_x0, *m_p, *m_X0, *m_U0, *m_X, *m_U, *m_k, *m_h, *m_c, *m_it, *m_st;
+        if (direct_env && !K && mapped(x0, &m_x0) && mapped(params, &m_p) && mapped(X0, &m_X0) && mapped(U0, &m_U0) && mapped(X, &m_X) &&
+            mapped(U, &m_U) && mapped(kff, &m_k) && mapped(hist, &m_h) && mapped(cost, &m_c) && mapped(iters, &m_it) && mapped(status, &m_st)) {
+            if (h->order_host.size() == Bz) CU(cudaMemcpyAsync(d_ord, h->order_host.data(), Bz * sizeof(int32_t), cudaMemcpyHostToDevice, h->st_cmp));
+            const int32_t* saved_order = h->order_dev;
+            const int saved_n = h->order_n, saved_peers = h->n_peers;
+            h->order_dev = h->order_host.size() == Bz ? d_ord : nullptr; h->order_n = B; h->n_peers = 0;
+            SolveArgs a;
+            memset(&a, 0, sizeof(a));
+            a.x0 = d_x0; a.params = d_p; a.X = d_X; a.U = d_U; a.K = nullptr; a.kff = kff ? d_k : nullptr; a.hist = hist ? d_h : nullptr;
+            a.iters = d_it; a.status = d_st; a.cost = d_c;
+            a.h_x0 = (const double*)m_x0; a.h_params = (const double*)m_p; a.h_X0 = (const double*)m_X0; a.h_U0 = (const double*)m_U0;
+            a.h_X = (double*)m_X; a.h_U = (double*)m_U; a.h_kff = (double*)m_k; a.h_hist = (double*)m_h; a.h_cost = (double*)m_c;
+            a.h_iters = (int*)m_it; a.h_status = (int*)m_st;
+            int rcl = launch_solve(h, B, a, h->st_cmp);
+            h->order_dev = saved_order; h->order_n = saved_n; h->n_peers = saved_peers;
+            if (rcl) return rcl;
+            CU(cudaStreamSynchronize(h->st_cmp));
+            return 0;
+        }
+    }
     // Chunk size: the copies of one chunk overlap the solve of another, so a batch needs several chunks whatever its
     // size (a fixed 16K left the 8192-problem shards of an 8-GPU run with one chunk: copy, solve, copy in series).
     // Default: a quarter of the batch, at least two problems per CTA slot (so a chunk still fills the GPU and its tail

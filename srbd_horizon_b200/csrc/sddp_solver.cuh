@@ -572,6 +572,11 @@ struct SolveArgs {
     int n_peers, rec;
     long long first;
     double* peers[SDDP_MAX_PEERS];
+    // host-direct mode (sddp_solve_batch_host on pinned buffers): mapped HOST pointers.  The CTA that takes problem b pulls its
+    // inputs over PCIe into the device arrays above (x0, params, X, U are then the handle's staging arrays) and stores its
+    // results straight into the caller's host arrays: one launch, every transfer rides under the solves of the other CTAs.
+    const double* h_x0; const double* h_params; const double* h_X0; const double* h_U0;
+    double* h_X; double* h_U; double* h_kff; double* h_hist; double* h_cost; int* h_iters; int* h_status;
 };
 
 // `scratch`: PACK_SCRATCH * NT doubles of shared memory nobody else uses during the call (one column per thread)
@@ -591,6 +596,24 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     const size_t xsz = (size_t)(N + 1) * NX, usz = (size_t)N * NU;
     const double* x0 = a.x0 + (size_t)b * NX;
     const double* P = a.params + (size_t)b * (N + 1) * NP;
+    if (a.h_params) {      // host-direct: this problem's inputs, straight from the caller's pinned buffers
+        const size_t psz = (size_t)(N + 1) * NP;
+        double* Pd = const_cast<double*>(P);
+        double* xd = const_cast<double*>(x0);
+        const double* hp = a.h_params + (size_t)b * psz;
+        const double* hX = a.h_X0 + (size_t)b * xsz;
+        const double* hU = a.h_U0 + (size_t)b * usz;
+        double* Xd = a.X + (size_t)b * xsz;
+        double* Ud = a.U + (size_t)b * usz;
+#pragma unroll 8
+        for (size_t i = tid; i < psz; i += NT) Pd[i] = hp[i];
+#pragma unroll 8
+        for (size_t i = tid; i < xsz; i += NT) Xd[i] = hX[i];
+#pragma unroll 8
+        for (size_t i = tid; i < usz; i += NT) Ud[i] = hU[i];
+        for (int i = tid; i < NX; i += NT) xd[i] = a.h_x0[(size_t)b * NX + i];
+        __syncthreads();
+    }
     double* X = a.X + (size_t)b * xsz;
     double* U = a.U + (size_t)b * usz;
     double* Kg = a.K ? a.K + (size_t)b * N * NU * NX : a.ws_K + (size_t)slot * N * NU * NX;
@@ -708,7 +731,15 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     }
     __syncthreads();
     if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
-    if (X != Xuser) {
+    if (a.h_X) {           // host-direct: results straight into the caller's pinned buffers (posted writes over PCIe)
+        double* hX = a.h_X + (size_t)b * xsz;
+        double* hU = a.h_U + (size_t)b * usz;
+        for (size_t i = tid; i < xsz; i += NT) hX[i] = X[i];
+        for (size_t i = tid; i < usz; i += NT) hU[i] = U[i];
+        if (a.h_kff) for (size_t i = tid; i < usz; i += NT) a.h_kff[(size_t)b * usz + i] = kg[i];
+        if (a.h_hist) for (int i = tid; i < c.max_iters * 4; i += NT) a.h_hist[(size_t)b * c.max_iters * 4 + i] = hist[i];
+        if (tid == 0) { a.h_iters[b] = it; a.h_status[b] = status; a.h_cost[b] = J; }
+    } else if (X != Xuser) {
         for (size_t i = tid; i < xsz; i += NT) Xuser[i] = X[i];
         for (size_t i = tid; i < usz; i += NT) Uuser[i] = U[i];
     }

@@ -174,8 +174,9 @@ class BatchedDDP:
 
     def solve_host(self, x0: np.ndarray, params: np.ndarray, X0: np.ndarray, U0: np.ndarray, gains: bool = False,
                    history: bool = False, out: Optional[Dict[str, np.ndarray]] = None, order=None) -> Dict[str, np.ndarray]:
-        """Same solve on HOST numpy buffers through `sddp_solve_batch_host` (chunked copies overlap the solves).
-        `out` may hold preallocated (pinned) X, U, iters, status, cost [, K, k, hist] arrays to reuse."""
+        """Same solve on HOST numpy buffers through `sddp_solve_batch_host`.  With pinned buffers (inputs and `out`) and no K
+        the whole batch is one launch whose CTAs move their own inputs and results over PCIe; otherwise chunked staged
+        copies overlap the solves.  `out` may hold preallocated (pinned) X, U, iters, status, cost [, K, k, hist] arrays."""
         B = x0.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -190,7 +191,7 @@ class BatchedDDP:
             out[name] = a
             return a
         X, U = buf("X", (B, N + 1, nx)), buf("U", (B, N, nu))
-        K = buf("K", (B, N, nu, nx)) if gains else None
+        K = buf("K", (B, N, nu, nx)) if gains is True else None      # gains="ff": the feed-forward term k only
         k = buf("k", (B, N, nu)) if gains else None
         hist = buf("hist", (B, self.cfg.max_iters, HIST)) if history else None
         iters, status, cost = buf("iters", (B,), np.int32), buf("status", (B,), np.int32), buf("cost", (B,))

@@ -341,3 +341,34 @@ def test_friction_cone_barrier_matches_oracle(dense, extra):
     assert not torch.equal(r.U, r0.U)            # the barrier does change the solution
     assert (ro["status"] == 0).mean() > 0.7
     _compare_solve(cfg, b, r, ro, B)
+
+
+def test_solve_host_direct_path_on_pinned_buffers():
+    """Pinned (mapped) host buffers take the host-direct path of sddp_solve_batch_host: one launch, the CTAs pull inputs and
+    push results over PCIe themselves.  Same results bit for bit as the device entry point and as the staged path
+    (pageable buffers), with and without a dispatch order, feed-forward gains and history included; K forces the staged path."""
+    cfg, b, s = _setup(MODEL_SRBD, 20, 700, {})         # more problems than CTA slots: the persistent kernel loops
+    r = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hin = [pin(b[k]) for k in ("x0", "params", "X0", "U0")]
+    B = 700
+    out = {"X": pin(np.zeros((B, 21, 37))), "U": pin(np.zeros((B, 20, 24))), "cost": pin(np.zeros(B)), "k": pin(np.zeros((B, 20, 24))),
+           "hist": pin(np.zeros((B, cfg.max_iters, 4))), "iters": pin(np.zeros(B, dtype=np.int32)), "status": pin(np.full(B, 77, dtype=np.int32))}
+    n0 = s.launches
+    rd = s.solve_host(*hin, out=out, order="schedule", history=True, gains="ff")
+    assert s.launches - n0 == 1                           # one launch for the whole batch
+    np.testing.assert_array_equal(rd["k"], cpu(r.k))
+    assert rd["X"] is out["X"]
+    for name in ("X", "U", "cost"):
+        np.testing.assert_array_equal(rd[name], cpu(getattr(r, name)))
+    np.testing.assert_array_equal(rd["iters"], cpu(r.iters))
+    np.testing.assert_array_equal(rd["status"], cpu(r.status))
+    np.testing.assert_array_equal(rd["hist"], cpu(r.hist))
+    rs = s.solve_host(b["x0"], b["params"], b["X0"], b["U0"], gains=True)      # pageable (and K): staged path
+    np.testing.assert_array_equal(rs["X"], rd["X"])
+    np.testing.assert_array_equal(rs["k"], cpu(r.k))
+    # in-place: X / U may alias the warm start
+    hX, hU = pin(b["X0"]), pin(b["U0"])
+    ri = s.solve_host(hin[0], hin[1], hX, hU, out={"X": hX, "U": hU, "cost": out["cost"], "iters": out["iters"], "status": out["status"]})
+    assert ri["X"] is hX
+    np.testing.assert_array_equal(hX, cpu(r.X))
