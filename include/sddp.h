@@ -162,11 +162,14 @@ int sddp_defects(SddpHandle *h, int B, const double *X, const double *U, const d
 
 /* Same solve with HOST buffers: copies in, solves, copies out, synchronises.
  * This is what a non-CUDA caller (the reference's Python loop) binds.  X0 / U0 are the warm start
- * (ddp.py:114,117), X / U receive the solution and may alias X0 / U0.  The batch is processed in
- * chunks so that the host<->device copies of one chunk overlap the solve of another (three streams);
- * pinned host buffers are needed for that overlap, pageable ones work but serialise.  Small batches (one chunk,
- * < 4 MB, the reference's one-problem use) take a single-stream path with one copy in and one copy out through a
- * pinned staging buffer of the handle. */
+ * (ddp.py:114,117), X / U receive the solution and may alias X0 / U0.  Three paths, same results bit for bit:
+ *  - host-direct: every buffer is mapped pinned host memory (cudaHostAlloc / cudaHostRegister) and K is NULL: ONE launch
+ *    for the whole batch; the CTA that takes a problem pulls its inputs over PCIe and stores its results straight into
+ *    the caller's arrays, so the transfers ride under the solves of the other CTAs (SDDP_HOST_DIRECT=0 disables it);
+ *  - small batches (< 4 MB, the reference's one-problem use): one copy in and one copy out through a pinned staging
+ *    buffer of the handle, one stream;
+ *  - otherwise chunks on three streams, so that the copies of one chunk overlap the solve of another (pageable
+ *    buffers work but serialise). */
 int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *params, const double *X0,
                           const double *U0, double *X, double *U, double *K, double *kff, double *hist,
                           int32_t *iters, int32_t *status, double *cost);
