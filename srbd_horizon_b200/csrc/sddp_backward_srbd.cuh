@@ -148,6 +148,9 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
 #ifndef SDDP_C2_UNROLL
 #define SDDP_C2_UNROLL 19
 #endif
+#ifndef SDDP_NO_DMMA
+#define SDDP_NO_DMMA 0     // 1: A/B build without tensor cores (vector FP64 register tiles for Wn = Es B, Vxx -= Wn^T Wn, K = -Es^T Wn)
+#endif
 #ifndef SDDP_ROTATE
 #define SDDP_ROTATE 0      // 148: rotate the warp roles of the d phase by blockIdx / 148 (A/B experiment, profiles/README.md)
 #endif
@@ -535,6 +538,30 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         //         above the diagonal are zero).  In place: a warp owns whole 8-column blocks
         //         (warp 0: blocks 0 and 4) and reads all of a block before it writes; the three row tiles of a block
         //         are independent DMMA chains of 2, 4 and 6 steps.
+#if SDDP_NO_DMMA
+        // (A/B build, profiles/README.md: the three dense products of a node on the vector FP64 pipe, register tiles fed
+        //  from shared memory, no tensor cores.)  h: one thread per (column, group of 8 rows); the column of B goes to
+        //  registers first because the product is formed in place.
+        {
+            const int c_ = tid % 40, g_ = tid / 40;
+            double bcol[NU];
+            if (tid < 120) {
+#pragma unroll
+                for (int l = 0; l < NU; l++) bcol[l] = S.W[l * LDW + c_];
+            }
+            __syncthreads();
+            if (tid < 120) {
+#pragma unroll 1
+                for (int ii = 0; ii < 8; ii++) {
+                    const int i = 8 * g_ + ii;
+                    double s_ = 0.0;
+#pragma unroll
+                    for (int l = 0; l < NU; l++) if (l <= i) s_ += S.Quu[i * NU + l] * bcol[l];
+                    S.W[i * LDW + c_] = S.rs[i] * s_;
+                }
+            }
+        }
+#else
         {
             const int fr = lane >> 2, fc = lane & 3;
             for (int J = warp; J < 5; J += NWARP) {
@@ -559,6 +586,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 }
             }
         }
+#endif
         STAMP(11);
         __syncthreads();
         PROF(12);
@@ -567,6 +595,62 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         //         Vx[37] = -|w0|^2 and y[37] = quy . k.
         // ---- g: [K | k] = -Es^T Wn: 3 x 5 tiles (rows i, columns c); Es is lower triangular, so row tile I starts
         //         at k0 = 8 I.
+#if SDDP_NO_DMMA
+        {
+            // f: 2 x 4 register tiles of the upper triangle of the 40 x 40 product Wn^T Wn (110 tiles, one per thread)
+            if (tid < 110) {
+                int pr_ = 0, rem = tid;
+                while (rem >= 2 * (10 - pr_)) { rem -= 2 * (10 - pr_); pr_++; }
+                const int ri = 2 * pr_ + (rem >= 10 - pr_ ? 1 : 0), cj = pr_ + (rem >= 10 - pr_ ? rem - (10 - pr_) : rem);
+                double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 4
+                for (int l = 0; l < NU; l++) {
+                    const double2 a = *reinterpret_cast<const double2*>(S.W + l * LDW + 2 * ri);
+                    const double2 b0 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * cj), b1 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * cj + 2);
+                    acc[0][0] += a.x * b0.x; acc[0][1] += a.x * b0.y; acc[0][2] += a.x * b1.x; acc[0][3] += a.x * b1.y;
+                    acc[1][0] += a.y * b0.x; acc[1][1] += a.y * b0.y; acc[1][2] += a.y * b1.x; acc[1][3] += a.y * b1.y;
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int gi = 2 * ri + r, gj = 4 * cj + q;
+                        const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
+                        const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
+                        const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
+                        double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
+                        double* d2 = m ? S.VT + gj * NX + gi : d1;
+                        if (ok) {
+                            const double v = 0.5 * (*s1 + *s2) - acc[r][q];
+                            *d1 = v;
+                            *d2 = v;
+                        }
+                    }
+            }
+            // g: [K | k] = -Et^T (diag(rs) Wn), 2 x 4 register tiles (12 x 10, one per thread); Et is lower triangular
+            if (tid < 120) {
+                const int I2 = tid / 10, J4 = tid - 10 * I2;
+                double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+                for (int l = 2 * I2; l < NU; l++) {
+                    const double2 e_ = *reinterpret_cast<const double2*>(S.Quu + l * NU + 2 * I2);
+                    const double r_ = S.rs[l];
+                    const double2 b0 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * J4), b1 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * J4 + 2);
+                    const double w0 = r_ * b0.x, w1 = r_ * b0.y, w2 = r_ * b1.x, w3 = r_ * b1.y;
+                    acc[0][0] += e_.x * w0; acc[0][1] += e_.x * w1; acc[0][2] += e_.x * w2; acc[0][3] += e_.x * w3;
+                    acc[1][0] += e_.y * w0; acc[1][1] += e_.y * w1; acc[1][2] += e_.y * w2; acc[1][3] += e_.y * w3;
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int i = 2 * I2 + r, cc = 4 * J4 + q;
+                        const double kv = -acc[r][q];
+                        if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
+                        if (cc == NX) { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
+                    }
+            }
+        }
+#else
         if constexpr (!LAT) {
         // Warp w takes tiles w, w+4, w+8, w+12 of each product, one after the other through the same code (a rolled loop:
         // the kernel is bound by instruction fetch, not by the latency of the DMMA chains, and four interleaved copies of
@@ -703,6 +787,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             }
         }
         }
+#endif
         STAMP(9);
         cp_wait_all();                         // the prefetch of node k-1 (issued in c1) is long done: this barrier also
         __syncthreads();                       // publishes it, so the next node starts without one of its own
