@@ -703,12 +703,12 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                         *d2 = v;
                     }
                 }
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int cc = 8 * gJ + 2 * fc + e, i = 8 * gI + fr;
-                    const double kv = e ? -g1 : -g0;
-                    if (cc < NX) const_cast<double*>(S.gp[0])[((size_t)k * NU + i) * NX + cc] = kv;
-                    if (cc == NX) { S.kk[i] = kv; const_cast<double*>(S.gp[1])[(size_t)k * NU + i] = kv; }
+                {
+                    const int i = 8 * gI + fr, cc = 8 * gJ + 2 * fc;
+                    double* Krow = const_cast<double*>(S.gp[0]) + ((size_t)k * NU + i) * NX;      // (pointers from shared memory: see prefetch)
+                    if (cc < NX) Krow[cc] = -g0;
+                    if (cc + 1 < NX) Krow[cc + 1] = -g1;
+                    if (cc + 1 == NX) { S.kk[i] = -g1; const_cast<double*>(S.gp[1])[(size_t)k * NU + i] = -g1; }      // column 37 is odd
                 }
             }
         }
