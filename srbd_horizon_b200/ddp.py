@@ -150,6 +150,7 @@ class BatchedDDP:
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         status = torch.empty(B, dtype=torch.int32, device=dev)
         cost = torch.empty(B, dtype=torch.float64, device=dev)
+        user_order = order is not None and not isinstance(order, str)
         if isinstance(order, str):
             if order != "schedule":
                 raise ValueError("order: None, 'schedule' or a permutation")
@@ -158,6 +159,10 @@ class BatchedDDP:
             order = torch.as_tensor(order, dtype=torch.int32, device=dev).contiguous()
             if order.shape != (B,):
                 raise ValueError("order must have one entry per problem")
+            # a caller's permutation is checked here: the kernel skips entries outside 0..B-1 and a problem that no entry
+            # names stays unsolved (status -1), but it cannot tell the caller (include/sddp.h, sddp_set_dispatch_order)
+            if user_order and not bool(torch.equal(torch.sort(order.to(torch.int64)).values, torch.arange(B, device=dev))):
+                raise ValueError("order must be a permutation of 0..B-1")
         with torch.cuda.device(dev):
             if gather is not None:
                 if gather.solver is not self:

@@ -144,3 +144,29 @@ def test_dispatch_order_changes_nothing_but_the_schedule():
     bad = np.zeros(B, dtype=np.int32)
     rc = s.L.sddp_set_dispatch_order(s.h, bad.ctypes.data_as(ctypes.c_void_p), B, 1)
     assert rc == -1 and b"permutation" in s.L.sddp_last_error(s.h)
+
+
+def test_device_dispatch_order_is_validated_by_the_wrapper():
+    """a device permutation reaches the kernel unchecked at the C ABI (documented in include/sddp.h: entries
+    outside 0..B-1 are skipped, a problem nobody names keeps status -1); `BatchedDDP.solve(order=<tensor>)` checks it."""
+    import ctypes
+    B, N = 40, 10
+    cfg = make_config(MODEL_SRBD, N, 0.05, EX)
+    b = make_batch(MODEL_SRBD, N, B)
+    s = BatchedDDP(cfg)
+    dup = torch.arange(B, dtype=torch.int32); dup[3] = 4
+    with pytest.raises(ValueError):
+        s.solve(b["x0"], b["params"], b["X0"], b["U0"], order=dup)
+    with pytest.raises(ValueError):
+        s.solve(b["x0"], b["params"], b["X0"], b["U0"], order=torch.arange(B, dtype=torch.int32) + 1)
+    # at the C ABI: out-of-range entries are skipped, the unnamed problem is left with status -1, nothing else is touched
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")
+    x0, p, X, U = t(b["x0"]), t(b["params"]), t(b["X0"]).clone(), t(b["U0"]).clone()
+    it = torch.zeros(B, dtype=torch.int32, device="cuda"); st = torch.zeros(B, dtype=torch.int32, device="cuda"); c = torch.zeros(B, dtype=torch.float64, device="cuda")
+    bad = torch.arange(B, dtype=torch.int32, device="cuda"); bad[7] = B + 5
+    vp = lambda a: ctypes.c_void_p(a.data_ptr())
+    assert s.L.sddp_set_dispatch_order(s.h, vp(bad), B, 0) == 0
+    assert s.L.sddp_solve_batch(s.h, B, vp(x0), vp(p), vp(X), vp(U), None, None, None, vp(it), vp(st), vp(c), None) == 0
+    s.L.sddp_set_dispatch_order(s.h, None, 0, 0)
+    torch.cuda.synchronize()
+    assert int(st[7]) == -1 and bool((st[torch.arange(B) != 7] == 0).all())
