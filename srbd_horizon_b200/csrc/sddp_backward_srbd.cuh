@@ -44,6 +44,7 @@ struct alignas(16) SmemSrbdT {
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
     const double* gp[8];       // base pointers of the per-node prefetches (registers are scarce in the node loops)
+    unsigned long long mbar[2];   // completion barriers of the bulk copies of K_k (forward_wave)
     int iflag[4];
     __device__ double* Kbuf(int b) { return Qxx + b * (NU * NX); }
     __device__ double* scr() { return VT; }
@@ -147,6 +148,9 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
 #endif
 #ifndef SDDP_C2_UNROLL
 #define SDDP_C2_UNROLL 19
+#endif
+#ifndef SDDP_BULK_PACK
+#define SDDP_BULK_PACK 0
 #endif
 #ifndef SDDP_NO_DMMA
 #define SDDP_NO_DMMA 0     // 1: A/B build without tensor cores (vector FP64 register tiles for Wn = Es B, Vxx -= Wn^T Wn, K = -Es^T Wn)
@@ -274,6 +278,9 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
     const double dt = c.dt;
     SyncBlock sync;
 
+    // (the 2 KB pack as one bulk copy: measured 1 % slower than 128 16-byte cp.async here -- every thread then polls a barrier
+    //  at every node -- so it is off by default; the 7.1 KB gain tile of the forward pass keeps its bulk copy)
+    const bool bulk = SDDP_BULK_PACK && M::PACK % 2 == 0 && ((((size_t)packs) | ((size_t)(S.nb[0] + NBL::OK)) | ((size_t)(S.nb[1] + NBL::OK))) & 15) == 0;
     auto prefetch = [&](int k) {       // node k -> buffer k & 1 (base pointers from shared memory: see forward_wave)
         double* nb = S.nb[k & 1];
         const double* Xs = S.gp[2] + (size_t)k * NX;
@@ -287,14 +294,20 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         const double* Ps = S.gp[5] + (size_t)k * NP;
         for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, Ps + i);
         const double* ps = S.gp[6] + (size_t)k * M::PACK;
-        if (((((size_t)ps) | ((size_t)(nb + NBL::OK))) & 15) == 0) { for (int i = 2 * tid; i < M::PACK; i += 2 * NT) cp_async16(nb + NBL::OK + i, ps + i); }
+        if (bulk) { if (tid == 0) bulk_g2s(nb + NBL::OK, ps, M::PACK * 8, &S.mbar[k & 1]); }      // the 2 KB pack: one bulk copy
+        else if (((((size_t)ps) | ((size_t)(nb + NBL::OK))) & 15) == 0) { for (int i = 2 * tid; i < M::PACK; i += 2 * NT) cp_async16(nb + NBL::OK + i, ps + i); }
         else { for (int i = tid; i < M::PACK; i += NT) cp_async8(nb + NBL::OK + i, ps + i); }
         cp_commit();
     };
+    // buffer k & 1 is used by nodes N-1, N-3, ... (or N-2, N-4, ...): phase parity of its barrier at node k
+    auto landed = [&](int k) { if (bulk) mbar_wait(&S.mbar[k & 1], ((N - 1 - k) >> 1) & 1); };
 
     // terminal node: Vx = l_Nx, Vxx = l_Nxx (ddp.py:216-226: costs only)
     __syncthreads();
-    if (tid == 0) { S.gp[0] = Kg; S.gp[1] = kg; S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P; S.gp[6] = packs; }
+    if (tid == 0) {
+        S.gp[0] = Kg; S.gp[1] = kg; S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P; S.gp[6] = packs;
+        if (bulk) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); fence_async_proxy(); }
+    }
     __syncthreads();
     {
         double* nb = S.nb[N & 1];
@@ -307,6 +320,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
     M::template expand<LDW>(c, NODE_TERM, S.nb[N & 1] + NBL::OX, nullptr, S.nb[N & 1] + NBL::OP, nullptr, S.Vx, S.Qu, S.VT, S.W, S.Quu, tid, NT, sync, S.escr);
     for (int i = tid; i < NX; i += NT) S.y[i] = S.Vx[i];
     cp_wait_all();
+    landed(N - 1);
     __syncthreads();                           // node N-1 landed
     PROF(19);
 
@@ -532,7 +546,15 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         __syncthreads();
         STAMP(8);
         PROF(11);
-        if (S.iflag[1]) { __syncthreads(); if (tid == 0) S.iflag[1] = 0; cp_wait_all(); __syncthreads(); return k + 1; }
+        if (S.iflag[1]) {      // a pivot was not positive: leave (the prefetch of node k-1 is in flight: wait for it first)
+            __syncthreads();
+            cp_wait_all();
+            if (k > 0) landed(k - 1);
+            __syncthreads();                   // nobody polls a barrier any more
+            if (tid == 0) { S.iflag[1] = 0; if (bulk) { mbar_inval(&S.mbar[0]); mbar_inval(&S.mbar[1]); } }
+            __syncthreads();
+            return k + 1;
+        }
 
         // ---- h: Wn = Es B = diag(rs) Et B (B = [Qux | Qu | quy], 24 x 40 in S.W; Et lower triangular in S.Quu, entries
         //         above the diagonal are zero).  In place: a warp owns whole 8-column blocks
@@ -790,6 +812,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 #endif
         STAMP(9);
         cp_wait_all();                         // the prefetch of node k-1 (issued in c1) is long done: this barrier also
+        if (k > 0) landed(k - 1);
         __syncthreads();                       // publishes it, so the next node starts without one of its own
         STAMP(10);
         PROF(13);
@@ -843,6 +866,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         double tot = S.red[R_TOT], a1 = S.red[R_ACC1], a2 = S.red[R_ACC2];
         if (fixed) { dV3[2] = a1; dV3[1] = a2; dV3[0] = tot - a1 - a2; }
         else       { dV3[2] = 0.0; dV3[0] = a1; dV3[1] = tot - a1; }
+        if (bulk) { mbar_inval(&S.mbar[0]); mbar_inval(&S.mbar[1]); }
     }
     __syncthreads();
     return 0;

@@ -48,6 +48,31 @@ SDDP_DEV void cp_async16(double* smem, const double* g) {
 SDDP_DEV void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 SDDP_DEV void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- 1-D bulk copies (the TMA unit without a tensor map: cp.async.bulk + mbarrier), for tiles whose size and addresses are
+//      multiples of 16 bytes: one thread issues one instruction for the whole tile instead of every thread a few cp.async
+#ifndef SDDP_BULK
+#define SDDP_BULK 1
+#endif
+SDDP_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SDDP_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+SDDP_DEV void mbar_inval(unsigned long long* bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+SDDP_DEV void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the issuing thread: expect `bytes` on the barrier, then the copy that delivers them
+SDDP_DEV void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+SDDP_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 template <class M>
 struct Smem {
     static constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
@@ -60,6 +85,7 @@ struct Smem {
     double red[16];
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
     const double* gp[8];                 // base pointers of the per-node prefetches (see forward_wave)
+    unsigned long long mbar[2];          // completion barriers of the bulk copies of K_k (forward_wave)
     int iflag[4];
     __device__ static int backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
                                    const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
@@ -394,6 +420,8 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
     const bool active = w < ncand;
     const double alpha = active ? S.alpha[w] : 0.0, omr = active ? 1.0 - S.rho[w] : 0.0;
     double J = 0.0;
+    // K_k by one bulk copy when the tile and both addresses are multiples of 16 bytes (always for SRBD with caller-owned gains)
+    const bool bulk = SDDP_BULK && (NU * NX) % 2 == 0 && ((((size_t)S.Kbuf(0)) | ((size_t)S.Kbuf(1)) | ((size_t)Kg)) & 15) == 0;
     // node k's inputs (K_k, k_k, X_k, U_k, d_k, p_k) are fetched with cp.async while node k-1 is computed
     // The six base pointers live in shared memory during the rollout: held in registers across the node loop they were
     // spilled (the kernel sits at its 128-register cap) and re-read from local memory at every node, a quarter of them L1 misses.
@@ -401,7 +429,8 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         double* nb = S.nb[k & 1];
         double* Kb = S.Kbuf(k & 1);
         const double* Ks = S.gp[0] + (size_t)k * NU * NX;
-        if ((NU * NX) % 2 == 0 && ((((size_t)Kb) | ((size_t)Ks)) & 15) == 0) { for (int e = 2 * tid; e < NU * NX; e += 2 * NT) cp_async16(Kb + e, Ks + e); }
+        if (bulk) { if (tid == 0) bulk_g2s(Kb, Ks, NU * NX * 8, &S.mbar[k & 1]); }      // one instruction for the 7.1 KB tile
+        else if ((NU * NX) % 2 == 0 && ((((size_t)Kb) | ((size_t)Ks)) & 15) == 0) { for (int e = 2 * tid; e < NU * NX; e += 2 * NT) cp_async16(Kb + e, Ks + e); }
         else { for (int e = tid; e < NU * NX; e += NT) cp_async8(Kb + e, Ks + e); }
         const double* Xs = S.gp[2] + (size_t)k * NX;
         const double* Ds = S.gp[3] + (size_t)k * NX;
@@ -414,7 +443,10 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         cp_commit();
     };
     __syncthreads();      // the buffers may still be in use by the caller's previous phase
-    if (tid == 0) { S.gp[0] = Kg; S.gp[1] = kg; S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P; }
+    if (tid == 0) {
+        S.gp[0] = Kg; S.gp[1] = kg; S.gp[2] = X; S.gp[3] = D; S.gp[4] = U; S.gp[5] = P;
+        if (bulk) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); fence_async_proxy(); }      // (also orders the earlier generic writes of the K buffers before the async-proxy writes)
+    }
     __syncthreads();
     prefetch(0);
     PROF(23);
@@ -431,6 +463,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         double Jw = 0.0;
         for (int k = 0; k < N; k++) {
             cp_wait_all();
+            if (bulk) mbar_wait(&S.mbar[k & 1], (k >> 1) & 1);
             __syncthreads();                  // node k landed; everyone is done with node k-1
             PROF(24);
             if (k + 1 < N) prefetch(k + 1);
@@ -513,7 +546,10 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         Jw = warp_sum(Jw);
         if (lane == 0) S.red[R_W0 + w] = Jw;
         __syncthreads();
-        if (tid == 0) S.Jc[0] = S.red[R_W0] + S.red[R_W0 + 1] + S.red[R_W0 + 2] + S.red[R_W0 + 3];
+        if (tid == 0) {
+            S.Jc[0] = S.red[R_W0] + S.red[R_W0 + 1] + S.red[R_W0 + 2] + S.red[R_W0 + 3];
+            if (bulk) { mbar_inval(&S.mbar[0]); mbar_inval(&S.mbar[1]); }
+        }
         __syncthreads();
         PROF(27);
         return;
@@ -521,6 +557,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
     for (int i = lane; i < NX; i += 32) xh[i] = x0[i];
     for (int k = 0; k < N; k++) {
         cp_wait_all();
+        if (bulk) mbar_wait(&S.mbar[k & 1], (k >> 1) & 1);
         __syncthreads();                  // node k landed for everyone; everyone is done with node k-1
         if (k + 1 < N) prefetch(k + 1);
         else {                            // terminal parameters go to the free buffer
@@ -553,6 +590,7 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         J += warp_node<M>(c, NODE_TERM, xh, nullptr, S.nb[N & 1] + NBL::OP, nullptr, nullptr, 0.0, S.sacc[w], lane);
         if (lane == 0) S.Jc[w] = J;
     }
+    if (bulk && tid == 0) { mbar_inval(&S.mbar[0]); mbar_inval(&S.mbar[1]); }
     __syncthreads();
 }
 
