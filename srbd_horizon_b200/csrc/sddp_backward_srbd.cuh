@@ -149,6 +149,9 @@ SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
 #ifndef SDDP_C2_UNROLL
 #define SDDP_C2_UNROLL 19
 #endif
+#ifndef SDDP_D1R
+#define SDDP_D1R 2         // pivot steps per trip of the rolled factorisation (the register frame is shifted once per trip)
+#endif
 #ifndef SDDP_BULK_PACK
 #define SDDP_BULK_PACK 0
 #endif
@@ -216,7 +219,7 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
     //  cycles per step, tools/microbench/ldlt.cu V10 / V16 -- but the elimination then loses the scaling invariance of
     //  symmetric LDL^T: at the first SRBD node behind a LIP-style tail, cond(Quu) = 2e9, the gains come out at 2e-8
     //  instead of 1e-13.)
-    constexpr int R = 4;
+    constexpr int R = SDDP_D1R;
     static_assert(NU % R == 0 && R % 2 == 0, "d1 frame");
     double b[NU];
 #pragma unroll

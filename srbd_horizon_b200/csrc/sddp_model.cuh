@@ -96,7 +96,7 @@ enum { NODE_FIRST = 0, NODE_MID = 1, NODE_TERM = 2, NODE_TAIL = 3 };   // TAIL: 
 
 #define SDDP_DEV __device__ __forceinline__
 #ifndef SDDP_E_UNROLL
-#define SDDP_E_UNROLL 2
+#define SDDP_E_UNROLL 1
 #endif
 #ifndef SDDP_NOINLINE
 #define SDDP_NOINLINE
@@ -593,6 +593,7 @@ struct SrbdT {
     // w tracking on the (w, w) diagonal), (2) the 44 other affine Hessian entries through the table at ZT_AOFF, (3) the
     // gradients lx (37) and lu (24), one per thread.  tid in [0, ZT_LAZY_THREADS); Qux = Qxx + ZT_QUX_OFF.
     // Compact descriptors: valid | hs << 1 | hoff << 3 | dst1 << 12 | dst2 << 24 | (affine value index + 1) << 36.
+    // (measured: as a real call, one copy instead of three, this function costs 10 % of the whole solve -- the ABI spills)
     SDDP_DEV static double aff_value(const DevCfg& c, int kind, const double* x, const double* p, int l) {
         const bool track = kind != NODE_FIRST, tail = kind == NODE_TAIL;
         if (l < 12) {      // (cd, cd) diagonal: relative_vel + cdotxy_tracking (prb.py:166-181) [+ velocity box]
