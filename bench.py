@@ -38,8 +38,8 @@ EX_OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}   
 F_NODE = 4 * 37 ** 3 + 8 * 37 ** 2 * 24 + 6 * 37 * 24 ** 2 + 24 ** 3 // 3 + 2 * 37 * 24     # 599,716 FLOP
 BYTES_NODE = 15720
 # measured DRAM traffic of solve_kernel per Riccati node-iteration: dram__bytes_read+write of one `ncu --set full`
-# capture (profiles/r1_solve_kernel_full_raw.csv: 26.55 GB for 4736 problems x 4.963 iterations x 50 nodes)
-TRAFFIC_NODE = 26.55e9 / (4736 * 4.963 * 50)
+# capture (profiles/r2_solve_kernel_full_raw.csv: 11.25 + 13.46 GB for 4736 problems x 4.963 iterations x 50 nodes)
+TRAFFIC_NODE = 24.71e9 / (4736 * 4.963 * 50)
 HBM_PEAK_FALLBACK = 6650.0
 FP64_NOMINAL_TFLOPS = 148 * 4 * 16 * 2 * 1.965e9 / 1e12      # 148 SMs x 64 FP64 FMA/clk x 2 x 1965 MHz = 37.2 (no FP64 entry in MEASURED_PEAKS.json)
 
