@@ -124,7 +124,15 @@ class BatchedDDP:
         guess of how many iterations a problem needs -- by default the commanded velocity |rdot_ref| (p[0:3] of the last
         node, prb.py:74), which correlates +0.5 with the iteration count inside a schedule (tools/iters_features.py)."""
         if isinstance(group, np.ndarray):
-            o1 = np.argsort(-np.asarray(effort), kind="stable")
+            effort = np.asarray(effort, dtype=np.float64)
+            if np.issubdtype(group.dtype, np.integer) and group.size and int(group.max()) - int(group.min()) < 64:
+                # few integer groups (the caller's schedule ids): one 16-bit key = group | quantised effort, which numpy sorts
+                # with a radix sort (two stable argsorts of 64K keys cost 17 ms, 3.5 % of an end-to-end step; this is 1 ms)
+                lo, hi = float(effort.min()), float(effort.max())
+                q = ((hi - effort) * (1023.0 / (hi - lo if hi > lo else 1.0))).astype(np.uint16)      # largest effort first
+                key = ((group - group.min()).astype(np.uint16) << 10) | q
+                return np.argsort(key, kind="stable").astype(np.int32)
+            o1 = np.argsort(-effort, kind="stable")
             return o1[np.argsort(np.asarray(group)[o1], kind="stable")].astype(np.int32)
         o1 = torch.argsort(effort, descending=True, stable=True)
         return o1[torch.argsort(group[o1], stable=True)].to(torch.int32)

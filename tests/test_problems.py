@@ -73,10 +73,18 @@ def test_dispatch_order_from_keys_groups_and_sorts():
     rng = np.random.default_rng(0)
     g = rng.integers(0, 7, size=500)
     e = rng.random(500)
-    o = BatchedDDP.order_from_keys(g, e)
+    gf = g.astype(np.float64)                      # general keys (the hash of dispatch_order): two stable sorts, exact
+    o = BatchedDDP.order_from_keys(gf, e)
     assert o.dtype == np.int32 and sorted(o.tolist()) == list(range(500))
     assert (np.diff(g[o]) >= 0).all()
     for k in range(7):
         assert (np.diff(e[o][g[o] == k]) <= 0).all()
-    ot = BatchedDDP.order_from_keys(torch.as_tensor(g), torch.as_tensor(e))
+    ot = BatchedDDP.order_from_keys(torch.as_tensor(gf), torch.as_tensor(e))
     assert np.array_equal(ot.numpy(), o)
+    # few integer groups (the caller's schedule ids): one radix sort of a 16-bit key, the effort quantised to 10 bits
+    oi = BatchedDDP.order_from_keys(g, e)
+    assert oi.dtype == np.int32 and sorted(oi.tolist()) == list(range(500))
+    assert (np.diff(g[oi]) >= 0).all()
+    quantum = (e.max() - e.min()) / 1023.0
+    for k in range(7):
+        assert (np.diff(e[oi][g[oi] == k]) <= quantum * 1.001).all()
