@@ -43,7 +43,17 @@
 extern "C" {
 #endif
 
-#define SDDP_ABI_VERSION 4
+#define SDDP_ABI_VERSION 5
+
+/* Element type of every array argument.  double in the product library (libsddp.so).  The optional fp32 build
+ * (libsddp_f32.so, compiled from the same sources with -DSDDP_F32; north_star "optional fp32 build ... within a stated
+ * tolerance") exports the same symbols with float arrays; sddp_real_bytes() tells a caller which one it has loaded.
+ * SddpConfig and scalar arguments are double in both. */
+#ifdef SDDP_F32
+typedef float sddp_real;
+#else
+typedef double sddp_real;
+#endif
 
 enum { SDDP_MODEL_SRBD = 0, SDDP_MODEL_LIP = 1 };
 enum { SDDP_INERTIA_LITERAL = 0, SDDP_INERTIA_ROTATED = 1 };   /* prb.py:99 as written / README.md:2 intent */
@@ -116,6 +126,7 @@ typedef struct SddpConfig {
 typedef struct SddpHandle SddpHandle;
 
 int sddp_abi_version(void);
+int sddp_real_bytes(void);   /* sizeof(sddp_real) of the loaded library: 8, or 4 for the fp32 build */
 size_t sddp_config_size(void);
 /* nx, nu, np of a model */
 int sddp_dims(int model, int *nx, int *nu, int *np);
@@ -135,30 +146,30 @@ int sddp_set_config(SddpHandle *h, const SddpConfig *cfg);
  * f[M][nx], fx[M][nx][nx], fu[M][nx][nu], l[M], lx[M][nx], lu[M][nu], lxx[M][nx][nx],
  * lux[M][nu][nx], luu[M][nu][nu].  Any output pointer may be NULL.  For SDDP_NODE_TERM
  * the dynamics and input outputs are written as zeros. */
-int sddp_eval_derivatives(SddpHandle *h, int M, const int32_t *kind, const double *x, const double *u,
-                          const double *p, double *f, double *fx, double *fu, double *l, double *lx,
-                          double *lu, double *lxx, double *lux, double *luu, void *stream);
+int sddp_eval_derivatives(SddpHandle *h, int M, const int32_t *kind, const sddp_real *x, const sddp_real *u,
+                          const sddp_real *p, sddp_real *f, sddp_real *fx, sddp_real *fu, sddp_real *l, sddp_real *lx,
+                          sddp_real *lu, sddp_real *lxx, sddp_real *lux, sddp_real *luu, void *stream);
 
 /* The solve (ddp.py:101).  X and U carry the warm start in and the solution out.
  * K, kff, hist may be NULL (gains then stay in the workspace). */
-int sddp_solve_batch(SddpHandle *h, int B, const double *x0, const double *params, double *X, double *U,
-                     double *K, double *kff, double *hist, int32_t *iters, int32_t *status, double *cost,
+int sddp_solve_batch(SddpHandle *h, int B, const sddp_real *x0, const sddp_real *params, sddp_real *X, sddp_real *U,
+                     sddp_real *K, sddp_real *kff, sddp_real *hist, int32_t *iters, int32_t *status, sddp_real *cost,
                      void *stream);
 
 /* Stage entry points used by the stage parity tests (north_star stages two to four).
  * defect[B][N][nx]; dV[B][3] = {D1, D2, C0}; rc[B] = 0 or failing node + 1. */
-int sddp_backward_pass(SddpHandle *h, int B, const double *X, const double *U, const double *params,
-                       const double *defect, double mu, double *K, double *kff, double *dV, int32_t *rc,
+int sddp_backward_pass(SddpHandle *h, int B, const sddp_real *X, const sddp_real *U, const sddp_real *params,
+                       const sddp_real *defect, double mu, sddp_real *K, sddp_real *kff, sddp_real *dV, int32_t *rc,
                        void *stream);
 /* n_alpha candidate step sizes per problem, evaluated in parallel: Jn[B][n_alpha],
  * Xn[B][n_alpha][N+1][nx], Un[B][n_alpha][N][nu] (Xn/Un may be NULL). rho[n_alpha] as alpha. */
-int sddp_forward_pass(SddpHandle *h, int B, int n_alpha, const double *alpha, const double *rho,
-                      const double *x0, const double *X, const double *U, const double *params,
-                      const double *defect, const double *K, const double *kff, double *Jn, double *Xn,
-                      double *Un, void *stream);
+int sddp_forward_pass(SddpHandle *h, int B, int n_alpha, const sddp_real *alpha, const sddp_real *rho,
+                      const sddp_real *x0, const sddp_real *X, const sddp_real *U, const sddp_real *params,
+                      const sddp_real *defect, const sddp_real *K, const sddp_real *kff, sddp_real *Jn, sddp_real *Xn,
+                      sddp_real *Un, void *stream);
 /* defect[B][N][nx] = f(X_k,U_k) - X_{k+1},  cost[B] = total cost (either may be NULL) */
-int sddp_defects(SddpHandle *h, int B, const double *X, const double *U, const double *params,
-                 double *defect, double *cost, void *stream);
+int sddp_defects(SddpHandle *h, int B, const sddp_real *X, const sddp_real *U, const sddp_real *params,
+                 sddp_real *defect, sddp_real *cost, void *stream);
 
 /* Same solve with HOST buffers: copies in, solves, copies out, synchronises.
  * This is what a non-CUDA caller (the reference's Python loop) binds.  X0 / U0 are the warm start
@@ -170,9 +181,9 @@ int sddp_defects(SddpHandle *h, int B, const double *X, const double *U, const d
  *    buffer of the handle, one stream;
  *  - otherwise chunks on three streams, so that the copies of one chunk overlap the solve of another (pageable
  *    buffers work but serialise). */
-int sddp_solve_batch_host(SddpHandle *h, int B, const double *x0, const double *params, const double *X0,
-                          const double *U0, double *X, double *U, double *K, double *kff, double *hist,
-                          int32_t *iters, int32_t *status, double *cost);
+int sddp_solve_batch_host(SddpHandle *h, int B, const sddp_real *x0, const sddp_real *params, const sddp_real *X0,
+                          const sddp_real *U0, sddp_real *X, sddp_real *U, sddp_real *K, sddp_real *kff, sddp_real *hist,
+                          int32_t *iters, int32_t *status, sddp_real *cost);
 
 /* Dispatch order of the next solves (scheduling only: results do not depend on it).  The persistent CTAs take
  * problems order[0], order[1], ... instead of 0, 1, ...; `order` must be a permutation of 0..n-1 and applies to
@@ -201,13 +212,13 @@ enum { SDDP_RECORD_TAIL = 3, SDDP_IPC_HANDLE_BYTES = 64, SDDP_MAX_RESULT_PEERS =
 long long sddp_record_doubles(const SddpHandle *h);
 /* (Re)allocates the handle-owned slab of n_records records with plain cudaMalloc (exportable with sddp_ipc_export);
  * n_records = 0 frees it.  Freed by sddp_destroy. */
-int sddp_slab_alloc(SddpHandle *h, long long n_records, double **out);
+int sddp_slab_alloc(SddpHandle *h, long long n_records, sddp_real **out);
 /* Thin wrappers of cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) / cudaIpcCloseMemHandle so that a
  * host language without CUDA bindings can exchange the 64 handle bytes over any channel it has. */
 int sddp_ipc_export(const void *dev_ptr, unsigned char handle[SDDP_IPC_HANDLE_BYTES]);
 int sddp_ipc_open(const unsigned char handle[SDDP_IPC_HANDLE_BYTES], void **dev_ptr);
 int sddp_ipc_close(void *dev_ptr);
-int sddp_set_result_peers(SddpHandle *h, int n_peers, double *const *slabs, long long first_record);
+int sddp_set_result_peers(SddpHandle *h, int n_peers, sddp_real *const *slabs, long long first_record);
 
 /* ---- receding-horizon glue on the device (the caller side of the path: dsrbd_example.py:102-131,158-160, wpg.py:68-101) ----
  * gait tables of wpg.steps_phase (wpg.py:19-64): four arrays of 21 entries, l_cycle, l_switch, r_cycle, r_switch (host pointers) */
@@ -217,11 +228,11 @@ int sddp_set_gait_tables(SddpHandle *h, const double *l_cycle, const double *l_s
  * (dsrbd_example.py:102-106, wpg.py:74-77), node N receives rdot_ref_cmd[b] and, per action[b]
  * (0 "step", 1 stance, 2 "jump"), the gait entries of wpg.py:80-99 at ref_id = step_counter[b] % 20;
  * step_counter[b] is incremented.  params[B][N+1][np], action/step_counter int32[B], rdot_ref_cmd[B][3]. */
-int sddp_mpc_advance(SddpHandle *h, int B, double *params, const int32_t *action, int32_t *step_counter,
-                     const double *rdot_ref_cmd, void *stream);
+int sddp_mpc_advance(SddpHandle *h, int B, sddp_real *params, const int32_t *action, int32_t *step_counter,
+                     const sddp_real *rdot_ref_cmd, void *stream);
 /* Plant step of the examples: state[b] <- EULER(state[b], u[b*u_stride .. +nu], dt), SRBD quaternion renormalised
  * (dsrbd_example.py:158-160, dlip_example.py:161-162).  state[B][nx] in place; u_stride in doubles (N*nu to use U[b][0]). */
-int sddp_plant_step(SddpHandle *h, int B, double *state, const double *u, long long u_stride, void *stream);
+int sddp_plant_step(SddpHandle *h, int B, sddp_real *state, const sddp_real *u, long long u_stride, void *stream);
 
 /* Measured FP64 FMA rate of the device (microbenchmark, TFLOP/s); used as the roofline peak. */
 int sddp_fp64_peak_tflops(double *out, void *stream);

@@ -35,19 +35,19 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(DevCfg c, SolveArgs a) 
 
 // Stage 1 alone: one CTA per (x,u,p) point, dense outputs.
 template <class M>
-__global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int* kind, const double* x, const double* u, const double* p,
-                                                  double* f, double* fx, double* fu, double* l, double* lx, double* lu, double* lxx,
-                                                  double* lux, double* luu) {
+__global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int* kind, const real* x, const real* u, const real* p,
+                                                  real* f, real* fx, real* fu, real* l, real* lx, real* lu, real* lxx,
+                                                  real* lux, real* luu) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<M>& S = *reinterpret_cast<Smem<M>*>(smem_raw);
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int tid = threadIdx.x;
     SyncBlock sync;
     using NBL = NodeBuf<M>;
-    double* xk = S.nb[0] + NBL::OX;
-    double* uk = S.nb[0] + NBL::OU;
-    double* pk = S.nb[0] + NBL::OP;
-    double* pack = S.nb[0] + NBL::OK;
+    real* xk = S.nb[0] + NBL::OX;
+    real* uk = S.nb[0] + NBL::OU;
+    real* pk = S.nb[0] + NBL::OP;
+    real* pack = S.nb[0] + NBL::OK;
     for (int m = blockIdx.x; m < npts; m += gridDim.x) {
         const int kd = kind[m];
         for (int i = tid; i < NX; i += NT) xk[i] = x[(size_t)m * NX + i];
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int*
             __syncthreads();
         }
         if (tid < 32) {
-            double J = warp_node<M>(c, kd, xk, uk, pk, S.vp, nullptr, 0.0, S.sacc[0], tid);
+            real J = warp_node<M>(c, kd, xk, uk, pk, S.vp, nullptr, 0.0, S.sacc[0], tid);
             if (tid == 0 && l) l[m] = J;
         }
         __syncthreads();
@@ -82,28 +82,28 @@ __global__ void __launch_bounds__(NT) eval_kernel(DevCfg c, int npts, const int*
 }
 
 template <class M, class SM, int MINB>
-__global__ void __launch_bounds__(NT, MINB) backward_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, const double* D,
-                                                      double mu, double* K, double* kff, double* dV, int* rc, double* ws_pack) {
+__global__ void __launch_bounds__(NT, MINB) backward_kernel(DevCfg c, int B, const real* X, const real* U, const real* P, const real* D,
+                                                      real mu, real* K, real* kff, real* dV, int* rc, real* ws_pack) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int tid = threadIdx.x, N = c.N;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const double* Xb = X + (size_t)b * (N + 1) * NX;
-        const double* Ub = U + (size_t)b * N * NU;
-        double* packs = ws_pack + (size_t)blockIdx.x * N * M::PACK;
+        const real* Xb = X + (size_t)b * (N + 1) * NX;
+        const real* Ub = U + (size_t)b * N * NU;
+        real* packs = ws_pack + (size_t)blockIdx.x * N * M::PACK;
         SM::prep(c, S, Xb, Ub, P + (size_t)b * (N + 1) * NP, packs, tid);
         int r = SM::backward(c, S, Xb, Ub, P + (size_t)b * (N + 1) * NP, D + (size_t)b * N * NX, packs, mu,
                              K + (size_t)b * N * NU * NX, kff + (size_t)b * N * NU, &S.red[12], true, tid);
-        if (tid == 0) { rc[b] = r; dV[3 * b] = S.red[12]; dV[3 * b + 1] = S.red[13]; dV[3 * b + 2] = S.red[14]; }
+        if (tid == 0) { rc[b] = r; dV[3 * b] = (real)S.red[12]; dV[3 * b + 1] = (real)S.red[13]; dV[3 * b + 2] = (real)S.red[14]; }
         __syncthreads();
     }
 }
 
 template <class M, class SM, int MINB>
-__global__ void __launch_bounds__(NT, MINB) forward_kernel(DevCfg c, int B, int n_alpha, const double* alpha, const double* rho, const double* x0,
-                                                     const double* X, const double* U, const double* P, const double* D, const double* K,
-                                                     const double* kff, double* Jn, double* Xn, double* Un, double* ws_xn, double* ws_un) {
+__global__ void __launch_bounds__(NT, MINB) forward_kernel(DevCfg c, int B, int n_alpha, const real* alpha, const real* rho, const real* x0,
+                                                     const real* X, const real* U, const real* P, const real* D, const real* K,
+                                                     const real* kff, real* Jn, real* Xn, real* Un, real* ws_xn, real* ws_un) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(DevCfg c, int B, int 
             __syncthreads();
             if (tid < ncand) { S.alpha[tid] = alpha[base + tid]; S.rho[tid] = rho[base + tid]; }
             __syncthreads();
-            double* xo = Xn ? Xn + ((size_t)b * n_alpha + base) * xsz : ws_xn + (size_t)blockIdx.x * NSLOT * xsz;
-            double* uo = Un ? Un + ((size_t)b * n_alpha + base) * usz : ws_un + (size_t)blockIdx.x * NSLOT * usz;
+            real* xo = Xn ? Xn + ((size_t)b * n_alpha + base) * xsz : ws_xn + (size_t)blockIdx.x * NSLOT * xsz;
+            real* uo = Un ? Un + ((size_t)b * n_alpha + base) * usz : ws_un + (size_t)blockIdx.x * NSLOT * usz;
             forward_wave<M, SM>(c, S, x0 + (size_t)b * NX, X + (size_t)b * xsz, U + (size_t)b * usz, P + (size_t)b * (N + 1) * NP,
                             D + (size_t)b * N * NX, K + (size_t)b * N * NU * NX, kff + (size_t)b * usz, ncand, xo, xsz, uo, usz, tid);
             if (tid < ncand) Jn[(size_t)b * n_alpha + base + tid] = S.Jc[tid];
@@ -125,13 +125,13 @@ __global__ void __launch_bounds__(NT, MINB) forward_kernel(DevCfg c, int B, int 
 }
 
 template <class M, class SM, int MINB>
-__global__ void __launch_bounds__(NT, MINB) defects_kernel(DevCfg c, int B, const double* X, const double* U, const double* P, double* D, double* cost) {
+__global__ void __launch_bounds__(NT, MINB) defects_kernel(DevCfg c, int B, const real* X, const real* U, const real* P, real* D, real* cost) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int tid = threadIdx.x, N = c.N;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        double J = defects_and_cost<M, SM>(c, S, X + (size_t)b * (N + 1) * NX, U + (size_t)b * N * NU, P + (size_t)b * (N + 1) * NP,
+        real J = defects_and_cost<M, SM>(c, S, X + (size_t)b * (N + 1) * NX, U + (size_t)b * N * NU, P + (size_t)b * (N + 1) * NP,
                                        D ? D + (size_t)b * N * NX : nullptr, tid);
         if (tid == 0 && cost) cost[b] = J;
     }
@@ -139,17 +139,17 @@ __global__ void __launch_bounds__(NT, MINB) defects_kernel(DevCfg c, int B, cons
 
 // ---- receding-horizon glue: schedule shift + gait fill, plant step
 template <class M>
-__global__ void mpc_advance_kernel(DevCfg c, int B, double* params, const int* action, int* counter, const double* cmd,
-                                   const double* tab /* l_cycle, l_switch, r_cycle, r_switch: 4 x 21 */) {
+__global__ void mpc_advance_kernel(DevCfg c, int B, real* params, const int* action, int* counter, const real* cmd,
+                                   const real* tab /* l_cycle, l_switch, r_cycle, r_switch: 4 x 21 */) {
     constexpr int NP = M::NP;
     const int N = c.N;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= B * NP) return;
     const int b = g / NP, p = g % NP;
-    double* P = params + (size_t)b * (N + 1) * NP;
+    real* P = params + (size_t)b * (N + 1) * NP;
     for (int j = 1; j <= N; j++) P[(size_t)(j - 1) * NP + p] = P[(size_t)j * NP + p];      // one node back
     const int act = action[b], ref_id = counter[b] % 20;                                     // wpg.py:71
-    double* last = P + (size_t)N * NP;
+    real* last = P + (size_t)N * NP;
     constexpr bool srbd = (M::NP == 19);
     constexpr int base = srbd ? 7 : 3;            // first (c_ref, cdot_switch) pair
     if (p < 3) last[p] = cmd[3 * b + p];                                                     // dsrbd_example.py:115-122
@@ -169,17 +169,17 @@ __global__ void counter_inc_kernel(int B, int* counter) {
 }
 
 template <class M>
-__global__ void plant_step_kernel(DevCfg c, int B, double* state, const double* u, long long u_stride) {
+__global__ void plant_step_kernel(DevCfg c, int B, real* state, const real* u, long long u_stride) {
     constexpr int NX = M::NX, NU = M::NU;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    double x[NX], uu[NU], acc[M::NACC < 6 ? 6 : M::NACC], xn[NX];
+    real x[NX], uu[NU], acc[M::NACC < 6 ? 6 : M::NACC], xn[NX];
     for (int i = 0; i < NX; i++) x[i] = state[(size_t)b * NX + i];
     for (int i = 0; i < NU; i++) uu[i] = u[(size_t)b * u_stride + i];
     M::accel(c, x, uu, acc);
     for (int i = 0; i < NX; i++) xn[i] = x[i] + c.dt * M::xdot_i(c, i, x, uu, acc);
     if (M::NP == 19) {      // SRBD: state[3:7] /= norm (dsrbd_example.py:160)
-        const double n = sqrt(xn[3] * xn[3] + xn[4] * xn[4] + xn[5] * xn[5] + xn[6] * xn[6]);
+        const real n = sqrt(xn[3] * xn[3] + xn[4] * xn[4] + xn[5] * xn[5] + xn[6] * xn[6]);
         for (int i = 3; i < 7; i++) xn[i] /= n;
     }
     for (int i = 0; i < NX; i++) state[(size_t)b * NX + i] = xn[i];
@@ -208,10 +208,10 @@ struct SddpHandle {
     DevCfg dc;
     int device, sms, slots, variant;
     size_t smem_bytes, eval_smem_bytes, ws_bytes;
-    double *ws_d, *ws_pack, *ws_xn, *ws_un, *ws_K, *ws_k;
+    real *ws_d, *ws_pack, *ws_xn, *ws_un, *ws_K, *ws_k;
     int* counter;
     unsigned long long* ztab;
-    double* gait;        // device copy of the four 21-entry wpg tables
+    real* gait;        // device copy of the four 21-entry wpg tables
     // staging for the *_host entry point
     void* stage; size_t stage_bytes;
     void* hstage; size_t hstage_bytes;       // pinned host staging of the small-batch path
@@ -219,8 +219,8 @@ struct SddpHandle {
     cudaEvent_t ev_last; bool ev_last_valid;   // recorded after the last launch that uses the workspace
     int host_chunk;
     long long launches;
-    double* slab; long long slab_records;       // handle-owned result slab (sddp_slab_alloc)
-    int n_peers; double* peers[SDDP_MAX_PEERS]; long long first_record;      // sddp_set_result_peers
+    real* slab; long long slab_records;       // handle-owned result slab (sddp_slab_alloc)
+    int n_peers; real* peers[SDDP_MAX_PEERS]; long long first_record;      // sddp_set_result_peers
     const int32_t* order_dev; int order_n;      // caller-owned device permutation for sddp_solve_batch
     std::vector<int32_t> order_host;            // copy of the host permutation for sddp_solve_batch_host
     char err[512];
@@ -444,14 +444,16 @@ static WsLayout ws_layout(const SddpConfig& c, int slots) {
     w.un = (size_t)slots * NSLOT * N * nu;
     w.K = (size_t)slots * N * nu * nx;
     w.k = (size_t)slots * N * nu;
-    w.total = (w.d + w.pack + w.xn + w.un + w.K + w.k) * sizeof(double) + 256;
+    w.total = (w.d + w.pack + w.xn + w.un + w.K + w.k) * sizeof(real) + 256;
     return w;
 }
 static const int kMaxSlotsPerSM = 6;
+static const size_t RB = sizeof(real);      // bytes per array element (include/sddp.h sddp_real)
 
 extern "C" {
 
 int sddp_abi_version(void) { return SDDP_ABI_VERSION; }
+int sddp_real_bytes(void) { return (int)sizeof(real); }
 size_t sddp_config_size(void) { return sizeof(SddpConfig); }
 
 int sddp_dims(int model, int* nx, int* nu, int* np) {
@@ -512,7 +514,7 @@ int sddp_create(const SddpConfig* cfg, SddpHandle** out) {
     h->slots = h->sms * occ;
     WsLayout w = ws_layout(h->cfg, h->slots);
     h->ws_bytes = w.total;
-    double* base = nullptr;
+    real* base = nullptr;
     ce = cudaMalloc((void**)&base, w.total);
     if (ce != cudaSuccess) { fail(nullptr, SDDP_ENOMEM, "cudaMalloc(workspace): %s%s", cudaGetErrorString(ce), ""); sddp_destroy(h); return SDDP_ENOMEM; }
     h->ws_d = base;
@@ -581,9 +583,9 @@ int sddp_launch_count(const SddpHandle* h, long long* out) {
         CU(mark_last(h, stream));                                                                                           \
     } while (0)
 
-int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const double* x, const double* u, const double* p,
-                          double* f, double* fx, double* fu, double* l, double* lx, double* lu, double* lxx, double* lux,
-                          double* luu, void* stream) {
+int sddp_eval_derivatives(SddpHandle* h, int M, const int32_t* kind, const real* x, const real* u, const real* p,
+                          real* f, real* fx, real* fu, real* l, real* lx, real* lu, real* lxx, real* lux,
+                          real* luu, void* stream) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
     if (M < 0 || (M > 0 && (!kind || !x || !u || !p))) return fail(h, SDDP_EINVAL, "%s%s", "eval_derivatives: bad arguments", "");
@@ -629,8 +631,8 @@ static int launch_solve(SddpHandle* h, int B, SolveArgs& a, cudaStream_t st) {
     return 0;
 }
 
-int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* params, double* X, double* U, double* K,
-                     double* kff, double* hist, int32_t* iters, int32_t* status, double* cost, void* stream) {
+int sddp_solve_batch(SddpHandle* h, int B, const real* x0, const real* params, real* X, real* U, real* K,
+                     real* kff, real* hist, int32_t* iters, int32_t* status, real* cost, void* stream) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!x0 || !params || !X || !U || !iters || !status || !cost)))
@@ -643,8 +645,8 @@ int sddp_solve_batch(SddpHandle* h, int B, const double* x0, const double* param
     return launch_solve(h, B, a, (cudaStream_t)stream);
 }
 
-int sddp_backward_pass(SddpHandle* h, int B, const double* X, const double* U, const double* params, const double* defect,
-                       double mu, double* K, double* kff, double* dV, int32_t* rc, void* stream) {
+int sddp_backward_pass(SddpHandle* h, int B, const real* X, const real* U, const real* params, const real* defect,
+                       double mu, real* K, real* kff, real* dV, int32_t* rc, void* stream) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!X || !U || !params || !defect || !K || !kff || !dV || !rc)))
@@ -655,9 +657,9 @@ int sddp_backward_pass(SddpHandle* h, int B, const double* X, const double* U, c
     return 0;
 }
 
-int sddp_forward_pass(SddpHandle* h, int B, int n_alpha, const double* alpha, const double* rho, const double* x0,
-                      const double* X, const double* U, const double* params, const double* defect, const double* K,
-                      const double* kff, double* Jn, double* Xn, double* Un, void* stream) {
+int sddp_forward_pass(SddpHandle* h, int B, int n_alpha, const real* alpha, const real* rho, const real* x0,
+                      const real* X, const real* U, const real* params, const real* defect, const real* K,
+                      const real* kff, real* Jn, real* Xn, real* Un, void* stream) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
     if (B < 0 || n_alpha < 1 || (B > 0 && (!alpha || !rho || !x0 || !X || !U || !params || !defect || !K || !kff || !Jn)))
@@ -669,7 +671,7 @@ int sddp_forward_pass(SddpHandle* h, int B, int n_alpha, const double* alpha, co
     return 0;
 }
 
-int sddp_defects(SddpHandle* h, int B, const double* X, const double* U, const double* params, double* defect, double* cost,
+int sddp_defects(SddpHandle* h, int B, const real* X, const real* U, const real* params, real* defect, real* cost,
                  void* stream) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
@@ -680,8 +682,8 @@ int sddp_defects(SddpHandle* h, int B, const double* X, const double* U, const d
     return 0;
 }
 
-int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* params, const double* X0, const double* U0,
-                          double* X, double* U, double* K, double* kff, double* hist, int32_t* iters, int32_t* status, double* cost) {
+int sddp_solve_batch_host(SddpHandle* h, int B, const real* x0, const real* params, const real* X0, const real* U0,
+                          real* X, real* U, real* K, real* kff, real* hist, int32_t* iters, int32_t* status, real* cost) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!x0 || !params || !X0 || !U0 || !X || !U || !iters || !status || !cost)))
@@ -693,7 +695,7 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     const size_t s_x0 = nx, s_p = (N + 1) * np, s_X = (N + 1) * nx, s_U = N * nu;              // doubles per problem
     const size_t s_K = K ? N * nu * nx : 0, s_k = kff ? s_U : 0, s_h = hist ? (size_t)h->cfg.max_iters * SDDP_HIST : 0;
     const size_t n_d = Bz * (s_x0 + s_p + s_X + s_U + s_K + s_k + s_h + 1);
-    const size_t bytes = n_d * sizeof(double) + 3 * Bz * sizeof(int32_t);
+    const size_t bytes = n_d * sizeof(real) + 3 * Bz * sizeof(int32_t);
     if (bytes > h->stage_bytes) {
         if (h->stage) cudaFree(h->stage);
         h->stage = nullptr; h->stage_bytes = 0;
@@ -713,14 +715,14 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         const char* env = getenv("SDDP_HOST_CHUNK");
         if (env && atoi(env) > 0) h->host_chunk = atoi(env);
     }
-    double* d_x0 = (double*)h->stage;
-    double* d_p = d_x0 + Bz * s_x0;
-    double* d_X = d_p + Bz * s_p;
-    double* d_U = d_X + Bz * s_X;
-    double* d_K = d_U + Bz * s_U;
-    double* d_k = d_K + Bz * s_K;
-    double* d_h = d_k + Bz * s_k;
-    double* d_c = d_h + Bz * s_h;
+    real* d_x0 = (real*)h->stage;
+    real* d_p = d_x0 + Bz * s_x0;
+    real* d_X = d_p + Bz * s_p;
+    real* d_U = d_X + Bz * s_X;
+    real* d_K = d_U + Bz * s_U;
+    real* d_k = d_K + Bz * s_K;
+    real* d_h = d_k + Bz * s_k;
+    real* d_c = d_h + Bz * s_h;
     int32_t* d_it = (int32_t*)(d_c + Bz);
     int32_t* d_st = d_it + Bz;
     int32_t* d_ord = d_st + Bz;
@@ -752,8 +754,8 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
             memset(&a, 0, sizeof(a));
             a.x0 = d_x0; a.params = d_p; a.X = d_X; a.U = d_U; a.K = nullptr; a.kff = kff ? d_k : nullptr; a.hist = hist ? d_h : nullptr;
             a.iters = d_it; a.status = d_st; a.cost = d_c;
-            a.h_x0 = (const double*)m_x0; a.h_params = (const double*)m_p; a.h_X0 = (const double*)m_X0; a.h_U0 = (const double*)m_U0;
-            a.h_X = (double*)m_X; a.h_U = (double*)m_U; a.h_kff = (double*)m_k; a.h_hist = (double*)m_h; a.h_cost = (double*)m_c;
+            a.h_x0 = (const real*)m_x0; a.h_params = (const real*)m_p; a.h_X0 = (const real*)m_X0; a.h_U0 = (const real*)m_U0;
+            a.h_X = (real*)m_X; a.h_U = (real*)m_U; a.h_kff = (real*)m_k; a.h_hist = (real*)m_h; a.h_cost = (real*)m_c;
             a.h_iters = (int*)m_it; a.h_status = (int*)m_st;
             int rcl = launch_solve(h, B, a, h->st_cmp);
             h->order_dev = saved_order; h->order_n = saved_n; h->n_peers = saved_peers;
@@ -775,8 +777,8 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
     const int nchunk = (B + chunk - 1) / chunk;
     // Small batches (the reference's own use: one problem per call): one pinned staging buffer, one copy in, one copy
     // out, one stream, no events -- the latency of a single solve is mostly launch and copy overhead otherwise.
-    const size_t in_bytes = Bz * (s_x0 + s_p + s_X + s_U) * sizeof(double);
-    const size_t out_bytes = bytes - Bz * (s_x0 + s_p) * sizeof(double) - Bz * sizeof(int32_t);      // X .. status
+    const size_t in_bytes = Bz * (s_x0 + s_p + s_X + s_U) * sizeof(real);
+    const size_t out_bytes = bytes - Bz * (s_x0 + s_p) * sizeof(real) - Bz * sizeof(int32_t);      // X .. status
     if (nchunk == 1 && in_bytes + out_bytes <= ((size_t)4 << 20) && h->order_host.empty()) {
         if (in_bytes + out_bytes > h->hstage_bytes) {
             if (h->hstage) cudaFreeHost(h->hstage);
@@ -785,11 +787,11 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
             if (e != cudaSuccess) return fail(h, SDDP_ENOMEM, "cudaHostAlloc(staging): %s%s", cudaGetErrorString(e), "");
             h->hstage_bytes = in_bytes + out_bytes;
         }
-        double* hi = (double*)h->hstage;
-        memcpy(hi, x0, Bz * s_x0 * 8);
-        memcpy(hi + Bz * s_x0, params, Bz * s_p * 8);
-        memcpy(hi + Bz * (s_x0 + s_p), X0, Bz * s_X * 8);
-        memcpy(hi + Bz * (s_x0 + s_p + s_X), U0, Bz * s_U * 8);
+        real* hi = (real*)h->hstage;
+        memcpy(hi, x0, Bz * s_x0 * RB);
+        memcpy(hi + Bz * s_x0, params, Bz * s_p * RB);
+        memcpy(hi + Bz * (s_x0 + s_p), X0, Bz * s_X * RB);
+        memcpy(hi + Bz * (s_x0 + s_p + s_X), U0, Bz * s_U * RB);
         CU(cudaMemcpyAsync(d_x0, hi, in_bytes, cudaMemcpyHostToDevice, h->st_cmp));
         const int keep_peers = h->n_peers;
         h->n_peers = 0;
@@ -799,16 +801,16 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         char* ho = (char*)h->hstage + in_bytes;
         CU(cudaMemcpyAsync(ho, d_X, out_bytes, cudaMemcpyDeviceToHost, h->st_cmp));
         CU(cudaStreamSynchronize(h->st_cmp));
-        const double* o = (const double*)ho;
-        memcpy(X, o, Bz * s_X * 8); o += Bz * s_X;
-        memcpy(U, o, Bz * s_U * 8); o += Bz * s_U;
-        if (K) memcpy(K, o, Bz * s_K * 8);
+        const real* o = (const real*)ho;
+        memcpy(X, o, Bz * s_X * RB); o += Bz * s_X;
+        memcpy(U, o, Bz * s_U * RB); o += Bz * s_U;
+        if (K) memcpy(K, o, Bz * s_K * RB);
         o += Bz * s_K;
-        if (kff) memcpy(kff, o, Bz * s_k * 8);
+        if (kff) memcpy(kff, o, Bz * s_k * RB);
         o += Bz * s_k;
-        if (hist) memcpy(hist, o, Bz * s_h * 8);
+        if (hist) memcpy(hist, o, Bz * s_h * RB);
         o += Bz * s_h;
-        memcpy(cost, o, Bz * 8); o += Bz;
+        memcpy(cost, o, Bz * RB); o += Bz;
         memcpy(iters, o, Bz * 4);
         memcpy(status, (const int32_t*)o + Bz, Bz * 4);
         return 0;
@@ -837,10 +839,10 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         auto cp = [&](void* dst, const void* src, size_t nbytes, cudaMemcpyKind kind, cudaStream_t st) {
             if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, nbytes, kind, st);
         };
-        cp(d_x0 + o * s_x0, x0 + o * s_x0, n * s_x0 * 8, cudaMemcpyHostToDevice, h->st_in);
-        cp(d_p + o * s_p, params + o * s_p, n * s_p * 8, cudaMemcpyHostToDevice, h->st_in);
-        cp(d_X + o * s_X, X0 + o * s_X, n * s_X * 8, cudaMemcpyHostToDevice, h->st_in);
-        cp(d_U + o * s_U, U0 + o * s_U, n * s_U * 8, cudaMemcpyHostToDevice, h->st_in);
+        cp(d_x0 + o * s_x0, x0 + o * s_x0, n * s_x0 * RB, cudaMemcpyHostToDevice, h->st_in);
+        cp(d_p + o * s_p, params + o * s_p, n * s_p * RB, cudaMemcpyHostToDevice, h->st_in);
+        cp(d_X + o * s_X, X0 + o * s_X, n * s_X * RB, cudaMemcpyHostToDevice, h->st_in);
+        cp(d_U + o * s_U, U0 + o * s_U, n * s_U * RB, cudaMemcpyHostToDevice, h->st_in);
         if (ordered) cp(d_ord + o, ordl.data() + o, n * 4, cudaMemcpyHostToDevice, h->st_in);
         if (e == cudaSuccess) e = cudaEventRecord(ev_in[c], h->st_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->st_cmp, ev_in[c], 0);
@@ -851,12 +853,12 @@ int sddp_solve_batch_host(SddpHandle* h, int B, const double* x0, const double* 
         if (rc) break;
         e = cudaEventRecord(ev_cmp[c], h->st_cmp);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->st_out, ev_cmp[c], 0);
-        cp(X + o * s_X, d_X + o * s_X, n * s_X * 8, cudaMemcpyDeviceToHost, h->st_out);
-        cp(U + o * s_U, d_U + o * s_U, n * s_U * 8, cudaMemcpyDeviceToHost, h->st_out);
-        if (K) cp(K + o * s_K, d_K + o * s_K, n * s_K * 8, cudaMemcpyDeviceToHost, h->st_out);
-        if (kff) cp(kff + o * s_k, d_k + o * s_k, n * s_k * 8, cudaMemcpyDeviceToHost, h->st_out);
-        if (hist) cp(hist + o * s_h, d_h + o * s_h, n * s_h * 8, cudaMemcpyDeviceToHost, h->st_out);
-        cp(cost + o, d_c + o, n * 8, cudaMemcpyDeviceToHost, h->st_out);
+        cp(X + o * s_X, d_X + o * s_X, n * s_X * RB, cudaMemcpyDeviceToHost, h->st_out);
+        cp(U + o * s_U, d_U + o * s_U, n * s_U * RB, cudaMemcpyDeviceToHost, h->st_out);
+        if (K) cp(K + o * s_K, d_K + o * s_K, n * s_K * RB, cudaMemcpyDeviceToHost, h->st_out);
+        if (kff) cp(kff + o * s_k, d_k + o * s_k, n * s_k * RB, cudaMemcpyDeviceToHost, h->st_out);
+        if (hist) cp(hist + o * s_h, d_h + o * s_h, n * s_h * RB, cudaMemcpyDeviceToHost, h->st_out);
+        cp(cost + o, d_c + o, n * RB, cudaMemcpyDeviceToHost, h->st_out);
         cp(iters + o, d_it + o, n * 4, cudaMemcpyDeviceToHost, h->st_out);
         cp(status + o, d_st + o, n * 4, cudaMemcpyDeviceToHost, h->st_out);
         if (e != cudaSuccess) rc = fail(h, SDDP_ECUDA, "solve_batch_host (copy out): %s%s", cudaGetErrorString(e), "");
@@ -879,7 +881,7 @@ long long sddp_record_doubles(const SddpHandle* h) {
     return (long long)(h->cfg.N + 1) * nx + (long long)h->cfg.N * nu + SDDP_RECORD_TAIL;
 }
 
-int sddp_slab_alloc(SddpHandle* h, long long n_records, double** out) {
+int sddp_slab_alloc(SddpHandle* h, long long n_records, real** out) {
     if (!h || !out || n_records < 0) return h ? fail(h, SDDP_EINVAL, "%s%s", "slab_alloc: bad arguments", "") : SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
     for (int p = 0; p < h->n_peers; p++)
@@ -888,7 +890,7 @@ int sddp_slab_alloc(SddpHandle* h, long long n_records, double** out) {
     *out = nullptr;
     if (n_records == 0) return 0;
     // plain cudaMalloc: the allocation base is what cudaIpcGetMemHandle exports
-    cudaError_t e = cudaMalloc((void**)&h->slab, (size_t)n_records * (size_t)sddp_record_doubles(h) * sizeof(double));
+    cudaError_t e = cudaMalloc((void**)&h->slab, (size_t)n_records * (size_t)sddp_record_doubles(h) * sizeof(real));
     if (e != cudaSuccess) { h->slab = nullptr; return fail(h, SDDP_ENOMEM, "cudaMalloc(result slab): %s%s", cudaGetErrorString(e), ""); }
     h->slab_records = n_records;
     *out = h->slab;
@@ -920,7 +922,7 @@ int sddp_ipc_close(void* dev_ptr) {
     return e == cudaSuccess ? 0 : fail(nullptr, SDDP_ECUDA, "cudaIpcCloseMemHandle: %s%s", cudaGetErrorString(e), "");
 }
 
-int sddp_set_result_peers(SddpHandle* h, int n_peers, double* const* slabs, long long first_record) {
+int sddp_set_result_peers(SddpHandle* h, int n_peers, real* const* slabs, long long first_record) {
     if (!h) return SDDP_EINVAL;
     if (n_peers < 0 || n_peers > SDDP_MAX_PEERS || (n_peers > 0 && !slabs) || first_record < 0)
         return fail(h, SDDP_EINVAL, "%s%s", "set_result_peers: 0..8 slabs, first_record >= 0", "");
@@ -950,14 +952,14 @@ int sddp_set_dispatch_order(SddpHandle* h, const int32_t* order, int n, int on_h
 int sddp_set_gait_tables(SddpHandle* h, const double* l_cycle, const double* l_switch, const double* r_cycle, const double* r_switch) {
     if (!h) return SDDP_EINVAL;
     if (!l_cycle || !l_switch || !r_cycle || !r_switch) return fail(h, SDDP_EINVAL, "%s%s", "set_gait_tables: four tables are required", "");
-    double tab[84];
-    for (int i = 0; i < 21; i++) { tab[i] = l_cycle[i]; tab[21 + i] = l_switch[i]; tab[42 + i] = r_cycle[i]; tab[63 + i] = r_switch[i]; }
+    real tab[84];
+    for (int i = 0; i < 21; i++) { tab[i] = (real)l_cycle[i]; tab[21 + i] = (real)l_switch[i]; tab[42 + i] = (real)r_cycle[i]; tab[63 + i] = (real)r_switch[i]; }
     if (!h->gait) CU(cudaMalloc((void**)&h->gait, sizeof(tab)));
     CU(cudaMemcpy(h->gait, tab, sizeof(tab), cudaMemcpyHostToDevice));
     return 0;
 }
 
-int sddp_mpc_advance(SddpHandle* h, int B, double* params, const int32_t* action, int32_t* step_counter, const double* rdot_ref_cmd,
+int sddp_mpc_advance(SddpHandle* h, int B, real* params, const int32_t* action, int32_t* step_counter, const real* rdot_ref_cmd,
                      void* stream) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
@@ -976,7 +978,7 @@ int sddp_mpc_advance(SddpHandle* h, int B, double* params, const int32_t* action
     return 0;
 }
 
-int sddp_plant_step(SddpHandle* h, int B, double* state, const double* u, long long u_stride, void* stream) {
+int sddp_plant_step(SddpHandle* h, int B, real* state, const real* u, long long u_stride, void* stream) {
     if (!h) return SDDP_EINVAL;
     if (int rcd = check_device(h)) return rcd;
     if (B < 0 || (B > 0 && (!state || !u))) return fail(h, SDDP_EINVAL, "%s%s", "plant_step: bad arguments", "");

@@ -30,30 +30,30 @@ template <class MT, bool LAT = false>
 struct alignas(16) SmemSrbdT {
     static constexpr int NX = 37, NU = 24, NP = 19;
     static constexpr int LDW = 44;   // row pitch of W: 88 words = 24 mod 32, so the 4 x 8 DMMA fragment loads are conflict free
-    double VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
-    double Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
-    double W[NU * LDW];        // B = [Qux | Qu | quy | .] -> Wn = Es B  (quy: lu + fu^T ys of the y recursion)
-    double Quu[NU * NU];       // Quu -> Et = Lt^-1 (unit lower triangular, zeros above the diagonal); Es = diag(rs) Et
-    double Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
-    double Qu[NU], kk[NU];
-    double invp[NU], rs[NU];   // d1: 1 / pivot_j; 1 / sqrt(pivot_j) (row scaling of Et, applied in h and g)
-    double prow[2][NU];        // d1: the published column of the current pivot step (ping-pong)
-    double nb[2][NodeBuf<MT>::SIZE];
-    double escr[24];           // expand scratch: E(oref) and the orientation residuals
-    double sacc[NWARP][8];
-    double red[16];
+    real VT[NX * NX + 1];    // Vxx', then T = Vxx' fx in place, then the new Vxx; forward: scratch
+    alignas(16) real Qxx[NX * NX + 1];   // forward: K of the current / next node (with W: 2 x 888 doubles)
+    real W[NU * LDW];        // B = [Qux | Qu | quy | .] -> Wn = Es B  (quy: lu + fu^T ys of the y recursion)
+    real Quu[NU * NU];       // Quu -> Et = Lt^-1 (unit lower triangular, zeros above the diagonal); Es = diag(rs) Et
+    real Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
+    real Qu[NU], kk[NU];
+    real invp[NU], rs[NU];   // d1: 1 / pivot_j; 1 / sqrt(pivot_j) (row scaling of Et, applied in h and g)
+    real prow[2][NU];        // d1: the published column of the current pivot step (ping-pong)
+    alignas(16) real nb[2][NodeBuf<MT>::SIZE];
+    real escr[24];           // expand scratch: E(oref) and the orientation residuals
+    real sacc[NWARP][8];
+    double red[16];          // reductions and the expected-decrease accumulators: double in both builds
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
-    const double* gp[8];       // base pointers of the per-node prefetches (registers are scarce in the node loops)
+    const real* gp[8];       // base pointers of the per-node prefetches (registers are scarce in the node loops)
     unsigned long long mbar[2];   // completion barriers of the bulk copies of K_k (forward_wave)
     int iflag[4];
-    __device__ double* Kbuf(int b) { return Qxx + b * (NU * NX); }
-    __device__ double* scr() { return VT; }
-    __device__ static int backward(const DevCfg& c, SmemSrbdT& S, const double* X, const double* U, const double* P, const double* D,
-                                   const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
+    __device__ real* Kbuf(int b) { return Qxx + b * (NU * NX); }
+    __device__ real* scr() { return VT; }
+    __device__ static int backward(const DevCfg& c, SmemSrbdT& S, const real* X, const real* U, const real* P, const real* D,
+                                   const real* packs, real mu, real* Kg, real* kg, double* dV3, bool has_gap, int tid);
     // rigid-body packs of nodes 0..N-1, one thread per node
-    __device__ static void prep(const DevCfg& c, SmemSrbdT& S, const double* X, const double* U, const double*, double* packs, int tid) {
+    __device__ static void prep(const DevCfg& c, SmemSrbdT& S, const real* X, const real* U, const real*, real* packs, int tid) {
         // scratch: VT, Qxx, W, Quu and the first vectors (all dead between the forward and the backward pass)
-        static_assert(offsetof(SmemSrbdT, Qu) >= PACK_SCRATCH * NT * sizeof(double), "pack scratch");
+        static_assert(offsetof(SmemSrbdT, Qu) >= PACK_SCRATCH * NT * sizeof(real), "pack scratch");
         compute_packs<MT>(c, X, U, packs, S.VT, tid);
     }
 };
@@ -61,14 +61,15 @@ using SmemSrbd = SmemSrbdT<Srbd>;
 using SmemSrbdI = SmemSrbdT<SrbdI>;
 using SmemSrbdL = SmemSrbdT<Srbd, true>;
 using SmemSrbdIL = SmemSrbdT<SrbdI, true>;
-static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 44, "forward K double buffer must fit in Qxx + W");
-static_assert(offsetof(SmemSrbd, W) - offsetof(SmemSrbd, Qxx) == ZT_QUX_OFF * sizeof(double) && SmemSrbd::LDW == ZT_LDUX, "descriptor table destinations (sddp.cu:build_ztab)");
+static_assert(2 * 24 * 37 <= (37 * 37 + 1) + 24 * 44, "forward K real buffer must fit in Qxx + W");
+static_assert(offsetof(SmemSrbd, W) - offsetof(SmemSrbd, Qxx) == ZT_QUX_OFF * sizeof(real) && SmemSrbd::LDW == ZT_LDUX, "descriptor table destinations (sddp.cu:build_ztab)");
 #define SDDP_INEQ_ON(c) (MT::HAS_INEQ && (c).ineq != 0)
 SDDP_DEV void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 struct Bar96 { __device__ void operator()() const { bar_named(2, 96); } };      // warps 1-3
 
 // D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Fragments (PTX ISA, m8n8k4 .f64): lane holds
 // A[lane/4][lane%4], B[lane%4][lane/4], C[lane/4][2*(lane%4) + {0,1}].
+// (fp32 build: operands converted on the way in, accumulators stay double -- the FP64 pipe is otherwise idle there)
 SDDP_DEV void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -83,6 +84,13 @@ SDDP_DEV double fast_rcp(double p) {
     e = fma(-p, x, 1.0);
     return fma(x, e, x);
 }
+// fp32 build: MUFU.RCP (about 1 ulp) and one Newton step
+SDDP_DEV float fast_rcp(float p) {
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(p));
+    const float e = fmaf(-p, x, 1.0f);
+    return fmaf(x, e, x);
+}
 
 #ifndef SDDP_ROW128
 #define SDDP_ROW128 1
@@ -91,13 +99,13 @@ SDDP_DEV double fast_rcp(double p) {
 // the same addresses (broadcast).  Loads first, then the FMAs, in batches of 8 (keeps the loads in flight together
 // without holding a whole second column in registers).  SDDP_ROW128: 128-bit loads (`row` is 16-byte aligned).
 template <int n, int I0 = 0, int I1 = n>
-SDDP_DEV void axpy_row(double* a, const double* row, int lo, double s) {
+SDDP_DEV void axpy_row(real* a, const real* row, int lo, real s) {
     static_assert(n % 8 == 0 && I0 % 8 == 0 && I1 % 8 == 0, "row length");
 #pragma unroll
     for (int i0 = I0; i0 < I1; i0 += 8) {
-        double2 c[4];
+        real2 c[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) if (i0 + 2 * q + 1 >= lo) c[q] = *reinterpret_cast<const double2*>(row + i0 + 2 * q);
+        for (int q = 0; q < 4; q++) if (i0 + 2 * q + 1 >= lo) c[q] = *reinterpret_cast<const real2*>(row + i0 + 2 * q);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = i0 + 2 * q;
@@ -108,11 +116,11 @@ SDDP_DEV void axpy_row(double* a, const double* row, int lo, double s) {
 }
 // row[i] = a[i] for lo <= i < n
 template <int n>
-SDDP_DEV void store_row(double* row, const double* a, int lo) {
+SDDP_DEV void store_row(real* row, const real* a, int lo) {
 #if SDDP_ROW128
 #pragma unroll
     for (int i = 0; i < n; i += 2) {
-        if (i >= lo) *reinterpret_cast<double2*>(row + i) = make_double2(a[i], a[i + 1]);
+        if (i >= lo) *reinterpret_cast<real2*>(row + i) = make_real2(a[i], a[i + 1]);
         else if (i + 1 >= lo) row[i + 1] = a[i + 1];
     }
 #else
@@ -122,14 +130,14 @@ SDDP_DEV void store_row(double* row, const double* a, int lo) {
 }
 
 // out[b] = sum_a v[a] * (dt Aoo)[a][b],  Aoo = d odot / d o = [[skew(w)/2, w/2], [-w^T/2, 0]];  hw = dt w / 2
-SDDP_DEV void contract_Aoo(const double* v, const double* hw, double* out) {
+SDDP_DEV void contract_Aoo(const real* v, const real* hw, real* out) {
     out[0] = v[1] * hw[2] - v[2] * hw[1] - v[3] * hw[0];
     out[1] = -v[0] * hw[2] + v[2] * hw[0] - v[3] * hw[1];
     out[2] = v[0] * hw[1] - v[1] * hw[0] - v[3] * hw[2];
     out[3] = v[0] * hw[0] + v[1] * hw[1] + v[2] * hw[2];
 }
 // out[b] = sum_a v[a] * (dt Aow)[a][b],  Aow = d odot / d w = [[(o_w I - skew(o_v))/2], [-o_v^T/2]];  ho = dt o / 2
-SDDP_DEV void contract_Aow(const double* v, const double* ho, double* out) {
+SDDP_DEV void contract_Aow(const real* v, const real* ho, real* out) {
     out[0] = v[0] * ho[3] - v[1] * ho[2] + v[2] * ho[1] - v[3] * ho[0];
     out[1] = v[0] * ho[2] + v[1] * ho[3] - v[2] * ho[0] - v[3] * ho[1];
     out[2] = -v[0] * ho[1] + v[1] * ho[0] + v[2] * ho[3] - v[3] * ho[2];
@@ -174,18 +182,18 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
     constexpr int NU = SMT::NU;
     bool bad = false;
     const int t = lane < NU ? lane : NU - 1;
-    double npinv = 0.0;                                          // -1 / pivot of this lane's column
+    real npinv = 0.0;                                          // -1 / pivot of this lane's column
     if constexpr (LAT) {
     // the fully unrolled form: lowest latency (small batches), 21 KB of straight-line code
-    double a[NU];
+    real a[NU];
 #pragma unroll
     for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
     __syncwarp();
-    double myinv = fast_rcp(a[0]);          // lane 0's pivot
+    real myinv = fast_rcp(a[0]);          // lane 0's pivot
 #pragma unroll
     for (int j = 0; j < NU; j++) {
         if (lane == j) {
-            const double p = a[j];
+            const real p = a[j];
             bad = !(p > 0.0) || !isfinite(p);
             npinv = -myinv;
             S.invp[j] = myinv;
@@ -193,7 +201,7 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
         }
         __syncwarp();
         if (j + 1 < NU) {
-            const double sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
+            const real sj = (lane == j) ? 0.0 : S.invp[j] * a[j];
             a[j + 1] -= S.Quu[j * NU + j + 1] * sj;
             myinv = fast_rcp(a[j + 1]);     // meaningful on lane j+1
             if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
@@ -202,8 +210,8 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < NU; i += 2) {
-        const double v0 = (i > t) ? npinv * a[i] : (i == t ? 1.0 : 0.0);
-        const double v1 = (i + 1 > t) ? npinv * a[i + 1] : (i + 1 == t ? 1.0 : 0.0);
+        const real v0 = (i > t) ? npinv * a[i] : (i == t ? real(1.0) : 0.0);
+        const real v1 = (i + 1 > t) ? npinv * a[i + 1] : (i + 1 == t ? real(1.0) : 0.0);
         if (lane < NU) { S.Quu[i * NU + lane] = v0; S.Quu[(i + 1) * NU + lane] = v1; }
     }
     } else {
@@ -221,18 +229,18 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
     //  instead of 1e-13.)
     constexpr int R = SDDP_D1R;
     static_assert(NU % R == 0 && R % 2 == 0, "d1 frame");
-    double b[NU];
+    real b[NU];
 #pragma unroll
     for (int i = 0; i < NU; i++) b[i] = S.Quu[i * NU + t];
     __syncwarp();
-    double myinv = fast_rcp(b[0]);                               // lane 0's pivot
+    real myinv = fast_rcp(b[0]);                               // lane 0's pivot
 #pragma unroll 1
     for (int jb = 0; jb < NU; jb += R) {
 #pragma unroll
         for (int s_ = 0; s_ < R; s_++) {
             const int j = jb + s_;
-            double* pr = S.prow[s_ & 1];                         // (R is even: j & 1 == s_ & 1)
-            const double m = b[s_];
+            real* pr = S.prow[s_ & 1];                         // (R is even: j & 1 == s_ & 1)
+            const real m = b[s_];
             if (lane == j) {
                 bad = !(m > 0.0) || !isfinite(m);
                 npinv = -myinv;
@@ -246,7 +254,7 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
 #endif
             }
             __syncwarp();
-            const double sj = (lane == j) ? 0.0 : S.invp[j] * m;
+            const real sj = (lane == j) ? 0.0 : S.invp[j] * m;
             b[s_ + 1] -= pr[s_ + 1] * sj;
             myinv = fast_rcp(b[s_ + 1]);                         // meaningful on lane j + 1
 #if SDDP_D1SKIP
@@ -258,7 +266,7 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
             axpy_row<NU>(b, pr, s_ + 2, sj);
 #endif
             // row j of Et: (t < j) -multiplier / pivot_t, (t == j) 1, (t > j) 0
-            const double ev = (lane < j) ? npinv * m : (lane == j ? 1.0 : 0.0);
+            const real ev = (lane < j) ? npinv * m : (lane == j ? real(1.0) : 0.0);
             if (lane < NU) S.Quu[j * NU + lane] = ev;
         }
 #pragma unroll
@@ -270,35 +278,35 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
 }
 
 template <class MT, bool LAT>
-__device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>& S, const double* X, const double* U, const double* P, const double* D,
-                                       const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid) {
+__device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>& S, const real* X, const real* U, const real* P, const real* D,
+                                       const real* packs, real mu, real* Kg, real* kg, double* dV3, bool has_gap, int tid) {
     using M = MT;
     using NBL = NodeBuf<MT>;
     constexpr int NZ = MT::NZ;
     const int N = c.N, lane = tid & 31, warp = tid >> 5;
     const bool fixed = c.rho_fixed > 0.0;
-    const double rho_b = fixed ? c.rho_fixed : 1.0;
-    const double dt = c.dt;
+    const real rho_b = fixed ? (real)c.rho_fixed : real(1.0);
+    const real dt = c.dt;
     SyncBlock sync;
 
     // (the 2 KB pack as one bulk copy: measured 1 % slower than 128 16-byte cp.async here -- every thread then polls a barrier
     //  at every node -- so it is off by default; the 7.1 KB gain tile of the forward pass keeps its bulk copy)
-    const bool bulk = SDDP_BULK_PACK && M::PACK % 2 == 0 && ((((size_t)packs) | ((size_t)(S.nb[0] + NBL::OK)) | ((size_t)(S.nb[1] + NBL::OK))) & 15) == 0;
+    const bool bulk = SDDP_BULK_PACK && M::PACK % RV == 0 && ((((size_t)packs) | ((size_t)(S.nb[0] + NBL::OK)) | ((size_t)(S.nb[1] + NBL::OK))) & 15) == 0;
     auto prefetch = [&](int k) {       // node k -> buffer k & 1 (base pointers from shared memory: see forward_wave)
-        double* nb = S.nb[k & 1];
-        const double* Xs = S.gp[2] + (size_t)k * NX;
-        const double* Ds = S.gp[3] + (size_t)k * NX;
+        real* nb = S.nb[k & 1];
+        const real* Xs = S.gp[2] + (size_t)k * NX;
+        const real* Ds = S.gp[3] + (size_t)k * NX;
         for (int i = tid; i < NX; i += NT) {
             cp_async8(nb + NBL::OX + i, Xs + i);
             if (has_gap) cp_async8(nb + NBL::OD + i, Ds + i);
         }
-        const double* Us = S.gp[4] + (size_t)k * NU;
+        const real* Us = S.gp[4] + (size_t)k * NU;
         for (int i = tid; i < NU; i += NT) cp_async8(nb + NBL::OU + i, Us + i);
-        const double* Ps = S.gp[5] + (size_t)k * NP;
+        const real* Ps = S.gp[5] + (size_t)k * NP;
         for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, Ps + i);
-        const double* ps = S.gp[6] + (size_t)k * M::PACK;
-        if (bulk) { if (tid == 0) bulk_g2s(nb + NBL::OK, ps, M::PACK * 8, &S.mbar[k & 1]); }      // the 2 KB pack: one bulk copy
-        else if (((((size_t)ps) | ((size_t)(nb + NBL::OK))) & 15) == 0) { for (int i = 2 * tid; i < M::PACK; i += 2 * NT) cp_async16(nb + NBL::OK + i, ps + i); }
+        const real* ps = S.gp[6] + (size_t)k * M::PACK;
+        if (bulk) { if (tid == 0) bulk_g2s(nb + NBL::OK, ps, M::PACK * (int)sizeof(real), &S.mbar[k & 1]); }      // the 2 KB pack: one bulk copy
+        else if (M::PACK % RV == 0 && ((((size_t)ps) | ((size_t)(nb + NBL::OK))) & 15) == 0) { for (int i = RV * tid; i < M::PACK; i += RV * NT) cp_async16(nb + NBL::OK + i, ps + i); }
         else { for (int i = tid; i < M::PACK; i += NT) cp_async8(nb + NBL::OK + i, ps + i); }
         cp_commit();
     };
@@ -313,7 +321,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
     }
     __syncthreads();
     {
-        double* nb = S.nb[N & 1];
+        real* nb = S.nb[N & 1];
         for (int i = tid; i < NX; i += NT) nb[NBL::OX + i] = X[(size_t)N * NX + i];
         for (int i = tid; i < NP; i += NT) nb[NBL::OP + i] = P[(size_t)N * NP + i];
     }
@@ -330,21 +338,21 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
     const unsigned long long c1d = __ldg(c.ztab + ZT_C1OFF + tid);     // this thread's Quu entries (see c1)
     for (int k = N - 1; k >= 0; k--) {
         const int kind = node_kind(c, k);
-        double* nb = S.nb[k & 1];
-        const double* xk = nb + NBL::OX;
-        const double* uk = nb + NBL::OU;
-        const double* pk = nb + NBL::OP;
-        double* cg = nb + NBL::OD;
-        const double* pack = nb + NBL::OK;
+        real* nb = S.nb[k & 1];
+        const real* xk = nb + NBL::OX;
+        const real* uk = nb + NBL::OU;
+        const real* pk = nb + NBL::OP;
+        real* cg = nb + NBL::OD;
+        const real* pack = nb + NBL::OK;
         STAMP(0);                              // node k has landed and everyone is done with node k+1: see the barrier that
         STAMP(1);                              // ends the f / g phase (and the one in front of the loop)
         PROF(8);
-        const double* Jac = pack + M::PK_JAC;
+        const real* Jac = pack + M::PK_JAC;
         PROF(9);
         // ---- c1: everything that needs Vxx' itself: gap shift, Quu = luu + fu^T Vxx' fu + mu I (written whole: luu of
         //          the wdot block is 2 gq Jac_f^T Jac_f, of the affine residuals a few constants, prb.py:200-204)
         if (tid < NX) {
-            double s = 0.0;
+            real s = 0.0;
             if (has_gap) {
 #pragma unroll 4
                 for (int j = 0; j < NX; j++) s += S.VT[tid * NX + j] * cg[j];
@@ -360,31 +368,33 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             // Threads 0..77 take one (f, f) entry (16 products) and one (cddot, cddot) entry, threads 78..127 three of
             // the remaining (cddot, f) / (cddot, cddot) entries (4 or 1 products): the assignment is a host-built
             // table (sddp.cu:build_ztab), four 16-bit descriptors per thread.
-            const double dt2 = dt * dt, g2 = 2.0 * c.gq;
+            const real dt2 = dt * dt, g2 = real(2.0) * c.gq;
             if (SDDP_INEQ_ON(c)) {          // inequality barriers (extension, off by default): 3 x 3 Hessian per foot -> escr
                 if (tid < 4) {
-                    double val, cg_[3];
-                    M::cone_terms_cold(c, uk + 6 * tid + 3, val, cg_, S.escr + 6 * tid);
+                    double val, cg_[3], ch_[6];
+                    M::cone_terms_cold(c, uk + 6 * tid + 3, val, cg_, ch_);
+#pragma unroll
+                    for (int q = 0; q < 6; q++) S.escr[6 * tid + q] = ch_[q];
                 }
                 __syncthreads();
             }
             if (tid < 78) {
                 const int fa = C1_I1(c1d), fb = C1_I2(c1d);
                 const int ka = fa % 3, kb = fb % 3;
-                const double* Ga = Jac + M::ZF + fa;
-                const double* Gb = Jac + M::ZF + fb;
-                const double a1 = Ga[0], a2 = Ga[NZ], a3 = Ga[2 * NZ], b1 = Gb[0], b2 = Gb[NZ], b3 = Gb[2 * NZ], im = c.inv_ms;
-                const double* Vr = S.VT + (M::XRD + ka) * NX;
-                const double* Vw = S.VT + M::XW * NX;
+                const real* Ga = Jac + M::ZF + fa;
+                const real* Gb = Jac + M::ZF + fb;
+                const real a1 = Ga[0], a2 = Ga[NZ], a3 = Ga[2 * NZ], b1 = Gb[0], b2 = Gb[NZ], b3 = Gb[2 * NZ], im = c.inv_ms;
+                const real* Vr = S.VT + (M::XRD + ka) * NX;
+                const real* Vw = S.VT + M::XW * NX;
                 const int cr = M::XRD + kb, cw = M::XW;
-                const double t0 = Vr[cr] * im + Vr[cw] * b1 + Vr[cw + 1] * b2 + Vr[cw + 2] * b3;
-                const double t1 = Vw[cr] * im + Vw[cw] * b1 + Vw[cw + 1] * b2 + Vw[cw + 2] * b3;
-                const double t2 = Vw[NX + cr] * im + Vw[NX + cw] * b1 + Vw[NX + cw + 1] * b2 + Vw[NX + cw + 2] * b3;
-                const double t3 = Vw[2 * NX + cr] * im + Vw[2 * NX + cw] * b1 + Vw[2 * NX + cw + 1] * b2 + Vw[2 * NX + cw + 2] * b3;
-                double v = dt2 * (im * t0 + a1 * t1 + a2 * t2 + a3 * t3) + g2 * (a1 * b1 + a2 * b2 + a3 * b3);
+                const real t0 = Vr[cr] * im + Vr[cw] * b1 + Vr[cw + 1] * b2 + Vr[cw + 2] * b3;
+                const real t1 = Vw[cr] * im + Vw[cw] * b1 + Vw[cw + 1] * b2 + Vw[cw + 2] * b3;
+                const real t2 = Vw[NX + cr] * im + Vw[NX + cw] * b1 + Vw[NX + cw + 1] * b2 + Vw[NX + cw + 2] * b3;
+                const real t3 = Vw[2 * NX + cr] * im + Vw[2 * NX + cw] * b1 + Vw[2 * NX + cw + 1] * b2 + Vw[2 * NX + cw + 2] * b3;
+                real v = dt2 * (im * t0 + a1 * t1 + a2 * t2 + a3 * t3) + g2 * (a1 * b1 + a2 * b2 + a3 * b3);
                 if (ka == kb) {                       // rddot rows of min_qddot; min_f and f_active on the diagonal
                     v += g2 * im * im;
-                    if (fa == fb) { const double sw1 = 1.0 - pk[8 + 2 * (fa / 3)]; v += 2.0 * (c.w_minf + c.w_fsw * sw1 * sw1) + mu; }
+                    if (fa == fb) { const real sw1 = real(1.0) - pk[8 + 2 * (fa / 3)]; v += real(2.0) * (c.w_minf + c.w_fsw * sw1 * sw1) + mu; }
                 }
                 if (SDDP_INEQ_ON(c) && fa / 3 == fb / 3) v += S.escr[6 * (fa / 3) + M::cone_hidx(ka, kb)];      // inequality barriers of the foot
                 const int ua = 6 * (fa / 3) + 3 + ka, ub = 6 * (fb / 3) + 3 + kb;
@@ -397,11 +407,11 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 const int ty = C1_TYPE(d), i1 = C1_I1(d), i2 = C1_I2(d);
                 if (ty == 0) continue;
                 int ua, ub;
-                double v;
+                real v;
                 if (ty == 2) {                        // (cddot ci, f fj)
                     const int kb = i2 % 3;
-                    const double* G = Jac + M::ZF + i2;
-                    const double* Vc = S.VT + (M::XCD + i1) * NX;
+                    const real* G = Jac + M::ZF + i2;
+                    const real* Vc = S.VT + (M::XCD + i1) * NX;
                     v = dt2 * (Vc[M::XRD + kb] * c.inv_ms + Vc[M::XW] * G[0] + Vc[M::XW + 1] * G[NZ] + Vc[M::XW + 2] * G[2 * NZ]);
                     ua = 6 * (i1 / 3) + i1 % 3; ub = 6 * (i2 / 3) + 3 + kb;
                 } else {                              // (cddot ca, cddot cb)
@@ -419,8 +429,8 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         STAMP(3);
         PROF(10);
 
-        const double* o = xk + M::XO;
-        const double* w = xk + M::XW;
+        const real* o = xk + M::XO;
+        const real* w = xk + M::XW;
 #if SDDP_ROTATE
         // Role rotation (experiment): the factorisation warp of co-resident CTAs sits on different SM sub-partitions
         const int vwarp = (warp + 4 - ((blockIdx.x / SDDP_ROTATE) & 3)) & 3, vt = vwarp * 32 + lane - 32;
@@ -430,7 +440,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         if (vwarp == 0) {
             // ---- d1: Quu + mu I = Lt D Lt^T; lane t owns column t.  Es = D^-1/2 Lt^-1 overwrites S.Quu row by row.
             if (has_gap) {   // gap terms of the model (the only use of cg after c1)
-                double g1 = 0, g2 = 0, yg = 0;
+                real g1 = 0, g2 = 0, yg = 0;
                 for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * cg[i]; g2 += cg[i] * S.sv[i]; yg += S.y[i] * cg[i]; }
                 g1 = rho_b * warp_sum(g1); g2 = rho_b * warp_sum(g2); yg = rho_b * warp_sum(yg);
                 if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
@@ -449,18 +459,18 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             // ---- c2: T = Vxx' fx = V + dt V A, in place, one thread per row (warps 1-2)
             const int r_ = vt;
             if (r_ < NX) {
-                double* row = S.VT + r_ * NX;
-                double vr[3], vo[4], vw[3];
+                real* row = S.VT + r_ * NX;
+                real vr[3], vo[4], vw[3];
 #pragma unroll
                 for (int q = 0; q < 3; q++) { vr[q] = row[M::XR + q]; vw[q] = row[M::XW + q]; }
 #pragma unroll
                 for (int q = 0; q < 4; q++) vo[q] = row[M::XO + q];
-                const double hw[3] = {0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
-                const double ho[4] = {0.5 * dt * o[0], 0.5 * dt * o[1], 0.5 * dt * o[2], 0.5 * dt * o[3]};
-                double to[4], tw[3];
+                const real hw[3] = {real(0.5) * dt * w[0], real(0.5) * dt * w[1], real(0.5) * dt * w[2]};
+                const real ho[4] = {real(0.5) * dt * o[0], real(0.5) * dt * o[1], real(0.5) * dt * o[2], real(0.5) * dt * o[3]};
+                real to[4], tw[3];
                 contract_Aoo(vo, hw, to);     // (V dt Aoo): o columns
                 contract_Aow(vo, ho, tw);     // (V dt Aow): w columns
-                const double dw0 = dt * vw[0], dw1 = dt * vw[1], dw2 = dt * vw[2];
+                const real dw0 = dt * vw[0], dw1 = dt * vw[1], dw2 = dt * vw[2];
                 // cd and rd columns first (they read the c and r entries before those are overwritten)
                 constexpr int C2U = LAT ? 19 : SDDP_C2_UNROLL;
 #pragma unroll C2U
@@ -469,7 +479,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 for (int q = 0; q < 3; q++) row[M::XRD + q] += dt * vr[q];
 #pragma unroll C2U
                 for (int z = 0; z < 19; z++) {        // r, o, c columns: + dt vw . dwdot/dz
-                    double v = row[z] + dw0 * Jac[z] + dw1 * Jac[NZ + z] + dw2 * Jac[2 * NZ + z];
+                    real v = row[z] + dw0 * Jac[z] + dw1 * Jac[NZ + z] + dw2 * Jac[2 * NZ + z];
                     if (z >= 3 && z < 7) v += (z == 3 ? to[0] : (z == 4 ? to[1] : (z == 5 ? to[2] : to[3])));
                     row[z] = v;
                 }
@@ -486,18 +496,18 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             //          Plain stores: lxx, lux, lx, lu are added afterwards (expand MODE 1)
             for (int task = vt; task < 39 * 3; task += 96) {
                 const int j = task % 39, g = task / 39;
-                const double* col = (j < NX) ? S.VT + j : (j == NX ? S.vp : S.ys);
+                const real* col = (j < NX) ? S.VT + j : (j == NX ? S.vp : S.ys);
                 const int cs = (j < NX) ? NX : 1;      // stride between rows of this "column"
-                double* oxx = (j < NX) ? S.Qxx + j : (j == NX ? S.Qx : S.qxy);
+                real* oxx = (j < NX) ? S.Qxx + j : (j == NX ? S.Qx : S.qxy);
                 const int os = (j < NX) ? NX : 1;
                 // tw = dt T[w, j] (+ 2 gq Jac[:, z_j] when column j is one of the wdot arguments r, o, c, w): the second
                 // term makes  Jac[:, z]^T tw  deliver the 2 gq Jac^T Jac part of lxx / lux on top of dt A^T T, so that
                 // only the curvature entries of the wdot block are left for the descriptor table (phase e)
                 const int zj = (j < M::XRD) ? j : ((j >= M::XW && j < M::XCD) ? j - 3 : -1);
-                double tw0 = dt * col[(M::XW + 0) * cs], tw1 = dt * col[(M::XW + 1) * cs], tw2 = dt * col[(M::XW + 2) * cs];
-                if (zj >= 0) { const double g2 = 2.0 * c.gq; tw0 += g2 * Jac[zj]; tw1 += g2 * Jac[NZ + zj]; tw2 += g2 * Jac[2 * NZ + zj]; }
+                real tw0 = dt * col[(M::XW + 0) * cs], tw1 = dt * col[(M::XW + 1) * cs], tw2 = dt * col[(M::XW + 2) * cs];
+                if (zj >= 0) { const real g2 = real(2.0) * c.gq; tw0 += g2 * Jac[zj]; tw1 += g2 * Jac[NZ + zj]; tw2 += g2 * Jac[2 * NZ + zj]; }
                 if (g == 0) {          // rows r, o, rd, w
-                    double tov[4];
+                    real tov[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) tov[q] = col[(M::XO + q) * cs];
 #pragma unroll
@@ -505,9 +515,9 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                         oxx[(M::XR + q) * os] = col[(M::XR + q) * cs] + (Jac[M::ZR + q] * tw0 + Jac[NZ + M::ZR + q] * tw1 + Jac[2 * NZ + M::ZR + q] * tw2);
                         oxx[(M::XRD + q) * os] = col[(M::XRD + q) * cs] + dt * col[(M::XR + q) * cs];
                     }
-                    const double hw[3] = {0.5 * dt * w[0], 0.5 * dt * w[1], 0.5 * dt * w[2]};
-                    const double ho[4] = {0.5 * dt * o[0], 0.5 * dt * o[1], 0.5 * dt * o[2], 0.5 * dt * o[3]};
-                    double ao[4], aw[3];
+                    const real hw[3] = {real(0.5) * dt * w[0], real(0.5) * dt * w[1], real(0.5) * dt * w[2]};
+                    const real ho[4] = {real(0.5) * dt * o[0], real(0.5) * dt * o[1], real(0.5) * dt * o[2], real(0.5) * dt * o[3]};
+                    real ao[4], aw[3];
                     contract_Aoo(tov, hw, ao);    // (dt Aoo)^T T[o,j]: row o_b = sum_a Aoo[a][b] T[o_a][j]
                     contract_Aow(tov, ho, aw);    // (dt Aow)^T T[o,j]: row w_b
 #pragma unroll
@@ -519,14 +529,14 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 } else if (g == 1) {   // rows c, cd
 #pragma unroll C3U
                     for (int q = 0; q < 12; q++) {
-                        double tc = col[(M::XC + q) * cs];
+                        real tc = col[(M::XC + q) * cs];
                         oxx[(M::XC + q) * os] = tc + (Jac[M::ZC + q] * tw0 + Jac[NZ + M::ZC + q] * tw1 + Jac[2 * NZ + M::ZC + q] * tw2);
                         oxx[(M::XCD + q) * os] = col[(M::XCD + q) * cs] + dt * tc;
                     }
                 } else {               // fu^T (.): rows cddot_i, f_i
-                    double* oux = S.W + j;           // columns NX, NX+1 of W: Qu = lu + fu^T v+ and quy = lu + fu^T ys
+                    real* oux = S.W + j;           // columns NX, NX+1 of W: Qu = lu + fu^T v+ and quy = lu + fu^T ys
                     const int us = LDW;
-                    const double trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
+                    const real trd[3] = {c.inv_ms * col[(M::XRD + 0) * cs], c.inv_ms * col[(M::XRD + 1) * cs], c.inv_ms * col[(M::XRD + 2) * cs]};
 #pragma unroll C3F
                     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -569,7 +579,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
         //  registers first because the product is formed in place.
         {
             const int c_ = tid % 40, g_ = tid / 40;
-            double bcol[NU];
+            real bcol[NU];
             if (tid < 120) {
 #pragma unroll
                 for (int l = 0; l < NU; l++) bcol[l] = S.W[l * LDW + c_];
@@ -579,7 +589,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 #pragma unroll 1
                 for (int ii = 0; ii < 8; ii++) {
                     const int i = 8 * g_ + ii;
-                    double s_ = 0.0;
+                    real s_ = 0.0;
 #pragma unroll
                     for (int l = 0; l < NU; l++) if (l <= i) s_ += S.Quu[i * NU + l] * bcol[l];
                     S.W[i * LDW + c_] = S.rs[i] * s_;
@@ -594,20 +604,20 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 #pragma unroll
                 for (int k0 = 0; k0 < NU; k0 += 4) {
                     const int l = k0 + fc;
-                    const double bv = S.W[l * LDW + 8 * J + fr];
+                    const real bv = S.W[l * LDW + 8 * J + fr];
 #pragma unroll
                     for (int I = 0; I < 3; I++) {
                         if (k0 > 8 * I + 7) continue;
                         const int i = 8 * I + fr;
-                        const double av = S.Quu[i * NU + l];
+                        const real av = S.Quu[i * NU + l];
                         dmma884(h0[I], h1[I], av, bv);
                     }
                 }
                 __syncwarp();
 #pragma unroll
                 for (int I = 0; I < 3; I++) {
-                    const double r = S.rs[8 * I + fr];
-                    *reinterpret_cast<double2*>(S.W + (8 * I + fr) * LDW + 8 * J + 2 * fc) = make_double2(r * h0[I], r * h1[I]);
+                    const real r = S.rs[8 * I + fr];
+                    *reinterpret_cast<real2*>(S.W + (8 * I + fr) * LDW + 8 * J + 2 * fc) = make_real2(r * h0[I], r * h1[I]);
                 }
             }
         }
@@ -627,11 +637,11 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 int pr_ = 0, rem = tid;
                 while (rem >= 2 * (10 - pr_)) { rem -= 2 * (10 - pr_); pr_++; }
                 const int ri = 2 * pr_ + (rem >= 10 - pr_ ? 1 : 0), cj = pr_ + (rem >= 10 - pr_ ? rem - (10 - pr_) : rem);
-                double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+                real acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll 4
                 for (int l = 0; l < NU; l++) {
-                    const double2 a = *reinterpret_cast<const double2*>(S.W + l * LDW + 2 * ri);
-                    const double2 b0 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * cj), b1 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * cj + 2);
+                    const real2 a = *reinterpret_cast<const real2*>(S.W + l * LDW + 2 * ri);
+                    const real2 b0 = *reinterpret_cast<const real2*>(S.W + l * LDW + 4 * cj), b1 = *reinterpret_cast<const real2*>(S.W + l * LDW + 4 * cj + 2);
                     acc[0][0] += a.x * b0.x; acc[0][1] += a.x * b0.y; acc[0][2] += a.x * b1.x; acc[0][3] += a.x * b1.y;
                     acc[1][0] += a.y * b0.x; acc[1][1] += a.y * b0.y; acc[1][2] += a.y * b1.x; acc[1][3] += a.y * b1.y;
                 }
@@ -641,12 +651,12 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                     for (int q = 0; q < 4; q++) {
                         const int gi = 2 * ri + r, gj = 4 * cj + q;
                         const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
-                        const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
-                        const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
-                        double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
-                        double* d2 = m ? S.VT + gj * NX + gi : d1;
+                        const real* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
+                        const real* s2 = m ? S.Qxx + gj * NX + gi : s1;
+                        real* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
+                        real* d2 = m ? S.VT + gj * NX + gi : d1;
                         if (ok) {
-                            const double v = 0.5 * (*s1 + *s2) - acc[r][q];
+                            const real v = real(0.5) * (*s1 + *s2) - acc[r][q];
                             *d1 = v;
                             *d2 = v;
                         }
@@ -655,12 +665,12 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             // g: [K | k] = -Et^T (diag(rs) Wn), 2 x 4 register tiles (12 x 10, one per thread); Et is lower triangular
             if (tid < 120) {
                 const int I2 = tid / 10, J4 = tid - 10 * I2;
-                double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+                real acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
                 for (int l = 2 * I2; l < NU; l++) {
-                    const double2 e_ = *reinterpret_cast<const double2*>(S.Quu + l * NU + 2 * I2);
-                    const double r_ = S.rs[l];
-                    const double2 b0 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * J4), b1 = *reinterpret_cast<const double2*>(S.W + l * LDW + 4 * J4 + 2);
-                    const double w0 = r_ * b0.x, w1 = r_ * b0.y, w2 = r_ * b1.x, w3 = r_ * b1.y;
+                    const real2 e_ = *reinterpret_cast<const real2*>(S.Quu + l * NU + 2 * I2);
+                    const real r_ = S.rs[l];
+                    const real2 b0 = *reinterpret_cast<const real2*>(S.W + l * LDW + 4 * J4), b1 = *reinterpret_cast<const real2*>(S.W + l * LDW + 4 * J4 + 2);
+                    const real w0 = r_ * b0.x, w1 = r_ * b0.y, w2 = r_ * b1.x, w3 = r_ * b1.y;
                     acc[0][0] += e_.x * w0; acc[0][1] += e_.x * w1; acc[0][2] += e_.x * w2; acc[0][3] += e_.x * w3;
                     acc[1][0] += e_.y * w0; acc[1][1] += e_.y * w1; acc[1][2] += e_.y * w2; acc[1][3] += e_.y * w3;
                 }
@@ -669,7 +679,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int i = 2 * I2 + r, cc = 4 * J4 + q;
-                        const double kv = -acc[r][q];
+                        const real kv = -acc[r][q];
                         if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
                         if (cc == NX) { S.kk[i] = kv; kg[(size_t)k * NU + i] = kv; }
                     }
@@ -689,8 +699,8 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                 const int fI = (int)((0x433222111100000ull >> (4 * t)) & 15), fJ = (int)((0x443432432143210ull >> (4 * t)) & 15);
                 const int gI = t / 5, gJ = t - 5 * gI;
                 double f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
-                const double* rf = S.W + fc * LDW + fr;
-                const double* qa = S.Quu + fc * NU + 8 * gI + fr;
+                const real* rf = S.W + fc * LDW + fr;
+                const real* qa = S.Quu + fc * NU + 8 * gI + fr;
 #pragma unroll
                 for (int k0 = 0; k0 < NU; k0 += 4) {
                     dmma884(f0, f1, rf[k0 * LDW + 8 * fI], rf[k0 * LDW + 8 * fJ]);
@@ -704,7 +714,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                     for (int e = 0; e < 2; e++) {
                         const int gj = 8 * fJ + 2 * fc + e;
                         if (gj >= gi) {
-                            const double v = 0.5 * (S.Qxx[gi * NX + gj] + S.Qxx[gj * NX + gi]) - (e ? f1 : f0);
+                            const real v = real(0.5) * (S.Qxx[gi * NX + gj] + S.Qxx[gj * NX + gi]) - (e ? f1 : f0);
                             S.VT[gi * NX + gj] = v;
                             S.VT[gj * NX + gi] = v;
                         }
@@ -716,24 +726,24 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                         // vectors Qx -> Vx and qxy -> y as one more row / column of the matrices, whose spare entry 37 is
                         // kept zero, so Vx[37] = -|w0|^2 and y[37] = quy . k; inactive lanes hit dummy addresses.
                         const int gj = 8 * fJ + 2 * fc + e;
-                        const double acc = e ? f1 : f0;
+                        const real acc = e ? f1 : f0;
                         const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
-                        const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
-                        const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
-                        double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
-                        double* d2 = m ? S.VT + gj * NX + gi : d1;
+                        const real* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
+                        const real* s2 = m ? S.Qxx + gj * NX + gi : s1;
+                        real* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
+                        real* d2 = m ? S.VT + gj * NX + gi : d1;
                         if (!ok) { s1 = s2 = S.Qx + NX; d1 = d2 = S.escr + 23; }
-                        const double v = 0.5 * (*s1 + *s2) - acc;
+                        const real v = real(0.5) * (*s1 + *s2) - acc;
                         *d1 = v;
                         *d2 = v;
                     }
                 }
                 {
                     const int i = 8 * gI + fr, cc = 8 * gJ + 2 * fc;
-                    double* Krow = const_cast<double*>(S.gp[0]) + ((size_t)k * NU + i) * NX;      // (pointers from shared memory: see prefetch)
+                    real* Krow = const_cast<real*>(S.gp[0]) + ((size_t)k * NU + i) * NX;      // (pointers from shared memory: see prefetch)
                     if (cc < NX) Krow[cc] = -g0;
                     if (cc + 1 < NX) Krow[cc + 1] = -g1;
-                    if (cc + 1 == NX) { S.kk[i] = -g1; const_cast<double*>(S.gp[1])[(size_t)k * NU + i] = -g1; }      // column 37 is odd
+                    if (cc + 1 == NX) { S.kk[i] = -g1; const_cast<real*>(S.gp[1])[(size_t)k * NU + i] = -g1; }      // column 37 is odd
                 }
             }
         }
@@ -754,8 +764,8 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             double fc0[4] = {0, 0, 0, 0}, fc1[4] = {0, 0, 0, 0}, gc0[4] = {0, 0, 0, 0}, gc1[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int k0 = 0; k0 < NU; k0 += 4) {
-                const double* r = S.W + (k0 + fc) * LDW + fr;
-                double av[4], bv[4];
+                const real* r = S.W + (k0 + fc) * LDW + fr;
+                real av[4], bv[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) { av[q] = r[8 * fI[q]]; bv[q] = r[8 * fJ[q]]; }
 #pragma unroll
@@ -764,8 +774,8 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 #pragma unroll
             for (int k0 = 0; k0 < NU; k0 += 4) {
                 const int l = k0 + fc;
-                double av[4], bv[4];
-                const double rl = S.rs[l];                  // Es^T Wn = Et^T (diag(rs) Wn)
+                real av[4], bv[4];
+                const real rl = S.rs[l];                  // Es^T Wn = Et^T (diag(rs) Wn)
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int i = 8 * gI[q] + fr;
@@ -785,14 +795,14 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
                     // vectors Qx -> Vx and qxy -> y as one more row / column of the matrices, whose spare entry 37 is
                     // kept zero, so Vx[37] = -|w0|^2 and y[37] = quy . k; inactive lanes hit dummy addresses.
                     const int gj = 8 * fJ[q] + 2 * fc + e;
-                    const double acc = e ? fc1[q] : fc0[q];
+                    const real acc = e ? fc1[q] : fc0[q];
                     const bool m = gj < NX, ok = gj >= gi && gj <= NX + 1 && gi <= NX;
-                    const double* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
-                    const double* s2 = m ? S.Qxx + gj * NX + gi : s1;
-                    double* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
-                    double* d2 = m ? S.VT + gj * NX + gi : d1;
+                    const real* s1 = m ? S.Qxx + gi * NX + gj : (gj == NX ? S.Qx : S.qxy) + gi;
+                    const real* s2 = m ? S.Qxx + gj * NX + gi : s1;
+                    real* d1 = m ? S.VT + gi * NX + gj : (gj == NX ? S.Vx : S.y) + gi;
+                    real* d2 = m ? S.VT + gj * NX + gi : d1;
                     if (!ok) { s1 = s2 = S.Qx + NX; d1 = d2 = S.escr + 23; }
-                    const double v = 0.5 * (*s1 + *s2) - acc;
+                    const real v = real(0.5) * (*s1 + *s2) - acc;
                     *d1 = v;
                     *d2 = v;
                 }
@@ -804,7 +814,7 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int cc = 8 * J + 2 * fc + e;
-                    const double kv = e ? -gc1[q] : -gc0[q];
+                    const real kv = e ? -gc1[q] : -gc0[q];
                     if (cc < NX) Kg[((size_t)k * NU + i) * NX + cc] = kv;
                     if (cc == NX) S.kk[i] = kv;
                     if (cc == NX) kg[(size_t)k * NU + i] = kv;
@@ -824,8 +834,8 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             // of BASELINE configs[4]): [Vxx Vx] -= mu [K k]^T [K k].  Qxx is dead after the barrier above, so [K | k] of this
             // node (the gains this CTA just wrote; L2 hits) is staged there at the pitch of W and the product runs as the
             // same upper-triangular tile syrk as phase f on the FP64 tensor cores; entry (37, 37) is |k|^2.
-            double* Ks = S.Qxx;
-            const double* Kn = S.gp[0] + (size_t)k * NU * NX;
+            real* Ks = S.Qxx;
+            const real* Kn = S.gp[0] + (size_t)k * NU * NX;
             for (int e = tid; e < NU * LDW; e += NT) {
                 const int l = e / LDW, cc = e - l * LDW;
                 Ks[e] = cc < NX ? Kn[l * NX + cc] : (cc == NX ? S.kk[l] : 0.0);
@@ -836,16 +846,16 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             for (int t = warp; t < 15; t += NWARP) {
                 const int fI = (int)((0x433222111100000ull >> (4 * t)) & 15), fJ = (int)((0x443432432143210ull >> (4 * t)) & 15);
                 double f0 = 0.0, f1 = 0.0;
-                const double* rf = Ks + fc * LDW + fr;
+                const real* rf = Ks + fc * LDW + fr;
 #pragma unroll
                 for (int k0 = 0; k0 < NU; k0 += 4) dmma884(f0, f1, rf[k0 * LDW + 8 * fI], rf[k0 * LDW + 8 * fJ]);
                 const int gi = 8 * fI + fr;
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int gj = 8 * fJ + 2 * fc + e;
-                    const double acc = e ? f1 : f0;
+                    const real acc = e ? f1 : f0;
                     if (gj >= gi && gj < NX) {              // (gi <= gj < NX)
-                        const double v = S.VT[gi * NX + gj] - mu * acc;
+                        const real v = S.VT[gi * NX + gj] - mu * acc;
                         S.VT[gi * NX + gj] = v;
                         S.VT[gj * NX + gi] = v;
                     } else if (gj == NX && gi < NX) S.Vx[gi] -= mu * acc;
@@ -859,9 +869,9 @@ __device__ int SmemSrbdT<MT, LAT>::backward(const DevCfg& c, SmemSrbdT<MT, LAT>&
             const double sk = (mu != 0.0) ? S.red[6] : 0.0;
             const double sq = S.y[NX];          // quy . k
             const double kQk = sw - mu * sk;
-            S.red[R_TOT] += S.red[R_G1] + 0.5 * S.red[R_G2] + (-sw) + 0.5 * kQk;
-            S.red[R_ACC2] += 0.5 * kQk;
-            S.red[R_ACC1] += fixed ? (S.red[R_YG] + 0.5 * S.red[R_G2]) : (S.red[R_YG] + sq);
+            S.red[R_TOT] += S.red[R_G1] + real(0.5) * S.red[R_G2] + (-sw) + real(0.5) * kQk;
+            S.red[R_ACC2] += real(0.5) * kQk;
+            S.red[R_ACC1] += fixed ? (S.red[R_YG] + real(0.5) * S.red[R_G2]) : (S.red[R_YG] + sq);
         }
     }
     __syncthreads();

@@ -32,16 +32,22 @@ constexpr unsigned FULL = 0xffffffffu;
 // per-node input buffer: x | u | p | d | (pack in the backward pass, k in the forward pass)
 template <class M>
 struct NodeBuf {
-    static constexpr int OX = 0, OU = M::NX, OP = M::NX + M::NU, OD = M::NX + M::NU + M::NP, OK = (2 * M::NX + M::NU + M::NP + 1) & ~1;
+    static constexpr int OX = 0, OU = M::NX, OP = M::NX + M::NU, OD = M::NX + M::NU + M::NP, OK = (2 * M::NX + M::NU + M::NP + RV - 1) & ~(RV - 1);
     static constexpr int TAIL = M::PACK > M::NU ? M::PACK : M::NU;
-    static constexpr int SIZE = (OK + TAIL + 1) & ~1;
+    static constexpr int SIZE = (OK + TAIL + RV - 1) & ~(RV - 1);
 };
 
-SDDP_DEV void cp_async8(double* smem, const double* g) {
+// one element (8 bytes; 4 in the fp32 build)
+SDDP_DEV void cp_async8(real* smem, const real* g) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+#ifdef SDDP_F32
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(g) : "memory");
+#else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+#endif
 }
-SDDP_DEV void cp_async16(double* smem, const double* g) {
+// RV elements (16 bytes)
+SDDP_DEV void cp_async16(real* smem, const real* g) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
 }
@@ -76,22 +82,22 @@ SDDP_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
 template <class M>
 struct Smem {
     static constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
-    double Vxx[NX * NX], Qxx[NX * NX], Qux[NU * NX], Quu[NU * NU];
-    double T[NX * (NX + NU)];            // Vxx [fx fu]; afterwards K of the node (NU*NX); forward: K_k
-    double fx[NX * NX], fu[NX * NU];     // dense; forward: per-candidate x^, u^, x^+
-    double Vx[NX], y[NX], Qx[NX], Qu[NU], vp[NX], sv[NX], ys[NX], quy[NU], qxy[NX], kk[NU], w0[NU];
-    double nb[2][NodeBuf<M>::SIZE];      // double-buffered per-node inputs (x, u, p, d, pack | k)
-    double sacc[NWARP][8];
-    double red[16];
+    real Vxx[NX * NX], Qxx[NX * NX], Qux[NU * NX], Quu[NU * NU];
+    real T[NX * (NX + NU)];            // Vxx [fx fu]; afterwards K of the node (NU*NX); forward: K_k
+    real fx[NX * NX], fu[NX * NU];     // dense; forward: per-candidate x^, u^, x^+
+    real Vx[NX], y[NX], Qx[NX], Qu[NU], vp[NX], sv[NX], ys[NX], quy[NU], qxy[NX], kk[NU], w0[NU];
+    real nb[2][NodeBuf<M>::SIZE];      // double-buffered per-node inputs (x, u, p, d, pack | k)
+    real sacc[NWARP][8];
+    double red[16];                      // reductions and the expected-decrease accumulators: double in both builds
     double alpha[NCAND], rho[NCAND], Jc[NCAND];
-    const double* gp[8];                 // base pointers of the per-node prefetches (see forward_wave)
+    const real* gp[8];                 // base pointers of the per-node prefetches (see forward_wave)
     unsigned long long mbar[2];          // completion barriers of the bulk copies of K_k (forward_wave)
     int iflag[4];
-    __device__ static int backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
-                                   const double* packs, double mu, double* Kg, double* kg, double* dV3, bool has_gap, int tid);
-    __device__ static void prep(const DevCfg& c, Smem<M>&, const double* X, const double* U, const double*, double* packs, int tid);
-    __device__ double* Kbuf(int b) { return T + b * (NU * NX); }   // forward pass: K of node k in buffer k & 1
-    __device__ double* scr() { return fx; }    // per-warp scratch
+    __device__ static int backward(const DevCfg& c, Smem<M>& S, const real* X, const real* U, const real* P, const real* D,
+                                   const real* packs, real mu, real* Kg, real* kg, double* dV3, bool has_gap, int tid);
+    __device__ static void prep(const DevCfg& c, Smem<M>&, const real* X, const real* U, const real*, real* packs, int tid);
+    __device__ real* Kbuf(int b) { return T + b * (NU * NX); }   // forward pass: K of node k in buffer k & 1
+    __device__ real* scr() { return fx; }    // per-warp scratch
 };
 enum { R_TOT = 0, R_ACC1 = 1, R_ACC2 = 2, R_G1 = 3, R_G2 = 4, R_YG = 5, R_W0 = 8 };
 
@@ -104,12 +110,14 @@ SDDP_DEV int node_kind(const DevCfg& c, int k) {
     return (c.lip_tail > 0 && k >= c.lip_tail) ? NODE_TAIL : NODE_MID;
 }
 
-SDDP_DEV double warp_sum(double s) {
+template <class T>
+SDDP_DEV T warp_sum(T s) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     return s;
 }
-SDDP_DEV double warp_max(double s) {
+template <class T>
+SDDP_DEV T warp_max(T s) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(FULL, s, o));
     return s;
@@ -118,10 +126,10 @@ SDDP_DEV double warp_max(double s) {
 // cost of one node (all lanes get the sum) and, if xnext != null, the Euler step
 //   xnext = xs + dt*ode(xs,us) - omr*dk
 template <class M>
-__device__ SDDP_NOINLINE double warp_node(const DevCfg& c, int kind, const double* xs, const double* us, const double* ps,
-                            double* xnext, const double* dk, double omr, double* sacc, int lane) {
+__device__ SDDP_NOINLINE double warp_node(const DevCfg& c, int kind, const real* xs, const real* us, const real* ps,
+                            real* xnext, const real* dk, real omr, real* sacc, int lane) {
     if (kind != NODE_TERM && M::NACC > 1) {
-        double acc[M::NACC];
+        real acc[M::NACC];
         M::accel(c, xs, us, acc, kind == NODE_TAIL);
         if (lane == 0) {
 #pragma unroll
@@ -129,10 +137,10 @@ __device__ SDDP_NOINLINE double warp_node(const DevCfg& c, int kind, const doubl
         }
         __syncwarp();
     }
-    double s = warp_sum(M::cost_lane(c, kind, lane, xs, us, ps, sacc));
+    const double s = warp_sum(M::cost_lane(c, kind, lane, xs, us, ps, sacc));
     if (xnext != nullptr && kind != NODE_TERM) {
         for (int i = lane; i < M::NX; i += 32) {
-            double v = xs[i] + c.dt * M::xdot_i(c, i, xs, us, sacc);
+            real v = xs[i] + c.dt * M::xdot_i(c, i, xs, us, sacc);
             if (dk != nullptr) v -= omr * dk[i];
             xnext[i] = v;
         }
@@ -145,14 +153,14 @@ __device__ SDDP_NOINLINE double warp_node(const DevCfg& c, int kind, const doubl
 // defects d_k = f(X_k,U_k) - X_{k+1} (if dout) and the total cost; warps stride over nodes.
 // Returns J to every thread.  Uses S.fx as per-warp scratch.
 template <class M, class SM>
-__device__ double defects_and_cost(const DevCfg& c, SM& S, const double* X, const double* U, const double* P,
-                                   double* dout, int tid) {
+__device__ double defects_and_cost(const DevCfg& c, SM& S, const real* X, const real* U, const real* P,
+                                   real* dout, int tid) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int N = c.N, lane = tid & 31, w = tid >> 5;
-    double* xs = S.scr() + w * (2 * NX + NU + NP);
-    double* us = xs + NX;
-    double* ps = us + NU;
-    double* xn = ps + NP;
+    real* xs = S.scr() + w * (2 * NX + NU + NP);
+    real* us = xs + NX;
+    real* ps = us + NU;
+    real* xn = ps + NP;
     double part = 0.0;
     for (int k = w; k <= N; k += NWARP) {
         const int kind = node_kind(c, k);
@@ -177,19 +185,19 @@ __device__ double defects_and_cost(const DevCfg& c, SM& S, const double* X, cons
 
 // open-loop rollout X_{k+1} = f(X_k, U_k) by warp 0 (single-shooting initialisation)
 template <class M, class SM>
-__device__ void open_loop_rollout(const DevCfg& c, SM& S, double* X, const double* U, int tid) {
+__device__ void open_loop_rollout(const DevCfg& c, SM& S, real* X, const real* U, int tid) {
     constexpr int NX = M::NX, NU = M::NU;
     const int lane = tid & 31;
     if (tid < 32) {
-        double* xs = S.scr();
-        double* us = xs + NX;
-        double* xn = us + NU;
+        real* xs = S.scr();
+        real* us = xs + NX;
+        real* xn = us + NU;
         for (int i = lane; i < NX; i += 32) xs[i] = X[i];
         for (int k = 0; k < c.N; k++) {
             for (int i = lane; i < NU; i += 32) us[i] = U[(size_t)k * NU + i];
             __syncwarp();
             if (M::NACC > 1) {
-                double acc[M::NACC];
+                real acc[M::NACC];
                 M::accel(c, xs, us, acc, node_kind(c, k) == NODE_TAIL);
                 if (lane == 0) {
 #pragma unroll
@@ -209,19 +217,19 @@ __device__ void open_loop_rollout(const DevCfg& c, SM& S, double* X, const doubl
 // ------------------------------------------------------------------------------------------------
 // Stage 2.  Returns 0 or (failing node + 1) to every thread.  dV3[0..2] (shared) = {D1, D2, C0}.
 template <class M>
-__device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P,
-                             const double* D, const double* packs, double mu, double* Kg, double* kg, double* dV3, int tid) {
+__device__ int backward_pass(const DevCfg& c, Smem<M>& S, const real* X, const real* U, const real* P,
+                             const real* D, const real* packs, real mu, real* Kg, real* kg, double* dV3, int tid) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP, LD = NX + NU;
     const int N = c.N, lane = tid & 31, warp = tid >> 5;
     const bool fixed = c.rho_fixed > 0.0;
-    const double rho_b = fixed ? c.rho_fixed : 1.0;
+    const real rho_b = fixed ? (real)c.rho_fixed : real(1.0);
     SyncBlock sync;
     using NBL = NodeBuf<M>;
-    double* xk = S.nb[0] + NBL::OX;
-    double* uk = S.nb[0] + NBL::OU;
-    double* pk = S.nb[0] + NBL::OP;
-    double* cg = S.nb[0] + NBL::OD;
-    double* pack = S.nb[0] + NBL::OK;
+    real* xk = S.nb[0] + NBL::OX;
+    real* uk = S.nb[0] + NBL::OU;
+    real* pk = S.nb[0] + NBL::OP;
+    real* cg = S.nb[0] + NBL::OD;
+    real* pack = S.nb[0] + NBL::OK;
 
     // terminal node: Vx = l_Nx, Vxx = l_Nxx (ddp.py:216-226: costs only)
     for (int i = tid; i < NX; i += NT) xk[i] = X[(size_t)N * NX + i];
@@ -247,7 +255,7 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
 
         // sv = Vxx' c, v+ = Vx' + sv, ys = y' (+ sv)
         if (tid < NX) {
-            double s = 0.0;
+            real s = 0.0;
             for (int j = 0; j < NX; j++) s += S.Vxx[tid * NX + j] * cg[j];
             S.sv[tid] = s;
             S.vp[tid] = S.Vx[tid] + s;
@@ -256,27 +264,27 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
         // T = Vxx' [fx fu]
         for (int e = tid; e < NX * LD; e += NT) {
             int i = e / LD, j = e % LD;
-            double s = 0.0;
+            real s = 0.0;
             if (j < NX) for (int l = 0; l < NX; l++) s += S.Vxx[i * NX + l] * S.fx[l * NX + j];
             else        for (int l = 0; l < NX; l++) s += S.Vxx[i * NX + l] * S.fu[l * NU + (j - NX)];
             S.T[e] = s;
         }
         __syncthreads();
         if (warp == 0) {   // gap terms of the model
-            double g1 = 0, g2 = 0, yg = 0;
+            real g1 = 0, g2 = 0, yg = 0;
             for (int i = lane; i < NX; i += 32) { g1 += S.Vx[i] * cg[i]; g2 += cg[i] * S.sv[i]; yg += S.y[i] * cg[i]; }
             g1 = warp_sum(g1); g2 = warp_sum(g2); yg = warp_sum(yg);
             if (lane == 0) { S.red[R_G1] = g1; S.red[R_G2] = g2; S.red[R_YG] = yg; }
         }
         // first-order quantities (Qx, Qu still hold lx, lu)
         if (tid < NX) {
-            double a = 0.0, b = 0.0;
+            real a = 0.0, b = 0.0;
             for (int l = 0; l < NX; l++) { a += S.fx[l * NX + tid] * S.ys[l]; b += S.fx[l * NX + tid] * S.vp[l]; }
             S.qxy[tid] = S.Qx[tid] + a;
             S.Qx[tid] += b;
         } else if (tid >= 64 && tid < 64 + NU) {
             int j = tid - 64;
-            double a = 0.0, b = 0.0;
+            real a = 0.0, b = 0.0;
             for (int l = 0; l < NX; l++) { a += S.fu[l * NU + j] * S.ys[l]; b += S.fu[l * NU + j] * S.vp[l]; }
             S.quy[j] = S.Qu[j] + a;
             S.Qu[j] += b;
@@ -284,19 +292,19 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
         // Qxx += fx^T Tx, Qux += fu^T Tx, Quu += fu^T Tu
         for (int e = tid; e < NX * NX; e += NT) {
             int i = e / NX, j = e % NX;
-            double s = 0.0;
+            real s = 0.0;
             for (int l = 0; l < NX; l++) s += S.fx[l * NX + i] * S.T[l * LD + j];
             S.Qxx[e] += s;
         }
         for (int e = tid; e < NU * NX; e += NT) {
             int i = e / NX, j = e % NX;
-            double s = 0.0;
+            real s = 0.0;
             for (int l = 0; l < NX; l++) s += S.fu[l * NU + i] * S.T[l * LD + j];
             S.Qux[e] += s;
         }
         for (int e = tid; e < NU * NU; e += NT) {
             int i = e / NU, j = e % NU;
-            double s = 0.0;
+            real s = 0.0;
             for (int l = 0; l < NX; l++) s += S.fu[l * NU + i] * S.T[l * LD + NX + j];
             S.Quu[e] += s;
         }
@@ -306,14 +314,14 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
         if (warp == 0) {
             int ok = 1;
             for (int j = 0; j < NU; j++) {
-                double s = 0.0;
+                real s = 0.0;
                 if (lane < NU && lane >= j) {
-                    s = 0.5 * (S.Quu[lane * NU + j] + S.Quu[j * NU + lane]) + (lane == j ? mu : 0.0);
+                    s = real(0.5) * (S.Quu[lane * NU + j] + S.Quu[j * NU + lane]) + (lane == j ? mu : 0.0);
                     for (int l = 0; l < j; l++) s -= S.Quu[lane * NU + l] * S.Quu[j * NU + l];
                 }
-                double piv = __shfl_sync(FULL, s, j);
+                real piv = __shfl_sync(FULL, s, j);
                 if (!(piv > 0.0) || !isfinite(piv)) { ok = 0; break; }
-                double d = sqrt(piv);
+                real d = sqrt(piv);
                 if (lane < NU && lane >= j) S.Quu[lane * NU + j] = (lane == j) ? d : s / d;
                 __syncwarp();
             }
@@ -325,25 +333,25 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
         // gains: one thread per right-hand side (NX columns of Qux, then Qu)
         if (tid <= NX) {
             const int t = tid;
-            double b[NU], kc[NU];
+            real b[NU], kc[NU];
 #pragma unroll
             for (int i = 0; i < NU; i++) b[i] = (t < NX) ? S.Qux[i * NX + t] : S.Qu[i];
 #pragma unroll
             for (int i = 0; i < NU; i++) {
-                double s = b[i];
+                real s = b[i];
 #pragma unroll
                 for (int l = 0; l < i; l++) s -= S.Quu[i * NU + l] * b[l];
                 b[i] = s / S.Quu[i * NU + i];
             }
 #pragma unroll
             for (int i = NU - 1; i >= 0; i--) {
-                double s = -b[i];
+                real s = -b[i];
 #pragma unroll
                 for (int l = i + 1; l < NU; l++) s -= S.Quu[l * NU + i] * kc[l];
                 kc[i] = s / S.Quu[i * NU + i];
             }
             if (t < NX) {
-                double yv = S.qxy[t];
+                real yv = S.qxy[t];
 #pragma unroll
                 for (int i = 0; i < NU; i++) {
                     S.Qux[i * NX + t] = b[i];                       // W
@@ -359,20 +367,20 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
         }
         __syncthreads();
         if (warp == 0) {   // model accumulators
-            double sw = 0, sk = 0, sq = 0;
+            real sw = 0, sk = 0, sq = 0;
             for (int i = lane; i < NU; i += 32) { sw += S.w0[i] * S.w0[i]; sk += S.kk[i] * S.kk[i]; sq += S.quy[i] * S.kk[i]; }
             sw = warp_sum(sw); sk = warp_sum(sk); sq = warp_sum(sq);
             if (lane == 0) {
-                double kQk = sw - mu * sk;
-                S.red[R_TOT] += S.red[R_G1] + 0.5 * S.red[R_G2] + (-sw) + 0.5 * kQk;
-                S.red[R_ACC2] += 0.5 * kQk;
-                S.red[R_ACC1] += fixed ? (S.red[R_YG] + 0.5 * S.red[R_G2]) : (S.red[R_YG] + sq);
+                real kQk = sw - mu * sk;
+                S.red[R_TOT] += S.red[R_G1] + real(0.5) * S.red[R_G2] + (-sw) + real(0.5) * kQk;
+                S.red[R_ACC2] += real(0.5) * kQk;
+                S.red[R_ACC1] += fixed ? (S.red[R_YG] + real(0.5) * S.red[R_G2]) : (S.red[R_YG] + sq);
             }
         }
         // Vx = Qx - W^T w0 - mu K^T k
         if (tid >= 64 && tid < 64 + NX) {
             int t = tid - 64;
-            double s = S.Qx[t];
+            real s = S.Qx[t];
             for (int l = 0; l < NU; l++) s -= S.Qux[l * NX + t] * S.w0[l] + mu * S.T[l * NX + t] * S.kk[l];
             S.Vx[t] = s;
         }
@@ -380,10 +388,10 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
         for (int e = tid; e < NX * NX; e += NT) {
             int i = e / NX, j = e % NX;
             if (j < i) continue;
-            double s = 0.5 * (S.Qxx[i * NX + j] + S.Qxx[j * NX + i]);
+            real s = real(0.5) * (S.Qxx[i * NX + j] + S.Qxx[j * NX + i]);
             for (int l = 0; l < NU; l++) s -= S.Qux[l * NX + i] * S.Qux[l * NX + j];
             if (mu != 0.0) {
-                double t = 0.0;
+                real t = 0.0;
                 for (int l = 0; l < NU; l++) t += S.T[l * NX + i] * S.T[l * NX + j];
                 s -= mu * t;
             }
@@ -405,40 +413,40 @@ __device__ int backward_pass(const DevCfg& c, Smem<M>& S, const double* X, const
 // Stage 3.  ncand (<= NCAND) candidate step sizes S.alpha[], S.rho[] rolled out in parallel, one warp each.
 // Trial trajectories go to Xn + cand*xn_stride / Un + cand*un_stride (global); costs to S.Jc[].
 template <class M, class SM>
-__device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const double* X, const double* U, const double* P,
-                             const double* D, const double* Kg, const double* kg, int ncand, double* Xn, size_t xn_stride,
-                             double* Un, size_t un_stride, int tid, int skip = 1 << 30) {
+__device__ void forward_wave(const DevCfg& c, SM& S, const real* x0, const real* X, const real* U, const real* P,
+                             const real* D, const real* Kg, const real* kg, int ncand, real* Xn, size_t xn_stride,
+                             real* Un, size_t un_stride, int tid, int skip = 1 << 30) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     using NBL = NodeBuf<M>;
     const int N = c.N, lane = tid & 31, w = tid >> 5;
-    double* xh = S.scr() + w * (2 * NX + NU);
-    double* uh = xh + NX;
-    double* xn = uh + NU;
+    real* xh = S.scr() + w * (2 * NX + NU);
+    real* uh = xh + NX;
+    real* xn = uh + NU;
     // candidate w writes trial slot w, stepping over slot `skip` (it holds the current trajectory, see solve_one)
-    double* Xo = Xn + (size_t)(w + (w >= skip ? 1 : 0)) * xn_stride;
-    double* Uo = Un + (size_t)(w + (w >= skip ? 1 : 0)) * un_stride;
+    real* Xo = Xn + (size_t)(w + (w >= skip ? 1 : 0)) * xn_stride;
+    real* Uo = Un + (size_t)(w + (w >= skip ? 1 : 0)) * un_stride;
     const bool active = w < ncand;
-    const double alpha = active ? S.alpha[w] : 0.0, omr = active ? 1.0 - S.rho[w] : 0.0;
-    double J = 0.0;
+    const real alpha = active ? (real)S.alpha[w] : 0.0, omr = active ? real(1.0) - (real)S.rho[w] : 0.0;
+    double J = 0.0;      // costs are summed in double in both builds (cost_lane)
     // K_k by one bulk copy when the tile and both addresses are multiples of 16 bytes (always for SRBD with caller-owned gains)
-    const bool bulk = SDDP_BULK && (NU * NX) % 2 == 0 && ((((size_t)S.Kbuf(0)) | ((size_t)S.Kbuf(1)) | ((size_t)Kg)) & 15) == 0;
+    const bool bulk = SDDP_BULK && (NU * NX) % RV == 0 && ((((size_t)S.Kbuf(0)) | ((size_t)S.Kbuf(1)) | ((size_t)Kg)) & 15) == 0;
     // node k's inputs (K_k, k_k, X_k, U_k, d_k, p_k) are fetched with cp.async while node k-1 is computed
     // The six base pointers live in shared memory during the rollout: held in registers across the node loop they were
     // spilled (the kernel sits at its 128-register cap) and re-read from local memory at every node, a quarter of them L1 misses.
     auto prefetch = [&](int k) {
-        double* nb = S.nb[k & 1];
-        double* Kb = S.Kbuf(k & 1);
-        const double* Ks = S.gp[0] + (size_t)k * NU * NX;
-        if (bulk) { if (tid == 0) bulk_g2s(Kb, Ks, NU * NX * 8, &S.mbar[k & 1]); }      // one instruction for the 7.1 KB tile
-        else if ((NU * NX) % 2 == 0 && ((((size_t)Kb) | ((size_t)Ks)) & 15) == 0) { for (int e = 2 * tid; e < NU * NX; e += 2 * NT) cp_async16(Kb + e, Ks + e); }
+        real* nb = S.nb[k & 1];
+        real* Kb = S.Kbuf(k & 1);
+        const real* Ks = S.gp[0] + (size_t)k * NU * NX;
+        if (bulk) { if (tid == 0) bulk_g2s(Kb, Ks, NU * NX * (int)sizeof(real), &S.mbar[k & 1]); }      // one instruction for the 7.1 KB tile
+        else if ((NU * NX) % RV == 0 && ((((size_t)Kb) | ((size_t)Ks)) & 15) == 0) { for (int e = RV * tid; e < NU * NX; e += RV * NT) cp_async16(Kb + e, Ks + e); }
         else { for (int e = tid; e < NU * NX; e += NT) cp_async8(Kb + e, Ks + e); }
-        const double* Xs = S.gp[2] + (size_t)k * NX;
-        const double* Ds = S.gp[3] + (size_t)k * NX;
+        const real* Xs = S.gp[2] + (size_t)k * NX;
+        const real* Ds = S.gp[3] + (size_t)k * NX;
         for (int i = tid; i < NX; i += NT) { cp_async8(nb + NBL::OX + i, Xs + i); cp_async8(nb + NBL::OD + i, Ds + i); }
-        const double* Us = S.gp[4] + (size_t)k * NU;
-        const double* ks = S.gp[1] + (size_t)k * NU;
+        const real* Us = S.gp[4] + (size_t)k * NU;
+        const real* ks = S.gp[1] + (size_t)k * NU;
         for (int i = tid; i < NU; i += NT) { cp_async8(nb + NBL::OU + i, Us + i); cp_async8(nb + NBL::OK + i, ks + i); }
-        const double* Ps = S.gp[5] + (size_t)k * NP;
+        const real* Ps = S.gp[5] + (size_t)k * NP;
         for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, Ps + i);
         cp_commit();
     };
@@ -456,8 +464,8 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         // One candidate (the usual first wave): its work is spread over the warps instead of leaving three idle.
         // Per node: warp 0 forms u = U + alpha k + K dx; then warp 0 integrates (accel, Euler step) while warp 1 sums
         // the state-indexed cost terms and warp 2 the input-indexed ones.  Two block barriers per node.
-        double* const xb0 = S.scr();                   // x^_k ping-pong: node k in xb0 + (k & 1) * NX (no pointer array: it would live in local memory)
-        double* ub = S.scr() + 2 * NX;
+        real* const xb0 = S.scr();                   // x^_k ping-pong: node k in xb0 + (k & 1) * NX (no pointer array: it would live in local memory)
+        real* ub = S.scr() + 2 * NX;
         for (int i = tid; i < NX; i += NT) xb0[i] = x0[i];
         if (tid == 0) { S.gp[6] = Xn; S.gp[7] = Un; }   // trial trajectory of this candidate (published by the barrier below)
         double Jw = 0.0;
@@ -468,22 +476,22 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             PROF(24);
             if (k + 1 < N) prefetch(k + 1);
             else {
-                double* nbt = S.nb[(k + 1) & 1];
+                real* nbt = S.nb[(k + 1) & 1];
                 for (int i = tid; i < NP; i += NT) cp_async8(nbt + NBL::OP + i, S.gp[5] + (size_t)N * NP + i);
                 cp_commit();
             }
             STAMP(12);
-            const double* nb = S.nb[k & 1];
-            const double* xc = xb0 + (k & 1) * NX;
+            const real* nb = S.nb[k & 1];
+            const real* xc = xb0 + (k & 1) * NX;
             constexpr int MV = (4 * NU + 31) & ~31;       // whole warps take part in the shuffles
             static_assert(MV <= NT - 32, "the last warp copies x^");
             static_assert(M::NPRE <= 2 * 8, "accel_pre result lives in rows 2-3 of sacc");
             if (tid < MV) {                    // u^ = U + alpha k + K dx: four threads per row of K, partial sums by shuffle
-                const double* Kb = S.Kbuf(k & 1);
-                const double* xk = nb + NBL::OX;
+                const real* Kb = S.Kbuf(k & 1);
+                const real* xk = nb + NBL::OX;
                 const int j = tid >> 2, part = tid & 3;
                 constexpr int CH = (NX + 3) / 4;
-                double t = 0.0;
+                real t = 0.0;
                 if (j < NU) {
 #pragma unroll
                     for (int q = 0; q < CH; q++) {
@@ -494,14 +502,14 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
                 t += __shfl_xor_sync(FULL, t, 1);
                 t += __shfl_xor_sync(FULL, t, 2);
                 if (j < NU && part == 0) {
-                    const double v = nb[NBL::OU + j] + S.alpha[0] * nb[NBL::OK + j] + t;      // (`alpha` is per warp = per candidate)
+                    const real v = nb[NBL::OU + j] + (real)S.alpha[0] * nb[NBL::OK + j] + t;      // (`alpha` is per warp = per candidate)
                     ub[j] = v;
-                    const_cast<double*>(S.gp[7])[(size_t)k * NU + j] = v;
+                    const_cast<real*>(S.gp[7])[(size_t)k * NU + j] = v;
                 }
             } else if (w == NWARP - 1) {       // meanwhile: copy x^ out, and the state-only part of the accelerations
-                for (int i = lane; i < NX; i += 32) const_cast<double*>(S.gp[6])[(size_t)k * NX + i] = xc[i];
+                for (int i = lane; i < NX; i += 32) const_cast<real*>(S.gp[6])[(size_t)k * NX + i] = xc[i];
                 if (M::NACC > 1) {
-                    double pre[M::NPRE];
+                    real pre[M::NPRE];
                     M::accel_pre(c, xc, pre);
                     if (lane == 0) {
 #pragma unroll
@@ -515,9 +523,9 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
             STAMP(14);
             const int kind = node_kind(c, k);
             if (w == 0) {
-                double* xn_ = xb0 + ((k + 1) & 1) * NX;
+                real* xn_ = xb0 + ((k + 1) & 1) * NX;
                 if (M::NACC > 1) {
-                    double acc[M::NACC];
+                    real acc[M::NACC];
                     M::accel_post(c, xc, ub, &S.sacc[0][0] + 16, acc, kind == NODE_TAIL);
                     if (lane == 0) {
 #pragma unroll
@@ -540,8 +548,8 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         }
         cp_wait_all();
         __syncthreads();
-        const double* xT = xb0 + (N & 1) * NX;
-        if (w == 0) for (int i = lane; i < NX; i += 32) const_cast<double*>(S.gp[6])[(size_t)N * NX + i] = xT[i];
+        const real* xT = xb0 + (N & 1) * NX;
+        if (w == 0) for (int i = lane; i < NX; i += 32) const_cast<real*>(S.gp[6])[(size_t)N * NX + i] = xT[i];
         if (w == 1) Jw += M::cost_lane(c, NODE_TERM, lane, xT, nullptr, S.nb[N & 1] + NBL::OP, S.sacc[0], 1);
         Jw = warp_sum(Jw);
         if (lane == 0) S.red[R_W0 + w] = Jw;
@@ -561,18 +569,18 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
         __syncthreads();                  // node k landed for everyone; everyone is done with node k-1
         if (k + 1 < N) prefetch(k + 1);
         else {                            // terminal parameters go to the free buffer
-            double* nb = S.nb[(k + 1) & 1];
+            real* nb = S.nb[(k + 1) & 1];
             for (int i = tid; i < NP; i += NT) cp_async8(nb + NBL::OP + i, S.gp[5] + (size_t)N * NP + i);
             cp_commit();
         }
         if (active) {
-            const double* nb = S.nb[k & 1];
-            const double* Kb = S.Kbuf(k & 1);
-            const double* xk = nb + NBL::OX;
+            const real* nb = S.nb[k & 1];
+            const real* Kb = S.Kbuf(k & 1);
+            const real* xk = nb + NBL::OX;
             for (int j = lane; j < NU; j += 32) {
-                double t = 0.0;
+                real t = 0.0;
                 for (int i = 0; i < NX; i++) t += Kb[j * NX + i] * (xh[i] - xk[i]);
-                double v = nb[NBL::OU + j] + alpha * nb[NBL::OK + j] + t;
+                real v = nb[NBL::OU + j] + alpha * nb[NBL::OK + j] + t;
                 uh[j] = v;
                 Uo[(size_t)k * NU + j] = v;
             }
@@ -597,11 +605,11 @@ __device__ void forward_wave(const DevCfg& c, SM& S, const double* x0, const dou
 // ------------------------------------------------------------------------------------------------
 struct SolveArgs {
     int B;
-    const double* x0; const double* params;
-    double* X; double* U; double* K; double* kff; double* hist;
-    int* iters; int* status; double* cost;
+    const real* x0; const real* params;
+    real* X; real* U; real* K; real* kff; real* hist;
+    int* iters; int* status; real* cost;
     // workspace, per resident CTA
-    double* ws_d; double* ws_pack; double* ws_xn; double* ws_un; double* ws_K; double* ws_k;
+    real* ws_d; real* ws_pack; real* ws_xn; real* ws_un; real* ws_K; real* ws_k;
     int* counter;
     const int* order;     // dispatch order (permutation of 0..B-1) or nullptr
     int sms;
@@ -609,18 +617,18 @@ struct SolveArgs {
     // peers[p] + (first + b) * rec for every p < n_peers -- own slab and, over NVLink, the slabs of the other GPUs
     int n_peers, rec;
     long long first;
-    double* peers[SDDP_MAX_PEERS];
+    real* peers[SDDP_MAX_PEERS];
     // host-direct mode (sddp_solve_batch_host on pinned buffers): mapped HOST pointers.  The CTA that takes problem b pulls its
     // inputs over PCIe into the device arrays above (x0, params, X, U are then the handle's staging arrays) and stores its
     // results straight into the caller's host arrays: one launch, every transfer rides under the solves of the other CTAs.
-    const double* h_x0; const double* h_params; const double* h_X0; const double* h_U0;
-    double* h_X; double* h_U; double* h_kff; double* h_hist; double* h_cost; int* h_iters; int* h_status;
+    const real* h_x0; const real* h_params; const real* h_X0; const real* h_U0;
+    real* h_X; real* h_U; real* h_kff; real* h_hist; real* h_cost; int* h_iters; int* h_status;
 };
 
 // `scratch`: PACK_SCRATCH * NT doubles of shared memory nobody else uses during the call (one column per thread)
 constexpr int PACK_SCRATCH = 10;
 template <class M>
-__device__ void compute_packs(const DevCfg& c, const double* X, const double* U, double* packs, double* scratch, int tid) {
+__device__ void compute_packs(const DevCfg& c, const real* X, const real* U, real* packs, real* scratch, int tid) {
     if (M::PACK > 1)
         for (int k = tid; k < c.N; k += NT)
             M::pack(c, node_kind(c, k), X + (size_t)k * M::NX, U + (size_t)k * M::NU, packs + (size_t)k * M::PACK, scratch + tid, NT);
@@ -632,17 +640,17 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     const int N = c.N;
     const size_t xsz = (size_t)(N + 1) * NX, usz = (size_t)N * NU;
-    const double* x0 = a.x0 + (size_t)b * NX;
-    const double* P = a.params + (size_t)b * (N + 1) * NP;
+    const real* x0 = a.x0 + (size_t)b * NX;
+    const real* P = a.params + (size_t)b * (N + 1) * NP;
     if (a.h_params) {      // host-direct: this problem's inputs, straight from the caller's pinned buffers
         const size_t psz = (size_t)(N + 1) * NP;
-        double* Pd = const_cast<double*>(P);
-        double* xd = const_cast<double*>(x0);
-        const double* hp = a.h_params + (size_t)b * psz;
-        const double* hX = a.h_X0 + (size_t)b * xsz;
-        const double* hU = a.h_U0 + (size_t)b * usz;
-        double* Xd = a.X + (size_t)b * xsz;
-        double* Ud = a.U + (size_t)b * usz;
+        real* Pd = const_cast<real*>(P);
+        real* xd = const_cast<real*>(x0);
+        const real* hp = a.h_params + (size_t)b * psz;
+        const real* hX = a.h_X0 + (size_t)b * xsz;
+        const real* hU = a.h_U0 + (size_t)b * usz;
+        real* Xd = a.X + (size_t)b * xsz;
+        real* Ud = a.U + (size_t)b * usz;
 #pragma unroll 8
         for (size_t i = tid; i < psz; i += NT) Pd[i] = hp[i];
 #pragma unroll 8
@@ -652,25 +660,26 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
         for (int i = tid; i < NX; i += NT) xd[i] = a.h_x0[(size_t)b * NX + i];
         __syncthreads();
     }
-    double* X = a.X + (size_t)b * xsz;
-    double* U = a.U + (size_t)b * usz;
-    double* Kg = a.K ? a.K + (size_t)b * N * NU * NX : a.ws_K + (size_t)slot * N * NU * NX;
-    double* kg = a.kff ? a.kff + (size_t)b * usz : a.ws_k + (size_t)slot * usz;
-    double* hist = a.hist ? a.hist + (size_t)b * c.max_iters * 4 : nullptr;
-    double* d = a.ws_d + (size_t)slot * N * NX;
-    double* packs = a.ws_pack + (size_t)slot * N * M::PACK;
+    real* X = a.X + (size_t)b * xsz;
+    real* U = a.U + (size_t)b * usz;
+    real* Kg = a.K ? a.K + (size_t)b * N * NU * NX : a.ws_K + (size_t)slot * N * NU * NX;
+    real* kg = a.kff ? a.kff + (size_t)b * usz : a.ws_k + (size_t)slot * usz;
+    real* hist = a.hist ? a.hist + (size_t)b * c.max_iters * 4 : nullptr;
+    real* d = a.ws_d + (size_t)slot * N * NX;
+    real* packs = a.ws_pack + (size_t)slot * N * M::PACK;
     // NSLOT trial slots per CTA: the accepted candidate's slot BECOMES the current trajectory (no copy per iteration),
     // the next waves use the other slots; the caller's X, U are written once, at the end.
-    double* Xn = a.ws_xn + (size_t)slot * NSLOT * xsz;
-    double* Un = a.ws_un + (size_t)slot * NSLOT * usz;
-    double* const Xuser = X;
-    double* const Uuser = U;
+    real* Xn = a.ws_xn + (size_t)slot * NSLOT * xsz;
+    real* Un = a.ws_un + (size_t)slot * NSLOT * usz;
+    real* const Xuser = X;
+    real* const Uuser = U;
     int cur = 1 << 30;      // trial slot that holds the current trajectory (none: it is still in the caller's buffers)
     const bool fixed = c.rho_fixed > 0.0;
 
     for (int i = tid; i < NX; i += NT) X[i] = x0[i];
     if (hist) for (int i = tid; i < c.max_iters * 4; i += NT) hist[i] = 0.0;
     __syncthreads();
+    // The scalar logic of the iteration (costs, expected decrease, step sizes, regularisation) is double in both builds.
     double J, dmax = 0.0;
     bool bad_start = false;      // a non-finite initial gap (NaN / inf in the warm start or x0)
     if (!c.ms) {
@@ -680,9 +689,9 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
         J = defects_and_cost<M, SM>(c, S, X, U, P, nullptr, tid);
     } else {
         J = defects_and_cost<M, SM>(c, S, X, U, P, d, tid);
-        double m = 0.0;
+        real m = 0.0;
         bool nf = false;
-        for (int i = tid; i < N * NX; i += NT) { const double v = fabs(d[i]); nf |= !(v <= 1.79e308); if (v > m) m = v; }      // fmax would drop a NaN
+        for (int i = tid; i < N * NX; i += NT) { const real v = fabs(d[i]); nf |= !(v <= 1.79e308); if (v > m) m = v; }      // fmax would drop a NaN
         m = warp_max(m);
         if ((tid & 31) == 0) S.red[R_W0 + (tid >> 5)] = m;
         bad_start = __syncthreads_or(nf) != 0;
@@ -704,7 +713,7 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
         }
         PROF(1);
         const double D1 = S.red[12], D2 = S.red[13], C0 = S.red[14];
-        double* h = hist ? hist + it * 4 : nullptr;
+        real* h = hist ? hist + it * 4 : nullptr;
         if (h && tid == 0) { h[0] = J; h[1] = 0.0; h[2] = mu; h[3] = dmax; }
         if (reg_fail) { status = 3; it++; break; }
         if (!isfinite(D1) || !isfinite(D2) || !isfinite(J)) { status = 4; it++; break; }
@@ -751,7 +760,8 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
             X = Xn + (size_t)cur * xsz;
             U = Un + (size_t)cur * usz;
             const double omr = 1.0 - rho_acc;
-            for (int i = tid; i < N * NX; i += NT) d[i] *= omr;
+            const real omr_r = (real)omr;
+            for (int i = tid; i < N * NX; i += NT) d[i] *= omr_r;
             dmax *= omr;
             const double dJ = J - Jn;
             J = Jn;
@@ -770,8 +780,8 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
     __syncthreads();
     if (tid == 0) { a.iters[b] = it; a.status[b] = status; a.cost[b] = J; }
     if (a.h_X) {           // host-direct: results straight into the caller's pinned buffers (posted writes over PCIe)
-        double* hX = a.h_X + (size_t)b * xsz;
-        double* hU = a.h_U + (size_t)b * usz;
+        real* hX = a.h_X + (size_t)b * xsz;
+        real* hU = a.h_U + (size_t)b * usz;
         for (size_t i = tid; i < xsz; i += NT) hX[i] = X[i];
         for (size_t i = tid; i < usz; i += NT) hU[i] = U[i];
         if (a.h_kff) for (size_t i = tid; i < usz; i += NT) a.h_kff[(size_t)b * usz + i] = kg[i];
@@ -786,10 +796,10 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
         // memory over NVLink / NVSwitch) while the other CTAs keep solving, so the transfer rides under the batch.
         const size_t off = (size_t)(a.first + b) * a.rec;
         for (size_t i = tid; i < xsz + usz + 3; i += NT) {
-            double v;
+            real v;
             if (i < xsz) v = X[i];
             else if (i < xsz + usz) v = U[i - xsz];
-            else v = (i == xsz + usz) ? J : (i == xsz + usz + 1 ? (double)it : (double)status);
+            else v = (i == xsz + usz) ? J : (i == xsz + usz + 1 ? (real)it : (real)status);
 #pragma unroll
             for (int p = 0; p < SDDP_MAX_PEERS; p++)
                 if (p < a.n_peers) a.peers[p][off + i] = v;
@@ -799,13 +809,13 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
 }
 
 template <class M>
-__device__ void Smem<M>::prep(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double*, double* packs, int tid) {
-    static_assert(M::PACK == 1 || sizeof(Smem<M>) >= PACK_SCRATCH * NT * sizeof(double), "pack scratch");
+__device__ void Smem<M>::prep(const DevCfg& c, Smem<M>& S, const real* X, const real* U, const real*, real* packs, int tid) {
+    static_assert(M::PACK == 1 || sizeof(Smem<M>) >= PACK_SCRATCH * NT * sizeof(real), "pack scratch");
     compute_packs<M>(c, X, U, packs, S.Vxx, tid);      // the matrices are dead between the forward and the backward pass
 }
 
 template <class M>
-__device__ int Smem<M>::backward(const DevCfg& c, Smem<M>& S, const double* X, const double* U, const double* P, const double* D,
-                                 const double* packs, double mu, double* Kg, double* kg, double* dV3, bool, int tid) {
+__device__ int Smem<M>::backward(const DevCfg& c, Smem<M>& S, const real* X, const real* U, const real* P, const real* D,
+                                 const real* packs, real mu, real* Kg, real* kg, double* dV3, bool, int tid) {
     return backward_pass<M>(c, S, X, U, P, D, packs, mu, Kg, kg, dV3, tid);
 }

@@ -48,10 +48,15 @@ class BatchResult:
 class BatchedDDP:
     """Thin owner of one `SddpHandle` (one device, one stream at a time)."""
 
-    def __init__(self, cfg: SddpConfig, device: Optional[torch.device] = None):
+    def __init__(self, cfg: SddpConfig, device: Optional[torch.device] = None, dtype: str = "f64"):
+        """dtype: "f64" (the product library, fp64 like the reference) or "f32" (the optional fp32 build libsddp_f32.so:
+        float arrays, float Riccati recursion; narrower than the reference, tolerance in tests/test_gpu_f32.py)."""
         if not torch.cuda.is_available():
             raise RuntimeError("srbd_horizon_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.L = _lib.lib()
+        self.L = _lib.lib(dtype)
+        self.dtype = dtype
+        self.tdtype = torch.float64 if dtype == "f64" else torch.float32
+        self.ndtype = np.float64 if dtype == "f64" else np.float32
         self.cfg = cfg.copy()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.nx, self.nu, self.np = DIMS[cfg.model]
@@ -81,7 +86,7 @@ class BatchedDDP:
 
     # -- helpers ------------------------------------------------------------------------------
     def _t(self, a, shape, name):
-        t = torch.as_tensor(a, dtype=torch.float64, device=self.device).contiguous()
+        t = torch.as_tensor(a, dtype=self.tdtype, device=self.device).contiguous()
         if tuple(t.shape) != tuple(shape):
             raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
@@ -142,7 +147,7 @@ class BatchedDDP:
         order: None (natural dispatch order), "schedule" (`dispatch_order(params)`) or an int32 device permutation.
         gather: a `parallel.ResultGather` of this solver: the kernel also stores every problem's result record into the
         whole-batch slabs it names (multi-GPU gather); `gather.finish()` afterwards returns the whole-batch views."""
-        x0 = torch.as_tensor(x0, dtype=torch.float64, device=self.device).contiguous()
+        x0 = torch.as_tensor(x0, dtype=self.tdtype, device=self.device).contiguous()
         B = x0.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
         x0 = self._t(x0, (B, nx), "x0")
@@ -152,12 +157,12 @@ class BatchedDDP:
         if not inplace:
             X, U = X.clone(), U.clone()
         dev = self.device
-        K = torch.empty((B, N, nu, nx), dtype=torch.float64, device=dev) if gains else None
-        k = torch.empty((B, N, nu), dtype=torch.float64, device=dev) if gains else None
-        hist = torch.empty((B, self.cfg.max_iters, HIST), dtype=torch.float64, device=dev) if history else None
+        K = torch.empty((B, N, nu, nx), dtype=self.tdtype, device=dev) if gains else None
+        k = torch.empty((B, N, nu), dtype=self.tdtype, device=dev) if gains else None
+        hist = torch.empty((B, self.cfg.max_iters, HIST), dtype=self.tdtype, device=dev) if history else None
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         status = torch.empty(B, dtype=torch.int32, device=dev)
-        cost = torch.empty(B, dtype=torch.float64, device=dev)
+        cost = torch.empty(B, dtype=self.tdtype, device=dev)
         user_order = order is not None and not isinstance(order, str)
         if isinstance(order, str):
             if order != "schedule":
@@ -197,12 +202,13 @@ class BatchedDDP:
         copies overlap the solves.  `out` may hold preallocated (pinned) X, U, iters, status, cost [, K, k, hist] arrays."""
         B = x0.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
-        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        c = lambda a: np.ascontiguousarray(a, dtype=self.ndtype)
         x0, params, X0, U0 = c(x0), c(params), c(X0), c(U0)
         if x0.shape != (B, nx) or params.shape != (B, N + 1, np_) or X0.shape != (B, N + 1, nx) or U0.shape != (B, N, nu):
             raise ValueError("solve_host: bad input shapes")
         out = dict(out) if out else {}
-        def buf(name, shape, dtype=np.float64):
+        def buf(name, shape, dtype=None):
+            dtype = dtype or self.ndtype
             a = out.get(name)
             if a is None or a.shape != tuple(shape) or a.dtype != dtype or not a.flags.c_contiguous:
                 a = np.empty(shape, dtype=dtype)
@@ -241,7 +247,7 @@ class BatchedDDP:
         dev = self.device
         kind = torch.as_tensor(kind, dtype=torch.int32, device=dev).contiguous()
         x = self._t(x, (M, nx), "x"); u = self._t(u, (M, nu), "u"); p = self._t(p, (M, np_), "p")
-        z = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+        z = lambda *s: torch.empty(s, dtype=self.tdtype, device=dev)
         out = dict(f=z(M, nx), fx=z(M, nx, nx), fu=z(M, nx, nu), l=z(M), lx=z(M, nx), lu=z(M, nu), lxx=z(M, nx, nx),
                    lux=z(M, nu, nx), luu=z(M, nu, nu))
         with torch.cuda.device(dev):
@@ -255,8 +261,8 @@ class BatchedDDP:
         X = self._t(X, (B, N + 1, nx), "X"); U = self._t(U, (B, N, nu), "U")
         params = self._t(params, (B, N + 1, np_), "params"); defect = self._t(defect, (B, N, nx), "defect")
         dev = self.device
-        K = torch.empty((B, N, nu, nx), dtype=torch.float64, device=dev); k = torch.empty((B, N, nu), dtype=torch.float64, device=dev)
-        dV = torch.empty((B, 3), dtype=torch.float64, device=dev); rc = torch.empty(B, dtype=torch.int32, device=dev)
+        K = torch.empty((B, N, nu, nx), dtype=self.tdtype, device=dev); k = torch.empty((B, N, nu), dtype=self.tdtype, device=dev)
+        dV = torch.empty((B, 3), dtype=self.tdtype, device=dev); rc = torch.empty(B, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(self.L.sddp_backward_pass(self.h, B, _ptr(X), _ptr(U), _ptr(params), _ptr(defect), float(mu), _ptr(K),
                                                  _ptr(k), _ptr(dV), _ptr(rc), self._stream()), self.h, self.L)
@@ -266,15 +272,15 @@ class BatchedDDP:
         B = X.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
         dev = self.device
-        alpha = torch.as_tensor(alpha, dtype=torch.float64, device=dev).contiguous()
-        rho = torch.as_tensor(rho, dtype=torch.float64, device=dev).contiguous()
+        alpha = torch.as_tensor(alpha, dtype=self.tdtype, device=dev).contiguous()
+        rho = torch.as_tensor(rho, dtype=self.tdtype, device=dev).contiguous()
         na = alpha.numel()
         x0 = self._t(x0, (B, nx), "x0"); X = self._t(X, (B, N + 1, nx), "X"); U = self._t(U, (B, N, nu), "U")
         params = self._t(params, (B, N + 1, np_), "params"); defect = self._t(defect, (B, N, nx), "defect")
         K = self._t(K, (B, N, nu, nx), "K"); k = self._t(k, (B, N, nu), "k")
-        Jn = torch.empty((B, na), dtype=torch.float64, device=dev)
-        Xn = torch.empty((B, na, N + 1, nx), dtype=torch.float64, device=dev) if trajectories else None
-        Un = torch.empty((B, na, N, nu), dtype=torch.float64, device=dev) if trajectories else None
+        Jn = torch.empty((B, na), dtype=self.tdtype, device=dev)
+        Xn = torch.empty((B, na, N + 1, nx), dtype=self.tdtype, device=dev) if trajectories else None
+        Un = torch.empty((B, na, N, nu), dtype=self.tdtype, device=dev) if trajectories else None
         with torch.cuda.device(dev):
             _lib.check(self.L.sddp_forward_pass(self.h, B, na, _ptr(alpha), _ptr(rho), _ptr(x0), _ptr(X), _ptr(U), _ptr(params),
                                                 _ptr(defect), _ptr(K), _ptr(k), _ptr(Jn), _ptr(Xn), _ptr(Un), self._stream()), self.h, self.L)
@@ -284,8 +290,8 @@ class BatchedDDP:
         B = X.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
         X = self._t(X, (B, N + 1, nx), "X"); U = self._t(U, (B, N, nu), "U"); params = self._t(params, (B, N + 1, np_), "params")
-        D = torch.empty((B, N, nx), dtype=torch.float64, device=self.device)
-        cost = torch.empty(B, dtype=torch.float64, device=self.device)
+        D = torch.empty((B, N, nx), dtype=self.tdtype, device=self.device)
+        cost = torch.empty(B, dtype=self.tdtype, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.L.sddp_defects(self.h, B, _ptr(X), _ptr(U), _ptr(params), _ptr(D), _ptr(cost), self._stream()), self.h, self.L)
         return D, cost
@@ -301,7 +307,7 @@ def fp64_peak_tflops() -> float:
 class DDPSolver:
     """Drop-in for the reference's `ddp.DDPSolver` (ddp.py:10-151) over a `prb.Problem`."""
 
-    def __init__(self, prb, opts: Optional[Dict] = None, device=None) -> None:
+    def __init__(self, prb, opts: Optional[Dict] = None, device=None, dtype: str = "f64") -> None:
         self.prb = prb
         self.opts = dict(opts or {})
         self.cfg = make_config(prb.model, prb.N, prb.getDt(), self.opts, prb.robot, prb.gains)
@@ -314,7 +320,7 @@ class DDPSolver:
         nx, nu, np_ = DIMS[prb.model]
         if (self.state_size, self.input_size) != (nx, nu):
             raise ValueError("problem variables do not match the model layout")
-        self.ddp_solver = BatchedDDP(self.cfg, device)
+        self.ddp_solver = BatchedDDP(self.cfg, device, dtype)
         N = prb.N
         self._x0 = np.zeros(nx)
         self._X = np.zeros((N + 1, nx))
@@ -348,7 +354,7 @@ class DDPSolver:
             self._have_x_ws = True
         r = self.ddp_solver.solve_host(self._x0[None], params[None], self._X[None], self._U[None], gains=True, history=True)
         self.last = {k: (v[0] if v is not None else None) for k, v in r.items()}
-        x, u = r["X"][0].T.copy(), r["U"][0].T.copy()      # nx x (N+1), nu x N as pyddp returns them (ddp.py:101)
+        x, u = r["X"][0].T.astype(np.float64), r["U"][0].T.astype(np.float64)      # nx x (N+1), nu x N as pyddp returns them (ddp.py:101)
         self._X, self._U = r["X"][0], r["U"][0]             # the next tick starts from this solution
         self.var_solution = self._createVarSolDict(x, u)
         self.var_solution["x_opt"] = x

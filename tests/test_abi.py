@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(_lib.SYMBOLS) == declared
-    assert L.sddp_abi_version() == 4 and L.sddp_config_size() == ctypes.sizeof(SddpConfig)
+    assert L.sddp_abi_version() == 5 and L.sddp_config_size() == ctypes.sizeof(SddpConfig)
 
 
 def test_inequality_options_are_checked_without_a_gpu():

@@ -16,12 +16,13 @@ ap.add_argument("--batch", type=int, default=1184)
 ap.add_argument("--N", type=int, default=50)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--no-gains", action="store_true")
+ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f32: the optional fp32 build (libsddp_f32.so)")
 ap.add_argument("--order", default="schedule", choices=["schedule", "index"], help="dispatch order (see sddp_set_dispatch_order)")
 a = ap.parse_args()
 cfg = make_config(MODEL_SRBD, a.N, 0.05, {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3})
 b = make_batch(MODEL_SRBD, a.N, a.batch, enumerate_schedules=True)
-s = BatchedDDP(cfg)
-t = lambda v: torch.as_tensor(v, dtype=torch.float64, device="cuda")
+s = BatchedDDP(cfg, dtype=a.dtype)
+t = lambda v: torch.as_tensor(v, dtype=s.tdtype, device="cuda")
 x0, p, X0, U0 = t(b["x0"]), t(b["params"]), t(b["X0"]), t(b["U0"])
 times = []
 for _ in range(a.reps):
