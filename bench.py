@@ -8,6 +8,8 @@ N = 50, every wpg.py gait schedule, sharded contiguously over the ranks).  One p
   python bench.py [--gpus N] [--steps K] [--warmup W]            CUDA path (this repo), BASELINE configs[4]
   python bench.py --config {0,1,2,3,4} [...]                      the other BASELINE configs (0/1: single-problem closed loop)
   python bench.py --impl reference [...]                          CPU oracle on the host cores
+  python bench.py --dtype f32 [...]                               the optional fp32 build (NARROWER than the reference's fp64;
+                                                                  stated tolerance in tests/test_gpu_f32.py) -- not the headline
 
 Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field).
 """
@@ -176,9 +178,9 @@ def workload_config(args, sample_note=None):
                                                           "all 60 wpg gait schedules round-robin" if spec["enumerate"] else "gait schedules drawn at random (70/20/10 % step/standing/jump)"),
          "batch": args.batch, "horizon": N_HORIZON, "opts": opts, "sharding": "contiguous batch slices per rank, results gathered on every rank (%s)" % args.gather,
          "dispatch": "problems dispatched grouped by contact schedule (device path: hash of the switch pattern of the parameters; host path: the (action, phase) the caller assigned; inside a schedule the largest commanded velocity first), recomputed inside every timed step; results do not depend on it",
-         "cache": "inputs larger than L2 (%.1f GB per step), no L2 flush" % (args.batch * (51 * 37 + 50 * 24 + 51 * 19 + 37) * 8 / 1e9),
+         "cache": "inputs larger than L2 (%.1f GB per step), no L2 flush" % (args.batch * (51 * 37 + 50 * 24 + 51 * 19 + 37) * (4 if getattr(args, "dtype", "f64") == "f32" else 8) / 1e9),
          "repeat": "every step re-solves the same batch from the same warm start (X, U cloned inside the timed region)",
-         "gains": "K[B,N,24,37] fp64 is materialised in HBM every step (%.1f GB for the whole batch)" % (args.batch * N_HORIZON * 24 * 37 * 8 / 1e9) if not args.no_gains
+         "gains": "K[B,N,24,37] %s is materialised in HBM every step (%.1f GB for the whole batch)" % (getattr(args, "dtype", "f64"), args.batch * N_HORIZON * 24 * 37 * (4 if getattr(args, "dtype", "f64") == "f32" else 8) / 1e9) if not args.no_gains
                   else "gains stay in the per-CTA workspace (--no-gains)"}
     if sample_note:
         c["sample"] = sample_note
@@ -200,7 +202,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work spent on the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=512)
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f32: the optional fp32 build libsddp_f32.so (batched configs only); narrower than the reference, labelled so in the line")
     args = ap.parse_args()
+    if args.dtype == "f32" and ("single" in CONFIGS[args.config] or args.impl == "reference"):
+        raise SystemExit("--dtype f32 applies to the batched CUDA configs (2, 3, 4)")
     spec = CONFIGS[args.config]
     if args.batch is None:
         args.batch = spec.get("batch", 1)
@@ -236,8 +242,9 @@ def main():
     Bl = hi - lo
     cfg = make_config(MODEL_SRBD, N_HORIZON, DT, dict(EX_OPTS, **spec["opts"]))
     batch = make_batch(MODEL_SRBD, N_HORIZON, Bl, first=lo, enumerate_schedules=spec["enumerate"], x_noise=spec["x_noise"])
-    solver = BatchedDDP(cfg, dev)
-    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    solver = BatchedDDP(cfg, dev, dtype=args.dtype)
+    esz = 8 if args.dtype == "f64" else 4
+    t = lambda a: torch.as_tensor(a, dtype=solver.tdtype, device=dev)
     x0, params, X0, U0 = t(batch["x0"]), t(batch["params"]), t(batch["X0"]), t(batch["U0"])
     gains = not args.no_gains
     gather = ResultGather(solver, args.batch, rank, world, mode=args.gather) if world > 1 else None
@@ -300,10 +307,10 @@ def main():
     value = args.batch / (ms_per_step * 1e-3)
 
     # ---- end to end through the public host API (pinned host buffers, copies inside the timed region)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=solver.ndtype)).pin_memory()
     hx0, hp, hX, hU = pin(batch["x0"]), pin(batch["params"]), pin(batch["X0"]), pin(batch["U0"])
     e2e_steps = max(1, min(args.steps, 3))
-    pin_out = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    pin_out = lambda shape, dt=solver.tdtype: torch.empty(shape, dtype=dt).pin_memory().numpy()
     hout = {"X": pin_out((Bl, N_HORIZON + 1, nx)), "U": pin_out((Bl, N_HORIZON, nu)), "cost": pin_out((Bl,)),
             "iters": pin_out((Bl,), torch.int32), "status": pin_out((Bl,), torch.int32)}
     # On the host the caller groups the problems by the gait schedule it assigned them (action, phase): cheaper than
@@ -319,8 +326,8 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = args.batch / float(t_e2e[0])
-    h2d = (hx0.numel() + hp.numel() + hX.numel() + hU.numel()) * 8
-    d2h = (hX.numel() + hU.numel() + Bl) * 8 + 2 * Bl * 4
+    h2d = (hx0.numel() + hp.numel() + hX.numel() + hU.numel()) * esz
+    d2h = (hX.numel() + hU.numel() + Bl) * esz + 2 * Bl * 4
 
     if rank != 0:
         if world > 1:
@@ -361,13 +368,21 @@ def main():
               "host_path_equals_device_path": bool(np.array_equal(rh["X"], r.X.cpu().numpy()) and np.array_equal(rh["U"], r.U.cpu().numpy())),
               "note": "max over the sample of max|X - X_oracle| / max|X_oracle| and the same for U, per problem"}
 
+    if args.dtype == "f32":
+        # the optional fp32 build: same dense-equivalent work against the nominal FP32 FMA rate (no measured FP32 peak);
+        # its results are NOT at the reference's precision -- `parity` above shows the distance to the fp64 oracle
+        f32_nominal = 2.0 * FP64_NOMINAL_TFLOPS
+        roofline.update({"bound": "fp32", "peak": f32_nominal, "frac": ach_tf / f32_nominal, "fp32_peak_source": "nominal: 148 SMs x 128 FP32 FMA/clk x 2 x 1965 MHz",
+                         "kernel": "solve_kernel<Srbd> of libsddp_f32.so", "traffic": None,
+                         "hbm": dict(roofline["hbm"], achieved=ach_gb / 2, frac=ach_gb / 2 / peaks.get("hbm_gbs", HBM_PEAK_FALLBACK), bytes_per_node_iteration=BYTES_NODE // 2)})
+        parity["note"] += "; fp32 build: the stated tolerance is 1e-2 on X and U (tests/test_gpu_f32.py; measured worst 2e-3, median 1e-6), not the 1e-9 of the fp64 build"
     latency = None
-    if not args.no_latency:
+    if not args.no_latency and args.dtype == "f64":
         latency = single_solve_latency(dev)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": workload_config(args),
         "ddp_iterations_per_sec": value * mean_iters, "mean_iters": mean_iters, "converged_frac": conv_frac,
         "clocks": clocks.summary(),
@@ -378,6 +393,9 @@ def main():
         "gather_ms_per_step": ms_per_step - ms_kernel if world > 1 else None, "gather_ok": gather_ok,
         "gains_materialised": gains, "wall_s_timed_region": t_wall, "latency": latency,
     }
+    if args.dtype == "f32":
+        line["precision_note"] = ("optional fp32 build (north_star): float storage and Riccati recursion, NARROWER than the reference's fp64; "
+                                  "not comparable with the fp64 headline line")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -747,9 +747,19 @@ __device__ void solve_one(const DevCfg& c, const SolveArgs& a, SM& S, int b, int
             PROF_INC(29);
             forward_wave<M, SM>(c, S, x0, X, U, P, d, Kg, kg, ncand, Xn, xsz, Un, usz, tid, cur);
             PROF(2);
+            // fp32 build only: the expected decrease dJm comes out of a float Riccati recursion, so it carries a rounding
+            // noise of about 1e-7 (1 + |J|) that does not shrink with the step size (C0, the gap-closing part, does not
+            // depend on alpha at all).  Without a floor of that size the test below rejects every candidate once the
+            // true decrease falls under the noise -- fixed-rate gap contraction (README.md:6) runs many such iterations
+            // while the gaps halve -- and the solve ends in LS_FAILED instead of converging.  0 in the fp64 build.
+#ifdef SDDP_F32
+#define SDDP_LS_NOISE +1e-6 * (1.0 + fabs(J))
+#else
+#define SDDP_LS_NOISE
+#endif
             for (int j = 0; j < ncand; j++) {
                 double am = al[j], dJm = C0 + am * D1 + am * am * D2, Jj = S.Jc[j];
-                if (isfinite(Jj) && Jj - J <= dJm + (1.0 - c.beta) * fabs(dJm)) {
+                if (isfinite(Jj) && Jj - J <= dJm + (1.0 - c.beta) * fabs(dJm) SDDP_LS_NOISE) {
                     accepted = true; sel = j; Jn = Jj; alpha_acc = am; rho_acc = fixed ? c.rho_fixed : am;
                     break;
                 }

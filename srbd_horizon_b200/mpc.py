@@ -60,14 +60,14 @@ class BatchedMPC:
         self._ct, self._torch, self._lib = ctypes, torch, _lib
         self.solver = solver
         dev = solver.device
-        t = lambda a, dt=torch.float64: torch.as_tensor(a, dtype=dt, device=dev).contiguous()
+        t = lambda a, dt=solver.tdtype: torch.as_tensor(a, dtype=dt, device=dev).contiguous()
         self.state = t(x0).clone()
         B = self.state.shape[0]
         self.B = B
         self.params = t(params).clone()
         N, nx, nu = solver.N, solver.nx, solver.nu
         self.X = self.state[:, None, :].repeat(1, N + 1, 1).contiguous()
-        self.U = t(U0).clone() if U0 is not None else torch.zeros((B, N, nu), dtype=torch.float64, device=dev)
+        self.U = t(U0).clone() if U0 is not None else torch.zeros((B, N, nu), dtype=solver.tdtype, device=dev)
         self.step_counter = torch.zeros(B, dtype=torch.int32, device=dev)
         c_init_z = float(solver.cfg.foot[2])
         tabs = [np.ascontiguousarray(a, dtype=np.float64) for a in gait_tables(c_init_z)]
@@ -81,7 +81,7 @@ class BatchedMPC:
         torch = self._torch
         s = self.solver
         a = torch.as_tensor(actions, dtype=torch.int32, device=s.device).contiguous()
-        cmd = torch.as_tensor(rdot_ref_cmd, dtype=torch.float64, device=s.device).contiguous()
+        cmd = torch.as_tensor(rdot_ref_cmd, dtype=s.tdtype, device=s.device).contiguous()
         assert a.shape == (self.B,) and cmd.shape == (self.B, 3)
         with torch.cuda.device(s.device):
             self._lib.check(s.L.sddp_mpc_advance(s.h, self.B, self._p(self.params), self._p(a), self._p(self.step_counter),

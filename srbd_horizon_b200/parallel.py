@@ -99,8 +99,8 @@ def solve_sharded(solve, x0, params, X0, U0, world: int, B: int, rank: int, chun
 class _DevArray:
     """__cuda_array_interface__ view of library-owned device memory, so that torch can alias it without a copy."""
 
-    def __init__(self, ptr: int, shape, owner):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr: int, shape, owner, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
         self._owner = owner
 
 
@@ -140,7 +140,7 @@ class ResultGather:
         with torch.cuda.device(solver.device):
             _lib.check(self.L.sddp_slab_alloc(solver.h, self.B, ctypes.byref(ptr)), solver.h, self.L)
         self.ptr = ptr.value
-        self.slab = torch.as_tensor(_DevArray(self.ptr, (self.B, self.rec), self), device=solver.device)
+        self.slab = torch.as_tensor(_DevArray(self.ptr, (self.B, self.rec), self, "<f8" if solver.dtype == "f64" else "<f4"), device=solver.device)
         self.peer_ptrs = []
         # the ordering collective runs on the stream with NCCL; with a host backend (gloo: the tests) the device is drained first
         self._on_stream = world > 1 and dist.get_backend(group) == "nccl"

@@ -30,6 +30,17 @@ def test_library_exports_every_declared_symbol():
     assert L.sddp_abi_version() == 5 and L.sddp_config_size() == ctypes.sizeof(SddpConfig)
 
 
+def test_f32_library_exports_the_same_header():
+    """The optional fp32 build: same symbols, float arrays (sddp_real_bytes() == 4), same SddpConfig."""
+    L = _lib.lib("f32")
+    for name in _header_functions():
+        assert hasattr(L, name), name
+    assert L.sddp_abi_version() == 5 and L.sddp_real_bytes() == 4 and _lib.lib().sddp_real_bytes() == 8
+    assert L.sddp_config_size() == ctypes.sizeof(SddpConfig)
+    cfg = make_config(MODEL_SRBD, 50, 0.05)
+    assert 0 < L.sddp_workspace_bytes(ctypes.byref(cfg)) < _lib.lib().sddp_workspace_bytes(ctypes.byref(cfg))
+
+
 def test_inequality_options_are_checked_without_a_gpu():
     """One library serves the inequality extensions (friction cone, bounds) and the model scheduler; bad values are
     rejected by the config check (no GPU needed: sddp_workspace_bytes returns 0 for a config it refuses)."""

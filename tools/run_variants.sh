@@ -1,7 +1,7 @@
-M="gcc__cache_requests_type_instruction.sum,gpu__time_duration.sum,smsp__inst_executed.sum"
-for v in "$@"; do
-  echo "== $v"
-  SDDP_LIB=$PWD/build_ab/$v.so python tools/run_solve.py --batch 8192 --reps 4 | tail -1
-  SDDP_LIB=$PWD/build_ab/$v.so python tools/run_solve.py --batch 1 --reps 5 | tail -1
-  SDDP_LIB=$PWD/build_ab/$v.so ncu --metrics $M --clock-control none -k regex:solve_kernel -s 1 -c 1 --csv python tools/run_solve.py --batch 4736 --reps 2 2>&1 | grep -E "gcc__|gpu__time|smsp__inst" | awk -F'","' '{print "   ", $(NF-2), $NF}'
+#!/bin/bash
+# A/B of kernel builds on the GPU box: tools/run_variants.sh DTYPE BATCH lib1.so lib2.so ...   (SDDP_LIB / SDDP_LIB_F32 overrides)
+DT=$1; B=$2; shift 2
+for L in "$@"; do
+  if [ "$DT" = "f32" ]; then export SDDP_LIB_F32=$PWD/$L; else export SDDP_LIB=$PWD/$L; fi
+  echo "== $L"; python tools/run_solve.py --batch $B --reps 4 --dtype $DT 2>&1 | tail -1
 done
