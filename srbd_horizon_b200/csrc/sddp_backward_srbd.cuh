@@ -24,6 +24,17 @@
 #include <cstddef>
 #include "sddp_solver.cuh"
 
+#ifndef SDDP_D1BLOCK
+// 1: the factorisation takes one 2 x 2 pivot block per step.  Default: on in the fp32 build only.  Measured on B200, 8192
+// problems: fp32 55.6 -> 48.6 ms (its factorisation is bound by the publish -> sync -> load chain that the block step
+// halves); fp64 60.70 -> 60.55 ms and a single solve 0.957 -> 0.981 ms (there the warp is held up by the FP64 / shared-
+// memory traffic of the three warps beside it, not by its own chain), so the fp64 library keeps one pivot per step.
+#ifdef SDDP_F32
+#define SDDP_D1BLOCK 1
+#else
+#define SDDP_D1BLOCK 0
+#endif
+#endif
 // LAT: the latency variant (batches smaller than the grid): unrolled factorisation and interleaved f/g tiles; otherwise the
 // throughput variant (rolled, a third of the code).  Same arithmetic up to the order of independent operations.
 template <class MT, bool LAT = false>
@@ -37,7 +48,7 @@ struct alignas(16) SmemSrbdT {
     real Vx[NX + 1], y[NX + 1], Qx[NX + 1], vp[NX + 1], ys[NX + 1], qxy[NX + 1], sv[NX + 1];
     real Qu[NU], kk[NU];
     real invp[NU], rs[NU];   // d1: 1 / pivot_j; 1 / sqrt(pivot_j) (row scaling of Et, applied in h and g)
-    real prow[2][NU];        // d1: the published column of the current pivot step (ping-pong)
+    real prow[SDDP_D1BLOCK ? 4 : 2][NU];   // d1: the published column(s) of the current pivot step / 2 x 2 block (ping-pong)
     alignas(16) real nb[2][NodeBuf<MT>::SIZE];
     real escr[24];           // expand scratch: E(oref) and the orientation residuals
     real sacc[NWARP][8];
@@ -111,6 +122,26 @@ SDDP_DEV void axpy_row(real* a, const real* row, int lo, real s) {
             const int i = i0 + 2 * q;
             if (i >= lo) a[i] -= c[q].x * s;
             if (i + 1 >= lo) a[i + 1] -= c[q].y * s;
+        }
+    }
+}
+// Two pivot steps at once (2 x 2 block, see ldlt_warp): a[i] -= row0[i] * s1;  a[i] -= (row1[i] - row0[i] * l) * s2  for lo <= i.
+// row1 is column j+1 WITHOUT the update of step j: every lane forms the updated entry itself, exactly as lane j+1 would have
+// (one more FMA per entry; applying row1 raw with a combined multiplier s1 - l s2 instead saves it, but the two large terms
+// then cancel in the accumulator and the factorisation loses the accuracy the 1e6-weighted blocks need).
+template <int n, int I0 = 0, int I1 = n>
+SDDP_DEV void axpy2_row(real* a, const real* row0, const real* row1, int lo, real l, real s1, real s2) {
+    static_assert(n % 8 == 0 && I0 % 8 == 0 && I1 % 8 == 0, "row length");
+#pragma unroll
+    for (int i0 = I0; i0 < I1; i0 += 8) {
+        real2 c0[4], c1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (i0 + 2 * q + 1 >= lo) { c0[q] = *reinterpret_cast<const real2*>(row0 + i0 + 2 * q); c1[q] = *reinterpret_cast<const real2*>(row1 + i0 + 2 * q); }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + 2 * q;
+            if (i >= lo) { a[i] -= c0[q].x * s1; a[i] -= fma(-c0[q].x, l, c1[q].x) * s2; }
+            if (i + 1 >= lo) { a[i + 1] -= c0[q].y * s1; a[i + 1] -= fma(-c0[q].y, l, c1[q].y) * s2; }
         }
     }
 }
@@ -190,6 +221,42 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
     for (int i = 0; i < NU; i++) a[i] = S.Quu[i * NU + t];
     __syncwarp();
     real myinv = fast_rcp(a[0]);          // lane 0's pivot
+#if SDDP_D1BLOCK
+    // 2 x 2 pivot blocks (see the rolled form below: same operations in the same order, so both variants give the same bits)
+#pragma unroll
+    for (int jb = 0; jb < NU; jb += 2) {
+        const real* pr0 = S.Quu + jb * NU;
+        const real* pr1 = S.Quu + (jb + 1) * NU;
+        const real m0 = a[jb];
+        if (lane == jb || lane == jb + 1) {
+            if (lane == jb) {
+                bad = !(m0 > 0.0) || !isfinite(m0);
+                npinv = -myinv;
+                S.invp[jb] = myinv;
+            }
+            store_row<NU>(S.Quu + lane * NU, a, jb);
+        }
+        __syncwarp();
+        const real p0inv = S.invp[jb], c01 = pr0[jb + 1], p1raw = pr1[jb + 1];
+        const real l = pr1[jb] * p0inv;      // lane j+1's own multiplier of step j (its copy of the symmetric entry)
+        const real p1 = fma(-c01, l, p1raw);
+        const real p1inv = fast_rcp(p1);
+        const real s1 = (lane == jb) ? real(0.0) : m0 * p0inv;
+        const real m1 = fma(-c01, s1, a[jb + 1]);
+        a[jb + 1] = m1;
+        if (lane == jb + 1) {
+            bad = !(p1 > 0.0) || !isfinite(p1);
+            npinv = -p1inv;
+        }
+        const real s2 = (lane == jb + 1) ? real(0.0) : m1 * p1inv;
+        if (jb + 2 < NU) {
+            a[jb + 2] -= pr0[jb + 2] * s1;
+            a[jb + 2] -= fma(-pr0[jb + 2], l, pr1[jb + 2]) * s2;
+            myinv = fast_rcp(a[jb + 2]);     // meaningful on lane jb + 2
+            axpy2_row<NU>(a, pr0, pr1, jb + 3, l, s1, s2);
+        }
+    }
+#else
 #pragma unroll
     for (int j = 0; j < NU; j++) {
         if (lane == j) {
@@ -207,6 +274,7 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
             if (j + 2 < NU) axpy_row<NU>(a, S.Quu + j * NU, j + 2, sj);
         }
     }
+#endif
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < NU; i += 2) {
@@ -227,13 +295,70 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
     //  cycles per step, tools/microbench/ldlt.cu V10 / V16 -- but the elimination then loses the scaling invariance of
     //  symmetric LDL^T: at the first SRBD node behind a LIP-style tail, cond(Quu) = 2e9, the gains come out at 2e-8
     //  instead of 1e-13.)
-    constexpr int R = SDDP_D1R;
-    static_assert(NU % R == 0 && R % 2 == 0, "d1 frame");
     real b[NU];
 #pragma unroll
     for (int i = 0; i < NU; i++) b[i] = S.Quu[i * NU + t];
     __syncwarp();
     real myinv = fast_rcp(b[0]);                               // lane 0's pivot
+#if SDDP_D1BLOCK
+    // One 2 x 2 pivot BLOCK per trip (round 2, tools/microbench/ldlt.cu V20 against V15: 5.5 K instead of 7.4 K cycles for
+    // the 24 steps): lanes j and j+1 publish their columns together -- column j final, column j+1 without the update of
+    // step j -- and after ONE warp sync every lane forms l = c' / p_j (c' = lane j+1's own copy of the symmetric entry:
+    // with it every lane reproduces lane j+1's update of its column bit for bit, which keeps the scaling invariance of
+    // symmetric LDL^T that the 1e6-weighted blocks need) and the Schur pivot p1 = p_{j+1} - c l itself
+    // (c = col_j[j+1]), its two multipliers s1 = a[j] / p_j and s2 = (a[j+1] - c s1) / p1, and applies both steps at once:
+    //   a[i] -= col_j[i] s1;  a[i] -= (col_{j+1}[i] - col_j[i] l) s2      (axpy2_row).
+    // Same elimination with the same shared-memory loads and one more FMA per entry, but one publish -> sync -> load round
+    // trip (the latency chain of a step) per two pivots instead of two.  Lane j skips its own step (s1 = 0), lane j+1 its own
+    // (s2 = 0), and both keep taking part afterwards (their registers then carry the columns of E, see above).
+    static_assert(NU % 2 == 0, "d1 frame");
+    int par = 0;
+#pragma unroll 1
+    for (int jb = 0; jb < NU; jb += 2, par ^= 2) {
+        const real* pr0 = S.prow[par];
+        const real* pr1 = S.prow[par + 1];
+        const real m0 = b[0];
+        if (lane == jb || lane == jb + 1) {
+            if (lane == jb) {
+                bad = !(m0 > 0.0) || !isfinite(m0);
+                npinv = -myinv;
+                S.invp[jb] = myinv;
+            }
+            real* pr = S.prow[par + (lane - jb)];
+            store_row<8>(pr, b, 0);
+            if (jb < 16) store_row<8>(pr + 8, b + 8, -8);
+            if (jb < 8) store_row<8>(pr + 16, b + 16, -16);
+        }
+        __syncwarp();
+        const real p0inv = S.invp[jb], c01 = pr0[1], p1raw = pr1[1];
+        const real l = pr1[0] * p0inv;       // lane j+1's own multiplier of step j (its copy of the symmetric entry)
+        const real p1 = fma(-c01, l, p1raw);
+        const real p1inv = fast_rcp(p1);
+        const real s1 = (lane == jb) ? real(0.0) : m0 * p0inv;
+        const real m1 = fma(-c01, s1, b[1]);
+        if (lane == jb + 1) {
+            bad = !(p1 > 0.0) || !isfinite(p1);
+            npinv = -p1inv;
+        }
+        const real s2 = (lane == jb + 1) ? real(0.0) : m1 * p1inv;
+        // the element that becomes the next pivot first, its reciprocal started at once (meaningful on lane jb + 2)
+        b[2] -= pr0[2] * s1;
+        b[2] -= fma(-pr0[2], l, pr1[2]) * s2;
+        myinv = fast_rcp(b[2]);
+        // chunks of 8 entries wholly in the zero tail of the frame (q >= NU - jb) are skipped (warp-uniform)
+        axpy2_row<NU, 0, 8>(b, pr0, pr1, 3, l, s1, s2);
+        if (jb < 16) axpy2_row<NU, 8, 16>(b, pr0, pr1, 3, l, s1, s2);
+        if (jb < 8) axpy2_row<NU, 16, 24>(b, pr0, pr1, 3, l, s1, s2);
+        // rows j and j+1 of Et: (t < row) -multiplier / pivot_t, (t == row) 1, (t > row) 0
+        const real e0 = (lane < jb) ? npinv * m0 : (lane == jb ? real(1.0) : real(0.0));
+        const real e1 = (lane < jb + 1) ? npinv * m1 : (lane == jb + 1 ? real(1.0) : real(0.0));
+        if (lane < NU) { S.Quu[jb * NU + lane] = e0; S.Quu[(jb + 1) * NU + lane] = e1; }
+#pragma unroll
+        for (int q = 0; q < NU; q++) b[q] = (q + 2 < NU) ? b[q + 2] : real(0.0);
+    }
+#else
+    constexpr int R = SDDP_D1R;
+    static_assert(NU % R == 0 && R % 2 == 0, "d1 frame");
 #pragma unroll 1
     for (int jb = 0; jb < NU; jb += R) {
 #pragma unroll
@@ -272,6 +397,7 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
 #pragma unroll
         for (int q = 0; q < NU; q++) b[q] = (q + R < NU) ? b[q + R] : 0.0;
     }
+#endif
     }
     if (lane < NU) S.rs[lane] = sqrt(-npinv);
     return bad;

@@ -7,6 +7,9 @@
 //   V3: V0 without the E trick (lanes <= j update dead values; reference for the cost of the chain alone)
 //   V4: V0 with the pivot chain through shuffles (1/pivot and col_j[j+1]) and the column through shared memory
 //   V10: by symmetry col_j[t] is lane t's own a[j]: every lane stores one entry, nobody publishes a column
+//   V20: V15 (rolled, R = 2) with the two pivot steps of a trip as ONE 2 x 2 block step: lanes j and j+1 publish their
+//        columns together (j+1 raw), every lane forms the Schur pivot p1 = p_{j+1} - c^2 / p_j itself and applies both
+//        updates at once, a[i] -= col_j[i] (s1 - l s2) + col_{j+1}[i] s2: one publish -> sync -> load round trip per two steps
 #include <cstdio>
 #include <cuda_runtime.h>
 #define FULL 0xffffffffu
@@ -60,7 +63,7 @@ __device__ __forceinline__ void store_row(double* row, const double* a, int lo) 
     }
 }
 
-struct alignas(16) Sm { double Q0[NU * NU]; double Quu[NU * NU]; double invp[NU]; double rs[NU]; double prow[2][NU]; };
+struct alignas(16) Sm { double Q0[NU * NU]; double Quu[NU * NU]; double invp[NU]; double rs[NU]; double prow[4][NU]; };
 __device__ int g_zero;
 __device__ __forceinline__ double tie(double s, double v, int zero) { return __hiloint2double(__double2hiint(s) + (__double2hiint(v) & zero), __double2loint(s)); }
 template <int I0, int I1>
@@ -170,6 +173,39 @@ __device__ __forceinline__ void ldlt(Sm& S, int lane) {
             }
 #pragma unroll
             for (int q = 0; q < NU; q++) a[q] = (q + R < NU) ? a[q + R] : 0.0;
+        }
+    } else if (V == 20) {
+        double npinv = 0.0;
+        int par = 0;
+#pragma unroll 1
+        for (int jb = 0; jb < NU; jb += 2, par ^= 2) {
+            double* pr0 = S.prow[par];
+            double* pr1 = S.prow[par + 1];
+            const double m0 = a[0];
+            if (lane == jb || lane == jb + 1) {
+                if (lane == jb) { npinv = -myinv; pinv = myinv; S.invp[jb] = myinv; }
+                store_row<true>(S.prow[par + (lane - jb)], a, 1);
+            }
+            __syncwarp();
+            const double p0inv = S.invp[jb], c = pr0[1], p1raw = pr1[1];
+            const double l = c * p0inv;
+            const double p1 = fma(-c, l, p1raw);
+            const double p1inv = fast_rcp(p1);
+            const double s1 = (lane == jb) ? 0.0 : m0 * p0inv;
+            const double m1 = fma(-c, s1, a[1]);
+            if (lane == jb + 1) { npinv = -p1inv; pinv = p1inv; }
+            const double s2 = (lane == jb + 1) ? 0.0 : m1 * p1inv;
+            const double g1 = fma(-l, s2, s1);
+            // the next pivot first, its reciprocal started at once
+            a[2] -= pr0[2] * g1; a[2] -= pr1[2] * s2;
+            myinv = fast_rcp(a[2]);
+            axpy_part<0, NU>(a, pr0, 3, g1);
+            axpy_part<0, NU>(a, pr1, 3, s2);
+            const double e0 = (lane < jb) ? npinv * m0 : (lane == jb ? 1.0 : 0.0);
+            const double e1 = (lane < jb + 1) ? npinv * m1 : (lane == jb + 1 ? 1.0 : 0.0);
+            if (lane < NU) { S.Quu[jb * NU + lane] = e0; S.Quu[(jb + 1) * NU + lane] = e1; }
+#pragma unroll
+            for (int q = 0; q < NU; q++) a[q] = (q + 2 < NU) ? a[q + 2] : 0.0;
         }
     } else if (V == 2) {
 #pragma unroll
@@ -315,5 +351,6 @@ int main() {
     run<15>("V15 = V11 with R=2", dQ, dout, dcyc, ref);
     run<16>("V16 = V11 with the symmetric publish of V10", dQ, dout, dcyc, ref);
     run<17>("V17 = V16 + a second warp sync per step", dQ, dout, dcyc, ref);
+    run<20>("V20 = V15 with one 2 x 2 block step per trip", dQ, dout, dcyc, ref);
     return 0;
 }
