@@ -119,6 +119,7 @@ def cpu_oracle_rate(cfg, batch, seconds: float, threads: int):
     """Times the CPU oracle (oracle/, the CPU restatement of the reference algorithm) on a bounded sample of the
     same workload with `threads` host threads.  Returns (solves/s, problems solved, mean iterations, the oracle's results)."""
     from oracle import oracle as O
+    O.native_twin()
     n = max(2 * threads, 8)
     sl = lambda k: (batch["x0"][:k], batch["params"][:k], batch["X0"][:k], batch["U0"][:k])
     t0 = time.perf_counter()
@@ -131,6 +132,11 @@ def cpu_oracle_rate(cfg, batch, seconds: float, threads: int):
         t1 = time.perf_counter() - t0
         n = target
     return n / t1, n, float(r["iters"].mean()), r
+
+
+def oracle_flags():
+    from oracle import oracle as O
+    return O.BUILD_FLAGS
 
 
 def run_reference(args, rank, world):
@@ -147,6 +153,7 @@ def run_reference(args, rank, world):
     sample = max(2 * threads, min(args.ref_sample, 64 * threads))
     batch = make_batch(MODEL_SRBD, N_HORIZON, sample, enumerate_schedules=spec["enumerate"], x_noise=spec["x_noise"])
     from oracle import oracle as O
+    O.native_twin()
     O.lib()
     times, iters = [], []
     for s in range(args.warmup + args.steps):
@@ -163,7 +170,7 @@ def run_reference(args, rank, world):
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, sample_note=f"each step = {sample} problems of the same seeded family"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} of {args.batch} problems per step, {threads} host threads, CPU oracle (C, -O3)"},
+                         "sample": f"{sample} of {args.batch} problems per step, {threads} host threads, CPU oracle (C, {O.BUILD_FLAGS})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mean_iters": sum(iters) / len(iters), "ddp_iterations_per_sec": value * sum(iters) / len(iters), "gpu_launches": 0,
     }
@@ -356,7 +363,7 @@ def main():
     threads = os.cpu_count() or 1
     cpu_rate, cpu_n, cpu_iters, ro = cpu_oracle_rate(cfg, batch, args.cpu_seconds, threads)
     cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port", "mean_iters": cpu_iters,
-                    "sample": f"first {cpu_n} of {args.batch} problems, {threads} host threads, CPU oracle (oracle/sddp_oracle.c, gcc -O3)"}
+                    "sample": f"first {cpu_n} of {args.batch} problems, {threads} host threads, CPU oracle (oracle/sddp_oracle.c, gcc {oracle_flags()})"}
     # parity of the timed GPU results against the oracle on that sample (outside every timed region)
     rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
     gX, gU, gc = r.X[:cpu_n].cpu().numpy(), r.U[:cpu_n].cpu().numpy(), r.cost[:cpu_n].cpu().numpy()
@@ -406,6 +413,7 @@ def closed_loop(kind, dev, ticks, skip, with_cpu=True):
     reference-facing DDPSolver.solve() (host numpy in and out: H2D + kernel + D2H), next to the single-thread oracle.
     Returns per-tick GPU ms, CPU ms and iteration counts after `skip` warm-up ticks."""
     from oracle import oracle as O
+    O.native_twin()
     from srbd_horizon_b200 import prb as P, wpg
     from srbd_horizon_b200.ddp import DDPSolver
     from srbd_horizon_b200.mpc import mpc_tick_references, plant_step

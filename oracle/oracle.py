@@ -15,6 +15,24 @@ from srbd_horizon_b200.config import DIMS, HIST, SddpConfig
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libsddp_oracle.so")
 _lib = None
+BUILD_FLAGS = "-O3 -march=x86-64-v3"      # of the library in use (oracle/Makefile; native_twin() changes it)
+
+
+def native_twin() -> str:
+    """For the TIMED CPU baseline of bench.py only ("a -O3 -march=native twin for timing"): compile the
+    same source for the host CPU of THIS box into oracle/_native/ and use it from now on.  The shipped library is
+    x86-64-v3 because it is built in another container; falls back to it (and says so) if gcc is missing or fails."""
+    global _LIB_PATH, _lib, BUILD_FLAGS
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "libsddp_oracle_native.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", out, os.path.join(_HERE, "sddp_oracle.c"), "-lm", "-lpthread"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
+        _LIB_PATH, _lib, BUILD_FLAGS = out, None, "-O3 -march=native (compiled on this box)"
+    except Exception:
+        pass
+    return BUILD_FLAGS
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
