@@ -16,7 +16,7 @@ import tempfile
 rep, kernel = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(root, "srbd_horizon_b200", "csrc", "libsddp.so")
+lib = os.environ.get("SDDP_NCU_LIB", os.path.join(root, "srbd_horizon_b200", "csrc", "libsddp.so"))      # SDDP_NCU_LIB: e.g. the fp32 build
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]

@@ -17,13 +17,14 @@ from srbd_horizon_b200.problems import make_batch
 
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=1); ap.add_argument("--N", type=int, default=50)
 ap.add_argument("--order", default="schedule")
+ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
 a = ap.parse_args()
 cfg = make_config(MODEL_SRBD, a.N, 0.05, {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3})
 b = make_batch(MODEL_SRBD, a.N, a.batch, enumerate_schedules=True)
-s = BatchedDDP(cfg)
-L = _lib.lib()
+s = BatchedDDP(cfg, dtype=a.dtype)
+L = _lib.lib(a.dtype)
 out = (ctypes.c_longlong * 32)()
-t = lambda v: torch.as_tensor(v, dtype=torch.float64, device="cuda")
+t = lambda v: torch.as_tensor(v, dtype=s.tdtype, device="cuda")
 x0, p, X0, U0 = t(b["x0"]), t(b["params"]), t(b["X0"]), t(b["U0"])
 # partition slots, in program order
 part = [(7, "queue pop (+ tail wait)"), (4, "init: x0, hist, defects + cost"), (0, "node packs (thread per node)"),
