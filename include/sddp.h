@@ -19,7 +19,8 @@
  *
  * Conventions
  *   - plain C, no C++/torch types; all array arguments are DEVICE pointers to
- *     fp64 (int32 for iters/status) unless the function name ends in _host;
+ *     sddp_real (double; float in the optional fp32 build; int32 for iters/status)
+ *     unless the function name ends in _host;
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
  *     work is enqueued on it, nothing synchronises except the *_host calls;
  *   - every function returns 0 on success, a negative SDDP_E* code otherwise,
