@@ -26,6 +26,9 @@ from tests.helpers import relerr
 
 EX_OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}   # dsrbd_example.py:55-58
 TOL_X, TOL_U, TOL_COST, TOL_K = 1e-2, 1e-2, 1e-5, 2e-2
+# inequality extensions (include/sddp.h): all of them on, tight enough to be active at the solution
+INEQ = dict(friction_cone_weight=5.0, friction_cone_mu=0.7, friction_cone_sharpness=8.0, force_bound_weight=2.0, force_bound=0.15,
+            unilateral_weight=3.0, cdot_bound_weight=4.0, cdot_bound=0.4, bound_sharpness=7.0)
 
 
 def _check(cfg, b, B, gains=True):
@@ -62,6 +65,7 @@ def test_f32_config4_schedules_within_stated_tolerance():
     (MODEL_SRBD, 20, {"dense_backward": 1}),                # generic dense Riccati kernel
     (MODEL_SRBD, 20, {"lip_tail_start": 10}),               # model scheduler
     (MODEL_LIP, 20, {}),                                    # dlip_example.py configuration (configs[0])
+    (MODEL_SRBD, 20, dict(INEQ)),                           # every inequality barrier on (the SrbdT<true> instantiation)
 ])
 def test_f32_solve_within_stated_tolerance(model, N, opts):
     B = 24
@@ -90,6 +94,25 @@ def test_f32_host_path_equals_device_path():
     np.testing.assert_array_equal(d["X"], h["X"])
     np.testing.assert_array_equal(d["U"], h["U"])
     np.testing.assert_array_equal(d["cost"], h["cost"])
+
+
+def test_f32_batched_closed_loop():
+    """BatchedMPC (device-side schedule shift, solve, plant step) on the fp32 build: ten ticks of 32 robots stay within the
+    stated tolerance of the same loop on the fp64 build."""
+    from srbd_horizon_b200.mpc import BatchedMPC
+    B, N = 32, 20
+    cfg = make_config(MODEL_SRBD, N, 0.05, EX_OPTS)
+    b = make_batch(MODEL_SRBD, N, B, seed=11)
+    loops = [BatchedMPC(BatchedDDP(cfg, dtype=dt), b["x0"], b["params"], b["U0"]) for dt in ("f64", "f32")]
+    act = np.zeros(B, dtype=np.int32)
+    cmd = np.tile([0.3, 0.0, 0.0], (B, 1))
+    for _ in range(10):
+        for m in loops:
+            r = m.tick(act, cmd)
+            assert bool((r.status == 0).all())
+    s64, s32 = loops[0].state.cpu().numpy(), loops[1].state.double().cpu().numpy()
+    assert loops[1].state.dtype == torch.float32
+    assert relerr(s32, s64) < TOL_X, relerr(s32, s64)
 
 
 def test_f32_drop_in_solver():
