@@ -58,7 +58,7 @@ def build(force: bool = False) -> str:
     outs = [os.path.join(CSRC, "libsddp.so"), os.path.join(CSRC, "libsddp_f32.so")]
     stale = any((not os.path.exists(o)) or any(os.path.getmtime(s) > os.path.getmtime(o) for s in srcs) for o in outs)
     if force or stale:
-        subprocess.check_call(["make", "-C", CSRC, "-B", "all"])
+        subprocess.check_call(["make", "-C", CSRC, "-B", "-j2", "all"])      # the two libraries in parallel
     return LIB_PATH
 
 
