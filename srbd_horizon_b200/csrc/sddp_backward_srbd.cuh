@@ -301,8 +301,7 @@ SDDP_D1ATTR bool ldlt_warp(SMT& S, int lane) {
     __syncwarp();
     real myinv = fast_rcp(b[0]);                               // lane 0's pivot
 #if SDDP_D1BLOCK
-    // One 2 x 2 pivot BLOCK per trip (round 2, tools/microbench/ldlt.cu V20 against V15: 5.5 K instead of 7.4 K cycles for
-    // the 24 steps): lanes j and j+1 publish their columns together -- column j final, column j+1 without the update of
+    // One 2 x 2 pivot BLOCK per trip (round 2, tools/microbench/ldlt.cu V21 against V15): lanes j and j+1 publish their columns together -- column j final, column j+1 without the update of
     // step j -- and after ONE warp sync every lane forms l = c' / p_j (c' = lane j+1's own copy of the symmetric entry:
     // with it every lane reproduces lane j+1's update of its column bit for bit, which keeps the scaling invariance of
     // symmetric LDL^T that the 1e6-weighted blocks need) and the Schur pivot p1 = p_{j+1} - c l itself

@@ -9,7 +9,10 @@
 //   V10: by symmetry col_j[t] is lane t's own a[j]: every lane stores one entry, nobody publishes a column
 //   V20: V15 (rolled, R = 2) with the two pivot steps of a trip as ONE 2 x 2 block step: lanes j and j+1 publish their
 //        columns together (j+1 raw), every lane forms the Schur pivot p1 = p_{j+1} - c^2 / p_j itself and applies both
-//        updates at once, a[i] -= col_j[i] (s1 - l s2) + col_{j+1}[i] s2: one publish -> sync -> load round trip per two steps
+//        updates at once: one publish -> sync -> load round trip per two steps.  V20: a[i] -= col_j[i] (s1 - l s2) + col_{j+1}[i] s2
+//        (two FMAs per entry; NOT what the solver uses: the two large terms cancel in the accumulator);
+//   V21: a[i] -= col_j[i] s1; a[i] -= (col_{j+1}[i] - col_j[i] l) s2 with l from lane j+1's own copy of the symmetric entry: the
+//        elimination of V15 bit for bit, three FMAs per entry (the solver's fp32 form, sddp_backward_srbd.cuh SDDP_D1BLOCK)
 #include <cstdio>
 #include <cuda_runtime.h>
 #define FULL 0xffffffffu
@@ -173,6 +176,47 @@ __device__ __forceinline__ void ldlt(Sm& S, int lane) {
             }
 #pragma unroll
             for (int q = 0; q < NU; q++) a[q] = (q + R < NU) ? a[q + R] : 0.0;
+        }
+    } else if (V == 21) {
+        double npinv = 0.0;
+        int par = 0;
+#pragma unroll 1
+        for (int jb = 0; jb < NU; jb += 2, par ^= 2) {
+            double* pr0 = S.prow[par];
+            double* pr1 = S.prow[par + 1];
+            const double m0 = a[0];
+            if (lane == jb || lane == jb + 1) {
+                if (lane == jb) { npinv = -myinv; pinv = myinv; S.invp[jb] = myinv; }
+                store_row<true>(S.prow[par + (lane - jb)], a, 0);
+            }
+            __syncwarp();
+            const double p0inv = S.invp[jb], c = pr0[1], p1raw = pr1[1];
+            const double l = pr1[0] * p0inv;
+            const double p1 = fma(-c, l, p1raw);
+            const double p1inv = fast_rcp(p1);
+            const double s1 = (lane == jb) ? 0.0 : m0 * p0inv;
+            const double m1 = fma(-c, s1, a[1]);
+            if (lane == jb + 1) { npinv = -p1inv; pinv = p1inv; }
+            const double s2 = (lane == jb + 1) ? 0.0 : m1 * p1inv;
+            a[2] -= pr0[2] * s1; a[2] -= fma(-pr0[2], l, pr1[2]) * s2;
+            myinv = fast_rcp(a[2]);
+#pragma unroll
+            for (int i0 = 0; i0 < NU; i0 += 8) {
+                double2 c0[4], c1[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (i0 + 2 * q + 1 >= 3) { c0[q] = *reinterpret_cast<const double2*>(pr0 + i0 + 2 * q); c1[q] = *reinterpret_cast<const double2*>(pr1 + i0 + 2 * q); }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = i0 + 2 * q;
+                    if (i >= 3) { a[i] -= c0[q].x * s1; a[i] -= fma(-c0[q].x, l, c1[q].x) * s2; }
+                    if (i + 1 >= 3) { a[i + 1] -= c0[q].y * s1; a[i + 1] -= fma(-c0[q].y, l, c1[q].y) * s2; }
+                }
+            }
+            const double e0 = (lane < jb) ? npinv * m0 : (lane == jb ? 1.0 : 0.0);
+            const double e1 = (lane < jb + 1) ? npinv * m1 : (lane == jb + 1 ? 1.0 : 0.0);
+            if (lane < NU) { S.Quu[jb * NU + lane] = e0; S.Quu[(jb + 1) * NU + lane] = e1; }
+#pragma unroll
+            for (int q = 0; q < NU; q++) a[q] = (q + 2 < NU) ? a[q + 2] : 0.0;
         }
     } else if (V == 20) {
         double npinv = 0.0;
@@ -352,5 +396,6 @@ int main() {
     run<16>("V16 = V11 with the symmetric publish of V10", dQ, dout, dcyc, ref);
     run<17>("V17 = V16 + a second warp sync per step", dQ, dout, dcyc, ref);
     run<20>("V20 = V15 with one 2 x 2 block step per trip", dQ, dout, dcyc, ref);
+    run<21>("V21 = V20, bit-identical elimination (3 FMAs)", dQ, dout, dcyc, ref);
     return 0;
 }
