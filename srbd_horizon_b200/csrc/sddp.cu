@@ -241,6 +241,10 @@ static int fail(SddpHandle* h, int code, const char* fmt, const char* a, const c
 // The handle's workspace serves one solve at a time: remember the end of the last launch that used it.
 static cudaError_t mark_last(SddpHandle* h, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
+    // Under CUDA-graph capture (mpc.BatchedMPC.capture: a whole MPC tick as one graph) nothing is recorded: an event recorded
+    // into a capturing stream cannot be synchronised on later, and the graph's own edges order its launches.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) { h->ev_last_valid = false; return cudaSuccess; }
     if (!h->ev_last && (e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming)) != cudaSuccess) return e;
     e = cudaEventRecord(h->ev_last, st);
     h->ev_last_valid = (e == cudaSuccess);

@@ -93,6 +93,48 @@ class BatchedMPC:
         with torch.cuda.device(s.device):
             self._lib.check(s.L.sddp_plant_step(s.h, self.B, self._p(self.state), self._p(self.U), s.N * s.nu, s._stream()), s.h, s.L)
 
+    # -- the tick as ONE CUDA graph (launch-bound small fleets: six launches and memsets become one graph launch) --------
+    def capture(self, gains: bool = False) -> None:
+        """Capture one tick -- schedule advance, solve warm-started in place, plant step -- into a CUDA graph.  Afterwards
+        `tick_graph(actions, cmd)` copies the two small inputs into static device buffers and replays the graph; results are
+        the same bits as `tick` (same kernels on the same buffers).  The dispatch hint of large fleets is not part of the
+        graph (it is a host decision per tick); meant for fleets below one problem per CTA slot, where launches dominate."""
+        torch = self._torch
+        dev = self.solver.device
+        self._g_act = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self._g_cmd = torch.zeros((self.B, 3), dtype=self.solver.tdtype, device=dev)
+        keep = [t.clone() for t in (self.state, self.params, self.X, self.U, self.step_counter)]
+        restore = lambda: [d.copy_(s) for d, s in zip((self.state, self.params, self.X, self.U, self.step_counter), keep)]
+
+        def body():
+            self.advance_schedule(self._g_act, self._g_cmd)
+            r = self.solver.solve(self.state, self.params, self.X, self.U, gains=gains, history=False, inplace=True)
+            self.plant_step()
+            return r
+
+        side = torch.cuda.Stream(device=dev)      # warm-up outside the capture (lazy allocations, module loading)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        restore()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_result = body()
+        restore()
+
+    def tick_graph(self, actions, rdot_ref_cmd):
+        """One closed-loop tick by replaying the captured graph; returns the BatchResult whose tensors the graph overwrites."""
+        torch = self._torch
+        if getattr(self, "_graph", None) is None:
+            raise RuntimeError("call capture() first")
+        self._g_act.copy_(torch.as_tensor(actions, dtype=torch.int32), non_blocking=True)
+        self._g_cmd.copy_(torch.as_tensor(rdot_ref_cmd, dtype=self.solver.tdtype), non_blocking=True)
+        self._graph.replay()
+        self.last = self._g_result
+        return self._g_result
+
     def tick(self, actions, rdot_ref_cmd, gains: bool = False):
         """One closed-loop tick for all B robots; returns the BatchResult of the solve (X, U alias the warm start)."""
         self.advance_schedule(actions, rdot_ref_cmd)

@@ -13,7 +13,7 @@ from srbd_horizon_b200 import wpg
 from srbd_horizon_b200.config import DIMS, MODEL_LIP, MODEL_SRBD, make_config
 from srbd_horizon_b200.ddp import BatchedDDP, DDPSolver
 from srbd_horizon_b200.mpc import BatchedMPC, mpc_tick_references, plant_step
-from srbd_horizon_b200.problems import nominal
+from srbd_horizon_b200.problems import make_batch, nominal
 
 OPTS = {"max_iters": 100, "alpha_converge_threshold": 1e-12, "beta": 1e-3}
 NAMES = {0: "step", 1: "standing", 2: "jump"}
@@ -84,6 +84,36 @@ def test_batched_closed_loop_equals_single_robot_loops():
             np.testing.assert_array_equal(sol["u_opt"].T, Ub[b])
             states[b] = plant_step(solvers[b].ddp_solver, states[b], sol["u_opt"][:, 0])
         np.testing.assert_allclose(mpc.state.cpu().numpy(), np.stack(states), rtol=0, atol=1e-15)
+
+
+def test_tick_as_cuda_graph_equals_tick():
+    """BatchedMPC.capture(): the whole tick (schedule advance, solve, plant step) as one CUDA graph; replays give the same
+    bits as the launch-by-launch tick, and a graph tick is one graph launch instead of six launches / memsets."""
+    import time
+    ns, B, ticks = 20, 6, 8
+    cfg = make_config(MODEL_SRBD, ns, 0.05, OPTS)
+    b = make_batch(MODEL_SRBD, ns, B, seed=21)
+    loops = [BatchedMPC(BatchedDDP(cfg), b["x0"], b["params"], b["U0"]) for _ in range(2)]
+    loops[1].capture()
+    rng = np.random.default_rng(2)
+    acts = rng.choice(3, size=(ticks, B), p=[0.7, 0.2, 0.1]).astype(np.int32)
+    cmd = np.tile([0.3, 0.0, 0.0], (B, 1))
+    for t in range(ticks):
+        r0 = loops[0].tick(acts[t], cmd)
+        r1 = loops[1].tick_graph(acts[t], cmd)
+        for f in ("X", "U", "iters", "status", "cost"):
+            assert torch.equal(getattr(r0, f), getattr(r1, f)), (t, f)
+        assert torch.equal(loops[0].state, loops[1].state) and torch.equal(loops[0].params, loops[1].params)
+        assert torch.equal(loops[0].step_counter, loops[1].step_counter)
+    ms = []
+    for m, fn in ((loops[0], loops[0].tick), (loops[1], loops[1].tick_graph)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(50):
+            fn(acts[t % ticks], cmd)
+        torch.cuda.synchronize()
+        ms.append(1e3 * (time.perf_counter() - t0) / 50)
+    print("closed-loop tick of %d robots: %.3f ms launch by launch, %.3f ms as one CUDA graph" % (B, ms[0], ms[1]))
 
 
 def test_plant_step_matches_example():
