@@ -187,7 +187,7 @@ def workload_config(args, sample_note=None):
          "dispatch": "problems dispatched grouped by contact schedule (device path: hash of the switch pattern of the parameters; host path: the (action, phase) the caller assigned; inside a schedule the largest commanded velocity first), recomputed inside every timed step; results do not depend on it",
          "cache": "inputs larger than L2 (%.1f GB per step), no L2 flush" % (args.batch * (51 * 37 + 50 * 24 + 51 * 19 + 37) * (4 if getattr(args, "dtype", "f64") == "f32" else 8) / 1e9),
          "repeat": "every step re-solves the same batch from the same warm start (X, U cloned inside the timed region)",
-         "gains": "K[B,N,24,37] %s is materialised in HBM every step (%.1f GB for the whole batch)" % (getattr(args, "dtype", "f64"), args.batch * N_HORIZON * 24 * 37 * (4 if getattr(args, "dtype", "f64") == "f32" else 8) / 1e9) if not args.no_gains
+         "gains": "K[B,N,24,37] %s is written to HBM every step into the buffer of the previous step (%.1f GB for the whole batch)" % (getattr(args, "dtype", "f64"), args.batch * N_HORIZON * 24 * 37 * (4 if getattr(args, "dtype", "f64") == "f32" else 8) / 1e9) if not args.no_gains
                   else "gains stay in the per-CTA workspace (--no-gains)"}
     if sample_note:
         c["sample"] = sample_note
@@ -257,10 +257,12 @@ def main():
     gather = ResultGather(solver, args.batch, rank, world, mode=args.gather) if world > 1 else None
     args.gather = gather.mode if gather else "single GPU"
 
+    res = [None]      # K, k, iters, status, cost of the previous step are overwritten (no allocation of K inside a step)
+
     def step():
         Xc, Uc = X0.clone(), U0.clone()
-        r = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True, order="schedule", gather=gather)
-        return r
+        res[0] = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True, order="schedule", gather=gather, out=res[0])
+        return res[0]
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -268,7 +270,21 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    t_w0 = time.perf_counter()
     for _ in range(args.warmup):
+        r = step()
+        if gather:
+            gather.finish()
+    sync_all()
+    # Clock ramp: at 4 - 8 GPUs a step is 60 - 120 ms, so W = 3 warm-up steps are a fraction of a second and a GPU that
+    # boosts late shows up in the max-over-ranks time of the K timed steps (seen at 4 GPUs: 97 / 113 / 140 ms for the same
+    # step).  More untimed steps, the same number on every rank, until about 1.5 s of warm-up have run.
+    t_w = torch.tensor([time.perf_counter() - t_w0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_w, op=dist.ReduceOp.MAX)
+    t_w = float(t_w[0])
+    extra_warmup = int(min(30, max(0, np.ceil((1.5 - t_w) / max(t_w / max(args.warmup, 1), 1e-3))))) if args.warmup > 0 else 0
+    for _ in range(extra_warmup):
         r = step()
         if gather:
             gather.finish()
@@ -283,7 +299,7 @@ def main():
             ev[s][0].record()
             Xc, Uc = X0.clone(), U0.clone()
             kev[s][0].record()
-            r = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True, order="schedule", gather=gather)
+            r = res[0] = solver.solve(x0, params, Xc, Uc, gains=gains, history=False, inplace=True, order="schedule", gather=gather, out=res[0])
             kev[s][1].record()
             if gather:      # push: a 4-byte all-reduce orders the peers' stores; nccl: one all-gather of the packed slab
                 gathered = gather.finish()
@@ -398,7 +414,7 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "parity_max_rel_err": parity["parity_max_rel_err"],
         "gather_ms_per_step": ms_per_step - ms_kernel if world > 1 else None, "gather_ok": gather_ok,
-        "gains_materialised": gains, "wall_s_timed_region": t_wall, "latency": latency,
+        "gains_materialised": gains, "wall_s_timed_region": t_wall, "latency": latency, "extra_untimed_warmup_steps": extra_warmup,
     }
     if args.dtype == "f32":
         line["precision_note"] = ("optional fp32 build (north_star): float storage and Riccati recursion, NARROWER than the reference's fp64; "

@@ -116,11 +116,11 @@ class BatchedDDP:
         # consists of short problems.  Key = -(number of swing entries) * 1e7 + hash of the pattern (< 1e7).
         if isinstance(params, np.ndarray):
             w = (1.0 + np.arange(n * len(cols), dtype=np.float64).reshape(n, len(cols))) ** 2
-            sw = params[:, :n, sl]
+            sw = params[:, :n, sl].astype(np.float64, copy=False)      # (float32 parameters of the fp32 build: the key needs 27 bits)
             key = np.einsum("bnc,nc->b", sw, w) - 1e7 * (1.0 - sw).sum(axis=(1, 2))
             return self.order_from_keys(key, (params[:, -1, 0:3] ** 2).sum(axis=1))
         w = (1.0 + torch.arange(n * len(cols), dtype=torch.float64, device=params.device).reshape(n, len(cols))) ** 2
-        sw = params[:, :n, sl]
+        sw = params[:, :n, sl].to(torch.float64)      # (float32 parameters of the fp32 build: the key needs 27 bits)
         return self.order_from_keys((sw * w).sum(dim=(1, 2)) - 1e7 * (1.0 - sw).sum(dim=(1, 2)), (params[:, -1, 0:3] ** 2).sum(dim=1))
 
     @staticmethod
@@ -142,11 +142,14 @@ class BatchedDDP:
         o1 = torch.argsort(effort, descending=True, stable=True)
         return o1[torch.argsort(group[o1], stable=True)].to(torch.int32)
 
-    def solve(self, x0, params, X0, U0, gains: bool = True, history: bool = True, inplace: bool = False, order=None, gather=None) -> BatchResult:
+    def solve(self, x0, params, X0, U0, gains: bool = True, history: bool = True, inplace: bool = False, order=None, gather=None,
+              out: Optional[BatchResult] = None) -> BatchResult:
         """x0[B,nx], params[B,N+1,np], warm starts X0[B,N+1,nx], U0[B,N,nu] (device tensors).
         order: None (natural dispatch order), "schedule" (`dispatch_order(params)`) or an int32 device permutation.
         gather: a `parallel.ResultGather` of this solver: the kernel also stores every problem's result record into the
-        whole-batch slabs it names (multi-GPU gather); `gather.finish()` afterwards returns the whole-batch views."""
+        whole-batch slabs it names (multi-GPU gather); `gather.finish()` afterwards returns the whole-batch views.
+        out: a BatchResult of an earlier call with the same shapes: its K, k, hist, iters, status, cost tensors are
+        overwritten instead of allocating new ones (K is 7.1 KB per node: a steady-state loop should not allocate it per call)."""
         x0 = torch.as_tensor(x0, dtype=self.tdtype, device=self.device).contiguous()
         B = x0.shape[0]
         N, nx, nu, np_ = self.N, self.nx, self.nu, self.np
@@ -157,12 +160,18 @@ class BatchedDDP:
         if not inplace:
             X, U = X.clone(), U.clone()
         dev = self.device
-        K = torch.empty((B, N, nu, nx), dtype=self.tdtype, device=dev) if gains else None
-        k = torch.empty((B, N, nu), dtype=self.tdtype, device=dev) if gains else None
-        hist = torch.empty((B, self.cfg.max_iters, HIST), dtype=self.tdtype, device=dev) if history else None
-        iters = torch.empty(B, dtype=torch.int32, device=dev)
-        status = torch.empty(B, dtype=torch.int32, device=dev)
-        cost = torch.empty(B, dtype=self.tdtype, device=dev)
+
+        def buf(name, shape, dtype):
+            t = getattr(out, name, None) if out is not None else None
+            if t is not None and tuple(t.shape) == tuple(shape) and t.dtype == dtype and t.device == dev and t.is_contiguous():
+                return t
+            return torch.empty(shape, dtype=dtype, device=dev)
+        K = buf("K", (B, N, nu, nx), self.tdtype) if gains else None
+        k = buf("k", (B, N, nu), self.tdtype) if gains else None
+        hist = buf("hist", (B, self.cfg.max_iters, HIST), self.tdtype) if history else None
+        iters = buf("iters", (B,), torch.int32)
+        status = buf("status", (B,), torch.int32)
+        cost = buf("cost", (B,), self.tdtype)
         user_order = order is not None and not isinstance(order, str)
         if isinstance(order, str):
             if order != "schedule":

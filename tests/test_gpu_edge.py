@@ -170,3 +170,23 @@ def test_device_dispatch_order_is_validated_by_the_wrapper():
     s.L.sddp_set_dispatch_order(s.h, None, 0, 0)
     torch.cuda.synchronize()
     assert int(st[7]) == -1 and bool((st[torch.arange(B) != 7] == 0).all())
+
+
+def test_solve_reuses_the_output_buffers_it_is_given():
+    """BatchedDDP.solve(out=previous result): K, k, hist, iters, status, cost are overwritten in place (a steady-state loop
+    allocates nothing per call), results unchanged."""
+    B, N = 40, 20
+    cfg = make_config(MODEL_SRBD, N, 0.05, EX)
+    b = make_batch(MODEL_SRBD, N, B, seed=9)
+    s = BatchedDDP(cfg)
+    r0 = s.solve(b["x0"], b["params"], b["X0"], b["U0"])
+    ref = {f: getattr(r0, f).clone() for f in ("X", "U", "K", "k", "hist", "iters", "status", "cost")}
+    ptrs = {f: getattr(r0, f).data_ptr() for f in ("K", "k", "hist", "iters", "status", "cost")}
+    r0.K.zero_(); r0.cost.zero_(); r0.iters.zero_()
+    r1 = s.solve(b["x0"], b["params"], b["X0"], b["U0"], out=r0)
+    for f, p in ptrs.items():
+        assert getattr(r1, f).data_ptr() == p, f
+    for f, v in ref.items():
+        assert torch.equal(getattr(r1, f), v), f
+    r2 = s.solve(b["x0"][:8], b["params"][:8], b["X0"][:8], b["U0"][:8], out=r1)      # other shapes: fresh buffers
+    assert r2.K.data_ptr() != ptrs["K"] and torch.equal(r2.X, ref["X"][:8])
